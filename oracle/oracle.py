@@ -1,0 +1,207 @@
+"""ctypes front-end of the CPU checker (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY — see the header of oracle/orb_oracle.c.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".inc"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        for name in ("orc_detect_and_compute", "orc_detect_with_pyramid", "orc_detect", "orc_screen_params",
+                     "orc_calc_descriptors", "orc_get_level", "orc_get_blurred_level", "orc_resize_linear_u8",
+                     "orc_gauss7_u8", "orc_fast9_16", "orc_hamming_match", "orc_match_filter",
+                     "orc_distribute_octtree"):
+            getattr(L, name).restype = C.c_int
+    return _LIB
+
+
+def _p(a, t=C.c_void_p):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    rc = lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    assert rc == 0
+    return dst
+
+
+def gauss7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    rc = lib().orc_gauss7_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    assert rc == 0
+    return dst
+
+
+def fast_atan2(y, x):
+    return float(lib().orc_fast_atan2(C.c_float(y), C.c_float(x)))
+
+
+def fast9_16(img, threshold, nonmax=True):
+    """img may be a non-contiguous 2-D view (ROI).  Returns int array [n,3] = (x, y, response), row-major."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    h, w = img.shape
+    cap = max(1, w * h)
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orc_fast9_16(C.c_void_p(img.ctypes.data), w, h, img.strides[0], int(threshold), int(nonmax), _p(out),
+                           cap)
+    return out[:n].copy()
+
+
+def distribute_octtree(kx, ky, kr, minX, maxX, minY, maxY, N):
+    kx = np.ascontiguousarray(kx, np.float32)
+    ky = np.ascontiguousarray(ky, np.float32)
+    kr = np.ascontiguousarray(kr, np.float32)
+    out = np.empty(max(1, len(kx)), np.int32)
+    n = lib().orc_distribute_octtree(_p(kx), _p(ky), _p(kr), len(kx), minX, maxX, minY, maxY, N, _p(out))
+    return out[:n].copy()
+
+
+def hamming_match(q, t):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+    idx = np.empty(len(q), np.int32)
+    dist = np.empty(len(q), np.int32)
+    lib().orc_hamming_match(_p(q), len(q), _p(t), len(t), _p(idx), _p(dist))
+    return idx, dist
+
+
+def match_filter(train_idx, dist, loop_class_id, cur_class_id):
+    train_idx = np.ascontiguousarray(train_idx, np.int32)
+    dist = np.ascontiguousarray(dist, np.int32)
+    lc = np.ascontiguousarray(loop_class_id, np.int32)
+    cc = np.ascontiguousarray(cur_class_id, np.int32)
+    pairs = np.empty((max(1, len(train_idx)), 2), np.int32)
+    n = lib().orc_match_filter(_p(train_idx), _p(dist), len(train_idx), _p(lc), _p(cc), _p(pairs))
+    return pairs[:n].copy()
+
+
+class ORBextractor:
+    """Mirror of myslam::ORBextractor (include/myslam/ORBextractor.h:47-138) over the C restatement."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST):
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = C.c_void_p(lib().orc_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST))
+        assert self._h
+        n = nlevels
+        self.scale = np.zeros(n, np.float32)
+        self.inv_scale = np.zeros(n, np.float32)
+        self.sigma2 = np.zeros(n, np.float32)
+        self.inv_sigma2 = np.zeros(n, np.float32)
+        self.quota = np.zeros(n, np.int32)
+        self.umax = np.zeros(16, np.int32)
+        lib().orc_get_tables(self._h, _p(self.scale), _p(self.inv_scale), _p(self.sigma2), _p(self.inv_sigma2),
+                             _p(self.quota), _p(self.umax))
+        self.cap = nfeatures + 3 * nlevels + 64
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self._h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _img(a):
+        a = np.ascontiguousarray(a, np.uint8)
+        assert a.ndim == 2
+        return a
+
+    def DetectAndCompute(self, image, mask=None, with_stats=False):
+        image = self._img(image)
+        mask = self._img(mask) if mask is not None else None
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        lc = np.zeros(self.nlevels, np.int32)
+        cands = np.zeros(self.nlevels, np.int32)
+        n = lib().orc_detect_and_compute(self._h, _p(image), _p(mask), image.shape[1], image.shape[0],
+                                         image.strides[0], mask.strides[0] if mask is not None else 0, _p(kps),
+                                         _p(desc), self.cap, _p(lc), _p(cands))
+        assert n <= self.cap
+        if with_stats:
+            return kps[:n].copy(), desc[:n].copy(), lc, cands
+        return kps[:n].copy(), desc[:n].copy()
+
+    def DetectWithPyramid(self, image, mask=None):
+        image = self._img(image)
+        mask = self._img(mask) if mask is not None else None
+        kps = np.zeros(self.cap, KP_DTYPE)
+        n = lib().orc_detect_with_pyramid(self._h, _p(image), _p(mask), image.shape[1], image.shape[0],
+                                          image.strides[0], mask.strides[0] if mask is not None else 0, _p(kps),
+                                          self.cap)
+        return kps[:n].copy()
+
+    def Detect(self, image, mask=None):
+        image = self._img(image)
+        mask = self._img(mask) if mask is not None else None
+        kps = np.zeros(self.cap, KP_DTYPE)
+        n = lib().orc_detect(self._h, _p(image), _p(mask), image.shape[1], image.shape[0], image.strides[0],
+                             mask.strides[0] if mask is not None else 0, _p(kps), self.cap)
+        return kps[:n].copy()
+
+    def ScreenAndComputeKPsParams(self, image, kps_in):
+        """Returns (mutated input, surviving keypoints) like the reference's in/out vectors."""
+        image = self._img(image)
+        kin = np.ascontiguousarray(kps_in, KP_DTYPE).copy()
+        out = np.zeros(max(1, len(kin)), KP_DTYPE)
+        n = lib().orc_screen_params(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0], _p(kin),
+                                    len(kin), _p(out))
+        return kin, out[:n].copy()
+
+    def CalcDescriptors(self, image, kps):
+        image = self._img(image)
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        desc = np.zeros((max(1, len(kps)), 32), np.uint8)
+        n = lib().orc_calc_descriptors(self._h, _p(image), image.shape[1], image.shape[0], image.strides[0], _p(kps),
+                                       len(kps), _p(desc))
+        return desc[:n].copy()
+
+    def level(self, level, mask=False):
+        w, h = C.c_int(), C.c_int()
+        lib().orc_get_level_size(self._h, level, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        rc = lib().orc_get_level(self._h, level, int(mask), _p(out))
+        assert rc == 0
+        return out
+
+    def blurred_level(self, level):
+        w, h = C.c_int(), C.c_int()
+        lib().orc_get_level_size(self._h, level, C.byref(w), C.byref(h))
+        out = np.empty((h.value, w.value), np.uint8)
+        rc = lib().orc_get_blurred_level(self._h, level, _p(out))
+        assert rc == 0
+        return out
