@@ -1,0 +1,137 @@
+/*
+ * slamb200.h — C ABI of the B200-native hot path of the stereo SLAM system.
+ *
+ * This is the drop-in boundary.  The reference (Mingrui-Yu/A-Simple-Stereo-SLAM-System-with-
+ * Deep-Loop-Closing, paths below relative to its root) has no FFI: its operator surface is the
+ * C++ classes compiled into libmyslam.so.  Each entry point here replaces the arithmetic behind
+ * one of those methods; the C++ adaptor classes in
+ *   a-simple-stereo-slam-system-with-deep-loop-closing_b200/host/
+ * keep the reference's class/method names on top of these calls.
+ *
+ * Conventions
+ *   - every function returns an int status: SB_OK (0) or a negative SB_ERR_*; nothing throws;
+ *   - opaque handles own all device memory and one CUDA stream; a handle is not thread-safe,
+ *     different handles are independent (the reference shares one ORBextractor between two
+ *     threads, src/system.cpp:54,66 — the adaptor gives each calling thread its own handle);
+ *   - "_dev" variants take DEVICE pointers, enqueue on the handle's stream and return without
+ *     synchronising; the plain variants take HOST pointers, copy in/out and synchronise;
+ *   - there is no CPU fallback: without a CUDA device every compute call returns SB_ERR_CUDA.
+ */
+#ifndef SLAMB200_H
+#define SLAMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_INVALID (-1)   /* bad argument (null pointer, size out of range, ...) */
+#define SB_ERR_CUDA (-2)      /* CUDA runtime error; sb_last_error() has the text */
+#define SB_ERR_CAPACITY (-3)  /* a per-call capacity fixed at create time was exceeded */
+#define SB_ERR_OVERFLOW (-4)  /* more FAST candidates on one pyramid level than the handle can hold */
+
+/* Text of the last error on the calling thread ("" if none). */
+const char *sb_last_error(void);
+/* Library version string and compiled SM architecture. */
+const char *sb_version(void);
+
+/* field-for-field cv::KeyPoint (28 bytes) */
+typedef struct sb_keypoint {
+    float x, y;      /* pt, level-0 pixel coordinates */
+    float size;      /* 7 from FAST, or 31*scale[octave] */
+    float angle;     /* degrees in [0,360), -1 if not computed */
+    float response;  /* FAST corner score */
+    int32_t octave;  /* pyramid level */
+    int32_t class_id;
+} sb_keypoint;
+
+/* ---------------------------------------------------------------------------------------------
+ * ORB extractor — replaces myslam::ORBextractor (include/myslam/ORBextractor.h:47-138,
+ * src/ORBextractor.cpp:384-1265).  One handle processes up to max_batch images of up to
+ * max_w x max_h pixels per call.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sb_orb sb_orb_t;
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cpp:384-445). */
+int sb_orb_create(sb_orb_t **h, int device, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                  int minThFAST, int max_w, int max_h, int max_batch);
+int sb_orb_destroy(sb_orb_t *h);
+/* Use `stream` (a cudaStream_t) instead of the handle's own stream for all later calls. */
+int sb_orb_set_stream(sb_orb_t *h, void *stream);
+/* Per-image keypoint capacity the caller must provide to the calls below
+ * (sum over levels of max(quota + 3, 4 * nIni) for the pyramid calls). */
+int sb_orb_capacity(const sb_orb_t *h);
+/* GetLevels / GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares /
+ * GetInverseScaleSigmaSquares (ORBextractor.h:88-106) and mnFeaturesPerLevel; each array has
+ * nlevels entries; any pointer may be null. */
+int sb_orb_get_tables(const sb_orb_t *h, int *nlevels, float *scale, float *inv_scale, float *sigma2,
+                      float *inv_sigma2, int *features_per_level);
+
+/* ORBextractor::DetectAndCompute (src/ORBextractor.cpp:922-985) on `batch` images.
+ *   img[b], mask[b] : CV_8UC1 planes, h rows of `stride` bytes (mask: `mstride`); mask == null or
+ *                     mask[b] == null means "all 255" (the reference requires a mask).
+ *   kps  [batch][cap], desc [batch][cap][32], counts [batch]; desc may be null
+ *                     (== ORBextractor::DetectWithPyramid, :1135-1176).
+ * Keypoints are level-major; inside a level in the reference's quadtree list order. */
+int sb_orb_detect_and_compute(sb_orb_t *h, int batch, const uint8_t *const *img, const uint8_t *const *mask, int w,
+                              int hgt, int stride, int mstride, sb_keypoint *kps, uint8_t *desc, int32_t *counts,
+                              int cap);
+/* Same, all pointers on the device; images are d_img + b * img_pitch_bytes (b < batch), masks
+ * likewise (d_mask may be null).  Asynchronous on the handle's stream. */
+int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes,
+                                  const uint8_t *d_mask, int64_t mask_pitch_bytes, int w, int hgt, int stride,
+                                  int mstride, sb_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts, int cap);
+
+/* ORBextractor::Detect (src/ORBextractor.cpp:989-1074): level 0 only, N = nfeatures, keypoints keep
+ * FAST's size 7 / angle -1 / octave 0.  The reference returns silently on an empty mask; here a
+ * null mask means "all 255". */
+int sb_orb_detect(sb_orb_t *h, int batch, const uint8_t *const *img, const uint8_t *const *mask, int w, int hgt,
+                  int stride, int mstride, sb_keypoint *kps, int32_t *counts, int cap);
+int sb_orb_detect_dev(sb_orb_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes, const uint8_t *d_mask,
+                      int64_t mask_pitch_bytes, int w, int hgt, int stride, int mstride, sb_keypoint *d_kps,
+                      int32_t *d_counts, int cap);
+
+/* ORBextractor::ScreenAndComputeKPsParams (src/ORBextractor.cpp:1083-1129) on one image.
+ * `in` [n_in] is mutated exactly like the reference mutates its input vector (pt /= scale,
+ * pt *= scale round trip); survivors are written to out[0 .. *n_out) in input order. */
+int sb_orb_screen_params(sb_orb_t *h, const uint8_t *img, int w, int hgt, int stride, sb_keypoint *in, int n_in,
+                         sb_keypoint *out, int32_t *n_out);
+/* ORBextractor::CalcDescriptors (src/ORBextractor.cpp:1180-1226): desc [n][32], row i <-> kps[i]. */
+int sb_orb_calc_descriptors(sb_orb_t *h, const uint8_t *img, int w, int hgt, int stride, const sb_keypoint *kps,
+                            int n, uint8_t *desc);
+
+/* Debug/inspection: copy pyramid level `level` of image `b` of the LAST call to the host.
+ * which: 0 = mvImagePyramid, 1 = Gaussian-blurred working Mat, 2 = mvMaskPyramid.
+ * out has lh rows of lw bytes (tight); lw/lh are returned. */
+int sb_orb_debug_level(sb_orb_t *h, int b, int level, int which, uint8_t *out, int out_bytes, int *lw, int *lh);
+/* Debug: FAST candidates handed to the quadtree for (image b, level): packed
+ * x | y << 12 | response << 24 (border-relative x, y), unordered.  *n receives the count. */
+int sb_orb_debug_candidates(sb_orb_t *h, int b, int level, uint32_t *out, int cap, int32_t *n);
+
+/* ---------------------------------------------------------------------------------------------
+ * Brute-force Hamming 1-NN — replaces cv::BFMatcher(NORM_HAMMING)::match as used by
+ * LoopClosing::MatchFeatures (src/loopclosing.cpp:33,172): for every query row the nearest train
+ * row, ties -> lowest trainIdx.  `batch` independent (query set, train set) problems per call.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sb_matcher sb_matcher_t;
+int sb_matcher_create(sb_matcher_t **m, int device, int max_batch, int max_rows);
+int sb_matcher_destroy(sb_matcher_t *m);
+int sb_matcher_set_stream(sb_matcher_t *m, void *stream);
+/* q [batch][cap][32], t [batch][cap][32], nq/nt [batch]  ->  train_idx, dist [batch][cap]
+ * (train_idx = -1, dist = -1 where the train set is empty). */
+int sb_hamming_match(sb_matcher_t *m, int batch, const uint8_t *q, const int32_t *nq, const uint8_t *t,
+                     const int32_t *nt, int cap, int32_t *train_idx, int32_t *dist);
+/* Device variant with explicit strides so descriptor sets can live interleaved (e.g. the
+ * [pair][left|right][cap][32] layout sb_orb_detect_and_compute_dev writes):
+ *   query set i = d_q + i * q_set_stride (bytes), its row count = d_nq[i * nq_stride]; train alike;
+ *   results at d_train_idx + i * out_stride (elements). */
+int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d_q, int64_t q_set_stride, const int32_t *d_nq,
+                         int nq_stride, const uint8_t *d_t, int64_t t_set_stride, const int32_t *d_nt,
+                         int nt_stride, int max_rows, int32_t *d_train_idx, int32_t *d_dist, int64_t out_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAMB200_H */

@@ -43,7 +43,7 @@ def lib():
         for name in ("orc_detect_and_compute", "orc_detect_with_pyramid", "orc_detect", "orc_screen_params",
                      "orc_calc_descriptors", "orc_get_level", "orc_get_blurred_level", "orc_resize_linear_u8",
                      "orc_gauss7_u8", "orc_fast9_16", "orc_hamming_match", "orc_match_filter",
-                     "orc_distribute_octtree"):
+                     "orc_distribute_octtree", "orc_debug_candidate_count"):
             getattr(L, name).restype = C.c_int
     return _LIB
 
@@ -172,6 +172,19 @@ class ORBextractor:
         n = lib().orc_detect(self._h, _p(image), _p(mask), image.shape[1], image.shape[0], image.strides[0],
                              mask.strides[0] if mask is not None else 0, _p(kps), self.cap)
         return kps[:n].copy()
+
+    def DetectWithCandidates(self, image, mask=None, cap=1 << 16):
+        """Detect() plus the FAST candidate list [n,3] = (x, y, response), border-relative, in the order the
+        reference's quadtree receives it (test hook)."""
+        buf = np.zeros((cap, 3), np.float32)
+        lib().orc_debug_arm_candidates(_p(buf), cap)
+        try:
+            kps = self.Detect(image, mask)
+            n = lib().orc_debug_candidate_count()
+        finally:
+            lib().orc_debug_arm_candidates(None, 0)
+        assert n <= cap
+        return kps, buf[:n].copy()
 
     def ScreenAndComputeKPsParams(self, image, kps_in):
         """Returns (mutated input, surviving keypoints) like the reference's in/out vectors."""

@@ -591,6 +591,12 @@ static void cand_push(cand_list *c, float x, float y, float r) {
     c->x[c->n] = x; c->y[c->n] = y; c->r[c->n] = r; c->n++;
 }
 
+/* test hook (not thread-safe): when armed, grid_fast_distribute copies its candidate list here */
+static float *g_dbg_xyr = NULL;
+static int g_dbg_cap = 0, g_dbg_n = 0;
+void orc_debug_arm_candidates(float *xyr, int cap) { g_dbg_xyr = xyr; g_dbg_cap = xyr ? cap : 0; g_dbg_n = 0; }
+int orc_debug_candidate_count(void) { return g_dbg_n; }
+
 static int grid_fast_distribute(const orc_extractor *e, const uint8_t *img, const uint8_t *mask, int cols, int rows,
                                 int stride, int mstride, int N, orc_keypoint *out, int cap, int *n_candidates) {
     const float W = 30;
@@ -628,6 +634,12 @@ static int grid_fast_distribute(const orc_extractor *e, const uint8_t *img, cons
     }
     free(fbuf);
     if (n_candidates) *n_candidates = cl.n;
+    if (g_dbg_cap > 0) { /* test hook: expose the candidate list in the reference's order */
+        g_dbg_n = cl.n;
+        for (int k = 0; k < cl.n && k < g_dbg_cap; k++) {
+            g_dbg_xyr[3 * k] = cl.x[k]; g_dbg_xyr[3 * k + 1] = cl.y[k]; g_dbg_xyr[3 * k + 2] = cl.r[k];
+        }
+    }
     int *sel = (int *)malloc(sizeof(int) * (size_t)(cl.n ? cl.n : 1));
     int ns = distribute_octtree(cl.x, cl.y, cl.r, cl.n, minBorderX, maxBorderX, minBorderY, maxBorderY, N, sel);
     int nout = 0;
