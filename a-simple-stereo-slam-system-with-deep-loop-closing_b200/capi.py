@@ -1,0 +1,258 @@
+"""ctypes binding of include/slamb200.h.  Class and method names follow the reference's operator
+surface (include/myslam/ORBextractor.h:47-138; cv::DescriptorMatcher::match as used at
+src/loopclosing.cpp:172) so that the parity tests read like calls into the reference."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+SB_OK, SB_ERR_INVALID, SB_ERR_CUDA, SB_ERR_CAPACITY, SB_ERR_OVERFLOW = 0, -1, -2, -3, -4
+
+
+class SlamB200Error(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"libslamb200 error {code}: {text}")
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(_HERE, "libslamb200.so")
+
+
+def lib():
+    """Loads the product library; raises if it has not been built (there is no fallback)."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C csrc); this package has no CPU fallback")
+        L = C.CDLL(path)
+        L.sb_last_error.restype = C.c_char_p
+        L.sb_version.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def last_error():
+    return lib().sb_last_error().decode()
+
+
+def _check(rc):
+    if rc != SB_OK:
+        raise SlamB200Error(rc, last_error())
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _dev_ptr(t):
+    """torch CUDA tensor / int address -> c_void_p."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(int(t))
+
+
+class ORBextractor:
+    """myslam::ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) on `device`."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_w=1241, max_h=376, max_batch=1,
+                 device=0):
+        self._h = C.c_void_p()
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.max_batch = max_batch
+        _check(lib().sb_orb_create(C.byref(self._h), device, nfeatures, C.c_float(scaleFactor), nlevels, iniThFAST,
+                                   minThFAST, max_w, max_h, max_batch))
+        self.cap = lib().sb_orb_capacity(self._h)
+        n = nlevels
+        self.scale = np.zeros(n, np.float32)
+        self.inv_scale = np.zeros(n, np.float32)
+        self.sigma2 = np.zeros(n, np.float32)
+        self.inv_sigma2 = np.zeros(n, np.float32)
+        self.quota = np.zeros(n, np.int32)
+        nl = C.c_int()
+        _check(lib().sb_orb_get_tables(self._h, C.byref(nl), _p(self.scale), _p(self.inv_scale), _p(self.sigma2),
+                                       _p(self.inv_sigma2), _p(self.quota)))
+
+    def close(self):
+        if self._h:
+            lib().sb_orb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- getters of the reference class (ORBextractor.h:88-106)
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactors(self):
+        return self.scale
+
+    def GetInverseScaleFactors(self):
+        return self.inv_scale
+
+    def GetScaleSigmaSquares(self):
+        return self.sigma2
+
+    def GetInverseScaleSigmaSquares(self):
+        return self.inv_sigma2
+
+    def set_stream(self, stream_ptr):
+        _check(lib().sb_orb_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def sync_status(self):
+        _check(lib().sb_orb_sync_status(self._h))
+
+    @staticmethod
+    def _imgs(images):
+        if isinstance(images, np.ndarray) and images.ndim == 2:
+            images = [images]
+        imgs = [np.ascontiguousarray(i, np.uint8) for i in images]
+        h, w = imgs[0].shape
+        assert all(i.shape == (h, w) for i in imgs)
+        return imgs, w, h
+
+    @staticmethod
+    def _ptr_array(arrs):
+        if arrs is None:
+            return None
+        PA = C.c_void_p * len(arrs)
+        return PA(*[a.ctypes.data if a is not None else None for a in arrs])
+
+    def _masks(self, masks, n, w, h):
+        if masks is None:
+            return None, None
+        if isinstance(masks, np.ndarray) and masks.ndim == 2:
+            masks = [masks]
+        ms = [np.ascontiguousarray(m, np.uint8) if m is not None else None for m in masks]
+        assert len(ms) == n and all(m is None or m.shape == (h, w) for m in ms)
+        return ms, self._ptr_array(ms)
+
+    def DetectAndComputeBatch(self, images, masks=None, descriptors=True):
+        """DetectAndCompute on a list of equally sized images -> list of (keypoints, descriptors)."""
+        imgs, w, h = self._imgs(images)
+        n = len(imgs)
+        ms, mptr = self._masks(masks, n, w, h)
+        kps = np.zeros((n, self.cap), KP_DTYPE)
+        desc = np.zeros((n, self.cap, 32), np.uint8) if descriptors else None
+        counts = np.zeros(n, np.int32)
+        _check(lib().sb_orb_detect_and_compute(self._h, n, self._ptr_array(imgs), mptr, w, h, w, w, _p(kps), _p(desc),
+                                               _p(counts), self.cap))
+        return [(kps[b, :counts[b]].copy(), desc[b, :counts[b]].copy() if descriptors else None) for b in range(n)]
+
+    def DetectAndCompute(self, image, mask=None):
+        return self.DetectAndComputeBatch([image], None if mask is None else [mask])[0]
+
+    def DetectWithPyramid(self, image, mask=None):
+        return self.DetectAndComputeBatch([image], None if mask is None else [mask], descriptors=False)[0][0]
+
+    def DetectBatch(self, images, masks=None):
+        imgs, w, h = self._imgs(images)
+        n = len(imgs)
+        ms, mptr = self._masks(masks, n, w, h)
+        kps = np.zeros((n, self.cap), KP_DTYPE)
+        counts = np.zeros(n, np.int32)
+        _check(lib().sb_orb_detect(self._h, n, self._ptr_array(imgs), mptr, w, h, w, w, _p(kps), _p(counts), self.cap))
+        return [kps[b, :counts[b]].copy() for b in range(n)]
+
+    def Detect(self, image, mask=None):
+        return self.DetectBatch([image], None if mask is None else [mask])[0]
+
+    def ScreenAndComputeKPsParams(self, image, kps_in):
+        """-> (input keypoints as the reference leaves them, surviving keypoints)."""
+        imgs, w, h = self._imgs(image)
+        kin = np.ascontiguousarray(kps_in, KP_DTYPE).copy()
+        out = np.zeros(max(1, len(kin)), KP_DTYPE)
+        n_out = C.c_int32()
+        _check(lib().sb_orb_screen_params(self._h, _p(imgs[0]), w, h, w, _p(kin), len(kin), _p(out), C.byref(n_out)))
+        return kin, out[:n_out.value].copy()
+
+    def CalcDescriptors(self, image, kps):
+        imgs, w, h = self._imgs(image)
+        k = np.ascontiguousarray(kps, KP_DTYPE)
+        desc = np.zeros((max(1, len(k)), 32), np.uint8)
+        _check(lib().sb_orb_calc_descriptors(self._h, _p(imgs[0]), w, h, w, _p(k), len(k), _p(desc)))
+        return desc[:len(k)].copy()
+
+    # -- asynchronous device entry points (torch tensors or raw addresses)
+    def detect_and_compute_dev(self, batch, d_img, img_pitch, w, h, stride, d_kps, d_desc, d_counts, cap, d_mask=None,
+                               mask_pitch=0, mstride=0):
+        _check(lib().sb_orb_detect_and_compute_dev(self._h, batch, _dev_ptr(d_img), C.c_int64(img_pitch),
+                                                   _dev_ptr(d_mask), C.c_int64(mask_pitch), w, h, stride, mstride,
+                                                   _dev_ptr(d_kps), _dev_ptr(d_desc), _dev_ptr(d_counts), cap))
+
+    # -- inspection
+    def debug_level(self, b, level, which=0):
+        lw, lh = C.c_int(), C.c_int()
+        _check(lib().sb_orb_debug_level(self._h, b, level, which, None, 0, C.byref(lw), C.byref(lh)))
+        out = np.empty((lh.value, lw.value), np.uint8)
+        _check(lib().sb_orb_debug_level(self._h, b, level, which, _p(out), out.size, C.byref(lw), C.byref(lh)))
+        return out
+
+    def debug_candidates(self, b, level, cap=1 << 15):
+        out = np.zeros(cap, np.uint32)
+        n = C.c_int32()
+        _check(lib().sb_orb_debug_candidates(self._h, b, level, _p(out), cap, C.byref(n)))
+        out = out[:n.value]
+        return np.stack([out & 0xfff, (out >> 12) & 0xfff, out >> 24], 1).astype(np.int64)
+
+
+class HammingMatcher:
+    """cv::BFMatcher(NORM_HAMMING): match(query, train) -> (trainIdx, distance) per query row."""
+
+    def __init__(self, max_batch=1, max_rows=4096, device=0):
+        self._h = C.c_void_p()
+        self.max_batch, self.max_rows = max_batch, max_rows
+        _check(lib().sb_matcher_create(C.byref(self._h), device, max_batch, max_rows))
+
+    def close(self):
+        if self._h:
+            lib().sb_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        _check(lib().sb_matcher_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def match_batch(self, queries, trains):
+        n = len(queries)
+        cap = max(1, max(max(len(q) for q in queries), max(len(t) for t in trains)))
+        Q = np.zeros((n, cap, 32), np.uint8)
+        T = np.zeros((n, cap, 32), np.uint8)
+        nq = np.array([len(q) for q in queries], np.int32)
+        nt = np.array([len(t) for t in trains], np.int32)
+        for b in range(n):
+            Q[b, :nq[b]] = np.asarray(queries[b], np.uint8).reshape(-1, 32)
+            T[b, :nt[b]] = np.asarray(trains[b], np.uint8).reshape(-1, 32)
+        idx = np.zeros((n, cap), np.int32)
+        dist = np.zeros((n, cap), np.int32)
+        _check(lib().sb_hamming_match(self._h, n, _p(Q), _p(nq), _p(T), _p(nt), cap, _p(idx), _p(dist)))
+        return [(idx[b, :nq[b]].copy(), dist[b, :nq[b]].copy()) for b in range(n)]
+
+    def match(self, query, train):
+        return self.match_batch([query], [train])[0]
+
+    def match_dev(self, batch, d_q, q_set_stride, d_nq, nq_stride, d_t, t_set_stride, d_nt, nt_stride, max_rows, d_idx,
+                  d_dist, out_stride):
+        _check(lib().sb_hamming_match_dev(self._h, batch, _dev_ptr(d_q), C.c_int64(q_set_stride), _dev_ptr(d_nq),
+                                          nq_stride, _dev_ptr(d_t), C.c_int64(t_set_stride), _dev_ptr(d_nt), nt_stride,
+                                          max_rows, _dev_ptr(d_idx), _dev_ptr(d_dist), C.c_int64(out_stride)))

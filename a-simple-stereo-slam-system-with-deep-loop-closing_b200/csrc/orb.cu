@@ -1,0 +1,1266 @@
+// orb.cu — B200 (sm_100a) ORB extractor behind the C ABI of include/slamb200.h.
+//
+// Replaces the arithmetic of myslam::ORBextractor (reference src/ORBextractor.cpp:384-1265) for a
+// BATCH of images per call.  Stage map (reference lines -> kernel):
+//   ComputePyramid            :1229-1265 -> k_copy_level0 + k_resize (one launch per level, chained)
+//   cv::FAST per 30-px cell   :838-883   -> k_fast_cells   (one CTA per cell; tile staged by TMA)
+//   DistributeOctTree         :586-810   -> k_quadtree     (one CTA per (image, level); qt_core.inl)
+//   GaussianBlur per level    :965-966   -> k_blur         (one launch for all levels; TMA halo tiles)
+//   IC_Angle + rBRIEF + output:27-98,:975-983 -> k_describe (one warp per keypoint)
+// Data layout in HBM: every image of the batch owns one "slab" holding its pyramid levels as
+// pitched u8 planes (pitch multiple of 128 B so that each level is a legal TMA tensor
+// [w, h, batch] with strides [pitch, slab]); a second slab array holds the blurred levels and an
+// optional third one the mask pyramid.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "orb_core.inl"
+#include "qt_core.inl"
+
+#define SB_MAX_LEVELS 12
+#define SB_CAND_CAP 16384       // FAST candidates one (image, level) can hand to the quadtree
+#define SB_CELL_LIST_CAP 1024   // local maxima one FAST cell can hold (a cell has < 60 x 60 tested pixels)
+#define FAST_THREADS 128
+#define QT_THREADS 256
+#define BLUR_TW 128
+#define BLUR_TH 32
+#define BLUR_BW 144  // BLUR_TW + 6 halo, rounded up to the 16-byte TMA granule
+#define BLUR_BH 38
+#define DESC_WARPS 8
+
+__device__ __align__(16) int8_t d_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+struct LevelGeom {
+    int w, h, pitch;
+    int fast_bw, fast_bh;      // TMA box of one FAST cell tile
+    long long off;             // byte offset of the level inside an image slab
+    int bw, bh;                // maxBorder - minBorder (the quadtree's box)
+    int nCols, nRows, wCell, hCell;
+    int quota;                 // mnFeaturesPerLevel[level]
+    int xtab, ytab;            // offsets into the resize tables
+    float scale, patch;        // mvScaleFactor[level], (float)(int)(31 * scale)
+};
+
+struct Geom {
+    LevelGeom lv[SB_MAX_LEVELS];
+    int nlevels;
+    long long slab;  // bytes per image
+    int umax[16];
+};
+
+struct Cell {  // one cv::FAST call of the reference's grid loop
+    short level, x0, y0, rw, rh, offx, offy, pad;
+};
+
+struct TmaMaps {
+    CUtensorMap m[SB_MAX_LEVELS];
+};
+
+// ================================================================================================
+// kernels
+// ================================================================================================
+
+// Level 0 = clone of the input (ComputePyramid :1240-1241, :1259-1260), re-pitched.
+__global__ void k_copy_level0(const uint8_t *__restrict__ src, long long src_img_pitch, int stride, int w, int h,
+                              uint8_t *__restrict__ dst, long long slab, int pitch, int batch) {
+    const int p4 = pitch >> 2;
+    const long long total = (long long)batch * h * p4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x4 = (int)(i % p4);
+        const long long r = i / p4;
+        const int y = (int)(r % h), b = (int)(r / h);
+        const uint8_t *s = src + b * src_img_pitch + (long long)y * stride;
+        const int x = x4 * 4;
+        uint32_t v = 0;
+        if (x + 3 < w) {
+            v = (uint32_t)s[x] | ((uint32_t)s[x + 1] << 8) | ((uint32_t)s[x + 2] << 16) | ((uint32_t)s[x + 3] << 24);
+        } else {
+            for (int k = 0; k < 4; k++)
+                if (x + k < w) v |= (uint32_t)s[x + k] << (8 * k);
+        }
+        *reinterpret_cast<uint32_t *>(dst + b * slab + (long long)y * pitch + x) = v;
+    }
+}
+
+// A "null mask" level 0: all 255.
+__global__ void k_fill_level0(uint8_t *dst, long long slab, int pitch, int h, int batch) {
+    const int p4 = pitch >> 2;
+    const long long total = (long long)batch * h * p4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x4 = (int)(i % p4);
+        const long long r = i / p4;
+        const int y = (int)(r % h), b = (int)(r / h);
+        *reinterpret_cast<uint32_t *>(dst + b * slab + (long long)y * pitch + x4 * 4) = 0xffffffffu;
+    }
+}
+
+// cv::resize(level-1 -> level, INTER_LINEAR), fixed point.  4 destination pixels per thread.
+__global__ void __launch_bounds__(256) k_resize(uint8_t *__restrict__ pyr, long long slab, LevelGeom src, LevelGeom dst,
+                                               const int *__restrict__ xofs, const short2 *__restrict__ xco,
+                                               const int *__restrict__ yofs, const short2 *__restrict__ yco) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= dst.w) return;
+    uint8_t *base = pyr + (long long)blockIdx.z * slab;
+    const int sy = yofs[dst.ytab + y];
+    const short2 bc = yco[dst.ytab + y];
+    const int sy0 = min(max(sy, 0), src.h - 1), sy1 = min(max(sy + 1, 0), src.h - 1);
+    const uint8_t *S0 = base + src.off + (long long)sy0 * src.pitch;
+    const uint8_t *S1 = base + src.off + (long long)sy1 * src.pitch;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = x0 + k;
+        if (x < dst.w) {
+            const int sx = xofs[dst.xtab + x];
+            const short2 ac = xco[dst.xtab + x];
+            const int sx1 = min(sx + 1, src.w - 1);
+            const int h0 = S0[sx] * ac.x + S0[sx1] * ac.y;
+            const int h1 = S1[sx] * ac.x + S1[sx1] * ac.y;
+            out |= (uint32_t)sb_lin_vert(h0, h1, bc.x, bc.y) << (8 * k);
+        }
+    }
+    *reinterpret_cast<uint32_t *>(base + dst.off + (long long)y * dst.pitch + x0) = out;
+}
+
+// cv::FAST(cell ROI, iniTh, nms) with the minTh fallback (ComputeKeyPointsOctTree :838-883 /
+// Detect :1015-1060), one CTA per cell.  The corner response does not depend on the threshold and
+// "corner at t" <=> response >= t, so one response plane serves both thresholds; 3x3 non-maximum
+// suppression is threshold independent for the survivors (a neighbour below t is also below the
+// survivor).  Only the ROI's inner [3, rw-3) x [3, rh-3) box is tested, outside counts as 0 —
+// exactly the per-cell semantics of the reference.
+struct FastArgs {
+    const Cell *cells;
+    const uint8_t *mask_pyr;  // null: no mask
+    uint32_t *cand;           // [batch][nlevels][SB_CAND_CAP]
+    int *cand_cnt;            // [batch][nlevels]
+    int *flags;               // [0] overflow
+    long long slab;
+    int nlevels, iniTh, minTh, tile_bytes;
+};
+
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ TmaMaps maps,
+                                                            const __grid_constant__ Geom g, FastArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_n, s_any;
+    uint8_t *tile = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);  // TMA destination
+    uint8_t *sc = tile + a.tile_bytes;
+    uint32_t *list = reinterpret_cast<uint32_t *>(tile + 2 * a.tile_bytes);
+
+    const Cell c = a.cells[blockIdx.x];
+    const int img = blockIdx.y;
+    const LevelGeom &L = g.lv[c.level];
+    const int BW = L.fast_bw, BH = L.fast_bh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) {
+        s_n = 0;
+        s_any = 0;
+        sb_mbar_init(&bar, 1);
+        sb_mbar_expect_tx(&bar, (uint32_t)(BW * BH));
+        sb_tma_load_3d(tile, &maps.m[c.level], c.x0, c.y0, img, &bar);
+    }
+    for (int i = tid; i < (BW * BH) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(sc)[i] = 0u;
+    __syncthreads();
+    sb_mbar_wait(&bar, 0);
+
+    const int t0 = min(a.iniTh, a.minTh);
+    for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
+        for (int x = 3 + lane; x < c.rw - 3; x += 32) {
+            const uint8_t *p = tile + y * BW + x;
+            if (sb_fast_maybe(p, BW, t0)) {
+                const int s = sb_fast_score(p, BW);
+                if (s >= t0) sc[y * BW + x] = (uint8_t)s;
+            }
+        }
+    __syncthreads();
+    for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
+        for (int x = 3 + lane; x < c.rw - 3; x += 32) {
+            const uint8_t *q = sc + y * BW + x;
+            const int s = q[0];
+            if (s > 0 && s > q[-1] && s > q[1] && s > q[-BW - 1] && s > q[-BW] && s > q[-BW + 1] && s > q[BW - 1] &&
+                s > q[BW] && s > q[BW + 1]) {
+                const int i = atomicAdd(&s_n, 1);
+                if (i < SB_CELL_LIST_CAP) list[i] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+                if (s >= a.iniTh) s_any = 1;
+            }
+        }
+    __syncthreads();
+    const int n = min(s_n, SB_CELL_LIST_CAP);
+    const int th = s_any ? a.iniTh : a.minTh;  // the reference's second cv::FAST call only if the first found nothing
+    const int slot = img * a.nlevels + c.level;
+    for (int i = tid; i < n; i += FAST_THREADS) {
+        const uint32_t w = list[i];
+        const int s = (int)(w >> 24);
+        if (s < th) continue;
+        const int x = (int)(w & 0xfff) + c.offx, y = (int)((w >> 12) & 0xfff) + c.offy;  // border-relative
+        // quirk Q1 (:871-877): the mask is read at the border-relative coordinates
+        if (a.mask_pyr && a.mask_pyr[(long long)img * a.slab + L.off + (long long)y * L.pitch + x] == 0) continue;
+        const int pos = atomicAdd(&a.cand_cnt[slot], 1);
+        if (pos < SB_CAND_CAP)
+            a.cand[(long long)slot * SB_CAND_CAP + pos] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+        else
+            a.flags[0] = 1;
+    }
+}
+
+// DistributeOctTree: one CTA per (image, level).
+struct QtArgs {
+    const uint32_t *cand;
+    const int *cand_cnt;
+    uint32_t *sel;   // [batch][nlevels][selcap]
+    int *sel_cnt;    // [batch][nlevels]
+    int nlevels, selcap, ncap, candcap_smem;
+    int N_override;  // > 0: Detect() — level 0 with N = nfeatures
+};
+
+static size_t qt_smem_bytes(int ncap) {
+    int P = 1;
+    while (P < ncap) P <<= 1;
+    size_t b = 0;
+    b += (size_t)ncap * 16;          // childcnt (also the 64-bit "best" array)
+    b += (size_t)P * 4;              // keys
+    b += 64 * 4;                     // scratch
+    b += 5 * (size_t)ncap * 4;       // ord cpre spre cbase ubase
+    b += 2 * (size_t)ncap * 8;       // boxes
+    b += 2 * (size_t)ncap * 2;       // counts
+    b += (size_t)SB_CAND_CAP * 2;    // cnode
+    b += (size_t)SB_CAND_CAP;        // cq
+    return b + 64;
+}
+
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__ Geom g, QtArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int level = blockIdx.x, img = blockIdx.y;
+    const LevelGeom &L = g.lv[level];
+    const int slot = img * a.nlevels + level;
+    const int ncap = a.ncap;
+    int P = 1;
+    while (P < ncap) P <<= 1;
+
+    QtCtx c;
+    uint8_t *p = smem;
+    c.childcnt = reinterpret_cast<int *>(p); p += (size_t)ncap * 16;
+    c.keys = reinterpret_cast<uint32_t *>(p); p += (size_t)P * 4;
+    c.scratch = reinterpret_cast<int *>(p); p += 64 * 4;
+    c.ord = reinterpret_cast<int *>(p); p += (size_t)ncap * 4;
+    c.cpre = reinterpret_cast<int *>(p); p += (size_t)ncap * 4;
+    c.spre = reinterpret_cast<int *>(p); p += (size_t)ncap * 4;
+    c.cbase = reinterpret_cast<int *>(p); p += (size_t)ncap * 4;
+    c.ubase = reinterpret_cast<int *>(p); p += (size_t)ncap * 4;
+    c.box[0] = reinterpret_cast<int16_t *>(p); p += (size_t)ncap * 8;
+    c.box[1] = reinterpret_cast<int16_t *>(p); p += (size_t)ncap * 8;
+    c.cnt[0] = reinterpret_cast<uint16_t *>(p); p += (size_t)ncap * 2;
+    c.cnt[1] = reinterpret_cast<uint16_t *>(p); p += (size_t)ncap * 2;
+    c.cnode = reinterpret_cast<uint16_t *>(p); p += (size_t)SB_CAND_CAP * 2;
+    c.cq = p;
+    c.cand = a.cand + (long long)slot * SB_CAND_CAP;
+    c.n = min(a.cand_cnt[slot], SB_CAND_CAP);
+    c.ncap = ncap;
+    c.width = L.bw;
+    c.height = L.bh;
+    c.N = a.N_override > 0 ? a.N_override : L.quota;
+    c.nCols = L.nCols;
+    c.wCell = L.wCell;
+    c.hCell = L.hCell;
+    const int S = qt_distribute(c, a.sel + (long long)slot * a.selcap, a.selcap);
+    if (threadIdx.x == 0) a.sel_cnt[slot] = min(S, a.selcap);
+}
+
+// GaussianBlur 7x7 sigma 2 on every level (DetectAndCompute :965-966, CalcDescriptors :1194-1199).
+// One CTA per 128 x 32 output tile; the 134 x 38 input window arrives as one TMA box (zero filled
+// outside the image); BORDER_REFLECT_101 is resolved by index inside the tile.
+struct BlurTile {
+    short level, tx, ty, pad;
+};
+struct BlurArgs {
+    const BlurTile *tiles;
+    uint8_t *blur;
+    long long slab;
+};
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps maps, const __grid_constant__ Geom g,
+                                             BlurArgs a) {
+    __shared__ __align__(128) uint8_t tile[BLUR_BH * BLUR_BW];
+    __shared__ __align__(16) uint16_t hrow[BLUR_BH * BLUR_TW];
+    __shared__ __align__(8) uint64_t bar;
+    const BlurTile t = a.tiles[blockIdx.x];
+    const int img = blockIdx.y;
+    const LevelGeom &L = g.lv[t.level];
+    const int x0 = t.tx * BLUR_TW, y0 = t.ty * BLUR_TH;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        sb_mbar_init(&bar, 1);
+        sb_mbar_expect_tx(&bar, BLUR_BH * BLUR_BW);
+        sb_tma_load_3d(tile, &maps.m[t.level], x0 - 3, y0 - 3, img, &bar);
+    }
+    __syncthreads();
+    sb_mbar_wait(&bar, 0);
+
+    const bool interior_x = x0 >= 3 && x0 + BLUR_TW + 3 <= L.w;
+    // horizontal pass: tile row r <-> image row y0 - 3 + r (rows outside the image are never used)
+    for (int i = tid; i < BLUR_BH * BLUR_TW; i += 256) {
+        const int r = i / BLUR_TW, cx = i % BLUR_TW;
+        const uint8_t *row = tile + r * BLUR_BW;
+        unsigned v;
+        if (interior_x) {
+            v = sb_gauss_row(row[cx], row[cx + 1], row[cx + 2], row[cx + 3], row[cx + 4], row[cx + 5], row[cx + 6]);
+        } else {
+            int ix[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                int gx = x0 + cx + k - 3;
+                gx = sb_reflect101(gx, L.w);
+                ix[k] = min(max(gx - (x0 - 3), 0), BLUR_BW - 1);  // clamp only guards columns past the image (unused)
+            }
+            v = sb_gauss_row(row[ix[0]], row[ix[1]], row[ix[2]], row[ix[3]], row[ix[4]], row[ix[5]], row[ix[6]]);
+        }
+        hrow[i] = (uint16_t)v;
+    }
+    __syncthreads();
+    // vertical pass: one warp per output row, 4 pixels per lane
+    const int lane = tid & 31, warp = tid >> 5;
+    uint8_t *out = a.blur + (long long)img * a.slab + L.off;
+    for (int ry = warp; ry < BLUR_TH; ry += 8) {
+        const int y = y0 + ry;
+        if (y >= L.h) break;
+        int rr[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) rr[k] = sb_reflect101(y + k - 3, L.h) - (y0 - 3);
+        const int cx = lane * 4;
+        if (x0 + cx >= L.w) continue;
+        uint32_t o = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = cx + j;
+            o |= (uint32_t)sb_gauss_col(hrow[rr[0] * BLUR_TW + c], hrow[rr[1] * BLUR_TW + c], hrow[rr[2] * BLUR_TW + c],
+                                        hrow[rr[3] * BLUR_TW + c], hrow[rr[4] * BLUR_TW + c], hrow[rr[5] * BLUR_TW + c],
+                                        hrow[rr[6] * BLUR_TW + c])
+                 << (8 * j);
+        }
+        *reinterpret_cast<uint32_t *>(out + (long long)y * L.pitch + x0 + cx) = o;
+    }
+}
+
+// IC_Angle (:27-55): moments over the radius-15 disc, one warp, lane = column u.
+static __device__ __forceinline__ float warp_ic_angle(const uint8_t *center, int pitch, const int *umax, int lane) {
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - SB_HALF_PATCH, au = abs(u);
+        m10 = u * center[u];
+#pragma unroll 5
+        for (int v = 1; v <= SB_HALF_PATCH; v++) {
+            if (au <= umax[v]) {
+                const int vp = center[u + v * pitch], vm = center[u - v * pitch];
+                m10 += u * (vp + vm);
+                m01 += v * (vp - vm);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    return sb_fast_atan2((float)m01, (float)m10);
+}
+
+// computeOrbDescriptor (:59-98): lane i produces byte i (pairs 8i .. 8i+7).
+static __device__ __forceinline__ uint32_t warp_brief_byte(const uint8_t *center, int pitch, float angle_deg,
+                                                           const int8_t *pat, int lane) {
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float ang = sb_fmul(angle_deg, factorPI);
+    double sn, cs;
+    sincos((double)ang, &sn, &cs);
+    const float a = (float)cs, b = (float)sn;
+    const int8_t *q = pat + lane * 32;
+    uint32_t val = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int t0 = sb_brief_sample(center, pitch, a, b, (float)q[4 * j], (float)q[4 * j + 1]);
+        const int t1 = sb_brief_sample(center, pitch, a, b, (float)q[4 * j + 2], (float)q[4 * j + 3]);
+        val |= (uint32_t)(t0 < t1) << j;
+    }
+    return val;
+}
+
+static __device__ __forceinline__ void warp_store_keypoint(sb_keypoint *dst, float x, float y, float size, float angle,
+                                                           float response, int octave, int class_id, int lane) {
+    uint32_t w;
+    switch (lane) {
+        case 0: w = __float_as_uint(x); break;
+        case 1: w = __float_as_uint(y); break;
+        case 2: w = __float_as_uint(size); break;
+        case 3: w = __float_as_uint(angle); break;
+        case 4: w = __float_as_uint(response); break;
+        case 5: w = (uint32_t)octave; break;
+        default: w = (uint32_t)class_id; break;
+    }
+    if (lane < 7) reinterpret_cast<uint32_t *>(dst)[lane] = w;
+}
+
+// Orientation, descriptor and the level-major output of DetectAndCompute (:905-906, :970-983).
+struct DescArgs {
+    const uint8_t *pyr, *blur;
+    const uint32_t *sel;
+    const int *sel_cnt;
+    sb_keypoint *kps;   // [batch][cap]
+    uint8_t *desc;      // [batch][cap][32] or null
+    int32_t *counts;    // [batch]
+    int *flags;         // [1] capacity
+    long long slab;
+    int nlevels, selcap, cap;
+};
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, DescArgs a) {
+    __shared__ int8_t pat[1024];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t *>(pat)[i] = reinterpret_cast<const uint32_t *>(d_pattern)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int level = blockIdx.y, img = blockIdx.z;
+    const int k = blockIdx.x * DESC_WARPS + warp;
+    const int *cnt = a.sel_cnt + img * a.nlevels;
+    int offset = 0, total = 0;
+    for (int l = 0; l < a.nlevels; l++) {
+        const int c = cnt[l];
+        if (l < level) offset += c;
+        total += c;
+    }
+    if (level == 0 && k == 0 && lane == 0) {
+        a.counts[img] = min(total, a.cap);
+        if (total > a.cap) a.flags[1] = 1;
+    }
+    if (k >= cnt[level] || offset + k >= a.cap) return;
+    const LevelGeom &L = g.lv[level];
+    const uint32_t w = a.sel[((long long)img * a.nlevels + level) * a.selcap + k];
+    const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;  // :895-896
+    const long long o = (long long)img * a.slab + L.off + (long long)y * L.pitch + x;
+    const float angle = warp_ic_angle(a.pyr + o, L.pitch, g.umax, lane);
+    const long long row = (long long)img * a.cap + offset + k;
+    if (a.desc) {
+        const uint32_t byte = warp_brief_byte(a.blur + o, L.pitch, angle, pat, lane);
+        a.desc[row * 32 + lane] = (uint8_t)byte;
+    }
+    float fx = (float)x, fy = (float)y;
+    if (level != 0) { fx = sb_fmul(fx, L.scale); fy = sb_fmul(fy, L.scale); }  // :975-981
+    warp_store_keypoint(a.kps + row, fx, fy, L.patch, angle, (float)(w >> 24), level, -1, lane);
+}
+
+// Output of Detect (:1062-1073): FAST's size 7 / angle -1 / octave 0 are kept (quirk Q4).
+__global__ void k_emit_detect(const uint32_t *sel, const int *sel_cnt, int nlevels, int selcap, sb_keypoint *kps,
+                              int32_t *counts, int cap, int *flags) {
+    const int img = blockIdx.y;
+    const int n = sel_cnt[img * nlevels];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) {
+        counts[img] = min(n, cap);
+        if (n > cap) flags[1] = 1;
+    }
+    if (k >= n || k >= cap) return;
+    const uint32_t w = sel[(long long)img * nlevels * selcap + k];
+    sb_keypoint kp;
+    kp.x = (float)((int)(w & 0xfff) + SB_EDGE - 3);
+    kp.y = (float)((int)((w >> 12) & 0xfff) + SB_EDGE - 3);
+    kp.size = 7.f;
+    kp.angle = -1.f;
+    kp.response = (float)(w >> 24);
+    kp.octave = 0;
+    kp.class_id = -1;
+    kps[(long long)img * cap + k] = kp;
+}
+
+// ScreenAndComputeKPsParams (:1083-1129): one warp per input keypoint; `kps` is mutated like the
+// reference mutates its input vector; keep[i] = 1 for survivors.
+static __device__ __forceinline__ bool is_fast_corner_at(const uint8_t *p, int pitch, int threshold) {
+    // isFastCorner (:449-511): more than 8 contiguous ring pixels darker than v - t or brighter than v + t
+    const int v = p[0];
+    uint32_t dark = 0, bright = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const int r = p[SB_RING_DY(k) * pitch + SB_RING_DX(k)];
+        dark |= (uint32_t)(r < v - threshold) << k;
+        bright |= (uint32_t)(r > v + threshold) << k;
+    }
+    dark |= dark << 16;      // the reference walks 25 entries = the ring plus its first 9 again
+    bright |= bright << 16;
+    bool hit = false;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        hit |= ((dark >> s) & 0x1ffu) == 0x1ffu;
+        hit |= ((bright >> s) & 0x1ffu) == 0x1ffu;
+    }
+    return hit;
+}
+
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_screen(const __grid_constant__ Geom g, const uint8_t *pyr,
+                                                           sb_keypoint *kps, int n, uint8_t *keep, int minTh) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+    if (i >= n) return;
+    sb_keypoint kp = kps[i];
+    const int level = kp.octave;
+    bool ok = level >= 0 && level < g.nlevels;
+    float x = kp.x, y = kp.y, angle = kp.angle, size = kp.size;
+    if (ok) {
+        const LevelGeom &L = g.lv[level];
+        x = sb_fdiv(x, L.scale);
+        y = sb_fdiv(y, L.scale);
+        ok = sb_fsub(y, (float)SB_EDGE) >= 0.f && sb_fadd(y, (float)SB_EDGE) < (float)L.h &&
+             sb_fsub(x, (float)SB_EDGE) >= 0.f && sb_fadd(x, (float)SB_EDGE) < (float)L.w;
+        if (ok) {
+            const uint8_t *c = pyr + L.off + (long long)sb_rint(y) * L.pitch + sb_rint(x);
+            ok = is_fast_corner_at(c, L.pitch, minTh);
+            if (ok) {
+                angle = warp_ic_angle(c, L.pitch, g.umax, lane);
+                size = sb_fmul(31.f, L.scale);
+            }
+        }
+        x = sb_fmul(x, L.scale);  // quirk Q5: the round trip happens for rejected keypoints too
+        y = sb_fmul(y, L.scale);
+    }
+    warp_store_keypoint(kps + i, x, y, size, angle, kp.response, kp.octave, kp.class_id, lane);
+    if (lane == 0) keep[i] = ok ? 1 : 0;
+}
+
+// CalcDescriptors (:1180-1226): row i = descriptor of keypoint i on the blurred level `octave`.
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_calc_desc(const __grid_constant__ Geom g, const uint8_t *blur,
+                                                              const sb_keypoint *kps, int n, uint8_t *desc) {
+    __shared__ int8_t pat[1024];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t *>(pat)[i] = reinterpret_cast<const uint32_t *>(d_pattern)[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const sb_keypoint kp = kps[i];
+    const LevelGeom &L = g.lv[kp.octave];
+    const float x = sb_fdiv(kp.x, L.scale), y = sb_fdiv(kp.y, L.scale);
+    const uint8_t *c = blur + L.off + (long long)sb_rint(y) * L.pitch + sb_rint(x);
+    desc[(long long)i * 32 + lane] = (uint8_t)warp_brief_byte(c, L.pitch, kp.angle, pat, lane);
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct sb_orb {
+    int device;
+    int nfeatures, nlevels, iniTh, minTh;
+    double scaleFactor;  // the reference keeps the float argument in a double member (ORBextractor.h:125)
+    int max_w, max_h, max_batch;
+    float scale[SB_MAX_LEVELS], inv_scale[SB_MAX_LEVELS], sigma2[SB_MAX_LEVELS], inv_sigma2[SB_MAX_LEVELS];
+    int quota[SB_MAX_LEVELS];
+    int umax[16];
+    cudaStream_t stream, own_stream, side_stream;
+    cudaEvent_t ev_fork, ev_join;
+    // geometry of the current image size
+    int cur_w, cur_h;
+    Geom geom;
+    TmaMaps fast_maps, blur_maps, blur_maps_mask_unused;
+    int n_cells, n_cells_l0, n_blur_tiles;
+    int fast_tile_bytes;
+    int selcap, ncap_pyr, ncap_detect;
+    long long slab_cap;  // bytes reserved per image
+    int kp_cap;          // sb_orb_capacity()
+    // device memory
+    uint8_t *d_pyr, *d_blur, *d_mask;
+    Cell *d_cells;
+    BlurTile *d_tiles;
+    int *d_xofs, *d_yofs;
+    short2 *d_xco, *d_yco;
+    uint32_t *d_cand, *d_sel;
+    int *d_cand_cnt, *d_sel_cnt, *d_flags;
+    int tab_cap, cell_cap, tile_cap;
+    // staging for the host-pointer entry points
+    uint8_t *d_in, *d_in_mask, *d_desc_out;
+    sb_keypoint *d_kps_out;
+    int32_t *d_counts_out;
+    uint8_t *d_keep;
+    size_t in_cap;
+    int stage_cap, stage_batch;
+    int *h_flags;  // pinned
+};
+
+static void free_orb(sb_orb *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->d_pyr,  h->d_blur, h->d_mask,     h->d_cells,   h->d_tiles,   h->d_xofs,    h->d_yofs,
+                    h->d_xco,  h->d_yco,  h->d_cand,     h->d_sel,     h->d_cand_cnt, h->d_sel_cnt, h->d_flags,
+                    h->d_in,   h->d_in_mask, h->d_desc_out, h->d_kps_out, h->d_counts_out, h->d_keep};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    delete h;
+}
+
+// ORBextractor::ORBextractor (:384-445): scale tables, per-level quotas, umax.
+static void build_tables(sb_orb *h) {
+    const int n = h->nlevels;
+    h->scale[0] = 1.0f;
+    h->sigma2[0] = 1.0f;
+    for (int i = 1; i < n; i++) {
+        h->scale[i] = (float)(h->scale[i - 1] * h->scaleFactor);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < n; i++) {
+        h->inv_scale[i] = 1.0f / h->scale[i];
+        h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+    }
+    const float factor = (float)(1.0f / h->scaleFactor);
+    float want = h->nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)n));
+    int sum = 0;
+    for (int l = 0; l < n - 1; l++) {
+        h->quota[l] = (int)lrintf(want);
+        sum += h->quota[l];
+        want *= factor;
+    }
+    h->quota[n - 1] = h->nfeatures - sum > 0 ? h->nfeatures - sum : 0;
+    // umax: quarter circle of radius 15, made symmetric about the diagonal
+    const int vmax = (int)floorf(SB_HALF_PATCH * sqrtf(2.f) / 2 + 1);
+    const int vmin = (int)ceilf(SB_HALF_PATCH * sqrtf(2.f) / 2);
+    const double r2 = (double)SB_HALF_PATCH * SB_HALF_PATCH;
+    memset(h->umax, 0, sizeof(h->umax));
+    for (int v = 0; v <= vmax; v++) h->umax[v] = (int)lrint(sqrt(r2 - (double)v * v));
+    for (int v = SB_HALF_PATCH, v0 = 0; v >= vmin; --v) {
+        while (h->umax[v0] == h->umax[v0 + 1]) ++v0;
+        h->umax[v] = v0;
+        ++v0;
+    }
+}
+
+static void level_size(const sb_orb *h, int w, int hgt, int level, int *lw, int *lh) {
+    if (level == 0) { *lw = w; *lh = hgt; return; }
+    *lw = (int)lrintf((float)w * h->inv_scale[level]);   // Size(cvRound(cols * scale), cvRound(rows * scale)) :1237-1238
+    *lh = (int)lrintf((float)hgt * h->inv_scale[level]);
+}
+
+static long long slab_bytes(const sb_orb *h, int w, int hgt) {
+    long long off = 0;
+    for (int l = 0; l < h->nlevels; l++) {
+        int lw, lh;
+        level_size(h, w, hgt, l, &lw, &lh);
+        if (lw < 1 || lh < 1) return -1;
+        off += (long long)sb_align_up((size_t)sb_align_up(lw, 128) * lh, 256);
+    }
+    return off;
+}
+
+static int quadtree_ncap(int N, int bw, int bh) {
+    const int nIni = (int)roundf((float)bw / (float)bh);
+    const int a = 4 * (nIni > 0 ? nIni : 1), b = N + 3;
+    return (a > b ? a : b) + 1;
+}
+
+// Everything that depends on the image size: level geometry, resize tables, FAST cells, blur tiles,
+// tensor maps.  Cached for the last (w, h).
+static int configure(sb_orb *h, int w, int hgt) {
+    if (h->cur_w == w && h->cur_h == hgt) return SB_OK;
+    SB_REQUIRE(w <= h->max_w && hgt <= h->max_h, "image larger than max_w x max_h given at create time");
+    Geom &g = h->geom;
+    memset(&g, 0, sizeof(g));
+    g.nlevels = h->nlevels;
+    memcpy(g.umax, h->umax, sizeof(g.umax));
+    std::vector<int> xofs, yofs;
+    std::vector<short2> xco, yco;
+    std::vector<Cell> cells;
+    std::vector<BlurTile> tiles;
+    long long off = 0;
+    int fast_tile = 0, selcap = 0, ncap_pyr = 0, kp_cap = 0;
+    for (int l = 0; l < h->nlevels; l++) {
+        LevelGeom &L = g.lv[l];
+        level_size(h, w, hgt, l, &L.w, &L.h);
+        // every level must hold at least one 30-px FAST cell inside the 16-px border (:826-836)
+        SB_REQUIRE(L.w - 32 >= 30 && L.h - 32 >= 30, "image too small for this number of pyramid levels");
+        L.pitch = (int)sb_align_up(L.w, 128);
+        L.off = off;
+        off += (long long)sb_align_up((size_t)L.pitch * L.h, 256);
+        L.scale = h->scale[l];
+        L.patch = (float)(int)(31 * h->scale[l]);
+        L.quota = h->quota[l];
+        // FAST grid (:826-836), float arithmetic as in the reference
+        const float width = (float)(L.w - 32), height = (float)(L.h - 32), W = 30.f;
+        L.bw = L.w - 32;
+        L.bh = L.h - 32;
+        L.nCols = (int)(width / W);
+        L.nRows = (int)(height / W);
+        L.wCell = (int)ceilf(width / L.nCols);
+        L.hCell = (int)ceilf(height / L.nRows);
+        SB_REQUIRE(L.wCell + 6 <= 72 && L.hCell + 6 <= 72, "FAST cell larger than supported");
+        L.fast_bw = (int)sb_align_up(L.wCell + 6, 16);
+        L.fast_bh = L.hCell + 6;
+        if (L.fast_bw * L.fast_bh > fast_tile) fast_tile = L.fast_bw * L.fast_bh;
+        const int minB = SB_EDGE - 3, maxBX = L.w - SB_EDGE + 3, maxBY = L.h - SB_EDGE + 3;
+        for (int i = 0; i < L.nRows; i++) {
+            const int iniY = minB + i * L.hCell;
+            int maxY = iniY + L.hCell + 6;
+            if (iniY >= maxBY - 3) continue;
+            if (maxY > maxBY) maxY = maxBY;
+            for (int j = 0; j < L.nCols; j++) {
+                const int iniX = minB + j * L.wCell;
+                int maxX = iniX + L.wCell + 6;
+                if (iniX >= maxBX - 6) continue;
+                if (maxX > maxBX) maxX = maxBX;
+                Cell c;
+                c.level = (short)l; c.x0 = (short)iniX; c.y0 = (short)iniY;
+                c.rw = (short)(maxX - iniX); c.rh = (short)(maxY - iniY);
+                c.offx = (short)(j * L.wCell); c.offy = (short)(i * L.hCell); c.pad = 0;
+                cells.push_back(c);
+            }
+        }
+        if (l == 0) h->n_cells_l0 = (int)cells.size();
+        // resize tables for level l from level l-1 (unused for l == 0)
+        L.xtab = (int)xofs.size();
+        L.ytab = (int)yofs.size();
+        if (l > 0) {
+            const LevelGeom &S = g.lv[l - 1];
+            for (int d = 0; d < L.w; d++) {
+                SbLinCoef c = sb_lin_coef(d, L.w, S.w, true);
+                xofs.push_back(c.s);
+                xco.push_back(make_short2(c.c0, c.c1));
+            }
+            for (int d = 0; d < L.h; d++) {
+                SbLinCoef c = sb_lin_coef(d, L.h, S.h, false);
+                yofs.push_back(c.s);
+                yco.push_back(make_short2(c.c0, c.c1));
+            }
+        }
+        for (int ty = 0; ty < sb_div_up(L.h, BLUR_TH); ty++)
+            for (int tx = 0; tx < sb_div_up(L.w, BLUR_TW); tx++) {
+                BlurTile t = {(short)l, (short)tx, (short)ty, 0};
+                tiles.push_back(t);
+            }
+        const int nc = quadtree_ncap(L.quota, L.bw, L.bh);
+        if (nc > ncap_pyr) ncap_pyr = nc;
+        kp_cap += nc - 1;
+    }
+    g.slab = off;
+    SB_REQUIRE(off <= h->slab_cap, "internal: slab larger than reserved");
+    h->ncap_pyr = ncap_pyr;
+    h->ncap_detect = quadtree_ncap(h->nfeatures, g.lv[0].bw, g.lv[0].bh);
+    selcap = (ncap_pyr > h->ncap_detect ? ncap_pyr : h->ncap_detect);
+    SB_REQUIRE(selcap <= h->selcap, "internal: selection capacity");
+    h->kp_cap = kp_cap > h->ncap_detect - 1 ? kp_cap : h->ncap_detect - 1;
+    SB_REQUIRE(qt_smem_bytes(ncap_pyr > h->ncap_detect ? ncap_pyr : h->ncap_detect) <= 220 * 1024,
+               "nfeatures too large for the on-chip quadtree");
+    h->fast_tile_bytes = (int)sb_align_up(fast_tile, 128);
+    h->n_cells = (int)cells.size();
+    h->n_blur_tiles = (int)tiles.size();
+    SB_REQUIRE((int)xofs.size() <= h->tab_cap && (int)yofs.size() <= h->tab_cap, "internal: table capacity");
+    SB_REQUIRE(h->n_cells <= h->cell_cap && h->n_blur_tiles <= h->tile_cap, "internal: cell/tile capacity");
+    cudaStream_t s = h->stream;
+    // the previous geometry may still be in use by queued kernels
+    SB_CUDA(cudaStreamSynchronize(s));
+    if (!xofs.empty()) {
+        SB_CUDA(cudaMemcpyAsync(h->d_xofs, xofs.data(), xofs.size() * 4, cudaMemcpyHostToDevice, s));
+        SB_CUDA(cudaMemcpyAsync(h->d_xco, xco.data(), xco.size() * 4, cudaMemcpyHostToDevice, s));
+        SB_CUDA(cudaMemcpyAsync(h->d_yofs, yofs.data(), yofs.size() * 4, cudaMemcpyHostToDevice, s));
+        SB_CUDA(cudaMemcpyAsync(h->d_yco, yco.data(), yco.size() * 4, cudaMemcpyHostToDevice, s));
+    }
+    SB_CUDA(cudaMemcpyAsync(h->d_cells, cells.data(), cells.size() * sizeof(Cell), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    for (int l = 0; l < h->nlevels; l++) {
+        const LevelGeom &L = g.lv[l];
+        const uint64_t dims[3] = {(uint64_t)L.w, (uint64_t)L.h, (uint64_t)h->max_batch};
+        const uint64_t strides[2] = {(uint64_t)L.pitch, (uint64_t)g.slab};
+        const uint32_t fbox[3] = {(uint32_t)L.fast_bw, (uint32_t)L.fast_bh, 1};
+        const uint32_t bbox[3] = {BLUR_BW, BLUR_BH, 1};
+        SB_TRY(sb_make_tensor_map_u8(&h->fast_maps.m[l], h->d_pyr + L.off, 3, dims, strides, fbox));
+        SB_TRY(sb_make_tensor_map_u8(&h->blur_maps.m[l], h->d_pyr + L.off, 3, dims, strides, bbox));
+    }
+    h->cur_w = w;
+    h->cur_h = hgt;
+    return SB_OK;
+}
+
+extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                             int minThFAST, int max_w, int max_h, int max_batch) {
+    sb_clear_error();
+    SB_REQUIRE(out, "null handle pointer");
+    *out = nullptr;
+    SB_REQUIRE(nfeatures >= 1 && nfeatures <= 20000, "nfeatures out of range [1, 20000]");
+    SB_REQUIRE(nlevels >= 1 && nlevels <= SB_MAX_LEVELS, "nlevels out of range [1, 12]");
+    SB_REQUIRE(scaleFactor > 1.0f || nlevels == 1, "scaleFactor must be > 1");
+    SB_REQUIRE(iniThFAST >= 1 && iniThFAST <= 255 && minThFAST >= 1 && minThFAST <= 255, "FAST thresholds out of range [1, 255]");
+    SB_REQUIRE(max_w >= 62 && max_w <= 4096 && max_h >= 62 && max_h <= 4096, "max_w / max_h out of range [62, 4096]");
+    SB_REQUIRE(max_batch >= 1 && max_batch <= 4096, "max_batch out of range [1, 4096]");
+    SB_TRY(sb_use_device(device));
+    sb_orb *h = new sb_orb();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->nfeatures = nfeatures;
+    h->scaleFactor = scaleFactor;
+    h->nlevels = nlevels;
+    h->iniTh = iniThFAST;
+    h->minTh = minThFAST;
+    h->max_w = max_w;
+    h->max_h = max_h;
+    h->max_batch = max_batch;
+    build_tables(h);
+    h->slab_cap = slab_bytes(h, max_w, max_h);
+    if (h->slab_cap < 0) {
+        delete h;
+        sb_set_error("max_w x max_h too small for %d pyramid levels", nlevels);
+        return SB_ERR_INVALID;
+    }
+    h->slab_cap += 4096;
+    // selection capacity: the largest quadtree node table any call can need
+    {
+        int ncap = 0;
+        for (int l = 0; l < nlevels; l++) {
+            int n = (h->quota[l] > 64 ? h->quota[l] : 64) + 3 + 1;
+            if (n > ncap) ncap = n;
+        }
+        int nd = (nfeatures > 64 ? nfeatures : 64) + 3 + 1;
+        h->selcap = (ncap > nd ? ncap : nd) + 600;  // 4 * nIni roots for very elongated images
+    }
+    h->tab_cap = 2 * (max_w + max_h) + 64;
+    h->cell_cap = 0;
+    h->tile_cap = 0;
+    for (int l = 0; l < nlevels; l++) {
+        int lw, lh;
+        level_size(h, max_w, max_h, l, &lw, &lh);
+        h->cell_cap += (lw / 30 + 1) * (lh / 30 + 1);
+        h->tile_cap += sb_div_up(lw, BLUR_TW) * sb_div_up(lh, BLUR_TH);
+    }
+#define SB_ALLOC(ptr, bytes)                                                        \
+    do {                                                                            \
+        cudaError_t e__ = cudaMalloc((void **)&(ptr), (bytes));                     \
+        if (e__ != cudaSuccess) {                                                   \
+            sb_set_error("cudaMalloc(%zu bytes) for %s -> %s", (size_t)(bytes), #ptr, cudaGetErrorString(e__)); \
+            free_orb(h);                                                            \
+            return SB_ERR_CUDA;                                                     \
+        }                                                                           \
+    } while (0)
+    const size_t B = (size_t)max_batch;
+    SB_ALLOC(h->d_pyr, B * h->slab_cap);
+    SB_ALLOC(h->d_blur, B * h->slab_cap);
+    SB_ALLOC(h->d_cells, (size_t)h->cell_cap * sizeof(Cell));
+    SB_ALLOC(h->d_tiles, (size_t)h->tile_cap * sizeof(BlurTile));
+    SB_ALLOC(h->d_xofs, (size_t)h->tab_cap * 4);
+    SB_ALLOC(h->d_yofs, (size_t)h->tab_cap * 4);
+    SB_ALLOC(h->d_xco, (size_t)h->tab_cap * 4);
+    SB_ALLOC(h->d_yco, (size_t)h->tab_cap * 4);
+    SB_ALLOC(h->d_cand, B * nlevels * SB_CAND_CAP * 4);
+    SB_ALLOC(h->d_sel, B * nlevels * h->selcap * 4);
+    SB_ALLOC(h->d_cand_cnt, B * nlevels * 4);
+    SB_ALLOC(h->d_sel_cnt, B * nlevels * 4);
+    SB_ALLOC(h->d_flags, 16);
+    cudaError_t e = cudaMemset(h->d_flags, 0, 16);
+    if (e == cudaSuccess) e = cudaMemset(h->d_sel_cnt, 0, B * nlevels * 4);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_flags, 16);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) {
+        sb_set_error("sb_orb_create: %s", cudaGetErrorString(e));
+        free_orb(h);
+        return SB_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    h->cur_w = h->cur_h = -1;
+    int rc = configure(h, max_w, max_h);  // validates the size now and makes sb_orb_capacity() meaningful
+    if (rc != SB_OK) {
+        free_orb(h);
+        return rc;
+    }
+    *out = h;
+    return SB_OK;
+}
+
+static int finish_and_check(sb_orb *h);
+
+extern "C" int sb_orb_destroy(sb_orb_t *h) {
+    if (h) {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        free_orb(h);
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_orb_set_stream(sb_orb_t *h, void *stream) {
+    SB_REQUIRE(h, "null handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return SB_OK;
+}
+
+extern "C" int sb_orb_sync_status(sb_orb_t *h) {
+    sb_clear_error();
+    SB_REQUIRE(h, "null handle");
+    SB_TRY(sb_use_device(h->device));
+    return finish_and_check(h);
+}
+
+extern "C" int sb_orb_capacity(const sb_orb_t *h) { return h ? h->kp_cap : SB_ERR_INVALID; }
+
+extern "C" int sb_orb_get_tables(const sb_orb_t *h, int *nlevels, float *scale, float *inv_scale, float *sigma2,
+                                 float *inv_sigma2, int *features_per_level) {
+    SB_REQUIRE(h, "null handle");
+    if (nlevels) *nlevels = h->nlevels;
+    for (int i = 0; i < h->nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->inv_scale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+        if (features_per_level) features_per_level[i] = h->quota[i];
+    }
+    return SB_OK;
+}
+
+// ---- pipeline pieces (all asynchronous on h->stream) ------------------------------------------------
+static int ensure_mask_buffer(sb_orb *h) {
+    if (h->d_mask) return SB_OK;
+    SB_CUDA(cudaMalloc((void **)&h->d_mask, (size_t)h->max_batch * h->slab_cap));
+    return SB_OK;
+}
+
+static int launch_pyramid(sb_orb *h, uint8_t *pyr, const uint8_t *d_img, long long img_pitch, int stride, int batch,
+                          int nlevels_to_build) {
+    const Geom &g = h->geom;
+    const LevelGeom &L0 = g.lv[0];
+    const long long total = (long long)batch * L0.h * (L0.pitch / 4);
+    const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (d_img)
+        k_copy_level0<<<blocks, 256, 0, h->stream>>>(d_img, img_pitch, stride, L0.w, L0.h, pyr, g.slab, L0.pitch, batch);
+    else
+        k_fill_level0<<<blocks, 256, 0, h->stream>>>(pyr, g.slab, L0.pitch, L0.h, batch);
+    for (int l = 1; l < nlevels_to_build; l++) {
+        const LevelGeom &D = g.lv[l];
+        dim3 grid(sb_div_up(sb_div_up(D.w, 4), 256), D.h, batch);
+        k_resize<<<grid, 256, 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_xofs, h->d_xco, h->d_yofs, h->d_yco);
+    }
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+static int launch_blur(sb_orb *h, int batch, cudaStream_t s) {
+    BlurArgs a = {h->d_tiles, h->d_blur, h->geom.slab};
+    k_blur<<<dim3(h->n_blur_tiles, batch), 256, 0, s>>>(h->blur_maps, h->geom, a);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool detect_only) {
+    const int nl = h->nlevels;
+    SB_CUDA(cudaMemsetAsync(h->d_cand_cnt, 0, (size_t)batch * nl * 4, h->stream));
+    FastArgs fa;
+    fa.cells = h->d_cells;
+    fa.mask_pyr = use_mask ? h->d_mask : nullptr;
+    fa.cand = h->d_cand;
+    fa.cand_cnt = h->d_cand_cnt;
+    fa.flags = h->d_flags;
+    fa.slab = h->geom.slab;
+    fa.nlevels = nl;
+    fa.iniTh = h->iniTh;
+    fa.minTh = h->minTh;
+    fa.tile_bytes = h->fast_tile_bytes;
+    const int ncells = detect_only ? h->n_cells_l0 : h->n_cells;
+    const size_t fsmem = 2 * (size_t)h->fast_tile_bytes + SB_CELL_LIST_CAP * 4 + 128;
+    k_fast_cells<<<dim3(ncells, batch), FAST_THREADS, fsmem, h->stream>>>(h->fast_maps, h->geom, fa);
+    QtArgs qa;
+    qa.cand = h->d_cand;
+    qa.cand_cnt = h->d_cand_cnt;
+    qa.sel = h->d_sel;
+    qa.sel_cnt = h->d_sel_cnt;
+    qa.nlevels = nl;
+    qa.selcap = h->selcap;
+    qa.ncap = detect_only ? h->ncap_detect : h->ncap_pyr;
+    qa.candcap_smem = SB_CAND_CAP;
+    qa.N_override = detect_only ? h->nfeatures : 0;
+    k_quadtree<<<dim3(detect_only ? 1 : nl, batch), QT_THREADS, qt_smem_bytes(qa.ncap), h->stream>>>(h->geom, qa);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+static int check_shapes(sb_orb *h, int batch, int w, int hgt, int stride, int cap) {
+    SB_REQUIRE(h, "null handle");
+    SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
+    SB_REQUIRE(w >= 62 && hgt >= 62 && stride >= w, "bad image size / stride");
+    SB_REQUIRE(cap >= 1, "cap must be positive");
+    SB_TRY(sb_use_device(h->device));
+    return configure(h, w, hgt);
+}
+
+// Reads the device flags after the stream drained (host-pointer entry points only).
+static int finish_and_check(sb_orb *h) {
+    SB_CUDA(cudaMemcpyAsync(h->h_flags, h->d_flags, 16, cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemsetAsync(h->d_flags, 0, 16, h->stream));
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_flags[0]) {
+        sb_set_error("more than %d FAST candidates on one pyramid level", SB_CAND_CAP);
+        return SB_ERR_OVERFLOW;
+    }
+    if (h->h_flags[1]) {
+        sb_set_error("keypoint capacity `cap` too small; use sb_orb_capacity()");
+        return SB_ERR_CAPACITY;
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes,
+                                             const uint8_t *d_mask, int64_t mask_pitch_bytes, int w, int hgt,
+                                             int stride, int mstride, sb_keypoint *d_kps, uint8_t *d_desc,
+                                             int32_t *d_counts, int cap) {
+    sb_clear_error();
+    SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
+    SB_REQUIRE(d_img && d_kps && d_counts, "null device pointer");
+    SB_REQUIRE(!d_mask || mstride >= w, "bad mask stride");
+    SB_TRY(launch_pyramid(h, h->d_pyr, d_img, img_pitch_bytes, stride, batch, h->nlevels));
+    if (d_mask) {
+        SB_TRY(ensure_mask_buffer(h));
+        SB_TRY(launch_pyramid(h, h->d_mask, d_mask, mask_pitch_bytes, mstride, batch, h->nlevels));
+    }
+    if (d_desc) {  // the blur only depends on the pyramid: run it beside FAST + quadtree
+        SB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        SB_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        SB_TRY(launch_blur(h, batch, h->side_stream));
+        SB_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+    }
+    SB_TRY(launch_fast_and_quadtree(h, batch, d_mask != nullptr, false));
+    if (d_desc) SB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    DescArgs da;
+    da.pyr = h->d_pyr;
+    da.blur = h->d_blur;
+    da.sel = h->d_sel;
+    da.sel_cnt = h->d_sel_cnt;
+    da.kps = d_kps;
+    da.desc = d_desc;
+    da.counts = d_counts;
+    da.flags = h->d_flags;
+    da.slab = h->geom.slab;
+    da.nlevels = h->nlevels;
+    da.selcap = h->selcap;
+    da.cap = cap;
+    k_describe<<<dim3(sb_div_up(h->ncap_pyr, DESC_WARPS), h->nlevels, batch), DESC_WARPS * 32, 0, h->stream>>>(h->geom, da);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+extern "C" int sb_orb_detect_dev(sb_orb_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes,
+                                 const uint8_t *d_mask, int64_t mask_pitch_bytes, int w, int hgt, int stride,
+                                 int mstride, sb_keypoint *d_kps, int32_t *d_counts, int cap) {
+    sb_clear_error();
+    SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
+    SB_REQUIRE(d_img && d_kps && d_counts, "null device pointer");
+    SB_REQUIRE(!d_mask || mstride >= w, "bad mask stride");
+    SB_TRY(launch_pyramid(h, h->d_pyr, d_img, img_pitch_bytes, stride, batch, 1));
+    if (d_mask) {
+        SB_TRY(ensure_mask_buffer(h));
+        SB_TRY(launch_pyramid(h, h->d_mask, d_mask, mask_pitch_bytes, mstride, batch, 1));
+    }
+    SB_TRY(launch_fast_and_quadtree(h, batch, d_mask != nullptr, true));
+    k_emit_detect<<<dim3(sb_div_up(h->ncap_detect, 256), batch), 256, 0, h->stream>>>(h->d_sel, h->d_sel_cnt, h->nlevels,
+                                                                                   h->selcap, d_kps, d_counts, cap,
+                                                                                   h->d_flags);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+// ---- host-pointer entry points: stage, run, copy back, synchronise ---------------------------------
+static int ensure_staging(sb_orb *h, int batch, size_t img_bytes, int cap, bool need_mask) {
+    const size_t need = (size_t)batch * img_bytes;
+    if (need > h->in_cap) {
+        SB_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->d_in) cudaFree(h->d_in);
+        if (h->d_in_mask) cudaFree(h->d_in_mask);
+        h->d_in = h->d_in_mask = nullptr;
+        h->in_cap = 0;
+        SB_CUDA(cudaMalloc((void **)&h->d_in, need));
+        h->in_cap = need;
+    }
+    if (need_mask && !h->d_in_mask) SB_CUDA(cudaMalloc((void **)&h->d_in_mask, h->in_cap));
+    if (cap > h->stage_cap || batch > h->stage_batch) {
+        SB_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->d_kps_out) cudaFree(h->d_kps_out);
+        if (h->d_desc_out) cudaFree(h->d_desc_out);
+        if (h->d_counts_out) cudaFree(h->d_counts_out);
+        if (h->d_keep) cudaFree(h->d_keep);
+        h->d_kps_out = nullptr; h->d_desc_out = nullptr; h->d_counts_out = nullptr; h->d_keep = nullptr;
+        const int c = cap > h->stage_cap ? cap : h->stage_cap, b = batch > h->stage_batch ? batch : h->stage_batch;
+        h->stage_cap = h->stage_batch = 0;
+        SB_CUDA(cudaMalloc((void **)&h->d_kps_out, (size_t)b * c * sizeof(sb_keypoint)));
+        SB_CUDA(cudaMalloc((void **)&h->d_desc_out, (size_t)b * c * 32));
+        SB_CUDA(cudaMalloc((void **)&h->d_counts_out, (size_t)b * 4));
+        SB_CUDA(cudaMalloc((void **)&h->d_keep, (size_t)b * c));
+        h->stage_cap = c;
+        h->stage_batch = b;
+    }
+    return SB_OK;
+}
+
+static int stage_images(sb_orb *h, int batch, const uint8_t *const *img, const uint8_t *const *mask, int w, int hgt,
+                        int stride, int mstride, bool *any_mask) {
+    const size_t img_bytes = (size_t)sb_align_up((size_t)w, 16) * hgt;
+    *any_mask = false;
+    if (mask)
+        for (int b = 0; b < batch; b++)
+            if (mask[b]) *any_mask = true;
+    for (int b = 0; b < batch; b++) SB_REQUIRE(img[b], "null image pointer");
+    const size_t row = sb_align_up((size_t)w, 16);
+    for (int b = 0; b < batch; b++) {
+        SB_CUDA(cudaMemcpy2DAsync(h->d_in + b * img_bytes, row, img[b], (size_t)stride, (size_t)w, (size_t)hgt,
+                                  cudaMemcpyHostToDevice, h->stream));
+        if (*any_mask) {
+            if (mask[b])
+                SB_CUDA(cudaMemcpy2DAsync(h->d_in_mask + b * img_bytes, row, mask[b], (size_t)mstride, (size_t)w,
+                                          (size_t)hgt, cudaMemcpyHostToDevice, h->stream));
+            else
+                SB_CUDA(cudaMemsetAsync(h->d_in_mask + b * img_bytes, 255, img_bytes, h->stream));
+        }
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_orb_detect_and_compute(sb_orb_t *h, int batch, const uint8_t *const *img, const uint8_t *const *mask,
+                                         int w, int hgt, int stride, int mstride, sb_keypoint *kps, uint8_t *desc,
+                                         int32_t *counts, int cap) {
+    sb_clear_error();
+    SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
+    SB_REQUIRE(img && kps && counts, "null pointer");
+    const int row = (int)sb_align_up((size_t)w, 16);
+    const size_t img_bytes = (size_t)row * hgt;
+    bool any_mask = false;
+    if (mask)
+        for (int b = 0; b < batch; b++)
+            if (mask[b]) any_mask = true;
+    SB_REQUIRE(!any_mask || mstride >= w, "bad mask stride");
+    SB_TRY(ensure_staging(h, batch, img_bytes, cap, any_mask));
+    SB_TRY(stage_images(h, batch, img, mask, w, hgt, stride, mstride, &any_mask));
+    SB_TRY(sb_orb_detect_and_compute_dev(h, batch, h->d_in, (int64_t)img_bytes, any_mask ? h->d_in_mask : nullptr,
+                                         (int64_t)img_bytes, w, hgt, row, row, h->d_kps_out, desc ? h->d_desc_out : nullptr,
+                                         h->d_counts_out, cap));
+    SB_CUDA(cudaMemcpyAsync(kps, h->d_kps_out, (size_t)batch * cap * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
+    if (desc) SB_CUDA(cudaMemcpyAsync(desc, h->d_desc_out, (size_t)batch * cap * 32, cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemcpyAsync(counts, h->d_counts_out, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    return finish_and_check(h);
+}
+
+extern "C" int sb_orb_detect(sb_orb_t *h, int batch, const uint8_t *const *img, const uint8_t *const *mask, int w,
+                             int hgt, int stride, int mstride, sb_keypoint *kps, int32_t *counts, int cap) {
+    sb_clear_error();
+    SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
+    SB_REQUIRE(img && kps && counts, "null pointer");
+    const int row = (int)sb_align_up((size_t)w, 16);
+    const size_t img_bytes = (size_t)row * hgt;
+    bool any_mask = false;
+    if (mask)
+        for (int b = 0; b < batch; b++)
+            if (mask[b]) any_mask = true;
+    SB_REQUIRE(!any_mask || mstride >= w, "bad mask stride");
+    SB_TRY(ensure_staging(h, batch, img_bytes, cap, any_mask));
+    SB_TRY(stage_images(h, batch, img, mask, w, hgt, stride, mstride, &any_mask));
+    SB_TRY(sb_orb_detect_dev(h, batch, h->d_in, (int64_t)img_bytes, any_mask ? h->d_in_mask : nullptr, (int64_t)img_bytes, w,
+                             hgt, row, row, h->d_kps_out, h->d_counts_out, cap));
+    SB_CUDA(cudaMemcpyAsync(kps, h->d_kps_out, (size_t)batch * cap * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemcpyAsync(counts, h->d_counts_out, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
+    return finish_and_check(h);
+}
+
+extern "C" int sb_orb_screen_params(sb_orb_t *h, const uint8_t *img, int w, int hgt, int stride, sb_keypoint *in,
+                                    int n_in, sb_keypoint *out, int32_t *n_out) {
+    sb_clear_error();
+    SB_REQUIRE(n_out, "null n_out");
+    *n_out = 0;
+    if (n_in <= 0) return SB_OK;
+    SB_TRY(check_shapes(h, 1, w, hgt, stride, n_in));
+    SB_REQUIRE(img && in && out, "null pointer");
+    const int row = (int)sb_align_up((size_t)w, 16);
+    const size_t img_bytes = (size_t)row * hgt;
+    SB_TRY(ensure_staging(h, 1, img_bytes, n_in, false));
+    const uint8_t *imgs[1] = {img};
+    bool any = false;
+    SB_TRY(stage_images(h, 1, imgs, nullptr, w, hgt, stride, 0, &any));
+    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, row, 1, h->nlevels));
+    SB_CUDA(cudaMemcpyAsync(h->d_kps_out, in, (size_t)n_in * sizeof(sb_keypoint), cudaMemcpyHostToDevice, h->stream));
+    k_screen<<<sb_div_up(n_in, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_pyr, h->d_kps_out, n_in, h->d_keep,
+                                                                           h->minTh);
+    SB_CUDA(cudaGetLastError());
+    std::vector<uint8_t> keep((size_t)n_in);
+    SB_CUDA(cudaMemcpyAsync(in, h->d_kps_out, (size_t)n_in * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemcpyAsync(keep.data(), h->d_keep, (size_t)n_in, cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    int m = 0;
+    for (int i = 0; i < n_in; i++)
+        if (keep[i]) out[m++] = in[i];  // survivors in input order (:1125)
+    *n_out = m;
+    return SB_OK;
+}
+
+extern "C" int sb_orb_calc_descriptors(sb_orb_t *h, const uint8_t *img, int w, int hgt, int stride,
+                                       const sb_keypoint *kps, int n, uint8_t *desc) {
+    sb_clear_error();
+    if (n <= 0) return SB_OK;
+    SB_TRY(check_shapes(h, 1, w, hgt, stride, n));
+    SB_REQUIRE(img && kps && desc, "null pointer");
+    for (int i = 0; i < n; i++) {
+        SB_REQUIRE(kps[i].octave >= 0 && kps[i].octave < h->nlevels, "keypoint octave out of range");
+        // the reference reads out of bounds for keypoints closer than the rBRIEF reach to the border
+        const LevelGeom &L = h->geom.lv[kps[i].octave];
+        const float x = kps[i].x / L.scale, y = kps[i].y / L.scale;
+        SB_REQUIRE(x >= 19.f && y >= 19.f && x < (float)(L.w - 19) && y < (float)(L.h - 19),
+                   "keypoint closer than 19 px to the border of its pyramid level");
+    }
+    const int row = (int)sb_align_up((size_t)w, 16);
+    const size_t img_bytes = (size_t)row * hgt;
+    SB_TRY(ensure_staging(h, 1, img_bytes, n, false));
+    const uint8_t *imgs[1] = {img};
+    bool any = false;
+    SB_TRY(stage_images(h, 1, imgs, nullptr, w, hgt, stride, 0, &any));
+    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, row, 1, h->nlevels));
+    SB_TRY(launch_blur(h, 1, h->stream));
+    SB_CUDA(cudaMemcpyAsync(h->d_kps_out, kps, (size_t)n * sizeof(sb_keypoint), cudaMemcpyHostToDevice, h->stream));
+    k_calc_desc<<<sb_div_up(n, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_blur, h->d_kps_out, n, h->d_desc_out);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaMemcpyAsync(desc, h->d_desc_out, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    return SB_OK;
+}
+
+// ---- inspection --------------------------------------------------------------------------------------
+extern "C" int sb_orb_debug_level(sb_orb_t *h, int b, int level, int which, uint8_t *out, int out_bytes, int *lw,
+                                  int *lh) {
+    sb_clear_error();
+    SB_REQUIRE(h && h->cur_w > 0, "no call has been made on this handle yet");
+    SB_REQUIRE(b >= 0 && b < h->max_batch && level >= 0 && level < h->nlevels && which >= 0 && which <= 2, "bad index");
+    SB_TRY(sb_use_device(h->device));
+    const LevelGeom &L = h->geom.lv[level];
+    if (lw) *lw = L.w;
+    if (lh) *lh = L.h;
+    if (!out) return SB_OK;
+    SB_REQUIRE(out_bytes >= L.w * L.h, "output buffer too small");
+    const uint8_t *src = which == 0 ? h->d_pyr : which == 1 ? h->d_blur : h->d_mask;
+    SB_REQUIRE(src, "that pyramid has not been built");
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    SB_CUDA(cudaMemcpy2D(out, (size_t)L.w, src + (long long)b * h->geom.slab + L.off, (size_t)L.pitch, (size_t)L.w,
+                         (size_t)L.h, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+extern "C" int sb_orb_debug_candidates(sb_orb_t *h, int b, int level, uint32_t *out, int cap, int32_t *n) {
+    sb_clear_error();
+    SB_REQUIRE(h && out && n, "null pointer");
+    SB_REQUIRE(b >= 0 && b < h->max_batch && level >= 0 && level < h->nlevels, "bad index");
+    SB_TRY(sb_use_device(h->device));
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    int cnt = 0;
+    SB_CUDA(cudaMemcpy(&cnt, h->d_cand_cnt + b * h->nlevels + level, 4, cudaMemcpyDeviceToHost));
+    if (cnt > SB_CAND_CAP) cnt = SB_CAND_CAP;
+    *n = cnt;
+    const int m = cnt < cap ? cnt : cap;
+    if (m > 0)
+        SB_CUDA(cudaMemcpy(out, h->d_cand + ((long long)b * h->nlevels + level) * SB_CAND_CAP, (size_t)m * 4,
+                           cudaMemcpyDeviceToHost));
+    return SB_OK;
+}

@@ -60,6 +60,9 @@ int sb_orb_create(sb_orb_t **h, int device, int nfeatures, float scaleFactor, in
 int sb_orb_destroy(sb_orb_t *h);
 /* Use `stream` (a cudaStream_t) instead of the handle's own stream for all later calls. */
 int sb_orb_set_stream(sb_orb_t *h, void *stream);
+/* Waits for the handle's stream and reports what the asynchronous "_dev" calls since the last
+ * check flagged on the device: SB_OK, SB_ERR_OVERFLOW or SB_ERR_CAPACITY. */
+int sb_orb_sync_status(sb_orb_t *h);
 /* Per-image keypoint capacity the caller must provide to the calls below
  * (sum over levels of max(quota + 3, 4 * nIni) for the pyramid calls). */
 int sb_orb_capacity(const sb_orb_t *h);
