@@ -6,6 +6,9 @@
 //   cv::FAST per 30-px cell   :838-883   -> k_fast_cells   (one CTA per cell; tile staged by TMA)
 //   DistributeOctTree         :586-810   -> k_quadtree     (one CTA per (image, level); qt_core.inl)
 //   GaussianBlur per level    :965-966   -> k_blur         (one launch for all levels; TMA halo tiles)
+// TMA note (measured on B200, tools/tma_probe.cu): the innermost box coordinate must be a multiple
+// of 16 bytes — negative / out-of-range coordinates are fine and zero filled — so tiles start at the
+// 16-byte boundary at or left of the wanted column.
 //   IC_Angle + rBRIEF + output:27-98,:975-983 -> k_describe (one warp per keypoint)
 // Data layout in HBM: every image of the batch owns one "slab" holding its pyramid levels as
 // pitched u8 planes (pitch multiple of 128 B so that each level is a legal TMA tensor
@@ -28,7 +31,8 @@
 #define QT_THREADS 256
 #define BLUR_TW 128
 #define BLUR_TH 32
-#define BLUR_BW 144  // BLUR_TW + 6 halo, rounded up to the 16-byte TMA granule
+#define BLUR_HX 16   // left halo: the innermost TMA coordinate must be a multiple of 16 bytes (measured: tools/tma_probe.cu)
+#define BLUR_BW 160  // BLUR_HX + BLUR_TW + 3, rounded up to the 16-byte TMA granule
 #define BLUR_BH 38
 #define DESC_WARPS 8
 
@@ -143,6 +147,8 @@ struct FastArgs {
     int *flags;               // [0] overflow
     long long slab;
     int nlevels, iniTh, minTh, tile_bytes;
+    uint8_t *dbg;  // inspection: tile + response plane of cell `dbg_cell` of image 0 (null in production calls)
+    int dbg_cell;
 };
 
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ TmaMaps maps,
@@ -159,13 +165,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const LevelGeom &L = g.lv[c.level];
     const int BW = L.fast_bw, BH = L.fast_bh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int xo = c.x0 & 15;  // the innermost TMA coordinate must be 16-byte aligned: ROI column x is tile column xo + x
 
     if (tid == 0) {
         s_n = 0;
         s_any = 0;
         sb_mbar_init(&bar, 1);
         sb_mbar_expect_tx(&bar, (uint32_t)(BW * BH));
-        sb_tma_load_3d(tile, &maps.m[c.level], c.x0, c.y0, img, &bar);
+        sb_tma_load_3d(tile, &maps.m[c.level], c.x0 - xo, c.y0, img, &bar);
     }
     for (int i = tid; i < (BW * BH) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(sc)[i] = 0u;
     __syncthreads();
@@ -174,16 +181,16 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     const int t0 = min(a.iniTh, a.minTh);
     for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
         for (int x = 3 + lane; x < c.rw - 3; x += 32) {
-            const uint8_t *p = tile + y * BW + x;
+            const uint8_t *p = tile + y * BW + xo + x;
             if (sb_fast_maybe(p, BW, t0)) {
                 const int s = sb_fast_score(p, BW);
-                if (s >= t0) sc[y * BW + x] = (uint8_t)s;
+                if (s >= t0) sc[y * BW + xo + x] = (uint8_t)s;
             }
         }
     __syncthreads();
     for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
         for (int x = 3 + lane; x < c.rw - 3; x += 32) {
-            const uint8_t *q = sc + y * BW + x;
+            const uint8_t *q = sc + y * BW + xo + x;
             const int s = q[0];
             if (s > 0 && s > q[-1] && s > q[1] && s > q[-BW - 1] && s > q[-BW] && s > q[-BW + 1] && s > q[BW - 1] &&
                 s > q[BW] && s > q[BW + 1]) {
@@ -193,6 +200,17 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
             }
         }
     __syncthreads();
+    if (a.dbg && img == 0 && (int)blockIdx.x == a.dbg_cell) {
+        for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) {
+            a.dbg[i] = tile[i];
+            a.dbg[a.tile_bytes + i] = sc[i];
+        }
+        if (tid == 0) {
+            int *info = reinterpret_cast<int *>(a.dbg + 2 * a.tile_bytes);
+            info[0] = BW; info[1] = BH; info[2] = xo; info[3] = c.x0; info[4] = c.y0; info[5] = c.rw; info[6] = c.rh;
+            info[7] = s_n; info[8] = s_any; info[9] = c.level;
+        }
+    }
     const int n = min(s_n, SB_CELL_LIST_CAP);
     const int th = s_any ? a.iniTh : a.minTh;  // the reference's second cv::FAST call only if the first found nothing
     const int slot = img * a.nlevels + c.level;
@@ -299,7 +317,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps ma
     if (tid == 0) {
         sb_mbar_init(&bar, 1);
         sb_mbar_expect_tx(&bar, BLUR_BH * BLUR_BW);
-        sb_tma_load_3d(tile, &maps.m[t.level], x0 - 3, y0 - 3, img, &bar);
+        sb_tma_load_3d(tile, &maps.m[t.level], x0 - BLUR_HX, y0 - 3, img, &bar);
     }
     __syncthreads();
     sb_mbar_wait(&bar, 0);
@@ -308,7 +326,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps ma
     // horizontal pass: tile row r <-> image row y0 - 3 + r (rows outside the image are never used)
     for (int i = tid; i < BLUR_BH * BLUR_TW; i += 256) {
         const int r = i / BLUR_TW, cx = i % BLUR_TW;
-        const uint8_t *row = tile + r * BLUR_BW;
+        const uint8_t *row = tile + r * BLUR_BW + (BLUR_HX - 3);
         unsigned v;
         if (interior_x) {
             v = sb_gauss_row(row[cx], row[cx + 1], row[cx + 2], row[cx + 3], row[cx + 4], row[cx + 5], row[cx + 6]);
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps ma
             for (int k = 0; k < 7; k++) {
                 int gx = x0 + cx + k - 3;
                 gx = sb_reflect101(gx, L.w);
-                ix[k] = min(max(gx - (x0 - 3), 0), BLUR_BW - 1);  // clamp only guards columns past the image (unused)
+                ix[k] = min(max(gx - (x0 - 3), -(BLUR_HX - 3)), BLUR_BW - 1 - (BLUR_HX - 3));  // clamp only guards columns past the image (unused)
             }
             v = sb_gauss_row(row[ix[0]], row[ix[1]], row[ix[2]], row[ix[3]], row[ix[4]], row[ix[5]], row[ix[6]]);
         }
@@ -584,6 +602,8 @@ struct sb_orb {
     size_t in_cap;
     int stage_cap, stage_batch;
     int *h_flags;  // pinned
+    uint8_t *dbg_buf;  // inspection only (sb_orb_debug_fast_cell)
+    int dbg_cell;
 };
 
 static void free_orb(sb_orb *h) {
@@ -695,7 +715,7 @@ static int configure(sb_orb *h, int w, int hgt) {
         L.wCell = (int)ceilf(width / L.nCols);
         L.hCell = (int)ceilf(height / L.nRows);
         SB_REQUIRE(L.wCell + 6 <= 72 && L.hCell + 6 <= 72, "FAST cell larger than supported");
-        L.fast_bw = (int)sb_align_up(L.wCell + 6, 16);
+        L.fast_bw = (int)sb_align_up(L.wCell + 6 + 15, 16);
         L.fast_bh = L.hCell + 6;
         if (L.fast_bw * L.fast_bh > fast_tile) fast_tile = L.fast_bw * L.fast_bh;
         const int minB = SB_EDGE - 3, maxBX = L.w - SB_EDGE + 3, maxBY = L.h - SB_EDGE + 3;
@@ -823,12 +843,13 @@ extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float sc
         int nd = (nfeatures > 64 ? nfeatures : 64) + 3 + 1;
         h->selcap = (ncap > nd ? ncap : nd) + 600;  // 4 * nIni roots for very elongated images
     }
-    h->tab_cap = 2 * (max_w + max_h) + 64;
+    h->tab_cap = 64;
     h->cell_cap = 0;
     h->tile_cap = 0;
     for (int l = 0; l < nlevels; l++) {
         int lw, lh;
         level_size(h, max_w, max_h, l, &lw, &lh);
+        h->tab_cap += lw > lh ? lw : lh;
         h->cell_cap += (lw / 30 + 1) * (lh / 30 + 1);
         h->tile_cap += sb_div_up(lw, BLUR_TW) * sb_div_up(lh, BLUR_TH);
     }
@@ -966,6 +987,8 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     fa.iniTh = h->iniTh;
     fa.minTh = h->minTh;
     fa.tile_bytes = h->fast_tile_bytes;
+    fa.dbg = h->dbg_buf;
+    fa.dbg_cell = h->dbg_cell;
     const int ncells = detect_only ? h->n_cells_l0 : h->n_cells;
     const size_t fsmem = 2 * (size_t)h->fast_tile_bytes + SB_CELL_LIST_CAP * 4 + 128;
     k_fast_cells<<<dim3(ncells, batch), FAST_THREADS, fsmem, h->stream>>>(h->fast_maps, h->geom, fa);
@@ -1262,5 +1285,27 @@ extern "C" int sb_orb_debug_candidates(sb_orb_t *h, int b, int level, uint32_t *
     if (m > 0)
         SB_CUDA(cudaMemcpy(out, h->d_cand + ((long long)b * h->nlevels + level) * SB_CAND_CAP, (size_t)m * 4,
                            cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+// Inspection: arm (buf != null) or disarm the capture of one FAST cell of image 0; after the next call
+// `out` (2 * tile_bytes + 64 bytes) holds the TMA tile, the response plane and 10 ints of geometry.
+extern "C" int sb_orb_debug_fast_cell(sb_orb_t *h, int cell, uint8_t *out, int out_bytes, int *tile_bytes) {
+    sb_clear_error();
+    SB_REQUIRE(h, "null handle");
+    SB_TRY(sb_use_device(h->device));
+    if (tile_bytes) *tile_bytes = h->fast_tile_bytes;
+    const int need = 2 * h->fast_tile_bytes + 64;
+    if (!out) {  // arm
+        if (!h->dbg_buf) SB_CUDA(cudaMalloc((void **)&h->dbg_buf, (size_t)need));
+        SB_CUDA(cudaMemset(h->dbg_buf, 0, (size_t)need));
+        h->dbg_cell = cell;
+        return SB_OK;
+    }
+    SB_REQUIRE(h->dbg_buf && out_bytes >= need, "not armed or buffer too small");
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    SB_CUDA(cudaMemcpy(out, h->dbg_buf, (size_t)need, cudaMemcpyDeviceToHost));
+    cudaFree(h->dbg_buf);
+    h->dbg_buf = nullptr;
     return SB_OK;
 }

@@ -53,23 +53,29 @@ SB_HD bool sb_fast_maybe(const uint8_t *p, int pitch, int t) {
 
 // Corner response = the largest threshold for which the pixel is still a FAST-9/16 corner:
 //   max over the 16 arcs of 9 contiguous ring pixels of  min(v - ring)  resp.  min(ring - v),  minus 1.
-// Running minima/maxima over windows 2, 4, 8 then 9 give all 16 arcs in 4 * 16 min + 4 * 16 max.
+// Running minima over windows 2, 4, 8 then 9 give all 16 arcs in 4 * 16 min per polarity.
+// Both polarities are written as minima of explicit differences (no "-max(...)"): ptxas 12.9 folds
+// max(a, -max3(...)) into VIMNMX3 for sm_100a and loses the negation (measured, tools/fast_probe.cu).
 SB_HD int sb_fast_score(const uint8_t *p, int pitch) {
     const int v = p[0];
-    int d[16];
+    int d[16], e[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = v - p[SB_RING_DY(k) * pitch + SB_RING_DX(k)];
-    int lo2[16], hi2[16], lo4[16], hi4[16];
+    for (int k = 0; k < 16; k++) {
+        const int r = p[SB_RING_DY(k) * pitch + SB_RING_DX(k)];
+        d[k] = v - r;  // > t  <=> ring pixel darker than v - t
+        e[k] = r - v;  // > t  <=> ring pixel brighter than v + t
+    }
+    int d2[16], e2[16], d4[16], e4[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { lo2[k] = sb_min(d[k], d[(k + 1) & 15]); hi2[k] = sb_max(d[k], d[(k + 1) & 15]); }
+    for (int k = 0; k < 16; k++) { d2[k] = sb_min(d[k], d[(k + 1) & 15]); e2[k] = sb_min(e[k], e[(k + 1) & 15]); }
 #pragma unroll
-    for (int k = 0; k < 16; k++) { lo4[k] = sb_min(lo2[k], lo2[(k + 2) & 15]); hi4[k] = sb_max(hi2[k], hi2[(k + 2) & 15]); }
+    for (int k = 0; k < 16; k++) { d4[k] = sb_min(d2[k], d2[(k + 2) & 15]); e4[k] = sb_min(e2[k], e2[(k + 2) & 15]); }
     int best = -256;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int lo9 = sb_min(sb_min(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);   // all darker by more than lo9 - 1
-        const int hi9 = sb_max(sb_max(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);   // all brighter by more than -hi9 - 1
-        best = sb_max(best, sb_max(lo9, -hi9));
+        const int d9 = sb_min(sb_min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int e9 = sb_min(sb_min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
+        best = sb_max(best, sb_max(d9, e9));
     }
     return best - 1;
 }

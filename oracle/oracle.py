@@ -127,7 +127,7 @@ class ORBextractor:
         self.umax = np.zeros(16, np.int32)
         lib().orc_get_tables(self._h, _p(self.scale), _p(self.inv_scale), _p(self.sigma2), _p(self.inv_sigma2),
                              _p(self.quota), _p(self.umax))
-        self.cap = nfeatures + 3 * nlevels + 64
+        self.cap = nfeatures + 67 * nlevels + 600  # each level may keep max(quota + 3, 4 * nIni) keypoints
 
     def __del__(self):
         try:
