@@ -35,10 +35,13 @@
 #define BLUR_BW 160  // BLUR_HX + BLUR_TW + 3, rounded up to the 16-byte TMA granule
 #define BLUR_BH 38
 #define DESC_WARPS 8
+#define SB_PROF_MAX 8192
 
 __device__ __align__(16) int8_t d_pattern[1024] = {
 #include "orb_pattern.inc"
 };
+
+enum { SB_STAGE_COPY = 0, SB_STAGE_RESIZE, SB_STAGE_FAST, SB_STAGE_QUADTREE, SB_STAGE_BLUR, SB_STAGE_DESCRIBE, SB_STAGE_COUNT };
 
 struct LevelGeom {
     int w, h, pitch;
@@ -604,7 +607,28 @@ struct sb_orb {
     int *h_flags;  // pinned
     uint8_t *dbg_buf;  // inspection only (sb_orb_debug_fast_cell)
     int dbg_cell;
+    // per-stage CUDA-event timing (sb_orb_profile): event pairs recorded on the launching stream
+    int prof_on, prof_n;
+    cudaEvent_t prof_ev[SB_PROF_MAX][2];
+    int prof_stage[SB_PROF_MAX], prof_launches[SB_PROF_MAX];
 };
+
+static void prof_begin(sb_orb *h, int stage, int launches, cudaStream_t s) {
+    if (!h->prof_on || h->prof_n >= SB_PROF_MAX) return;
+    const int i = h->prof_n;
+    if (!h->prof_ev[i][0]) {
+        cudaEventCreate(&h->prof_ev[i][0]);
+        cudaEventCreate(&h->prof_ev[i][1]);
+    }
+    h->prof_stage[i] = stage;
+    h->prof_launches[i] = launches;
+    cudaEventRecord(h->prof_ev[i][0], s);
+}
+static void prof_end(sb_orb *h, cudaStream_t s) {
+    if (!h->prof_on || h->prof_n >= SB_PROF_MAX) return;
+    cudaEventRecord(h->prof_ev[h->prof_n][1], s);
+    h->prof_n++;
+}
 
 static void free_orb(sb_orb *h) {
     if (!h) return;
@@ -619,6 +643,10 @@ static void free_orb(sb_orb *h) {
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    for (int i = 0; i < SB_PROF_MAX; i++) {
+        if (h->prof_ev[i][0]) cudaEventDestroy(h->prof_ev[i][0]);
+        if (h->prof_ev[i][1]) cudaEventDestroy(h->prof_ev[i][1]);
+    }
     delete h;
 }
 
@@ -953,22 +981,28 @@ static int launch_pyramid(sb_orb *h, uint8_t *pyr, const uint8_t *d_img, long lo
     const LevelGeom &L0 = g.lv[0];
     const long long total = (long long)batch * L0.h * (L0.pitch / 4);
     const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    prof_begin(h, SB_STAGE_COPY, 1, h->stream);
     if (d_img)
         k_copy_level0<<<blocks, 256, 0, h->stream>>>(d_img, img_pitch, stride, L0.w, L0.h, pyr, g.slab, L0.pitch, batch);
     else
         k_fill_level0<<<blocks, 256, 0, h->stream>>>(pyr, g.slab, L0.pitch, L0.h, batch);
+    prof_end(h, h->stream);
+    if (nlevels_to_build > 1) prof_begin(h, SB_STAGE_RESIZE, nlevels_to_build - 1, h->stream);
     for (int l = 1; l < nlevels_to_build; l++) {
         const LevelGeom &D = g.lv[l];
         dim3 grid(sb_div_up(sb_div_up(D.w, 4), 256), D.h, batch);
         k_resize<<<grid, 256, 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_xofs, h->d_xco, h->d_yofs, h->d_yco);
     }
+    if (nlevels_to_build > 1) prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
 
 static int launch_blur(sb_orb *h, int batch, cudaStream_t s) {
     BlurArgs a = {h->d_tiles, h->d_blur, h->geom.slab};
+    prof_begin(h, SB_STAGE_BLUR, 1, s);
     k_blur<<<dim3(h->n_blur_tiles, batch), 256, 0, s>>>(h->blur_maps, h->geom, a);
+    prof_end(h, s);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
@@ -991,7 +1025,9 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     fa.dbg_cell = h->dbg_cell;
     const int ncells = detect_only ? h->n_cells_l0 : h->n_cells;
     const size_t fsmem = 2 * (size_t)h->fast_tile_bytes + SB_CELL_LIST_CAP * 4 + 128;
+    prof_begin(h, SB_STAGE_FAST, 1, h->stream);
     k_fast_cells<<<dim3(ncells, batch), FAST_THREADS, fsmem, h->stream>>>(h->fast_maps, h->geom, fa);
+    prof_end(h, h->stream);
     QtArgs qa;
     qa.cand = h->d_cand;
     qa.cand_cnt = h->d_cand_cnt;
@@ -1002,7 +1038,9 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     qa.ncap = detect_only ? h->ncap_detect : h->ncap_pyr;
     qa.candcap_smem = SB_CAND_CAP;
     qa.N_override = detect_only ? h->nfeatures : 0;
+    prof_begin(h, SB_STAGE_QUADTREE, 1, h->stream);
     k_quadtree<<<dim3(detect_only ? 1 : nl, batch), QT_THREADS, qt_smem_bytes(qa.ncap), h->stream>>>(h->geom, qa);
+    prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
@@ -1066,7 +1104,9 @@ extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8
     da.nlevels = h->nlevels;
     da.selcap = h->selcap;
     da.cap = cap;
+    prof_begin(h, SB_STAGE_DESCRIBE, 1, h->stream);
     k_describe<<<dim3(sb_div_up(h->ncap_pyr, DESC_WARPS), h->nlevels, batch), DESC_WARPS * 32, 0, h->stream>>>(h->geom, da);
+    prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
@@ -1307,5 +1347,34 @@ extern "C" int sb_orb_debug_fast_cell(sb_orb_t *h, int cell, uint8_t *out, int o
     SB_CUDA(cudaMemcpy(out, h->dbg_buf, (size_t)need, cudaMemcpyDeviceToHost));
     cudaFree(h->dbg_buf);
     h->dbg_buf = nullptr;
+    return SB_OK;
+}
+
+// Per-stage timing with CUDA events on the launching streams.  enable != 0 starts a fresh recording.
+extern "C" int sb_orb_profile(sb_orb_t *h, int enable) {
+    sb_clear_error();
+    SB_REQUIRE(h, "null handle");
+    SB_TRY(sb_use_device(h->device));
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    SB_CUDA(cudaStreamSynchronize(h->side_stream));
+    h->prof_on = enable != 0;
+    if (enable) h->prof_n = 0;
+    return SB_OK;
+}
+
+// Sums the recorded intervals per stage (SB_ORB_STAGE_*): ms[nstages], launches[nstages].
+extern "C" int sb_orb_profile_read(sb_orb_t *h, float *ms, int32_t *launches, int nstages) {
+    sb_clear_error();
+    SB_REQUIRE(h && ms && launches && nstages >= SB_STAGE_COUNT, "bad arguments");
+    SB_TRY(sb_use_device(h->device));
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    SB_CUDA(cudaStreamSynchronize(h->side_stream));
+    for (int i = 0; i < nstages; i++) { ms[i] = 0.f; launches[i] = 0; }
+    for (int i = 0; i < h->prof_n; i++) {
+        float t = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i][0], h->prof_ev[i][1]));
+        ms[h->prof_stage[i]] += t;
+        launches[h->prof_stage[i]] += h->prof_launches[i];
+    }
     return SB_OK;
 }

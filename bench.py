@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 hot path: KITTI-shaped stereo frames/s through ORB extract (both views,
+2000 features, 8-level pyramid) + left<->right Hamming match  (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--pairs B]
+
+One "step" = one batch of B synthetic stereo pairs (1241x376 u8) through the whole path.
+  value : frames/s with the inputs already resident in HBM (device entry points, CUDA events)
+  e2e   : frames/s through the host-pointer C ABI (pinned host buffers, H2D + D2H inside the timed region)
+  --impl reference : the CPU restatement of the reference (oracle/, all host cores) on the same workload
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "a-simple-stereo-slam-system-with-deep-loop-closing_b200"
+
+W, H = 1241, 376
+ORB_PARAMS = (2000, 1.2, 8, 20, 7)
+METRIC = "KITTI stereo frames/s (extract+match+local-BA) @1/2/4/8 B200; % HBM roofline"
+WORKLOAD = "config 2: ORB extract (both views) + L<->R Hamming match, 1241x376 stereo, 2000 feats/frame, synthetic replay"
+STAGES = ["copy_level0", "resize_pyramid", "fast_cells", "quadtree", "gauss_blur", "describe"]
+
+
+def pyramid_bytes():
+    """Bytes of the 8 pyramid levels of one image."""
+    inv = [np.float32(1.0)]
+    s = np.float32(1.0)
+    for _ in range(1, 8):
+        s = np.float32(np.float64(s) * np.float64(np.float32(1.2)))
+        inv.append(np.float32(1.0) / s)
+    sizes = [(W, H)] + [(int(np.rint(np.float32(W) * i)), int(np.rint(np.float32(H) * i))) for i in inv[1:]]
+    return [w * h for w, h in sizes]
+
+
+def algorithmic_bytes(stage, n_images, n_kps, n_cands):
+    """Compulsory HBM bytes of one launch group of `stage` over n_images images."""
+    lv = pyramid_bytes()
+    if stage == "copy_level0":
+        return n_images * 2 * lv[0]
+    if stage == "resize_pyramid":
+        return n_images * sum(lv[l - 1] + lv[l] for l in range(1, 8))
+    if stage == "fast_cells":
+        return n_images * sum(lv) + 4 * n_cands
+    if stage == "quadtree":
+        return 4 * n_cands + 4 * n_kps
+    if stage == "gauss_blur":
+        return n_images * 2 * sum(lv)
+    if stage == "describe":
+        return n_kps * (749 + 512 + 28 + 32 + 4)
+    if stage == "hamming_match":
+        return n_kps * 32 + (n_kps // 2) * 8
+    raise KeyError(stage)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class CpuReference:
+    """The CPU restatement of the reference path (oracle/: ORBextractor::DetectAndCompute on both views +
+    BFMatcher Hamming), one extractor per worker thread (the C code releases the GIL)."""
+
+    def __init__(self, cores):
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle as O
+        O.build()
+        self.O, self.cores = O, cores
+        self.local = threading.local()
+        self.pool = ThreadPoolExecutor(cores)
+
+    def _one(self, pair):
+        if not hasattr(self.local, "ext"):
+            self.local.ext = self.O.ORBextractor(*ORB_PARAMS)
+        _, dl = self.local.ext.DetectAndCompute(pair[0])
+        _, dr = self.local.ext.DetectAndCompute(pair[1])
+        idx, _ = self.O.hamming_match(dl, dr)
+        return len(idx)
+
+    def run(self, frames):
+        """frames [n, 2, H, W] -> seconds"""
+        t0 = time.perf_counter()
+        list(self.pool.map(self._one, list(frames)))
+        return time.perf_counter() - t0
+
+
+def cpu_reference_fps(frames, cores):
+    ref = CpuReference(cores)
+    ref.run(frames[:cores])   # warm: library load, per-thread extractors
+    return len(frames) / ref.run(frames)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    synth = importlib.import_module(PKG + ".synth")
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 8)
+    frames = synth.stereo_batch(0, per_step)
+    ref = CpuReference(cores)
+    for _ in range(args.warmup):
+        ref.run(frames)
+    total = sum(ref.run(frames) for _ in range(args.steps))
+    value = per_step * args.steps / total
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "frames_per_step": per_step},
+           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+                            "sample": f"{per_step} synthetic stereo frames per step through oracle/ (C restatement of "
+                                      "ORBextractor::DetectAndCompute + BFMatcher; the reference itself needs OpenCV/g2o "
+                                      "and cannot be built here), one extractor per thread"},
+           "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=64, help="stereo pairs per step")
+    ap.add_argument("--pool", type=int, default=192, help="distinct resident stereo pairs (> L2 in total)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module(PKG)
+    synth = importlib.import_module(PKG + ".synth")
+    lib = pkg.lib()
+    B, P = args.pairs, max(args.pool, args.pairs)
+    P = (P // B) * B
+
+    # ---- inputs: a pool of distinct frames, larger than L2 (126 MB) in total, resident in HBM
+    t0 = time.perf_counter()
+    uniq = min(P, 48)
+    base = synth.stereo_batch(1000 * rank, uniq)
+    pool_np = np.empty((P, 2, H, W), np.uint8)
+    for i in range(P):   # vertical shifts of the unique frames: distinct bytes, same statistics
+        pool_np[i] = np.roll(base[i % uniq], 7 * (i // uniq), axis=1)
+    pool = torch.from_numpy(pool_np).cuda()
+    gen_s = time.perf_counter() - t0
+
+    stream = torch.cuda.Stream()
+    ext = pkg.ORBextractor(*ORB_PARAMS, max_w=W, max_h=H, max_batch=2 * B, device=local_rank)
+    mat = pkg.HammingMatcher(max_batch=B, max_rows=ext.cap, device=local_rank)
+    ext.set_stream(stream.cuda_stream)
+    mat.set_stream(stream.cuda_stream)
+    cap = ext.cap
+    kps = torch.zeros((2 * B, cap, 28), dtype=torch.uint8, device="cuda")
+    desc = torch.zeros((2 * B, cap, 32), dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(2 * B, dtype=torch.int32, device="cuda")
+    midx = torch.full((B, cap), -1, dtype=torch.int32, device="cuda")
+    mdist = torch.full((B, cap), -1, dtype=torch.int32, device="cuda")
+
+    def step_dev(i):
+        off = (i * B) % P
+        ext.detect_and_compute_dev(2 * B, pool[off], H * W, W, H, W, kps, desc, counts, cap)
+        mat.match_dev(B, desc, 2 * cap * 32, counts, 2, desc[0, :, :].data_ptr() + cap * 32, 2 * cap * 32,
+                      counts.data_ptr() + 4, 2, cap, midx, mdist, cap)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step_dev(i)
+        ext.sync_status()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        time.sleep(0.3)
+        lib.sb_orb_profile(ext._h, 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        e0.record(stream)
+        for i in range(args.steps):
+            off = ((args.warmup + i) * B) % P
+            ext.detect_and_compute_dev(2 * B, pool[off], H * W, W, H, W, kps, desc, counts, cap)
+            m_ev[i][0].record(stream)
+            mat.match_dev(B, desc, 2 * cap * 32, counts, 2, desc[0, :, :].data_ptr() + cap * 32, 2 * cap * 32,
+                          counts.data_ptr() + 4, 2, cap, midx, mdist, cap)
+            m_ev[i][1].record(stream)
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ext.sync_status()
+    dev_ms = e0.elapsed_time(e1)
+    ms = np.zeros(6, np.float32)
+    launches = np.zeros(6, np.int32)
+    lib.sb_orb_profile_read(ext._h, C.c_void_p(ms.ctypes.data), C.c_void_p(launches.ctypes.data), 6)
+    lib.sb_orb_profile(ext._h, 0)
+    match_ms = float(sum(a.elapsed_time(b) for a, b in m_ev))
+    n_kps = int(counts.sum().item())
+    cand_np = np.zeros(1, np.int64)
+    n_cands = 0
+    for b in range(0, 2 * B, max(1, 2 * B // 4)):   # sample a few images for the candidate count
+        for level in range(8):
+            n_cands += len(ext.debug_candidates(b, level))
+    n_cands = int(n_cands * (2 * B) / len(range(0, 2 * B, max(1, 2 * B // 4))))
+    n_matched = int((mdist >= 0).sum().item())
+
+    # ---- e2e: the host-pointer C ABI with pinned host buffers (H2D + D2H inside the timed region)
+    hp = min(P, 2 * B)
+    host_pool = torch.from_numpy(pool_np[:hp]).pin_memory()
+    h_kps = torch.zeros((2 * B, cap, 28), dtype=torch.uint8).pin_memory()
+    h_desc = torch.zeros((2 * B, cap, 32), dtype=torch.uint8).pin_memory()
+    h_counts = torch.zeros(2 * B, dtype=torch.int32).pin_memory()
+    h_midx = torch.zeros((B, cap), dtype=torch.int32).pin_memory()
+    h_mdist = torch.zeros((B, cap), dtype=torch.int32).pin_memory()
+    PA = C.c_void_p * (2 * B)
+    img_bytes = H * W
+
+    def step_host(i):
+        off = (i * B) % hp
+        base_ptr = host_pool.data_ptr() + off * 2 * img_bytes
+        ptrs = PA(*[base_ptr + k * img_bytes for k in range(2 * B)])
+        rc = lib.sb_orb_detect_and_compute(ext._h, 2 * B, ptrs, None, W, H, W, W, C.c_void_p(h_kps.data_ptr()),
+                                           C.c_void_p(h_desc.data_ptr()), C.c_void_p(h_counts.data_ptr()), cap)
+        assert rc == 0, pkg.last_error()
+        # match on the descriptors still resident on the device side of the extractor handle is not
+        # exposed by the C ABI; the host-pointer matcher call re-uploads them (counted in h2d bytes)
+        nq = h_counts[0::2].contiguous()
+        nt = h_counts[1::2].contiguous()
+        q = h_desc[0::2]
+        t = h_desc[1::2]
+        return q, t, nq, nt
+
+    h_q = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+    h_t = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+
+    def step_host_full(i):
+        q, t, nq, nt = step_host(i)
+        h_q.copy_(q)
+        h_t.copy_(t)
+        rc = lib.sb_hamming_match(mat._h, B, C.c_void_p(h_q.data_ptr()), C.c_void_p(nq.data_ptr()),
+                                  C.c_void_p(h_t.data_ptr()), C.c_void_p(nt.data_ptr()), cap,
+                                  C.c_void_p(h_midx.data_ptr()), C.c_void_p(h_mdist.data_ptr()))
+        assert rc == 0, pkg.last_error()
+
+    for i in range(3):
+        step_host_full(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host_full(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = 2 * B * img_bytes + 2 * B * cap * 32 + 2 * B * 4
+    d2h = 2 * B * cap * (28 + 32) + 2 * B * 4 + 2 * B * cap * 4
+
+    # ---- aggregate over ranks (max time)
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    frames = B * args.steps * world
+    value = frames / (dev_ms_max * 1e-3)
+    e2e_value = frames / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        stage_ms = {s: float(ms[i]) for i, s in enumerate(STAGES)}
+        stage_ms["hamming_match"] = match_ms
+        stage_launches = {s: int(launches[i]) for i, s in enumerate(STAGES)}
+        stage_launches["hamming_match"] = args.steps
+        top = max(stage_ms, key=stage_ms.get)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        groups = stage_launches[top] / (7 if top == "resize_pyramid" else 1)
+        per_group_ms = stage_ms[top] / max(groups, 1)
+        abytes = algorithmic_bytes(top, 2 * B, n_kps, n_cands)
+        achieved = abytes / (per_group_ms * 1e-3) / 1e9
+        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": abytes, "ms_per_launch": per_group_ms,
+                    "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                    "stage_gbs": {k: algorithmic_bytes(k, 2 * B, n_kps, n_cands) / (stage_ms[k] / args.steps * 1e-3) / 1e9
+                                  for k in stage_ms if stage_ms[k] > 0}}
+        out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+               "config": {"workload": WORKLOAD, "stereo_pairs_per_step_per_gpu": B, "resident_pool_pairs": P,
+                          "l2_policy": f"inputs larger than L2: {P * 2 * img_bytes / 1e6:.0f} MB pool of distinct frames cycled",
+                          "keypoints_per_frame": n_kps / (2 * B), "matches_per_pair": n_matched / B,
+                          "sharding": "frames round-robin by rank, no data-path collective"},
+               "clocks": clocks,
+               "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e2e_ms_max / args.steps,
+                       "api": "sb_orb_detect_and_compute + sb_hamming_match (host pointers, pinned)"},
+               "gpu_launches": int(sum(stage_launches.values())),
+               "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = max(2 * cores, 16)
+            sample = pool_np[:min(n, P)]
+            fps = cpu_reference_fps(sample, cores)
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                   "sample": f"{len(sample)} of the same synthetic stereo frames through oracle/ (C restatement "
+                                             "of the reference's OpenCV-based path), one extractor per thread"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

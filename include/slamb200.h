@@ -113,6 +113,22 @@ int sb_orb_debug_level(sb_orb_t *h, int b, int level, int which, uint8_t *out, i
  * x | y << 12 | response << 24 (border-relative x, y), unordered.  *n receives the count. */
 int sb_orb_debug_candidates(sb_orb_t *h, int b, int level, uint32_t *out, int cap, int32_t *n);
 
+/* Inspection: capture the TMA tile and response plane of one FAST cell of image 0 during the next call. */
+int sb_orb_debug_fast_cell(sb_orb_t *h, int cell, uint8_t *out, int out_bytes, int *tile_bytes);
+
+/* Per-stage timing with CUDA events recorded on the streams the kernels are launched on.
+ * sb_orb_profile(h, 1) starts a fresh recording, sb_orb_profile(h, 0) stops it;
+ * sb_orb_profile_read sums device milliseconds and kernel launches per stage. */
+#define SB_ORB_STAGE_COPY 0      /* level 0 re-pitch                    */
+#define SB_ORB_STAGE_RESIZE 1    /* pyramid levels 1 .. n-1             */
+#define SB_ORB_STAGE_FAST 2      /* grid FAST + NMS + threshold select  */
+#define SB_ORB_STAGE_QUADTREE 3  /* DistributeOctTree                   */
+#define SB_ORB_STAGE_BLUR 4      /* Gaussian 7x7 on every level         */
+#define SB_ORB_STAGE_DESCRIBE 5  /* IC_Angle + rBRIEF + output          */
+#define SB_ORB_STAGE_COUNT 6
+int sb_orb_profile(sb_orb_t *h, int enable);
+int sb_orb_profile_read(sb_orb_t *h, float *ms, int32_t *launches, int nstages);
+
 /* ---------------------------------------------------------------------------------------------
  * Brute-force Hamming 1-NN — replaces cv::BFMatcher(NORM_HAMMING)::match as used by
  * LoopClosing::MatchFeatures (src/loopclosing.cpp:33,172): for every query row the nearest train
