@@ -54,3 +54,97 @@ def stereo_batch(seed0, batch, w=KITTI_W, h=KITTI_H):
     for b in range(batch):
         out[b, 0], out[b, 1] = stereo_pair(seed0 + b, w, h)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Local-BA windows.  Poses are T_cw as (qx, qy, qz, qw, tx, ty, tz) — Sophus'
+# storage order — landmarks are world points, observations are left-camera pixels.
+# ---------------------------------------------------------------------------------------------------
+KITTI_K = (KITTI_FX, KITTI_FY, KITTI_CX, KITTI_CY)
+IDENTITY_EXT = (0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0)  # left camera extrinsics = identity (src/system.cpp:141-142)
+
+
+def _rot_y(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+def _so3_exp(w):
+    th = np.linalg.norm(w)
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + W
+    return np.eye(3) + np.sin(th) / th * W + (1 - np.cos(th)) / th ** 2 * W @ W
+
+
+def _quat_from_R(R):
+    tr = np.trace(R)
+    if tr > 0:
+        s = np.sqrt(tr + 1.0) * 2
+        q = np.array([(R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s, 0.25 * s])
+    else:
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = np.sqrt(1.0 + R[i, i] - R[j, j] - R[k, k]) * 2
+        q = np.zeros(4)
+        q[i] = 0.25 * s
+        q[j] = (R[j, i] + R[i, j]) / s
+        q[k] = (R[k, i] + R[i, k]) / s
+        q[3] = (R[k, j] - R[j, k]) / s
+    if q[3] < 0:
+        q = -q
+    return q / np.linalg.norm(q)
+
+
+def pose7(R, t):
+    return np.concatenate([_quat_from_R(R), t])
+
+
+def ba_window(seed, n_poses=7, n_points=300, pix_noise=1.0, outlier_frac=0.05, pose_noise=(0.02, 0.2), point_noise=0.3,
+              fixed_frac=0.3, w=KITTI_W, h=KITTI_H):
+    """One sliding window.  Returns a dict of numpy arrays:
+    poses0 [P,7] / points0 [L,3] (perturbed start), poses_gt / points_gt, fixed [L] u8,
+    obs_pose / obs_point [E] i32, uv [E,2] f64."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = KITTI_K
+    centres, Rs = [], []
+    z = 0.0
+    for i in range(n_poses):
+        centres.append(np.array([rng.normal(0, 0.05), rng.normal(0, 0.02), z]))
+        Rs.append(_rot_y(rng.normal(0, 0.03)).T)      # R_cw
+        z += rng.uniform(6.0, 8.0)                     # keyframe spacing read off result/trajectory.txt:1-5
+    poses_gt = np.stack([pose7(R, -R @ c) for R, c in zip(Rs, centres)])
+    # landmarks in the union frustum, depth 5-50 m ahead of a random keyframe
+    pts = np.empty((n_points, 3))
+    for j in range(n_points):
+        k = rng.integers(0, n_poses)
+        d = rng.uniform(5.0, 50.0)
+        u, v = rng.uniform(0, w), rng.uniform(0, h)
+        pc = np.array([(u - cx) / fx * d, (v - cy) / fy * d, d])
+        pts[j] = Rs[k].T @ pc + centres[k]
+    obs_pose, obs_point, uv = [], [], []
+    for j in range(n_points):
+        for i in range(n_poses):
+            pc = Rs[i] @ (pts[j] - centres[i])
+            if pc[2] <= 0.5:
+                continue
+            u, v = fx * pc[0] / pc[2] + cx, fy * pc[1] / pc[2] + cy
+            if 0 <= u < w and 0 <= v < h:
+                nu, nv = rng.normal(0, pix_noise, 2) if pix_noise > 0 else (0.0, 0.0)
+                if rng.uniform() < outlier_frac:
+                    nu, nv = rng.uniform(-50, 50, 2)
+                obs_pose.append(i)
+                obs_point.append(j)
+                uv.append((np.float32(u + nu), np.float32(v + nv)))  # cv::KeyPoint::pt is float
+    fixed = (rng.uniform(size=n_points) < fixed_frac).astype(np.uint8)
+    poses0 = poses_gt.copy()
+    for i in range(n_poses):
+        dR = _so3_exp(rng.normal(0, pose_noise[0], 3)) if pose_noise[0] > 0 else np.eye(3)
+        dt = rng.normal(0, pose_noise[1], 3) if pose_noise[1] > 0 else np.zeros(3)
+        R = dR @ Rs[i]
+        poses0[i] = pose7(R, dR @ (-Rs[i] @ centres[i]) + dt)
+    points0 = pts + (rng.normal(0, point_noise, pts.shape) if point_noise > 0 else 0.0)
+    points0[fixed == 1] = pts[fixed == 1]   # fixed landmarks were optimised by earlier windows
+    return {"poses0": poses0, "points0": points0, "poses_gt": poses_gt, "points_gt": pts, "fixed": fixed,
+            "obs_pose": np.array(obs_pose, np.int32), "obs_point": np.array(obs_point, np.int32),
+            "uv": np.array(uv, np.float64).reshape(-1, 2)}

@@ -43,7 +43,7 @@ def lib():
         for name in ("orc_detect_and_compute", "orc_detect_with_pyramid", "orc_detect", "orc_screen_params",
                      "orc_calc_descriptors", "orc_get_level", "orc_get_blurred_level", "orc_resize_linear_u8",
                      "orc_gauss7_u8", "orc_fast9_16", "orc_hamming_match", "orc_match_filter",
-                     "orc_distribute_octtree", "orc_debug_candidate_count"):
+                     "orc_distribute_octtree", "orc_debug_candidate_count", "orc_ba_solve"):
             getattr(L, name).restype = C.c_int
     return _LIB
 
@@ -218,3 +218,55 @@ class ORBextractor:
         rc = lib().orc_get_blurred_level(self._h, level, _p(out))
         assert rc == 0
         return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# local bundle adjustment (oracle/ba_oracle.c)
+# ---------------------------------------------------------------------------------------------------
+def ba_solve(poses, points, fixed, obs_pose, obs_point, uv, K, ext7=(0, 0, 0, 1, 0, 0, 0), huber_delta=5.991,
+             chi2_th=5.991, outer_max=5, inner_iters=10):
+    """Backend::OptimizeActiveMap's solver part.  Returns (poses, points, chi2, outlier, info)."""
+    poses = np.ascontiguousarray(poses, np.float64).copy()
+    points = np.ascontiguousarray(points, np.float64).copy()
+    fixed = np.ascontiguousarray(fixed, np.uint8)
+    op = np.ascontiguousarray(obs_pose, np.int32)
+    ol = np.ascontiguousarray(obs_point, np.int32)
+    uv = np.ascontiguousarray(uv, np.float64)
+    K = np.ascontiguousarray(K, np.float64)
+    ext = np.ascontiguousarray(ext7, np.float64)
+    chi2 = np.zeros(max(1, len(op)), np.float64)
+    outl = np.zeros(max(1, len(op)), np.uint8)
+    info = np.zeros(4, np.int32)
+    rc = lib().orc_ba_solve(len(poses), len(points), len(op), _p(poses), _p(points), _p(fixed), _p(op), _p(ol), _p(uv),
+                            _p(K), _p(ext), C.c_double(huber_delta), C.c_double(chi2_th), outer_max, inner_iters,
+                            _p(chi2), _p(outl), _p(info))
+    assert rc == 0
+    return poses, points, chi2[:len(op)], outl[:len(op)], info
+
+
+def se3_exp(d):
+    d = np.ascontiguousarray(d, np.float64)
+    R = np.zeros(9)
+    t = np.zeros(3)
+    lib().orc_se3_exp(_p(d), _p(R), _p(t))
+    return R.reshape(3, 3), t
+
+
+def pose_oplus(pose7, d):
+    p = np.ascontiguousarray(pose7, np.float64).copy()
+    d = np.ascontiguousarray(d, np.float64)
+    lib().orc_pose_oplus(_p(p), _p(d))
+    return p
+
+
+def ba_edge(pose7, pt, uv, K, ext7=(0, 0, 0, 1, 0, 0, 0)):
+    """-> (error[2], A[2,6], B[2,3]) of one EdgeProjection."""
+    pose7 = np.ascontiguousarray(pose7, np.float64)
+    pt = np.ascontiguousarray(pt, np.float64)
+    uv = np.ascontiguousarray(uv, np.float64)
+    K = np.ascontiguousarray(K, np.float64)
+    ext = np.ascontiguousarray(ext7, np.float64)
+    err, A, B = np.zeros(2), np.zeros(12), np.zeros(6)
+    lib().orc_ba_edge_error(_p(pose7), _p(pt), _p(uv), _p(K), _p(ext), _p(err))
+    lib().orc_ba_edge_jacobians(_p(pose7), _p(pt), _p(K), _p(ext), _p(A), _p(B))
+    return err, A.reshape(2, 6), B.reshape(2, 3)
