@@ -256,3 +256,77 @@ class HammingMatcher:
         _check(lib().sb_hamming_match_dev(self._h, batch, _dev_ptr(d_q), C.c_int64(q_set_stride), _dev_ptr(d_nq),
                                           nq_stride, _dev_ptr(d_t), C.c_int64(t_set_stride), _dev_ptr(d_nt), nt_stride,
                                           max_rows, _dev_ptr(d_idx), _dev_ptr(d_dist), C.c_int64(out_stride)))
+
+
+class LocalBA:
+    """The g2o solve of Backend::OptimizeActiveMap (src/backend.cpp:126-269), batched over windows."""
+
+    def __init__(self, max_windows=1, max_poses=7, max_points=1024, max_obs=8192, device=0):
+        self._h = C.c_void_p()
+        self.W, self.MP, self.ML, self.MO = max_windows, max_poses, max_points, max_obs
+        _check(lib().sb_ba_create(C.byref(self._h), device, max_windows, max_poses, max_points, max_obs))
+
+    def close(self):
+        if self._h:
+            lib().sb_ba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        _check(lib().sb_ba_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def pack(self, windows):
+        """list of dicts (poses0, points0, fixed, obs_pose, obs_point, uv) -> padded batch arrays"""
+        n = len(windows)
+        b = {"np": np.zeros(n, np.int32), "nl": np.zeros(n, np.int32), "ne": np.zeros(n, np.int32),
+             "poses": np.zeros((n, self.MP, 7)), "points": np.zeros((n, self.ML, 3)),
+             "fixed": np.zeros((n, self.ML), np.uint8), "op": np.zeros((n, self.MO), np.int32),
+             "ol": np.zeros((n, self.MO), np.int32), "uv": np.zeros((n, self.MO, 2))}
+        b["poses"][:, :, 3] = 1.0
+        for k, w in enumerate(windows):
+            p, l, e = len(w["poses0"]), len(w["points0"]), len(w["obs_pose"])
+            b["np"][k], b["nl"][k], b["ne"][k] = p, l, e
+            b["poses"][k, :p] = w["poses0"]
+            b["points"][k, :l] = w["points0"]
+            b["fixed"][k, :l] = w["fixed"]
+            b["op"][k, :e] = w["obs_pose"]
+            b["ol"][k, :e] = w["obs_point"]
+            b["uv"][k, :e] = w["uv"]
+        return b
+
+    def solve(self, windows, K, ext7=(0, 0, 0, 1, 0, 0, 0), huber_delta=5.991, chi2_th=5.991, outer_max=5,
+              inner_iters=10):
+        """-> list of (poses, points, chi2, outlier, info) per window."""
+        b = self.pack(windows)
+        n = len(windows)
+        K = np.ascontiguousarray(K, np.float64)
+        ext = np.ascontiguousarray(ext7, np.float64)
+        chi2 = np.zeros((n, self.MO))
+        outl = np.zeros((n, self.MO), np.uint8)
+        info = np.zeros((n, 4), np.int32)
+        _check(lib().sb_ba_solve(self._h, n, _p(b["np"]), _p(b["nl"]), _p(b["ne"]), _p(b["poses"]), _p(b["points"]),
+                                 _p(b["fixed"]), _p(b["op"]), _p(b["ol"]), _p(b["uv"]), _p(K), _p(ext),
+                                 C.c_double(huber_delta), C.c_double(chi2_th), outer_max, inner_iters, _p(chi2), _p(outl),
+                                 _p(info)))
+        out = []
+        for k in range(n):
+            p, l, e = b["np"][k], b["nl"][k], b["ne"][k]
+            out.append((b["poses"][k, :p].copy(), b["points"][k, :l].copy(), chi2[k, :e].copy(), outl[k, :e].copy(),
+                        info[k].copy()))
+        return out
+
+    def solve_dev(self, n, d, K, ext7=(0, 0, 0, 1, 0, 0, 0), huber_delta=5.991, chi2_th=5.991, outer_max=5,
+                  inner_iters=10):
+        """d: dict of device tensors with the keys of pack() plus chi2, outlier, info."""
+        K = np.ascontiguousarray(K, np.float64)
+        ext = np.ascontiguousarray(ext7, np.float64)
+        _check(lib().sb_ba_solve_dev(self._h, n, _dev_ptr(d["np"]), _dev_ptr(d["nl"]), _dev_ptr(d["ne"]),
+                                     _dev_ptr(d["poses"]), _dev_ptr(d["points"]), _dev_ptr(d["fixed"]), _dev_ptr(d["op"]),
+                                     _dev_ptr(d["ol"]), _dev_ptr(d["uv"]), _p(K), _p(ext), C.c_double(huber_delta),
+                                     C.c_double(chi2_th), outer_max, inner_iters, _dev_ptr(d["chi2"]),
+                                     _dev_ptr(d["outlier"]), _dev_ptr(d["info"])))

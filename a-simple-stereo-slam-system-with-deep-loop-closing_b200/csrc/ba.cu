@@ -1,0 +1,722 @@
+// ba.cu — batched sliding-window local bundle adjustment on B200 (sm_100a), double precision.
+//
+// Replaces the solver inside Backend::OptimizeActiveMap (reference src/backend.cpp:126-269): g2o's
+// Levenberg-Marquardt over BlockSolver_6_3 with the landmarks marginalised (Schur complement), the
+// reference's EdgeProjection / VertexPose / VertexXYZ arithmetic (include/myslam/g2o_types.h:25-59,
+// 106-153), Huber kernel (delta 5.991) and the outer "up to 5 x optimize(10)" loop (:212-232).
+//
+// One CTA solves one window from start to finish (all LM iterations and trials inside ONE launch, no
+// host round trip); a launch solves a batch of independent windows.  Nothing is stored per edge: the
+// 2x6 / 2x3 Jacobians are ~60 flops and are recomputed wherever they are needed, so the working set
+// per window is the 6x6 pose blocks and the reduced (6P)^2 system in shared memory plus 18 doubles
+// per landmark in L2.  Every sum runs in a fixed order (no floating-point atomics): results are
+// bit-reproducible run to run.  The only index structure is edge_of[landmark][pose].
+//
+// All arithmetic is fp64 like g2o's: the window has no fixed pose, its gauge is held only by the LM
+// damping and the fixed landmarks, and fp32 normal equations do not keep the 1e-4 parity bound there.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+#define BA_THREADS 256
+#define BA_MAX_POSES 16
+
+struct sb_ba {
+    int device, max_windows, max_poses, max_points, max_obs;
+    cudaStream_t stream, own_stream;
+    // device copies of the batch (host-pointer entry point) and per-window workspace
+    int32_t *d_np, *d_nl, *d_ne, *d_info;
+    double *d_poses, *d_points, *d_uv, *d_chi2;
+    uint8_t *d_fixed, *d_outlier;
+    int32_t *d_op, *d_ol;
+    int32_t *d_edge_of;  // [W][ML][MP]
+    double *d_lm;        // [W][ML][18]: Hll(6) bl(3) Dinv(6) xl(3)
+    double *d_ptbak;     // [W][ML][3]
+    double *d_err;       // [W][2][MO][2]
+};
+
+struct BaArgs {
+    const int32_t *np, *nl, *ne;
+    double *poses;           // [W][MP][7] in/out
+    double *points;          // [W][ML][3] in/out
+    const uint8_t *fixed;    // [W][ML]
+    const int32_t *op, *ol;  // [W][MO]
+    const double *uv;        // [W][MO][2]
+    double *chi2;            // [W][MO] out
+    uint8_t *outlier;        // [W][MO] out
+    int32_t *info;           // [W][4] out: outer rounds, LM iterations, inliers, outliers (or -1: bad input)
+    int32_t *edge_of;
+    double *lm, *ptbak, *err;
+    int MP, ML, MO;
+    double fx, fy, cx, cy;
+    double extR[9], extT[3];
+    double delta, chi2_th;
+    int outer_max, inner_iters;
+};
+
+// ---- small dense helpers ------------------------------------------------------------------------------
+static __device__ __forceinline__ void quat_to_R(const double *q, double *R) {  // q = (x, y, z, w)
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+
+static __device__ void R_to_quat(const double *R, double *q) {  // -> (x, y, z, w), w >= 0
+    const double tr = R[0] + R[4] + R[8];
+    double x, y, z, w;
+    if (tr > 0) {
+        const double s = sqrt(tr + 1.0) * 2; w = 0.25 * s; x = (R[7] - R[5]) / s; y = (R[2] - R[6]) / s; z = (R[3] - R[1]) / s;
+    } else if (R[0] > R[4] && R[0] > R[8]) {
+        const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2; w = (R[7] - R[5]) / s; x = 0.25 * s; y = (R[1] + R[3]) / s; z = (R[2] + R[6]) / s;
+    } else if (R[4] > R[8]) {
+        const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2; w = (R[2] - R[6]) / s; x = (R[1] + R[3]) / s; y = 0.25 * s; z = (R[5] + R[7]) / s;
+    } else {
+        const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2; w = (R[3] - R[1]) / s; x = (R[2] + R[6]) / s; y = (R[5] + R[7]) / s; z = 0.25 * s;
+    }
+    if (w < 0) { x = -x; y = -y; z = -z; w = -w; }
+    const double n = sqrt(x * x + y * y + z * z + w * w);
+    q[0] = x / n; q[1] = y / n; q[2] = z / n; q[3] = w / n;
+}
+
+// Sophus SE3d::exp([upsilon, omega]) applied on the left: Rt <- exp(d) * Rt  (VertexPose::oplusImpl)
+static __device__ void pose_oplus(double *Rt, const double *d) {
+    const double wx = d[3], wy = d[4], wz = d[5];
+    const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+    double a, b, c;
+    if (th < 1e-10) { a = 1.0 - th2 / 6.0; b = 0.5 - th2 / 24.0; c = 1.0 / 6.0 - th2 / 120.0; }
+    else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; c = (th - sin(th)) / (th2 * th); }
+    const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double W2[9], E[9], V[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) W2[3 * i + j] = W[3 * i] * W[j] + W[3 * i + 1] * W[3 + j] + W[3 * i + 2] * W[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const double I = (i % 4 == 0) ? 1.0 : 0.0;
+        E[i] = I + a * W[i] + b * W2[i];
+        V[i] = I + b * W[i] + c * W2[i];
+    }
+    double Et[3], Rn[9], tn[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) Et[i] = V[3 * i] * d[0] + V[3 * i + 1] * d[1] + V[3 * i + 2] * d[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) Rn[3 * i + j] = E[3 * i] * Rt[j] + E[3 * i + 1] * Rt[3 + j] + E[3 * i + 2] * Rt[6 + j];
+        tn[i] = E[3 * i] * Rt[9] + E[3 * i + 1] * Rt[10] + E[3 * i + 2] * Rt[11] + Et[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) Rt[i] = Rn[i];
+    Rt[9] = tn[0]; Rt[10] = tn[1]; Rt[11] = tn[2];
+}
+
+// RobustKernelHuber::robustify -> rho(e2) and rho'(e2)
+static __device__ __forceinline__ void huber(double e2, double delta, double &rho0, double &rho1) {
+    const double dsqr = delta * delta;
+    if (e2 <= dsqr) { rho0 = e2; rho1 = 1.0; }
+    else { const double s = sqrt(e2); rho0 = 2 * s * delta - dsqr; rho1 = delta / s; }
+}
+
+struct EdgeCtx {
+    const BaArgs *a;
+    const double *Rt;   // shared: [MP][12]
+    const double *pts;  // global: [ML][3]
+    const double *uv;   // global: [MO][2]
+    const int32_t *op, *ol;
+};
+
+// camera-frame point of edge e:  ext * (T * p)
+static __device__ __forceinline__ void edge_cam(const EdgeCtx &c, int i, int j, double *pe, double *RR) {
+    const double *T = c.Rt + 12 * i;
+    const double *p = c.pts + 3 * j;
+    const double px = p[0], py = p[1], pz = p[2];
+    double pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) pc[r] = T[3 * r] * px + T[3 * r + 1] * py + T[3 * r + 2] * pz + T[9 + r];
+    const BaArgs &a = *c.a;
+#pragma unroll
+    for (int r = 0; r < 3; r++) pe[r] = a.extR[3 * r] * pc[0] + a.extR[3 * r + 1] * pc[1] + a.extR[3 * r + 2] * pc[2] + a.extT[r];
+    if (RR) {
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) RR[3 * r + k] = a.extR[3 * r] * T[k] + a.extR[3 * r + 1] * T[3 + k] + a.extR[3 * r + 2] * T[6 + k];
+    }
+}
+
+// EdgeProjection::computeError (g2o_types.h:115-122)
+static __device__ __forceinline__ void edge_error(const EdgeCtx &c, int e, double *r) {
+    double pe[3];
+    edge_cam(c, c.op[e], c.ol[e], pe, nullptr);
+    const BaArgs &a = *c.a;
+    const double px = a.fx * pe[0] + a.cx * pe[2], py = a.fy * pe[1] + a.cy * pe[2];
+    r[0] = c.uv[2 * e] - px / pe[2];
+    r[1] = c.uv[2 * e + 1] - py / pe[2];
+}
+
+// EdgeProjection::linearizeOplus (:124-144) + Huber weight of the stored error
+static __device__ __forceinline__ void edge_lin(const EdgeCtx &c, int e, const double *err, double *A, double *B, double *r,
+                                                double &w) {
+    double pe[3], RR[9];
+    edge_cam(c, c.op[e], c.ol[e], pe, RR);
+    const BaArgs &a = *c.a;
+    const double X = pe[0], Y = pe[1], Z = pe[2];
+    const double Zinv = 1.0 / (Z + 1e-18), Zinv2 = Zinv * Zinv;
+    A[0] = -a.fx * Zinv; A[1] = 0; A[2] = a.fx * X * Zinv2; A[3] = a.fx * X * Y * Zinv2; A[4] = -a.fx - a.fx * X * X * Zinv2; A[5] = a.fx * Y * Zinv;
+    A[6] = 0; A[7] = -a.fy * Zinv; A[8] = a.fy * Y * Zinv2; A[9] = a.fy + a.fy * Y * Y * Zinv2; A[10] = -a.fy * X * Y * Zinv2; A[11] = -a.fy * X * Zinv;
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) B[3 * rr + k] = A[6 * rr] * RR[k] + A[6 * rr + 1] * RR[3 + k] + A[6 * rr + 2] * RR[6 + k];
+    r[0] = err[2 * e];
+    r[1] = err[2 * e + 1];
+    double rho0;
+    huber(r[0] * r[0] + r[1] * r[1], a.delta, rho0, w);
+}
+
+// ---- block-wide deterministic reductions ----------------------------------------------------------------
+static __device__ double block_sum(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double s = 0;
+    for (int k = 0; k < BA_THREADS / 32; k++) s += red[k];
+    return s;
+}
+static __device__ double block_max(double v, double *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double s = red[0];
+    for (int k = 1; k < BA_THREADS / 32; k++) s = fmax(s, red[k]);
+    return s;
+}
+
+// computeActiveErrors + activeRobustChi2
+// `err` always receives the errors; `err_lin` (nullable) a second copy that stays untouched by the LM
+// trials: the Huber weights of the linearised system belong to the state it was linearised at.
+static __device__ double compute_errors(const EdgeCtx &c, int ne, double *err, double *err_lin, double *red) {
+    double chi = 0;
+    for (int e = threadIdx.x; e < ne; e += BA_THREADS) {
+        double r[2], rho0, rho1;
+        edge_error(c, e, r);
+        err[2 * e] = r[0];
+        err[2 * e + 1] = r[1];
+        if (err_lin) { err_lin[2 * e] = r[0]; err_lin[2 * e + 1] = r[1]; }
+        huber(r[0] * r[0] + r[1] * r[1], c.a->delta, rho0, rho1);
+        chi += rho0;
+    }
+    return block_sum(chi, red);
+}
+
+__global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__ BaArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    const int w = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int np = a.np[w], nl = a.nl[w], ne = a.ne[w];
+    const int MP = a.MP;
+    const int n6 = 6 * np;
+    double *Rt = sm;                    // [MP][12]
+    double *Rtb = Rt + 12 * MP;         // backup (push / pop)
+    double *Hpp = Rtb + 12 * MP;        // [MP][36]
+    double *bp = Hpp + 36 * MP;         // [6 MP]
+    double *xs = bp + 6 * MP;           // [6 MP]
+    double *S = xs + 6 * MP;            // [(6 MP)^2]
+    double *red = S + 36 * MP * MP;     // [16]
+    __shared__ int s_bad;
+    double *poses = a.poses + (size_t)w * MP * 7;
+    double *pts = a.points + (size_t)w * a.ML * 3;
+    const uint8_t *fixed = a.fixed + (size_t)w * a.ML;
+    const int32_t *op = a.op + (size_t)w * a.MO, *ol = a.ol + (size_t)w * a.MO;
+    int32_t *edge_of = a.edge_of + (size_t)w * a.ML * MP;
+    double *lm = a.lm + (size_t)w * a.ML * 18;
+    double *ptb = a.ptbak + (size_t)w * a.ML * 3;
+    double *err = a.err + (size_t)w * a.MO * 4;   // errors of the last evaluation
+    double *elin = err + (size_t)a.MO * 2;         // errors at the linearisation state
+    int32_t *info = a.info + 4 * w;
+
+    // ---- input checks and the edge_of[landmark][pose] table
+    if (tid == 0) s_bad = (np < 1 || np > MP || nl < 0 || nl > a.ML || ne < 0 || ne > a.MO) ? 1 : 0;
+    __syncthreads();
+    if (!s_bad) {
+        for (int k = tid; k < nl * MP; k += BA_THREADS) edge_of[k] = -1;
+        __syncthreads();
+        for (int e = tid; e < ne; e += BA_THREADS) {
+            const int i = op[e], j = ol[e];
+            if (i < 0 || i >= np || j < 0 || j >= nl) s_bad = 1;
+            else if (atomicCAS(&edge_of[j * MP + i], -1, e) != -1) s_bad = 2;  // one keyframe observes a landmark twice
+        }
+    }
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) { info[0] = -1; info[1] = -s_bad; info[2] = info[3] = 0; }
+        return;
+    }
+    for (int i = tid; i < np; i += BA_THREADS) {
+        quat_to_R(poses + 7 * i, Rt + 12 * i);
+        Rt[12 * i + 9] = poses[7 * i + 4]; Rt[12 * i + 10] = poses[7 * i + 5]; Rt[12 * i + 11] = poses[7 * i + 6];
+    }
+    __syncthreads();
+
+    EdgeCtx c;
+    c.a = &a; c.Rt = Rt; c.pts = pts; c.uv = a.uv + (size_t)w * a.MO * 2; c.op = op; c.ol = ol;
+
+    int rounds = 0, lm_total = 0, inl = 0, outl = 0;
+    for (int outer = 0; outer < a.outer_max;) {  // src/backend.cpp:212-232
+        // ================= optimizer.optimize(inner_iters): Levenberg-Marquardt =================
+        double lambda = 0, ni = 2;
+        bool terminated = false;
+        for (int it = 0; it < a.inner_iters && !terminated; it++) {
+            double currentChi = compute_errors(c, ne, err, elin, red);
+            // ---- buildSystem.  Pose blocks: one warp per pose, lanes over the landmarks it observes.
+            for (int i = wid; i < np; i += BA_THREADS / 32) {
+                double h[21], g[6];
+#pragma unroll
+                for (int k = 0; k < 21; k++) h[k] = 0;
+#pragma unroll
+                for (int k = 0; k < 6; k++) g[k] = 0;
+                for (int j = lane; j < nl; j += 32) {
+                    const int e = edge_of[j * MP + i];
+                    if (e < 0) continue;
+                    double A[12], B[6], r[2], wgt;
+                    edge_lin(c, e, elin, A, B, r, wgt);
+                    int k = 0;
+#pragma unroll
+                    for (int p = 0; p < 6; p++) {
+                        g[p] += -wgt * (A[p] * r[0] + A[6 + p] * r[1]);
+#pragma unroll
+                        for (int q = p; q < 6; q++) h[k++] += wgt * (A[p] * A[q] + A[6 + p] * A[6 + q]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 21; k++)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) h[k] += __shfl_down_sync(0xffffffffu, h[k], o);
+#pragma unroll
+                for (int k = 0; k < 6; k++)
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) g[k] += __shfl_down_sync(0xffffffffu, g[k], o);
+                if (lane == 0) {
+                    int k = 0;
+                    for (int p = 0; p < 6; p++) {
+                        bp[6 * i + p] = g[p];
+                        for (int q = p; q < 6; q++) { Hpp[36 * i + 6 * p + q] = h[k]; Hpp[36 * i + 6 * q + p] = h[k]; k++; }
+                    }
+                }
+            }
+            // Landmark blocks: one thread per free landmark.  lm[j] = Hll(6: 00 01 02 11 12 22) bl(3) Dinv(6) xl(3)
+            for (int j = tid; j < nl; j += BA_THREADS) {
+                if (fixed[j]) continue;
+                double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+                for (int i = 0; i < np; i++) {
+                    const int e = edge_of[j * MP + i];
+                    if (e < 0) continue;
+                    double A[12], B[6], r[2], wgt;
+                    edge_lin(c, e, elin, A, B, r, wgt);
+                    g[0] += -wgt * (B[0] * r[0] + B[3] * r[1]);
+                    g[1] += -wgt * (B[1] * r[0] + B[4] * r[1]);
+                    g[2] += -wgt * (B[2] * r[0] + B[5] * r[1]);
+                    H[0] += wgt * (B[0] * B[0] + B[3] * B[3]); H[1] += wgt * (B[0] * B[1] + B[3] * B[4]); H[2] += wgt * (B[0] * B[2] + B[3] * B[5]);
+                    H[3] += wgt * (B[1] * B[1] + B[4] * B[4]); H[4] += wgt * (B[1] * B[2] + B[4] * B[5]); H[5] += wgt * (B[2] * B[2] + B[5] * B[5]);
+                }
+                double *L = lm + 18 * j;
+#pragma unroll
+                for (int k = 0; k < 6; k++) L[k] = H[k];
+                L[6] = g[0]; L[7] = g[1]; L[8] = g[2];
+            }
+            __syncthreads();
+            if (it == 0) {  // computeLambdaInit: 1e-5 * largest diagonal entry of H over the free vertices
+                double mx = 0;
+                for (int k = tid; k < n6; k += BA_THREADS) mx = fmax(mx, fabs(Hpp[36 * (k / 6) + 7 * (k % 6)]));
+                for (int j = tid; j < nl; j += BA_THREADS)
+                    if (!fixed[j]) mx = fmax(mx, fmax(fabs(lm[18 * j]), fmax(fabs(lm[18 * j + 3]), fabs(lm[18 * j + 5]))));
+                lambda = 1e-5 * block_max(mx, red);
+                ni = 2;
+            }
+            double rho = 0;
+            int qmax = 0;
+            do {
+                // ---- push(): backup of the state
+                for (int k = tid; k < 12 * np; k += BA_THREADS) Rtb[k] = Rt[k];
+                for (int k = tid; k < 3 * nl; k += BA_THREADS) ptb[k] = pts[k];
+                // ---- (Hll + lambda I)^-1 per landmark
+                int bad = 0;
+                for (int j = tid; j < nl; j += BA_THREADS) {
+                    if (fixed[j]) continue;
+                    double *L = lm + 18 * j;
+                    const double A0 = L[0] + lambda, b = L[1], cc = L[2], d = L[3] + lambda, e = L[4], f = L[5] + lambda;
+                    const double c00 = d * f - e * e, c01 = cc * e - b * f, c02 = b * e - cc * d;
+                    const double det = A0 * c00 + b * c01 + cc * c02;
+                    if (det == 0 || det != det) bad = 1;
+                    const double id = 1.0 / det;
+                    L[9] = c00 * id; L[10] = c01 * id; L[11] = c02 * id;
+                    L[12] = (A0 * f - cc * cc) * id; L[13] = (b * cc - A0 * e) * id; L[14] = (A0 * d - b * b) * id;
+                }
+                int ok = !__syncthreads_or(bad);
+                // ---- Schur complement: S(i1,i2) = Hpp'(i1,i2) - sum_j Hpl(i1,j) Dinv_j Hpl(i2,j)^T, one warp per block
+                //      (upper triangle), lanes over landmarks; the diagonal pass also reduces b.
+                const int nblk = np * (np + 1) / 2;
+                for (int blk = wid; blk < nblk && ok; blk += BA_THREADS / 32) {
+                    int i1 = 0, rem = blk;
+                    while (rem >= np - i1) { rem -= np - i1; i1++; }
+                    const int i2 = i1 + rem;
+                    double acc[36], gb[6];
+#pragma unroll
+                    for (int k = 0; k < 36; k++) acc[k] = 0;
+#pragma unroll
+                    for (int k = 0; k < 6; k++) gb[k] = 0;
+                    for (int j = lane; j < nl; j += 32) {
+                        if (fixed[j]) continue;
+                        const int e1 = edge_of[j * MP + i1], e2 = edge_of[j * MP + i2];
+                        if (e1 < 0 || e2 < 0) continue;
+                        const double *L = lm + 18 * j;
+                        const double D[9] = {L[9], L[10], L[11], L[10], L[12], L[13], L[11], L[13], L[14]};
+                        double A1[12], B1[6], r1[2], w1, A2[12], B2[6], r2[2], w2;
+                        edge_lin(c, e1, elin, A1, B1, r1, w1);
+                        if (e2 == e1) {
+#pragma unroll
+                            for (int k = 0; k < 12; k++) A2[k] = A1[k];
+#pragma unroll
+                            for (int k = 0; k < 6; k++) B2[k] = B1[k];
+                            w2 = w1;
+                        } else {
+                            edge_lin(c, e2, elin, A2, B2, r2, w2);
+                        }
+                        // M = w1 w2 B1 D B2^T (2x2);  Hpl(i1) D Hpl(i2)^T = A1^T M A2
+                        double BD[6];
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                            for (int k = 0; k < 3; k++) BD[3 * rr + k] = B1[3 * rr] * D[k] + B1[3 * rr + 1] * D[3 + k] + B1[3 * rr + 2] * D[6 + k];
+                        double M[4];
+#pragma unroll
+                        for (int rr = 0; rr < 2; rr++)
+#pragma unroll
+                            for (int s2 = 0; s2 < 2; s2++)
+                                M[2 * rr + s2] = w1 * w2 * (BD[3 * rr] * B2[3 * s2] + BD[3 * rr + 1] * B2[3 * s2 + 1] + BD[3 * rr + 2] * B2[3 * s2 + 2]);
+#pragma unroll
+                        for (int p = 0; p < 6; p++) {
+                            const double t0 = A1[p] * M[0] + A1[6 + p] * M[2], t1 = A1[p] * M[1] + A1[6 + p] * M[3];
+#pragma unroll
+                            for (int q = 0; q < 6; q++) acc[6 * p + q] += t0 * A2[q] + t1 * A2[6 + q];
+                        }
+                        if (i1 == i2) {  // b_schur(i1) -= Hpl(i1,j) Dinv_j bl_j = A1^T w1 (B1 Dinv bl)
+                            const double v0 = BD[0] * L[6] + BD[1] * L[7] + BD[2] * L[8], v1 = BD[3] * L[6] + BD[4] * L[7] + BD[5] * L[8];
+#pragma unroll
+                            for (int p = 0; p < 6; p++) gb[p] += w1 * (A1[p] * v0 + A1[6 + p] * v1);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 36; k++)
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+                    if (i1 == i2) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++)
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) gb[k] += __shfl_down_sync(0xffffffffu, gb[k], o);
+                    }
+                    if (lane == 0) {
+                        for (int p = 0; p < 6; p++)
+                            for (int q = 0; q < 6; q++) {
+                                double v = -acc[6 * p + q];
+                                if (i1 == i2) v += Hpp[36 * i1 + 6 * p + q] + (p == q ? lambda : 0.0);
+                                S[(6 * i1 + p) * n6 + 6 * i2 + q] = v;
+                                S[(6 * i2 + q) * n6 + 6 * i1 + p] = v;
+                            }
+                        if (i1 == i2)
+                            for (int p = 0; p < 6; p++) xs[6 * i1 + p] = bp[6 * i1 + p] - gb[p];
+                    }
+                }
+                __syncthreads();
+                // ---- Cholesky of the reduced system (lower triangle, in place) and the two triangular solves
+                if (ok) {
+                    for (int j = 0; j < n6; j++) {
+                        if (tid == 0) {
+                            double d = S[j * n6 + j];
+                            s_bad = !(d > 0);
+                            S[j * n6 + j] = sqrt(d);
+                        }
+                        __syncthreads();
+                        if (s_bad) break;
+                        const double dj = S[j * n6 + j];
+                        for (int i = j + 1 + tid; i < n6; i += BA_THREADS) S[i * n6 + j] /= dj;
+                        __syncthreads();
+                        // trailing update of the lower triangle
+                        const int m = n6 - j - 1;
+                        for (int k = tid; k < m * m; k += BA_THREADS) {
+                            const int r = j + 1 + k / m, cc = j + 1 + k % m;
+                            if (cc <= r) S[r * n6 + cc] -= S[r * n6 + j] * S[cc * n6 + j];
+                        }
+                        __syncthreads();
+                    }
+                    ok = !s_bad;
+                    __syncthreads();
+                    if (tid == 0) s_bad = 0;
+                    if (ok && wid == 0) {  // forward / backward substitution by one warp
+                        for (int i = 0; i < n6; i++) {
+                            double v = 0;
+                            for (int k = lane; k < i; k += 32) v += S[i * n6 + k] * xs[k];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                            if (lane == 0) xs[i] = (xs[i] - v) / S[i * n6 + i];
+                            __syncwarp();
+                        }
+                        for (int i = n6 - 1; i >= 0; i--) {
+                            double v = 0;
+                            for (int k = i + 1 + lane; k < n6; k += 32) v += S[k * n6 + i] * xs[k];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                            if (lane == 0) xs[i] = (xs[i] - v) / S[i * n6 + i];
+                            __syncwarp();
+                        }
+                    }
+                    __syncthreads();
+                }
+                double scale = 0;
+                if (ok) {
+                    // ---- landmark increments: xl = Dinv (bl - sum_i Hpl(i,j)^T xs_i), then the state update
+                    for (int j = tid; j < nl; j += BA_THREADS) {
+                        if (fixed[j]) continue;
+                        double *L = lm + 18 * j;
+                        double v[3] = {L[6], L[7], L[8]};
+                        for (int i = 0; i < np; i++) {
+                            const int e = edge_of[j * MP + i];
+                            if (e < 0) continue;
+                            double A[12], B[6], r[2], wgt;
+                            edge_lin(c, e, elin, A, B, r, wgt);
+                            double u0 = 0, u1 = 0;  // u = w A xs_i  (2)
+#pragma unroll
+                            for (int p = 0; p < 6; p++) { u0 += A[p] * xs[6 * i + p]; u1 += A[6 + p] * xs[6 * i + p]; }
+                            u0 *= wgt; u1 *= wgt;
+                            v[0] -= B[0] * u0 + B[3] * u1; v[1] -= B[1] * u0 + B[4] * u1; v[2] -= B[2] * u0 + B[5] * u1;
+                        }
+                        const double x0 = L[9] * v[0] + L[10] * v[1] + L[11] * v[2];
+                        const double x1 = L[10] * v[0] + L[12] * v[1] + L[13] * v[2];
+                        const double x2 = L[11] * v[0] + L[13] * v[1] + L[14] * v[2];
+                        L[15] = x0; L[16] = x1; L[17] = x2;
+                        scale += x0 * (lambda * x0 + L[6]) + x1 * (lambda * x1 + L[7]) + x2 * (lambda * x2 + L[8]);
+                    }
+                    for (int k = tid; k < n6; k += BA_THREADS) scale += xs[k] * (lambda * xs[k] + bp[k]);
+                    scale = block_sum(scale, red);
+                    // every Jacobian above used the un-updated state: only now move it
+                    for (int j = tid; j < nl; j += BA_THREADS) {
+                        if (fixed[j]) continue;
+                        pts[3 * j] += lm[18 * j + 15]; pts[3 * j + 1] += lm[18 * j + 16]; pts[3 * j + 2] += lm[18 * j + 17];
+                    }
+                    for (int i = tid; i < np; i += BA_THREADS) pose_oplus(Rt + 12 * i, xs + 6 * i);
+                    __syncthreads();
+                }
+                double tempChi = compute_errors(c, ne, err, nullptr, red);
+                if (!ok) tempChi = 1.7976931348623157e308;
+                rho = (currentChi - tempChi) / (scale + 1e-3);
+                if (rho > 0 && isfinite(tempChi)) {
+                    double alpha = 1. - pow(2 * rho - 1, 3);
+                    alpha = fmin(alpha, 2. / 3.);
+                    lambda *= fmax(1. / 3., alpha);
+                    ni = 2;
+                    currentChi = tempChi;
+                } else {
+                    lambda *= ni;
+                    ni *= 2;
+                    __syncthreads();
+                    for (int k = tid; k < 12 * np; k += BA_THREADS) Rt[k] = Rtb[k];   // pop(); err keeps the trial's values
+                    for (int k = tid; k < 3 * nl; k += BA_THREADS) pts[k] = ptb[k];
+                    __syncthreads();
+                }
+                qmax++;
+            } while (rho < 0 && qmax < 10);
+            lm_total++;
+            if (qmax == 10 || rho == 0) terminated = true;
+        }
+        rounds++;
+        // ---- inlier ratio on chi2 of the last evaluated errors (:216-227)
+        int ci = 0, co = 0;
+        for (int e = tid; e < ne; e += BA_THREADS) {
+            const double c2 = err[2 * e] * err[2 * e] + err[2 * e + 1] * err[2 * e + 1];
+            if (c2 > a.chi2_th) co++; else ci++;
+        }
+        inl = (int)(block_sum((double)ci, red) + 0.5);
+        outl = (int)(block_sum((double)co, red) + 0.5);
+        const double ratio = inl / (double)(inl + outl);
+        if (ratio > 0.5) break;
+        outer++;
+    }
+    // ---- outputs
+    double *chi2 = a.chi2 + (size_t)w * a.MO;
+    uint8_t *outlier = a.outlier + (size_t)w * a.MO;
+    for (int e = tid; e < ne; e += BA_THREADS) {
+        const double c2 = err[2 * e] * err[2 * e] + err[2 * e + 1] * err[2 * e + 1];
+        chi2[e] = c2;
+        outlier[e] = c2 > a.chi2_th;
+    }
+    for (int i = tid; i < np; i += BA_THREADS) {
+        R_to_quat(Rt + 12 * i, poses + 7 * i);
+        poses[7 * i + 4] = Rt[12 * i + 9]; poses[7 * i + 5] = Rt[12 * i + 10]; poses[7 * i + 6] = Rt[12 * i + 11];
+    }
+    if (tid == 0) { info[0] = rounds; info[1] = lm_total; info[2] = inl; info[3] = outl; }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+static size_t ba_smem_bytes(int MP) { return sizeof(double) * (size_t)(12 * MP * 2 + 36 * MP + 6 * MP * 2 + 36 * MP * MP + 16); }
+
+static void free_ba(sb_ba *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->d_np, h->d_nl, h->d_ne, h->d_info, h->d_poses, h->d_points, h->d_uv, h->d_chi2, h->d_fixed,
+                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_lm, h->d_ptbak, h->d_err};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_poses, int max_points, int max_obs) {
+    sb_clear_error();
+    SB_REQUIRE(out, "null handle pointer");
+    *out = nullptr;
+    SB_REQUIRE(max_windows >= 1 && max_windows <= 65535, "max_windows out of range [1, 65535]");
+    SB_REQUIRE(max_poses >= 1 && max_poses <= BA_MAX_POSES, "max_poses out of range [1, 16]");
+    SB_REQUIRE(max_points >= 1 && max_points <= (1 << 20), "max_points out of range");
+    SB_REQUIRE(max_obs >= 1 && max_obs <= (1 << 24), "max_obs out of range");
+    SB_TRY(sb_use_device(device));
+    sb_ba *h = new sb_ba();
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    h->max_windows = max_windows;
+    h->max_poses = max_poses;
+    h->max_points = max_points;
+    h->max_obs = max_obs;
+    const size_t W = max_windows, MP = max_poses, ML = max_points, MO = max_obs;
+    cudaError_t e = cudaSuccess;
+#define BA_ALLOC(ptr, bytes) \
+    if (e == cudaSuccess) e = cudaMalloc((void **)&(ptr), (bytes))
+    BA_ALLOC(h->d_np, W * 4);
+    BA_ALLOC(h->d_nl, W * 4);
+    BA_ALLOC(h->d_ne, W * 4);
+    BA_ALLOC(h->d_info, W * 16);
+    BA_ALLOC(h->d_poses, W * MP * 7 * 8);
+    BA_ALLOC(h->d_points, W * ML * 3 * 8);
+    BA_ALLOC(h->d_uv, W * MO * 2 * 8);
+    BA_ALLOC(h->d_chi2, W * MO * 8);
+    BA_ALLOC(h->d_fixed, W * ML);
+    BA_ALLOC(h->d_outlier, W * MO);
+    BA_ALLOC(h->d_op, W * MO * 4);
+    BA_ALLOC(h->d_ol, W * MO * 4);
+    BA_ALLOC(h->d_edge_of, W * ML * MP * 4);
+    BA_ALLOC(h->d_lm, W * ML * 18 * 8);
+    BA_ALLOC(h->d_ptbak, W * ML * 3 * 8);
+    BA_ALLOC(h->d_err, W * MO * 4 * 8);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_bytes(BA_MAX_POSES));
+    if (e != cudaSuccess) {
+        sb_set_error("sb_ba_create: %s", cudaGetErrorString(e));
+        free_ba(h);
+        return SB_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return SB_OK;
+}
+
+extern "C" int sb_ba_destroy(sb_ba_t *h) {
+    if (h) {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        free_ba(h);
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_ba_set_stream(sb_ba_t *h, void *stream) {
+    SB_REQUIRE(h, "null handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return SB_OK;
+}
+
+static void quat7_to_ext(const double *p, double *R, double *t) {
+    const double n = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+    const double x = p[0] / n, y = p[1] / n, z = p[2] / n, w = p[3] / n;
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+    t[0] = p[4]; t[1] = p[5]; t[2] = p[6];
+}
+
+extern "C" int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_poses, const int32_t *d_n_points,
+                               const int32_t *d_n_obs, double *d_poses, double *d_points, const uint8_t *d_fixed,
+                               const int32_t *d_obs_pose, const int32_t *d_obs_point, const double *d_uv, const double *K,
+                               const double *cam_ext7, double huber_delta, double chi2_th, int outer_max,
+                               int inner_iters, double *d_chi2, uint8_t *d_outlier, int32_t *d_info) {
+    sb_clear_error();
+    SB_REQUIRE(h, "null handle");
+    SB_REQUIRE(n_windows >= 1 && n_windows <= h->max_windows, "n_windows out of range [1, max_windows]");
+    SB_REQUIRE(d_n_poses && d_n_points && d_n_obs && d_poses && d_points && d_fixed && d_obs_pose && d_obs_point && d_uv &&
+                   d_chi2 && d_outlier && d_info && K && cam_ext7,
+               "null pointer");
+    SB_REQUIRE(huber_delta > 0 && outer_max >= 1 && inner_iters >= 1, "bad solver parameters");
+    SB_TRY(sb_use_device(h->device));
+    BaArgs a;
+    a.np = d_n_poses; a.nl = d_n_points; a.ne = d_n_obs;
+    a.poses = d_poses; a.points = d_points; a.fixed = d_fixed; a.op = d_obs_pose; a.ol = d_obs_point; a.uv = d_uv;
+    a.chi2 = d_chi2; a.outlier = d_outlier; a.info = d_info;
+    a.edge_of = h->d_edge_of; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err;
+    a.MP = h->max_poses; a.ML = h->max_points; a.MO = h->max_obs;
+    a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
+    quat7_to_ext(cam_ext7, a.extR, a.extT);
+    a.delta = huber_delta; a.chi2_th = chi2_th; a.outer_max = outer_max; a.inner_iters = inner_iters;
+    k_ba_solve<<<n_windows, BA_THREADS, ba_smem_bytes(h->max_poses), h->stream>>>(a);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+extern "C" int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t *n_points,
+                           const int32_t *n_obs, double *poses, double *points, const uint8_t *fixed,
+                           const int32_t *obs_pose, const int32_t *obs_point, const double *uv, const double *K,
+                           const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
+                           double *chi2, uint8_t *outlier, int32_t *info) {
+    sb_clear_error();
+    SB_REQUIRE(h, "null handle");
+    SB_REQUIRE(n_windows >= 1 && n_windows <= h->max_windows, "n_windows out of range [1, max_windows]");
+    SB_REQUIRE(n_poses && n_points && n_obs && poses && points && fixed && obs_pose && obs_point && uv && chi2 && outlier && info,
+               "null pointer");
+    SB_TRY(sb_use_device(h->device));
+    const size_t W = n_windows, MP = h->max_poses, ML = h->max_points, MO = h->max_obs;
+    cudaStream_t s = h->stream;
+    SB_CUDA(cudaMemcpyAsync(h->d_np, n_poses, W * 4, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_nl, n_points, W * 4, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_ne, n_obs, W * 4, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_poses, poses, W * MP * 56, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_points, points, W * ML * 24, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_fixed, fixed, W * ML, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_op, obs_pose, W * MO * 4, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_ol, obs_point, W * MO * 4, cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_uv, uv, W * MO * 16, cudaMemcpyHostToDevice, s));
+    SB_TRY(sb_ba_solve_dev(h, n_windows, h->d_np, h->d_nl, h->d_ne, h->d_poses, h->d_points, h->d_fixed, h->d_op, h->d_ol,
+                           h->d_uv, K, cam_ext7, huber_delta, chi2_th, outer_max, inner_iters, h->d_chi2, h->d_outlier,
+                           h->d_info));
+    SB_CUDA(cudaMemcpyAsync(poses, h->d_poses, W * MP * 56, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(points, h->d_points, W * ML * 24, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(chi2, h->d_chi2, W * MO * 8, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(outlier, h->d_outlier, W * MO, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaMemcpyAsync(info, h->d_info, W * 16, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    for (size_t w = 0; w < W; w++)
+        if (info[4 * w] < 0) {
+            sb_set_error("window %zu: %s", w, info[4 * w + 1] == -2 ? "a keyframe observes the same landmark twice" : "counts or indices out of range");
+            return SB_ERR_INVALID;
+        }
+    return SB_OK;
+}

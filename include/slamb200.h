@@ -150,6 +150,37 @@ int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d_q, int64_t
                          int nq_stride, const uint8_t *d_t, int64_t t_set_stride, const int32_t *d_nt,
                          int nt_stride, int max_rows, int32_t *d_train_idx, int32_t *d_dist, int64_t out_stride);
 
+/* ---------------------------------------------------------------------------------------------
+ * Local bundle adjustment — replaces the g2o solve inside Backend::OptimizeActiveMap
+ * (src/backend.cpp:126-269; edge/vertex arithmetic include/myslam/g2o_types.h:25-59,106-153):
+ * Levenberg-Marquardt with the landmarks marginalised (Schur), Huber kernel, up to `outer_max`
+ * rounds of `inner_iters` iterations until more than half of the edges have chi2 <= chi2_th.
+ * A call solves `n_windows` independent windows; every window owns a fixed-capacity slot:
+ *   poses  [W][max_poses][7]   in/out  qx qy qz qw tx ty tz of T_cw (Sophus storage order); no pose is fixed
+ *   points [W][max_points][3]  in/out  world positions
+ *   fixed  [W][max_points]     1 = landmark kept constant (first observer outside the window, :175-177)
+ *   obs_pose / obs_point [W][max_obs], uv [W][max_obs][2]  one EdgeProjection per entry (information I2)
+ *   K = fx fy cx cy,  cam_ext7 = extrinsics of the observing camera (identity for the left camera)
+ *   chi2 [W][max_obs]   e'e of each edge at the last error evaluation (what EdgeProjection::chi2() returns
+ *                       after optimize()),  outlier [W][max_obs] = chi2 > chi2_th (:236-251)
+ *   info [W][4] = outer rounds run, LM iterations run, inliers, outliers
+ * The reference's values: huber_delta 5.991, chi2_th 5.991, outer_max 5, inner_iters 10.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sb_ba sb_ba_t;
+int sb_ba_create(sb_ba_t **h, int device, int max_windows, int max_poses, int max_points, int max_obs);
+int sb_ba_destroy(sb_ba_t *h);
+int sb_ba_set_stream(sb_ba_t *h, void *stream);
+int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t *n_points, const int32_t *n_obs,
+                double *poses, double *points, const uint8_t *fixed, const int32_t *obs_pose, const int32_t *obs_point,
+                const double *uv, const double *K, const double *cam_ext7, double huber_delta, double chi2_th,
+                int outer_max, int inner_iters, double *chi2, uint8_t *outlier, int32_t *info);
+/* Same with every array on the device (K and cam_ext7 stay host pointers); asynchronous. */
+int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_poses, const int32_t *d_n_points,
+                    const int32_t *d_n_obs, double *d_poses, double *d_points, const uint8_t *d_fixed,
+                    const int32_t *d_obs_pose, const int32_t *d_obs_point, const double *d_uv, const double *K,
+                    const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
+                    double *d_chi2, uint8_t *d_outlier, int32_t *d_info);
+
 #ifdef __cplusplus
 }
 #endif

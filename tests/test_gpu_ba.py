@@ -1,0 +1,87 @@
+"""Parity of the CUDA local bundle adjustment with the CPU oracle (g2o-faithful LM + Schur restatement of
+Backend::OptimizeActiveMap, src/backend.cpp:126-269).  Tolerance from BASELINE.json north_star: poses and
+landmark positions within 1e-4 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def rel_close(got, want):
+    return np.all(np.abs(got - want) <= RTOL * np.maximum(1.0, np.abs(want)))
+
+
+@pytest.fixture(scope="module")
+def ba(pkg):
+    b = pkg.LocalBA(max_windows=8, max_poses=7, max_points=512, max_obs=4096)
+    yield b
+    b.close()
+
+
+def check_window(oracle, synth, w, got, **kw):
+    p, x, chi2, outl, info = oracle.ba_solve(w["poses0"], w["points0"], w["fixed"], w["obs_pose"], w["obs_point"], w["uv"],
+                                             synth.KITTI_K, **kw)
+    gp, gx, gchi2, goutl, ginfo = got
+    assert np.array_equal(ginfo, info), (ginfo, info)
+    assert rel_close(gp, p), np.abs(gp - p).max()
+    assert rel_close(gx, x), np.abs(gx - x).max()
+    assert rel_close(gchi2, chi2), np.abs(gchi2 - chi2).max()
+    # outlier flags may only differ where chi2 sits within the tolerance of the threshold
+    diff = goutl != outl
+    assert np.all(np.abs(chi2[diff] - 5.991) < 1e-3)
+    return np.abs(gp - p).max(), np.abs(gx - x).max()
+
+
+def test_batch_of_windows_matches_oracle(ba, oracle, synth):
+    windows = [synth.ba_window(s) for s in range(8)]
+    res = ba.solve(windows, synth.KITTI_K)
+    worst = [check_window(oracle, synth, w, r) for w, r in zip(windows, res)]
+    # fp64 on both sides: the agreement is far inside the 1e-4 bound
+    assert max(a for a, _ in worst) < 1e-7 and max(b for _, b in worst) < 1e-6
+    for w, (p, x, chi2, outl, info) in zip(windows, res):
+        assert info[0] == 1 and info[1] == 10
+        assert np.abs(p - w["poses_gt"])[:, 4:].max() < np.abs(w["poses0"] - w["poses_gt"])[:, 4:].max()
+
+
+def test_ragged_windows_and_edge_cases(ba, oracle, synth):
+    w_small = synth.ba_window(20, n_poses=3, n_points=40)
+    w_clean = synth.ba_window(21, pix_noise=0.0, outlier_frac=0.0)
+    w_allfixed = synth.ba_window(22, n_points=100)
+    w_allfixed["fixed"][:] = 1                                   # pose-only: every landmark is a constraint
+    w_nofixed = synth.ba_window(23, n_points=150, fixed_frac=0.0)  # pure gauge freedom, held by the damping only
+    windows = [w_small, w_clean, w_allfixed, w_nofixed]
+    res = ba.solve(windows, synth.KITTI_K)
+    for w, r in zip(windows, res):
+        check_window(oracle, synth, w, r)
+    assert np.array_equal(res[2][1], w_allfixed["points0"])     # fixed landmarks never move
+
+
+def test_many_outliers_trigger_more_outer_rounds(ba, oracle, synth):
+    """Inlier ratio <= 0.5 after a round => the reference runs optimize(10) again, up to 5 times (:212-232)."""
+    w = synth.ba_window(30, n_points=120, outlier_frac=0.7)
+    res = ba.solve([w], synth.KITTI_K)
+    check_window(oracle, synth, w, res[0])
+    assert res[0][4][0] > 1
+
+
+def test_other_solver_parameters(ba, oracle, synth):
+    w = synth.ba_window(31, n_points=80)
+    kw = dict(huber_delta=1.0, chi2_th=3.0, outer_max=2, inner_iters=4)
+    res = ba.solve([w], synth.KITTI_K, **kw)
+    check_window(oracle, synth, w, res[0], **kw)
+
+
+def test_bad_input_is_reported(pkg, ba, synth):
+    w = synth.ba_window(40, n_points=30)
+    w["obs_point"] = w["obs_point"].copy()
+    w["obs_point"][3] = 999
+    with pytest.raises(pkg.SlamB200Error):
+        ba.solve([w], synth.KITTI_K)
+    w = synth.ba_window(41, n_points=30)
+    w["obs_pose"] = np.concatenate([w["obs_pose"], w["obs_pose"][:1]])   # the same (keyframe, landmark) twice
+    w["obs_point"] = np.concatenate([w["obs_point"], w["obs_point"][:1]])
+    w["uv"] = np.concatenate([w["uv"], w["uv"][:1]])
+    with pytest.raises(pkg.SlamB200Error):
+        ba.solve([w], synth.KITTI_K)
