@@ -330,3 +330,59 @@ class LocalBA:
                                      _dev_ptr(d["ol"]), _dev_ptr(d["uv"]), _p(K), _p(ext), C.c_double(huber_delta),
                                      C.c_double(chi2_th), outer_max, inner_iters, _dev_ptr(d["chi2"]),
                                      _dev_ptr(d["outlier"]), _dev_ptr(d["info"])))
+
+
+class DeepLCDScorer:
+    """DeepLCD::score over the keyframe database + LoopClosing::DetectLoop (src/deeplcd.cpp:35-39,
+    src/loopclosing.cpp:124-161)."""
+    FP32, FP16 = 0, 1
+
+    def __init__(self, capacity=1024, dtype=1, max_queries=1, device=0):
+        self._h = C.c_void_p()
+        self.capacity, self.max_queries = capacity, max_queries
+        _check(lib().sb_lcd_create(C.byref(self._h), device, capacity, dtype, max_queries))
+
+    def close(self):
+        if self._h:
+            lib().sb_lcd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return lib().sb_lcd_size(self._h)
+
+    def set_stream(self, stream_ptr):
+        _check(lib().sb_lcd_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def add(self, kf_id, descr):
+        d = np.ascontiguousarray(descr, np.float32).reshape(1064)
+        _check(lib().sb_lcd_add(self._h, C.c_int64(kf_id), _p(d)))
+
+    def add_batch(self, kf_ids, descr):
+        ids = np.ascontiguousarray(kf_ids, np.int64)
+        d = np.ascontiguousarray(descr, np.float32).reshape(len(ids), 1064)
+        _check(lib().sb_lcd_add_batch(self._h, len(ids), _p(ids), _p(d)))
+
+    def remove(self, kf_id):
+        _check(lib().sb_lcd_remove(self._h, C.c_int64(kf_id)))
+
+    def score(self, queries):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, 1064)
+        out = np.zeros((len(q), len(self)), np.float32)
+        _check(lib().sb_lcd_score(self._h, len(q), _p(q), _p(out)))
+        return out
+
+    def score_dev(self, nq, d_queries, d_scores, stride):
+        _check(lib().sb_lcd_score_dev(self._h, nq, _dev_ptr(d_queries), _dev_ptr(d_scores), stride))
+
+    def DetectLoop(self, cur_kf_id, query, thres_high=0.94, thres_low=0.92, min_gap=20, max_suspected=3):
+        q = np.ascontiguousarray(query, np.float32).reshape(1064)
+        found, cnt, best, mx = C.c_int(), C.c_int(), C.c_int64(), C.c_float()
+        _check(lib().sb_lcd_detect_loop(self._h, C.c_int64(cur_kf_id), _p(q), C.c_float(thres_high), C.c_float(thres_low),
+                                        min_gap, max_suspected, C.byref(found), C.byref(best), C.byref(mx), C.byref(cnt)))
+        return bool(found.value), best.value, mx.value, cnt.value

@@ -148,3 +148,27 @@ def ba_window(seed, n_poses=7, n_points=300, pix_noise=1.0, outlier_frac=0.05, p
     return {"poses0": poses0, "points0": points0, "poses_gt": poses_gt, "points_gt": pts, "fixed": fixed,
             "obs_pose": np.array(obs_pose, np.int32), "obs_point": np.array(obs_point, np.int32),
             "uv": np.array(uv, np.float64).reshape(-1, 2)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# DeepLCD database (SURVEY.md §8d config 4): unit-norm 1064-d descriptors with planted near-duplicates
+# at the loop pairs of the reference's result/loopEdges.txt.
+# ---------------------------------------------------------------------------------------------------
+LOOP_PAIRS = [(389, 27), (395, 30), (402, 35), (408, 38), (414, 42), (421, 46), (428, 50), (582, 100), (589, 104),
+              (596, 109), (603, 113), (610, 117), (690, 160), (697, 165), (704, 170), (711, 175), (718, 180)]
+
+
+def lcd_database(seed=0, n=742, dim=1064, pairs=LOOP_PAIRS, cos=0.96):
+    """[n, dim] float32, rows L2-normalised; row a of every (a, b) in `pairs` has cosine ~`cos` with row b."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(0, 1, (n, dim))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    for a, b in pairs:
+        if a < n and b < n:
+            noise = rng.normal(0, 1, dim)
+            noise -= (noise @ d[b]) * d[b]
+            noise /= np.linalg.norm(noise)
+            d[a] = cos * d[b] + np.sqrt(1 - cos * cos) * noise
+    d = d.astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)   # descriptor /= descriptor.norm() in fp32 (src/deeplcd.cpp:88)
+    return d

@@ -181,6 +181,34 @@ int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_poses, const i
                     const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
                     double *d_chi2, uint8_t *d_outlier, int32_t *d_info);
 
+/* ---------------------------------------------------------------------------------------------
+ * DeepLCD descriptor scoring — replaces DeepLCD::score (src/deeplcd.cpp:35-39) and the database
+ * scan of LoopClosing::DetectLoop (src/loopclosing.cpp:124-161).  Descriptors are the 1064-float,
+ * L2-normalised outputs of DeepLCD::calcDescr (src/deeplcd.cpp:55-91); the database keeps one row per
+ * keyframe in ascending keyframe id (the reference's std::map order), stored fp32 or fp16 in HBM.
+ * --------------------------------------------------------------------------------------------- */
+#define SB_LCD_DIM 1064
+#define SB_LCD_FP32 0
+#define SB_LCD_FP16 1
+typedef struct sb_lcd sb_lcd_t;
+int sb_lcd_create(sb_lcd_t **h, int device, int capacity, int dtype, int max_queries);
+int sb_lcd_destroy(sb_lcd_t *h);
+int sb_lcd_set_stream(sb_lcd_t *h, void *stream);
+int sb_lcd_size(const sb_lcd_t *h);
+/* LoopClosing::AddToDatabase (src/loopclosing.cpp:651-659); ids ascending. */
+int sb_lcd_add(sb_lcd_t *h, int64_t kf_id, const float *descr);
+int sb_lcd_add_batch(sb_lcd_t *h, int n, const int64_t *kf_ids, const float *descr);
+/* _mvDatabase.erase(id) (src/loopclosing.cpp:73-75). */
+int sb_lcd_remove(sb_lcd_t *h, int64_t kf_id);
+/* scores [nq][size]: DeepLCD::score of every query against every row (fp32 accumulate). */
+int sb_lcd_score(sb_lcd_t *h, int nq, const float *queries, float *scores);
+int sb_lcd_score_dev(sb_lcd_t *h, int nq, const float *d_queries, float *d_scores, int score_stride);
+/* LoopClosing::DetectLoop: the reference's values are thres_high 0.94, thres_low 0.92
+ * (config LCD.similarityScoreThreshold.{high,low}), min_gap 20, max_suspected 3. */
+int sb_lcd_detect_loop(sb_lcd_t *h, int64_t cur_kf_id, const float *query, float thres_high, float thres_low,
+                       int min_gap, int max_suspected, int *found, int64_t *best_id, float *max_score,
+                       int *n_suspected);
+
 #ifdef __cplusplus
 }
 #endif

@@ -270,3 +270,27 @@ def ba_edge(pose7, pt, uv, K, ext7=(0, 0, 0, 1, 0, 0, 0)):
     lib().orc_ba_edge_error(_p(pose7), _p(pt), _p(uv), _p(K), _p(ext), _p(err))
     lib().orc_ba_edge_jacobians(_p(pose7), _p(pt), _p(K), _p(ext), _p(A), _p(B))
     return err, A.reshape(2, 6), B.reshape(2, 3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# DeepLCD scoring (numpy restatement of src/deeplcd.cpp:35-39 and src/loopclosing.cpp:124-161)
+# ---------------------------------------------------------------------------------------------------
+def lcd_score(d1, d2):
+    """DeepLCD::score: float result = d1.transpose() * d2 (fp32)."""
+    return np.float32(np.dot(np.asarray(d1, np.float32), np.asarray(d2, np.float32)))
+
+
+def lcd_detect_loop(db_ids, db_descr, cur_id, cur_descr, thres_high=0.94, thres_low=0.92, min_gap=20, max_suspected=3):
+    """LoopClosing::DetectLoop -> (found, bestId, maxScore, cntSuspected).  db_ids ascending (std::map)."""
+    max_score, cnt, best = np.float32(0), 0, 0
+    for i, d in zip(db_ids, db_descr):
+        if (int(cur_id) - int(i)) % (1 << 64) < min_gap:   # unsigned long arithmetic, and `break`
+            break
+        s = lcd_score(cur_descr, d)
+        if s > max_score:
+            max_score, best = s, int(i)
+        if s > np.float32(thres_low):
+            cnt += 1
+    if max_score < np.float32(thres_high) or cnt > max_suspected:
+        return False, best, float(max_score), cnt
+    return True, best, float(max_score), cnt
