@@ -386,3 +386,39 @@ class DeepLCDScorer:
         _check(lib().sb_lcd_detect_loop(self._h, C.c_int64(cur_kf_id), _p(q), C.c_float(thres_high), C.c_float(thres_low),
                                         min_gap, max_suspected, C.byref(found), C.byref(best), C.byref(mx), C.byref(cnt)))
         return bool(found.value), best.value, mx.value, cnt.value
+
+
+class PoseGraph:
+    """The g2o solve of LoopClosing::PoseGraphOptimization (src/loopclosing.cpp:537-646)."""
+
+    def __init__(self, max_vertices=1024, max_edges=2048, device=0):
+        self._h = C.c_void_p()
+        _check(lib().sb_posegraph_create(C.byref(self._h), device, max_vertices, max_edges))
+
+    def close(self):
+        if self._h:
+            lib().sb_posegraph_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        _check(lib().sb_posegraph_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def solve(self, poses, fixed, v0, v1, meas, iters=20):
+        """-> (poses [n,7], info dict)"""
+        p = np.ascontiguousarray(poses, np.float64).copy()
+        fx = np.ascontiguousarray(fixed, np.uint8)
+        a = np.ascontiguousarray(v0, np.int32)
+        b = np.ascontiguousarray(v1, np.int32)
+        z = np.ascontiguousarray(meas, np.float64)
+        info = np.zeros(4, np.int32)
+        stats = np.zeros(2, np.float64)
+        _check(lib().sb_posegraph_solve(self._h, len(p), _p(p), _p(fx), len(a), _p(a), _p(b), _p(z), iters, _p(info),
+                                        _p(stats)))
+        return p, {"lm_iters": int(info[0]), "trials": int(info[1]), "free": int(info[2]), "loops": int(info[3]),
+                   "chi2_start": float(stats[0]), "chi2": float(stats[1])}

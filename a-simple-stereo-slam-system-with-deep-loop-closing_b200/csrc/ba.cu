@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "se3.cuh"
 
 #define BA_THREADS 256
 #define BA_MAX_POSES 16
@@ -54,65 +55,6 @@ struct BaArgs {
     double delta, chi2_th;
     int outer_max, inner_iters;
 };
-
-// ---- small dense helpers ------------------------------------------------------------------------------
-static __device__ __forceinline__ void quat_to_R(const double *q, double *R) {  // q = (x, y, z, w)
-    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-    const double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
-    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
-    R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
-    R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
-}
-
-static __device__ void R_to_quat(const double *R, double *q) {  // -> (x, y, z, w), w >= 0
-    const double tr = R[0] + R[4] + R[8];
-    double x, y, z, w;
-    if (tr > 0) {
-        const double s = sqrt(tr + 1.0) * 2; w = 0.25 * s; x = (R[7] - R[5]) / s; y = (R[2] - R[6]) / s; z = (R[3] - R[1]) / s;
-    } else if (R[0] > R[4] && R[0] > R[8]) {
-        const double s = sqrt(1.0 + R[0] - R[4] - R[8]) * 2; w = (R[7] - R[5]) / s; x = 0.25 * s; y = (R[1] + R[3]) / s; z = (R[2] + R[6]) / s;
-    } else if (R[4] > R[8]) {
-        const double s = sqrt(1.0 + R[4] - R[0] - R[8]) * 2; w = (R[2] - R[6]) / s; x = (R[1] + R[3]) / s; y = 0.25 * s; z = (R[5] + R[7]) / s;
-    } else {
-        const double s = sqrt(1.0 + R[8] - R[0] - R[4]) * 2; w = (R[3] - R[1]) / s; x = (R[2] + R[6]) / s; y = (R[5] + R[7]) / s; z = 0.25 * s;
-    }
-    if (w < 0) { x = -x; y = -y; z = -z; w = -w; }
-    const double n = sqrt(x * x + y * y + z * z + w * w);
-    q[0] = x / n; q[1] = y / n; q[2] = z / n; q[3] = w / n;
-}
-
-// Sophus SE3d::exp([upsilon, omega]) applied on the left: Rt <- exp(d) * Rt  (VertexPose::oplusImpl)
-static __device__ void pose_oplus(double *Rt, const double *d) {
-    const double wx = d[3], wy = d[4], wz = d[5];
-    const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
-    double a, b, c;
-    if (th < 1e-10) { a = 1.0 - th2 / 6.0; b = 0.5 - th2 / 24.0; c = 1.0 / 6.0 - th2 / 120.0; }
-    else { a = sin(th) / th; b = (1.0 - cos(th)) / th2; c = (th - sin(th)) / (th2 * th); }
-    const double W[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
-    double W2[9], E[9], V[9];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) W2[3 * i + j] = W[3 * i] * W[j] + W[3 * i + 1] * W[3 + j] + W[3 * i + 2] * W[6 + j];
-#pragma unroll
-    for (int i = 0; i < 9; i++) {
-        const double I = (i % 4 == 0) ? 1.0 : 0.0;
-        E[i] = I + a * W[i] + b * W2[i];
-        V[i] = I + b * W[i] + c * W2[i];
-    }
-    double Et[3], Rn[9], tn[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) Et[i] = V[3 * i] * d[0] + V[3 * i + 1] * d[1] + V[3 * i + 2] * d[2];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-#pragma unroll
-        for (int j = 0; j < 3; j++) Rn[3 * i + j] = E[3 * i] * Rt[j] + E[3 * i + 1] * Rt[3 + j] + E[3 * i + 2] * Rt[6 + j];
-        tn[i] = E[3 * i] * Rt[9] + E[3 * i + 1] * Rt[10] + E[3 * i + 2] * Rt[11] + Et[i];
-    }
-#pragma unroll
-    for (int i = 0; i < 9; i++) Rt[i] = Rn[i];
-    Rt[9] = tn[0]; Rt[10] = tn[1]; Rt[11] = tn[2];
-}
 
 // RobustKernelHuber::robustify -> rho(e2) and rho'(e2)
 static __device__ __forceinline__ void huber(double e2, double delta, double &rho0, double &rho1) {

@@ -172,3 +172,68 @@ def lcd_database(seed=0, n=742, dim=1064, pairs=LOOP_PAIRS, cos=0.96):
     d = d.astype(np.float32)
     d /= np.linalg.norm(d, axis=1, keepdims=True)   # descriptor /= descriptor.norm() in fp32 (src/deeplcd.cpp:88)
     return d
+
+
+# ---------------------------------------------------------------------------------------------------
+# Pose graph: keyframes on a closed route driven ~1.97 times, sequential edges
+# from noisy odometry, loop edges where the route is revisited.  Poses are T_cw in Sophus storage order.
+# ---------------------------------------------------------------------------------------------------
+def pose_graph(seed=0, n=742, n_loops=17, n_active=7, odo_noise=(0.0005, 0.02), loop_noise=(0.001, 0.01), radius=300.0):
+    """Returns dict: poses0 [n,7] (dead-reckoned start), poses_gt [n,7], fixed [n] u8, v0/v1 [m] i32, meas [m,7].
+    Edge k connects vertex v0 (the later keyframe) to v1 like EdgePoseGraph: measurement = T_v0 * T_v1^-1."""
+    rng = np.random.default_rng(seed)
+    per_rev = max(8, int(round(n / 1.97)))
+    Rs, ts = [], []
+    for i in range(n):
+        ang = 2 * np.pi * i / per_rev
+        c = np.array([radius * np.sin(ang), 0.02 * i, radius * (1 - np.cos(ang))])   # slow climb: revisits are near, not equal
+        Rwc = _rot_y(ang)
+        Rs.append(Rwc.T)
+        ts.append(-Rwc.T @ c)
+    Rs, ts = np.array(Rs), np.array(ts)
+
+    def rel(i, j, noise):   # T_i * T_j^-1 with noise on the left
+        R = Rs[i] @ Rs[j].T
+        t = ts[i] - R @ ts[j]
+        dR = _so3_exp(rng.normal(0, noise[0], 3))
+        return dR @ R, dR @ t + rng.normal(0, noise[1], 3)
+
+    v0, v1, meas = [], [], []
+    for i in range(1, n):
+        R, t = rel(i, i - 1, odo_noise)
+        v0.append(i); v1.append(i - 1); meas.append(pose7(R, t))
+    loops = []
+    if n > per_rev + 25 and n_loops > 0:
+        cand = np.linspace(per_rev + 12, n - n_active - 3, n_loops).astype(int)
+        for i in cand:
+            j = int(i - per_rev + rng.integers(-2, 3))
+            if 0 < j < i - 20:
+                loops.append((int(i), j))
+    for i, j in loops:
+        R, t = rel(i, j, loop_noise)
+        v0.append(i); v1.append(j); meas.append(pose7(R, t))
+    # dead reckoning from the noisy odometry
+    p0R, p0t = [Rs[0]], [ts[0]]
+    for k in range(n - 1):
+        q = meas[k]
+        Rm = _quat_to_R_np(q[:4])
+        p0R.append(Rm @ p0R[-1])
+        p0t.append(Rm @ p0t[-1] + q[4:])
+    # the reference corrects the current keyframe through the loop before optimising: start the fixed tail at truth
+    fixed = np.zeros(n, np.uint8)
+    fixed[0] = 1
+    fixed[max(0, n - n_active):] = 1
+    if loops:
+        fixed[loops[-1][1]] = 1
+    poses0 = np.stack([pose7(R, t) for R, t in zip(p0R, p0t)])
+    poses_gt = np.stack([pose7(R, t) for R, t in zip(Rs, ts)])
+    poses0[fixed == 1] = poses_gt[fixed == 1]
+    return {"poses0": poses0, "poses_gt": poses_gt, "fixed": fixed, "v0": np.array(v0, np.int32),
+            "v1": np.array(v1, np.int32), "meas": np.array(meas), "loops": loops}
+
+
+def _quat_to_R_np(q):
+    x, y, z, w = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])

@@ -209,6 +209,29 @@ int sb_lcd_detect_loop(sb_lcd_t *h, int64_t cur_kf_id, const float *query, float
                        int min_gap, int max_suspected, int *found, int64_t *best_id, float *max_score,
                        int *n_suspected);
 
+/* ---------------------------------------------------------------------------------------------
+ * Pose-graph optimisation — replaces the g2o solve inside LoopClosing::PoseGraphOptimization
+ * (src/loopclosing.cpp:537-646; EdgePoseGraph include/myslam/g2o_types.h:157-190): Levenberg-
+ * Marquardt, `iters` iterations (the reference: 20), numeric Jacobians (step 1e-9) as g2o computes
+ * them for an edge without linearizeOplus, information I6, no robust kernel.
+ *   poses [n][7] in/out (qx qy qz qw tx ty tz of T_cw), vertices in ascending keyframe id;
+ *   fixed [n]: the reference fixes the active keyframes, the loop keyframe and keyframe 0 (:559-562);
+ *   edge k: vertex v0[k] -> vertex v1[k] with measurement meas[k] = T_v0 * T_v1^-1
+ *           (mRelativePoseToLastKF / mRelativePoseToLoopKF, :571-599).
+ * The graph must be a chain plus at most 64 long-range edges between free vertices (KITTI-00: 17).
+ *   info [4] = LM iterations, LM trials, free vertices, long-range edges;  stats [2] = chi2 before, after.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sb_posegraph sb_posegraph_t;
+int sb_posegraph_create(sb_posegraph_t **h, int device, int max_vertices, int max_edges);
+int sb_posegraph_destroy(sb_posegraph_t *h);
+int sb_posegraph_set_stream(sb_posegraph_t *h, void *stream);
+int sb_posegraph_solve(sb_posegraph_t *h, int n_vertices, double *poses, const uint8_t *fixed, int n_edges,
+                       const int32_t *v0, const int32_t *v1, const double *meas, int iters, int32_t *info,
+                       double *stats);
+int sb_posegraph_solve_dev(sb_posegraph_t *h, int n_vertices, double *d_poses, const uint8_t *d_fixed, int n_edges,
+                           const int32_t *d_v0, const int32_t *d_v1, const double *d_meas, int iters, int32_t *d_info,
+                           double *d_stats);
+
 #ifdef __cplusplus
 }
 #endif
