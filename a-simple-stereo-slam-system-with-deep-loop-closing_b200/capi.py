@@ -422,3 +422,64 @@ class PoseGraph:
                                         _p(stats)))
         return p, {"lm_iters": int(info[0]), "trials": int(info[1]), "free": int(info[2]), "loops": int(info[3]),
                    "chi2_start": float(stats[0]), "chi2": float(stats[1])}
+
+
+class StereoFrontend:
+    """DetectAndCompute on both views + Hamming match(left -> right) for a batch of frames in one call
+    (sb_stereo_*): host buffers in, host buffers out; submit()/wait() for pipelining with a second handle."""
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_w=1241, max_h=376, max_pairs=1,
+                 device=0):
+        self._h = C.c_void_p()
+        self.max_pairs = max_pairs
+        _check(lib().sb_stereo_create(C.byref(self._h), device, nfeatures, C.c_float(scaleFactor), nlevels, iniThFAST,
+                                      minThFAST, max_w, max_h, max_pairs))
+        self.cap = lib().sb_stereo_capacity(self._h)
+
+    def close(self):
+        if self._h:
+            lib().sb_stereo_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def alloc_outputs(self, pairs, pinned=False):
+        """Output buffers for submit(): dict of numpy arrays (backed by pinned torch tensors if pinned)."""
+        shapes = {"kps": ((pairs, 2, self.cap), KP_DTYPE), "desc": ((pairs, 2, self.cap, 32), np.uint8),
+                  "counts": ((pairs, 2), np.int32), "midx": ((pairs, self.cap), np.int32),
+                  "mdist": ((pairs, self.cap), np.int32)}
+        out = {}
+        if pinned:
+            import torch
+            out["_keep"] = []
+            for k, (shp, dt) in shapes.items():
+                nbytes = int(np.prod(shp)) * np.dtype(dt).itemsize
+                t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+                out["_keep"].append(t)
+                out[k] = t.numpy().view(dt).reshape(shp)
+        else:
+            for k, (shp, dt) in shapes.items():
+                out[k] = np.zeros(shp, dt)
+        return out
+
+    def submit(self, images, out):
+        """images: uint8 [pairs, 2, h, w] (C-contiguous; pinned for asynchronous copies)."""
+        pairs, two, h, w = images.shape
+        assert two == 2 and images.dtype == np.uint8 and images.flags["C_CONTIGUOUS"]
+        _check(lib().sb_stereo_submit(self._h, pairs, C.c_void_p(images.ctypes.data), C.c_int64(2 * h * w), C.c_int64(h * w),
+                                      w, h, w, _p(out["kps"]), _p(out["desc"]), _p(out["counts"]), _p(out["midx"]),
+                                      _p(out["mdist"])))
+
+    def wait(self):
+        _check(lib().sb_stereo_wait(self._h))
+
+    def extract_match(self, images):
+        images = np.ascontiguousarray(images, np.uint8)
+        out = self.alloc_outputs(images.shape[0])
+        self.submit(images, out)
+        self.wait()
+        return out

@@ -1,10 +1,13 @@
 #!/usr/bin/env python
 """Benchmark of the B200 hot path: KITTI-shaped stereo frames/s through ORB extract (both views,
-2000 features, 8-level pyramid) + left<->right Hamming match  (BASELINE.json config 2).
+2000 features, 8-level pyramid) + left<->right Hamming match + one sliding-window local BA per frame
+(BASELINE.json configs 2 + 3).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--pairs B]
 
-One "step" = one batch of B synthetic stereo pairs (1241x376 u8) through the whole path.
+One "step" = one batch of B synthetic stereo pairs (1241x376 u8) through extract + match, plus B local-BA
+windows (7 keyframes x 300 landmarks, ~1400 observations) — one window per frame, although the live system
+only optimises once per keyframe (~1 frame in 6).
   value : frames/s with the inputs already resident in HBM (device entry points, CUDA events)
   e2e   : frames/s through the host-pointer C ABI (pinned host buffers, H2D + D2H inside the timed region)
   --impl reference : the CPU restatement of the reference (oracle/, all host cores) on the same workload
@@ -28,9 +31,12 @@ PKG = "a-simple-stereo-slam-system-with-deep-loop-closing_b200"
 
 W, H = 1241, 376
 ORB_PARAMS = (2000, 1.2, 8, 20, 7)
+KITTI_K = (718.856, 718.856, 607.1928, 185.2157)
 METRIC = "KITTI stereo frames/s (extract+match+local-BA) @1/2/4/8 B200; % HBM roofline"
-WORKLOAD = "config 2: ORB extract (both views) + L<->R Hamming match, 1241x376 stereo, 2000 feats/frame, synthetic replay"
+WORKLOAD = ("config 3: ORB extract (both views, 2000 feats) + L<->R Hamming match + sliding-window local BA "
+            "(7 KFs x 300 landmarks, one window per frame), 1241x376 stereo, synthetic replay")
 STAGES = ["copy_level0", "resize_pyramid", "fast_cells", "quadtree", "gauss_blur", "describe"]
+BA_CAPS = dict(max_poses=7, max_points=320, max_obs=2304)
 
 
 def pyramid_bytes():
@@ -61,6 +67,8 @@ def algorithmic_bytes(stage, n_images, n_kps, n_cands):
         return n_kps * (749 + 512 + 28 + 32 + 4)
     if stage == "hamming_match":
         return n_kps * 32 + (n_kps // 2) * 8
+    if stage == "local_ba":
+        return 0   # filled by the caller: observations + points + poses of the batch
     raise KeyError(stage)
 
 
@@ -124,25 +132,29 @@ class CpuReference:
         self.local = threading.local()
         self.pool = ThreadPoolExecutor(cores)
 
-    def _one(self, pair):
+    def _one(self, job):
+        pair, win = job
         if not hasattr(self.local, "ext"):
             self.local.ext = self.O.ORBextractor(*ORB_PARAMS)
         _, dl = self.local.ext.DetectAndCompute(pair[0])
         _, dr = self.local.ext.DetectAndCompute(pair[1])
         idx, _ = self.O.hamming_match(dl, dr)
+        if win is not None:   # Backend::OptimizeActiveMap's solve on one window
+            self.O.ba_solve(win["poses0"], win["points0"], win["fixed"], win["obs_pose"], win["obs_point"], win["uv"], KITTI_K)
         return len(idx)
 
-    def run(self, frames):
-        """frames [n, 2, H, W] -> seconds"""
+    def run(self, frames, windows=None):
+        """frames [n, 2, H, W] (+ one BA window per frame) -> seconds"""
+        jobs = [(frames[i], windows[i % len(windows)] if windows else None) for i in range(len(frames))]
         t0 = time.perf_counter()
-        list(self.pool.map(self._one, list(frames)))
+        list(self.pool.map(self._one, jobs))
         return time.perf_counter() - t0
 
 
-def cpu_reference_fps(frames, cores):
+def cpu_reference_fps(frames, windows, cores):
     ref = CpuReference(cores)
-    ref.run(frames[:cores])   # warm: library load, per-thread extractors
-    return len(frames) / ref.run(frames)
+    ref.run(frames[:cores], windows)   # warm: library load, per-thread extractors
+    return len(frames) / ref.run(frames, windows)
 
 
 def run_reference(args, rank, world):
@@ -152,10 +164,11 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     per_step = max(cores, 8)
     frames = synth.stereo_batch(0, per_step)
+    windows = [synth.ba_window(s) for s in range(per_step)]
     ref = CpuReference(cores)
     for _ in range(args.warmup):
-        ref.run(frames)
-    total = sum(ref.run(frames) for _ in range(args.steps))
+        ref.run(frames, windows)
+    total = sum(ref.run(frames, windows) for _ in range(args.steps))
     value = per_step * args.steps / total
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
@@ -163,8 +176,8 @@ def run_reference(args, rank, world):
            "config": {"workload": WORKLOAD, "frames_per_step": per_step},
            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                             "sample": f"{per_step} synthetic stereo frames per step through oracle/ (C restatement of "
-                                      "ORBextractor::DetectAndCompute + BFMatcher; the reference itself needs OpenCV/g2o "
-                                      "and cannot be built here), one extractor per thread"},
+                                      "ORBextractor::DetectAndCompute + BFMatcher + the g2o-faithful LM/Schur BA; the reference "
+                                      "itself needs OpenCV/g2o and cannot be built here), one frame per thread"},
            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -175,8 +188,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=64, help="stereo pairs per step")
+    ap.add_argument("--pairs", type=int, default=64, help="stereo pairs (and BA windows) per step")
     ap.add_argument("--pool", type=int, default=192, help="distinct resident stereo pairs (> L2 in total)")
+    ap.add_argument("--no-ba", action="store_true", help="config 2 only: extract + match")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -200,34 +214,58 @@ def main():
     lib = pkg.lib()
     B, P = args.pairs, max(args.pool, args.pairs)
     P = (P // B) * B
+    with_ba = not args.no_ba
 
     # ---- inputs: a pool of distinct frames, larger than L2 (126 MB) in total, resident in HBM
-    t0 = time.perf_counter()
     uniq = min(P, 48)
     base = synth.stereo_batch(1000 * rank, uniq)
     pool_np = np.empty((P, 2, H, W), np.uint8)
-    for i in range(P):   # vertical shifts of the unique frames: distinct bytes, same statistics
-        pool_np[i] = np.roll(base[i % uniq], 7 * (i // uniq), axis=1)
+    for i in range(P):   # horizontal shifts of the unique frames: distinct bytes, same statistics
+        pool_np[i] = np.roll(base[i % uniq], 7 * (i // uniq), axis=-1)
     pool = torch.from_numpy(pool_np).cuda()
-    gen_s = time.perf_counter() - t0
+    n_uniq_w = 16
+    windows = [synth.ba_window(100 * rank + s) for s in range(n_uniq_w)]
+    windows = [windows[i % n_uniq_w] for i in range(B)]
 
-    stream = torch.cuda.Stream()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     ext = pkg.ORBextractor(*ORB_PARAMS, max_w=W, max_h=H, max_batch=2 * B, device=local_rank)
     mat = pkg.HammingMatcher(max_batch=B, max_rows=ext.cap, device=local_rank)
-    ext.set_stream(stream.cuda_stream)
-    mat.set_stream(stream.cuda_stream)
+    ba = pkg.LocalBA(max_windows=B, device=local_rank, **BA_CAPS)
+    ext.set_stream(s1.cuda_stream)
+    mat.set_stream(s1.cuda_stream)
+    ba.set_stream(s2.cuda_stream)
     cap = ext.cap
     kps = torch.zeros((2 * B, cap, 28), dtype=torch.uint8, device="cuda")
     desc = torch.zeros((2 * B, cap, 32), dtype=torch.uint8, device="cuda")
     counts = torch.zeros(2 * B, dtype=torch.int32, device="cuda")
     midx = torch.full((B, cap), -1, dtype=torch.int32, device="cuda")
     mdist = torch.full((B, cap), -1, dtype=torch.int32, device="cuda")
+    bh = ba.pack(windows)                                  # host batch (padded slots)
+    bd = {k: torch.from_numpy(v).cuda() for k, v in bh.items()}
+    bd0 = {"poses": bd["poses"].clone(), "points": bd["points"].clone()}
+    bd["chi2"] = torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.float64, device="cuda")
+    bd["outlier"] = torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.uint8, device="cuda")
+    bd["info"] = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+    ba_bytes = int(bh["ne"].sum()) * (8 + 16 + 8 + 1) + int(bh["nl"].sum()) * (48 + 1) + int(bh["np"].sum()) * 112
 
-    def step_dev(i):
+    def step_dev(i, ev=None):
         off = (i * B) % P
+        if with_ba:
+            with torch.cuda.stream(s2):
+                bd["poses"].copy_(bd0["poses"], non_blocking=True)      # every step starts from the same windows
+                bd["points"].copy_(bd0["points"], non_blocking=True)
+                if ev:
+                    ev[2].record(s2)
+                ba.solve_dev(B, bd, KITTI_K)
+                if ev:
+                    ev[3].record(s2)
         ext.detect_and_compute_dev(2 * B, pool[off], H * W, W, H, W, kps, desc, counts, cap)
+        if ev:
+            ev[0].record(s1)
         mat.match_dev(B, desc, 2 * cap * 32, counts, 2, desc[0, :, :].data_ptr() + cap * 32, 2 * cap * 32,
                       counts.data_ptr() + 4, 2, cap, midx, mdist, cap)
+        if ev:
+            ev[1].record(s1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -235,92 +273,96 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            step_dev(i)
-        ext.sync_status()
-        barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        time.sleep(0.3)
-        lib.sb_orb_profile(ext._h, 1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        e0.record(stream)
-        for i in range(args.steps):
-            off = ((args.warmup + i) * B) % P
-            ext.detect_and_compute_dev(2 * B, pool[off], H * W, W, H, W, kps, desc, counts, cap)
-            m_ev[i][0].record(stream)
-            mat.match_dev(B, desc, 2 * cap * 32, counts, 2, desc[0, :, :].data_ptr() + cap * 32, 2 * cap * 32,
-                          counts.data_ptr() + 4, 2, cap, midx, mdist, cap)
-            m_ev[i][1].record(stream)
-        e1.record(stream)
-        barrier()
-        clocks = sampler.stop()
-        ext.sync_status()
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    ext.sync_status()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    lib.sb_orb_profile(ext._h, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    s2.wait_stream(s1)
+    e0.record(s1)
+    s2.wait_stream(s1)
+    for i in range(args.steps):
+        step_dev(args.warmup + i, evs[i])
+    s1.wait_stream(s2)
+    e1.record(s1)
+    barrier()
+    clocks = sampler.stop()
+    ext.sync_status()
     dev_ms = e0.elapsed_time(e1)
     ms = np.zeros(6, np.float32)
     launches = np.zeros(6, np.int32)
     lib.sb_orb_profile_read(ext._h, C.c_void_p(ms.ctypes.data), C.c_void_p(launches.ctypes.data), 6)
     lib.sb_orb_profile(ext._h, 0)
-    match_ms = float(sum(a.elapsed_time(b) for a, b in m_ev))
+    match_ms = float(sum(e[0].elapsed_time(e[1]) for e in evs))
+    ba_ms = float(sum(e[2].elapsed_time(e[3]) for e in evs)) if with_ba else 0.0
     n_kps = int(counts.sum().item())
-    cand_np = np.zeros(1, np.int64)
-    n_cands = 0
-    for b in range(0, 2 * B, max(1, 2 * B // 4)):   # sample a few images for the candidate count
-        for level in range(8):
-            n_cands += len(ext.debug_candidates(b, level))
-    n_cands = int(n_cands * (2 * B) / len(range(0, 2 * B, max(1, 2 * B // 4))))
+    sample_imgs = list(range(0, 2 * B, max(1, 2 * B // 4)))
+    n_cands = sum(len(ext.debug_candidates(b, level)) for b in sample_imgs for level in range(8))
+    n_cands = int(n_cands * (2 * B) / len(sample_imgs))
     n_matched = int((mdist >= 0).sum().item())
+    ba_info = bd["info"].cpu().numpy() if with_ba else np.zeros((B, 4), np.int32)
 
-    # ---- e2e: the host-pointer C ABI with pinned host buffers (H2D + D2H inside the timed region)
-    hp = min(P, 2 * B)
+    # ---- e2e: the host-pointer C ABI with pinned host buffers (H2D + D2H inside the timed region):
+    #      two sb_stereo handles used alternately (copies of one batch overlap the kernels of the other)
+    #      and sb_ba_solve on pinned host arrays.
+    del ext, mat
+    hp = min(P, 4 * B)
     host_pool = torch.from_numpy(pool_np[:hp]).pin_memory()
-    h_kps = torch.zeros((2 * B, cap, 28), dtype=torch.uint8).pin_memory()
-    h_desc = torch.zeros((2 * B, cap, 32), dtype=torch.uint8).pin_memory()
-    h_counts = torch.zeros(2 * B, dtype=torch.int32).pin_memory()
-    h_midx = torch.zeros((B, cap), dtype=torch.int32).pin_memory()
-    h_mdist = torch.zeros((B, cap), dtype=torch.int32).pin_memory()
-    PA = C.c_void_p * (2 * B)
-    img_bytes = H * W
+    host_np = host_pool.numpy()
+    fes = [pkg.StereoFrontend(*ORB_PARAMS, max_w=W, max_h=H, max_pairs=B, device=local_rank) for _ in range(2)]
+    outs = [fe.alloc_outputs(B, pinned=True) for fe in fes]
+    hb = {k: torch.from_numpy(v).pin_memory() for k, v in bh.items()}
+    hb0 = {"poses": hb["poses"].clone(), "points": hb["points"].clone()}
+    h_chi2 = torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.float64).pin_memory()
+    h_outl = torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.uint8).pin_memory()
+    h_info = torch.zeros((B, 4), dtype=torch.int32).pin_memory()
+    Kd = np.ascontiguousarray(KITTI_K, np.float64)
+    ext7 = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
 
-    def step_host(i):
-        off = (i * B) % hp
-        base_ptr = host_pool.data_ptr() + off * 2 * img_bytes
-        ptrs = PA(*[base_ptr + k * img_bytes for k in range(2 * B)])
-        rc = lib.sb_orb_detect_and_compute(ext._h, 2 * B, ptrs, None, W, H, W, W, C.c_void_p(h_kps.data_ptr()),
-                                           C.c_void_p(h_desc.data_ptr()), C.c_void_p(h_counts.data_ptr()), cap)
-        assert rc == 0, pkg.last_error()
-        # match on the descriptors still resident on the device side of the extractor handle is not
-        # exposed by the C ABI; the host-pointer matcher call re-uploads them (counted in h2d bytes)
-        nq = h_counts[0::2].contiguous()
-        nt = h_counts[1::2].contiguous()
-        q = h_desc[0::2]
-        t = h_desc[1::2]
-        return q, t, nq, nt
-
-    h_q = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
-    h_t = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
-
-    def step_host_full(i):
-        q, t, nq, nt = step_host(i)
-        h_q.copy_(q)
-        h_t.copy_(t)
-        rc = lib.sb_hamming_match(mat._h, B, C.c_void_p(h_q.data_ptr()), C.c_void_p(nq.data_ptr()),
-                                  C.c_void_p(h_t.data_ptr()), C.c_void_p(nt.data_ptr()), cap,
-                                  C.c_void_p(h_midx.data_ptr()), C.c_void_p(h_mdist.data_ptr()))
+    def ba_host():
+        hb["poses"].copy_(hb0["poses"])
+        hb["points"].copy_(hb0["points"])
+        rc = lib.sb_ba_solve(ba._h, B, C.c_void_p(hb["np"].data_ptr()), C.c_void_p(hb["nl"].data_ptr()),
+                             C.c_void_p(hb["ne"].data_ptr()), C.c_void_p(hb["poses"].data_ptr()),
+                             C.c_void_p(hb["points"].data_ptr()), C.c_void_p(hb["fixed"].data_ptr()),
+                             C.c_void_p(hb["op"].data_ptr()), C.c_void_p(hb["ol"].data_ptr()), C.c_void_p(hb["uv"].data_ptr()),
+                             C.c_void_p(Kd.ctypes.data), C.c_void_p(ext7.ctypes.data), C.c_double(5.991), C.c_double(5.991),
+                             5, 10, C.c_void_p(h_chi2.data_ptr()), C.c_void_p(h_outl.data_ptr()),
+                             C.c_void_p(h_info.data_ptr()))
         assert rc == 0, pkg.last_error()
 
-    for i in range(3):
-        step_host_full(i)
+    def run_host(nsteps):
+        pending = [False, False]
+        for i in range(nsteps):
+            k = i % 2
+            if pending[k]:
+                fes[k].wait()
+            off = (i * B) % hp
+            fes[k].submit(host_np[off:off + B], outs[k])
+            pending[k] = True
+            if with_ba:
+                ba_host()
+        for k in range(2):
+            if pending[k]:
+                fes[k].wait()
+
+    run_host(4)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_host_full(i)
+    run_host(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = 2 * B * img_bytes + 2 * B * cap * 32 + 2 * B * 4
+    img_bytes = H * W
+    h2d = 2 * B * img_bytes
     d2h = 2 * B * cap * (28 + 32) + 2 * B * 4 + 2 * B * cap * 4
+    if with_ba:
+        h2d += sum(int(hb[k].numel() * hb[k].element_size()) for k in ("np", "nl", "ne", "poses", "points", "fixed", "op", "ol", "uv"))
+        d2h += int(hb["poses"].numel() * 8 + hb["points"].numel() * 8 + h_chi2.numel() * 8 + h_outl.numel() + h_info.numel() * 4)
 
     # ---- aggregate over ranks (max time)
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -336,6 +378,13 @@ def main():
         stage_ms["hamming_match"] = match_ms
         stage_launches = {s: int(launches[i]) for i, s in enumerate(STAGES)}
         stage_launches["hamming_match"] = args.steps
+        if with_ba:
+            stage_ms["local_ba"] = ba_ms
+            stage_launches["local_ba"] = args.steps
+
+        def abytes(k):
+            return ba_bytes if k == "local_ba" else algorithmic_bytes(k, 2 * B, n_kps, n_cands)
+
         top = max(stage_ms, key=stage_ms.get)
         peaks = {}
         try:
@@ -346,35 +395,37 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         groups = stage_launches[top] / (7 if top == "resize_pyramid" else 1)
         per_group_ms = stage_ms[top] / max(groups, 1)
-        abytes = algorithmic_bytes(top, 2 * B, n_kps, n_cands)
-        achieved = abytes / (per_group_ms * 1e-3) / 1e9
+        achieved = abytes(top) / (per_group_ms * 1e-3) / 1e9
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": abytes, "ms_per_launch": per_group_ms,
+                    "algorithmic_bytes_per_launch": abytes(top), "ms_per_launch": per_group_ms,
                     "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                    "stage_gbs": {k: algorithmic_bytes(k, 2 * B, n_kps, n_cands) / (stage_ms[k] / args.steps * 1e-3) / 1e9
-                                  for k in stage_ms if stage_ms[k] > 0}}
+                    "stage_gbs": {k: abytes(k) / (stage_ms[k] / args.steps * 1e-3) / 1e9 for k in stage_ms if stage_ms[k] > 0},
+                    "note": "stages on the two streams overlap; stage times are CUDA-event intervals on the launching stream"}
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-               "config": {"workload": WORKLOAD, "stereo_pairs_per_step_per_gpu": B, "resident_pool_pairs": P,
+               "vs_baseline": None, "dtype": "u8 (extract/match), f64 (BA)", "data": "synthetic",
+               "config": {"workload": WORKLOAD if with_ba else "config 2: ORB extract (both views) + L<->R Hamming match only",
+                          "stereo_pairs_per_step_per_gpu": B, "ba_windows_per_step_per_gpu": B if with_ba else 0,
+                          "resident_pool_pairs": P,
                           "l2_policy": f"inputs larger than L2: {P * 2 * img_bytes / 1e6:.0f} MB pool of distinct frames cycled",
                           "keypoints_per_frame": n_kps / (2 * B), "matches_per_pair": n_matched / B,
-                          "sharding": "frames round-robin by rank, no data-path collective"},
+                          "ba_obs_per_window": float(bh["ne"].mean()), "ba_lm_iterations_per_window": float(ba_info[:, 1].mean()),
+                          "sharding": "frames and windows round-robin by rank, no data-path collective"},
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_ms_max / args.steps,
-                       "api": "sb_orb_detect_and_compute + sb_hamming_match (host pointers, pinned)"},
+                       "api": "sb_stereo_submit/wait on two handles + sb_ba_solve (host pointers, pinned)"},
                "gpu_launches": int(sum(stage_launches.values())),
                "roofline": roofline}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = max(2 * cores, 16)
             sample = pool_np[:min(n, P)]
-            fps = cpu_reference_fps(sample, cores)
+            fps = cpu_reference_fps(sample, windows if with_ba else None, cores)
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                   "sample": f"{len(sample)} of the same synthetic stereo frames through oracle/ (C restatement "
-                                             "of the reference's OpenCV-based path), one extractor per thread"}
+                                   "sample": f"{len(sample)} of the same synthetic stereo frames (+ one BA window each) through "
+                                             "oracle/ (C restatement of the reference's OpenCV/g2o-based path), one frame per thread"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -151,6 +151,31 @@ int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d_q, int64_t
                          int nt_stride, int max_rows, int32_t *d_train_idx, int32_t *d_dist, int64_t out_stride);
 
 /* ---------------------------------------------------------------------------------------------
+ * Stereo front end in one call — ORBextractor::DetectAndCompute (src/ORBextractor.cpp:922-985) on the
+ * left and the right view of `pairs` frames, then BFMatcher-Hamming match(query = left descriptors,
+ * train = right descriptors) with the semantics of src/loopclosing.cpp:172; host buffers in and out,
+ * descriptors stay on the device between the stages.  sb_stereo_submit only enqueues on the handle's
+ * stream (truly asynchronous when the host buffers are pinned) and sb_stereo_wait synchronises, so two
+ * handles used alternately overlap copies with kernels.
+ *   images: frame p's left plane at images + p * frame_pitch, its right plane view_pitch bytes later,
+ *           each `hgt` rows of `stride` bytes;
+ *   kps [pairs][2][cap], desc [pairs][2][cap][32], counts [pairs][2], match_idx / match_dist [pairs][cap]
+ *   with cap = sb_stereo_capacity().
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sb_stereo sb_stereo_t;
+int sb_stereo_create(sb_stereo_t **h, int device, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
+                     int minThFAST, int max_w, int max_h, int max_pairs);
+int sb_stereo_destroy(sb_stereo_t *h);
+int sb_stereo_capacity(const sb_stereo_t *h);
+int sb_stereo_submit(sb_stereo_t *h, int pairs, const uint8_t *images, int64_t frame_pitch, int64_t view_pitch, int w,
+                     int hgt, int stride, sb_keypoint *kps, uint8_t *desc, int32_t *counts, int32_t *match_idx,
+                     int32_t *match_dist);
+int sb_stereo_wait(sb_stereo_t *h);
+int sb_stereo_extract_match(sb_stereo_t *h, int pairs, const uint8_t *images, int64_t frame_pitch, int64_t view_pitch,
+                            int w, int hgt, int stride, sb_keypoint *kps, uint8_t *desc, int32_t *counts,
+                            int32_t *match_idx, int32_t *match_dist);
+
+/* ---------------------------------------------------------------------------------------------
  * Local bundle adjustment — replaces the g2o solve inside Backend::OptimizeActiveMap
  * (src/backend.cpp:126-269; edge/vertex arithmetic include/myslam/g2o_types.h:25-59,106-153):
  * Levenberg-Marquardt with the landmarks marginalised (Schur), Huber kernel, up to `outer_max`

@@ -1,0 +1,52 @@
+"""The C-ABI library loads on a machine without a GPU and exports every symbol include/slamb200.h declares;
+compute entry points fail loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "slamb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(pkg):
+    lib = pkg.lib()
+    names = declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_version_and_error_text(pkg):
+    assert b"sm_100a" in pkg.lib().sb_version()
+    assert isinstance(pkg.last_error(), str)
+
+
+def test_no_cpu_fallback_without_a_device(pkg):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a CUDA device is present")
+    for make in (lambda: pkg.ORBextractor(2000, 1.2, 8, 20, 7), lambda: pkg.HammingMatcher(), lambda: pkg.LocalBA(),
+                 lambda: pkg.DeepLCDScorer(), lambda: pkg.PoseGraph(), lambda: pkg.StereoFrontend(2000, 1.2, 8, 20, 7)):
+        with pytest.raises(pkg.SlamB200Error) as e:
+            make()
+        assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_argument_validation_needs_no_device(pkg):
+    h = C.c_void_p()
+    assert pkg.lib().sb_orb_create(C.byref(h), 0, 0, C.c_float(1.2), 8, 20, 7, 1241, 376, 1) == -1   # nfeatures = 0
+    assert "nfeatures" in pkg.last_error()
+    assert pkg.lib().sb_ba_create(C.byref(h), 0, 1, 99, 10, 10) == -1                                 # too many poses
+    assert pkg.lib().sb_lcd_create(C.byref(h), 0, 10, 7, 1) == -1                                     # bad dtype
