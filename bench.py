@@ -364,6 +364,46 @@ def main():
         h2d += sum(int(hb[k].numel() * hb[k].element_size()) for k in ("np", "nl", "ne", "poses", "points", "fixed", "op", "ol", "uv"))
         d2h += int(hb["poses"].numel() * 8 + hb["points"].numel() * 8 + h_chi2.numel() * 8 + h_outl.numel() + h_info.numel() * 4)
 
+    # ---- config 4/5 extras (outside the timed region): DeepLCD scoring of every keyframe against the database,
+    #      the single all-gather of keyframe poses (round-robin ownership) and the pose graph on every rank
+    par = importlib.import_module(PKG + ".parallel")
+    extras = {}
+    try:
+        n_kf = 742
+        g = synth.pose_graph(0, n=n_kf)
+        mine = par.shard_indices(n_kf, rank, world)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        full = par.allgather_kf_poses(g["poses0"][mine], n_kf, rank, world, device="cuda")
+        torch.cuda.synchronize()
+        extras["kf_pose_allgather_ms"] = (time.perf_counter() - t0) * 1e3
+        assert np.array_equal(full, g["poses0"])
+        pgs = pkg.PoseGraph(1024, 2048, device=local_rank)
+        pgs.solve(full, g["fixed"], g["v0"], g["v1"], g["meas"])
+        t0 = time.perf_counter()
+        _, pinfo = pgs.solve(full, g["fixed"], g["v0"], g["v1"], g["meas"])
+        extras["posegraph_ms"] = (time.perf_counter() - t0) * 1e3
+        extras["posegraph"] = {"vertices": n_kf, "edges": int(len(g["v0"])), "chi2_start": pinfo["chi2_start"], "chi2": pinfo["chi2"]}
+        db = synth.lcd_database(0)
+        lcd = pkg.DeepLCDScorer(capacity=1024, dtype=1, max_queries=n_kf, device=local_rank)
+        lcd.add_batch(np.arange(n_kf), db)
+        dq = torch.from_numpy(db).cuda()
+        dscore = torch.zeros((n_kf, n_kf), dtype=torch.float32, device="cuda")
+        sl = torch.cuda.Stream()
+        lcd.set_stream(sl.cuda_stream)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lcd.score_dev(n_kf, dq, dscore, n_kf)
+        a0.record(sl)
+        for _ in range(10):
+            lcd.score_dev(n_kf, dq, dscore, n_kf)
+        a1.record(sl)
+        torch.cuda.synchronize()
+        lms = a0.elapsed_time(a1) / 10
+        extras["lcd_score_queries_per_s"] = n_kf / (lms * 1e-3)
+        extras["lcd_score_gbs"] = n_kf * n_kf * 1088 * 2 / (lms * 1e-3) / 1e9
+    except Exception as ex:   # the extras never invalidate the headline measurement
+        extras["error"] = repr(ex)
+
     # ---- aggregate over ranks (max time)
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -417,7 +457,8 @@ def main():
                        "ms_per_step": e2e_ms_max / args.steps,
                        "api": "sb_stereo_submit/wait on two handles + sb_ba_solve (host pointers, pinned)"},
                "gpu_launches": int(sum(stage_launches.values())),
-               "roofline": roofline}
+               "roofline": roofline,
+               "loop_closing_extras": extras}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = max(2 * cores, 16)
