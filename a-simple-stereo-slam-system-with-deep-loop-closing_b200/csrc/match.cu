@@ -22,18 +22,25 @@ struct sb_matcher {
     int32_t *d_nq, *d_nt, *d_idx, *d_dist;
 };
 
+// Partial 1-NN over one slice of the train set.  The result of a slice is folded into out_idx[] with
+// atomicMin on the key (distance << 22 | train index): the minimum key is the smallest distance and,
+// among equal distances, the lowest train index — exactly BFMatcher's tie rule, independent of the
+// order in which the slices finish.  k_hamming_decode then splits the key into (index, distance).
+#define MATCH_KEY_SHIFT 22
 __global__ void __launch_bounds__(MATCH_THREADS) k_hamming(const uint8_t *__restrict__ q, long long q_set_stride,
                                                           const int32_t *__restrict__ nq_arr, int nq_stride,
                                                           const uint8_t *__restrict__ t, long long t_set_stride,
                                                           const int32_t *__restrict__ nt_arr, int nt_stride, int max_rows,
-                                                          int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist,
-                                                          long long out_stride) {
+                                                          uint32_t *__restrict__ out_key, long long out_stride, int nslices) {
     __shared__ uint4 ts[MATCH_CHUNK * 2];
-    const int set = blockIdx.y;
+    const int set = blockIdx.z;
     const int nq = min(nq_arr[(long long)set * nq_stride], max_rows);
     const int nt = min(nt_arr[(long long)set * nt_stride], max_rows);
     const int q0 = blockIdx.x * MATCH_QB;
     if (q0 >= nq) return;
+    const int per = (((nt + nslices - 1) / nslices) + MATCH_CHUNK - 1) / MATCH_CHUNK * MATCH_CHUNK;  // rows per slice
+    const int t_begin = blockIdx.y * per, t_end = min(nt, t_begin + per);
+    if (t_begin >= t_end) return;
     const uint4 *Q = reinterpret_cast<const uint4 *>(q + (long long)set * q_set_stride);
     const uint4 *T = reinterpret_cast<const uint4 *>(t + (long long)set * t_set_stride);
 
@@ -48,8 +55,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_hamming(const uint8_t *__rest
         best[k] = 0x7fffffff;
         bidx[k] = -1;
     }
-    for (int c0 = 0; c0 < nt; c0 += MATCH_CHUNK) {
-        const int cn = min(MATCH_CHUNK, nt - c0);
+    for (int c0 = t_begin; c0 < t_end; c0 += MATCH_CHUNK) {
+        const int cn = min(MATCH_CHUNK, t_end - c0);
         __syncthreads();
         for (int i = threadIdx.x; i < cn * 2; i += MATCH_THREADS) ts[i] = T[2 * c0 + i];
         __syncthreads();
@@ -71,11 +78,25 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_hamming(const uint8_t *__rest
 #pragma unroll
     for (int k = 0; k < MATCH_QPT; k++) {
         const int qi = q0 + k * MATCH_THREADS + threadIdx.x;
-        if (qi < nq) {
-            out_idx[(long long)set * out_stride + qi] = bidx[k];
-            out_dist[(long long)set * out_stride + qi] = bidx[k] < 0 ? -1 : best[k];
-        }
+        if (qi < nq && bidx[k] >= 0)
+            atomicMin(&out_key[(long long)set * out_stride + qi], ((uint32_t)best[k] << MATCH_KEY_SHIFT) | (uint32_t)bidx[k]);
     }
+}
+
+__global__ void k_hamming_init(const int32_t *__restrict__ nq_arr, int nq_stride, int max_rows, uint32_t *out_key,
+                               long long out_stride) {
+    const int set = blockIdx.y, qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi < min(nq_arr[(long long)set * nq_stride], max_rows)) out_key[(long long)set * out_stride + qi] = 0xffffffffu;
+}
+
+__global__ void k_hamming_decode(const int32_t *__restrict__ nq_arr, int nq_stride, int max_rows, int32_t *idx_key,
+                                 int32_t *out_dist, long long out_stride) {
+    const int set = blockIdx.y, qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= min(nq_arr[(long long)set * nq_stride], max_rows)) return;
+    const uint32_t key = (uint32_t)idx_key[(long long)set * out_stride + qi];
+    const bool none = key == 0xffffffffu;
+    idx_key[(long long)set * out_stride + qi] = none ? -1 : (int32_t)(key & ((1u << MATCH_KEY_SHIFT) - 1u));
+    out_dist[(long long)set * out_stride + qi] = none ? -1 : (int32_t)(key >> MATCH_KEY_SHIFT);
 }
 
 static void free_matcher(sb_matcher *m) {
@@ -140,13 +161,22 @@ extern "C" int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d
     sb_clear_error();
     SB_REQUIRE(m, "null handle");
     SB_REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
-    SB_REQUIRE(max_rows >= 1, "max_rows must be positive");
+    SB_REQUIRE(max_rows >= 1 && max_rows <= (1 << 20), "max_rows out of range [1, 2^20]");
     SB_REQUIRE(d_q && d_t && d_nq && d_nt && d_train_idx && d_dist, "null device pointer");
     SB_REQUIRE(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0 && (q_set_stride & 15) == 0 && (t_set_stride & 15) == 0,
                "descriptor sets must be 16-byte aligned");
     SB_TRY(sb_use_device(m->device));
-    k_hamming<<<dim3(sb_div_up(max_rows, MATCH_QB), batch), MATCH_THREADS, 0, m->stream>>>(
-        d_q, q_set_stride, d_nq, nq_stride, d_t, t_set_stride, d_nt, nt_stride, max_rows, d_train_idx, d_dist, out_stride);
+    // enough CTAs to fill 148 SMs: slice the train set when the batch alone does not
+    const int qblocks = sb_div_up(max_rows, MATCH_QB);
+    int nslices = 1;
+    while (nslices < 8 && (long long)qblocks * batch * nslices < 148 * 12 && max_rows / (nslices * 2) >= MATCH_CHUNK) nslices *= 2;
+    k_hamming_init<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows,
+                                                                                 reinterpret_cast<uint32_t *>(d_train_idx), out_stride);
+    k_hamming<<<dim3(qblocks, nslices, batch), MATCH_THREADS, 0, m->stream>>>(d_q, q_set_stride, d_nq, nq_stride, d_t, t_set_stride,
+                                                                              d_nt, nt_stride, max_rows,
+                                                                              reinterpret_cast<uint32_t *>(d_train_idx), out_stride, nslices);
+    k_hamming_decode<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows, d_train_idx, d_dist,
+                                                                                   out_stride);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }

@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
                                                             const __grid_constant__ Geom g, FastArgs a) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_n, s_any;
+    __shared__ int s_n, s_any, s_np;
     uint8_t *tile = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);  // TMA destination
     uint8_t *sc = tile + a.tile_bytes;
     uint32_t *list = reinterpret_cast<uint32_t *>(tile + 2 * a.tile_bytes);
+    uint16_t *plist = reinterpret_cast<uint16_t *>(tile + 2 * a.tile_bytes + SB_CELL_LIST_CAP * 4);  // <= one entry per tile pixel
 
     const Cell c = a.cells[blockIdx.x];
     const int img = blockIdx.y;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     if (tid == 0) {
         s_n = 0;
         s_any = 0;
+        s_np = 0;
         sb_mbar_init(&bar, 1);
         sb_mbar_expect_tx(&bar, (uint32_t)(BW * BH));
         sb_tma_load_3d(tile, &maps.m[c.level], c.x0 - xo, c.y0, img, &bar);
@@ -181,27 +183,42 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     __syncthreads();
     sb_mbar_wait(&bar, 0);
 
+    // Phase 1: pixels that pass the cheap necessary test are compacted into a list, so that the response
+    // (about 100 instructions) is later computed by full warps instead of a few lanes of every warp.
     const int t0 = min(a.iniTh, a.minTh);
     for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
-        for (int x = 3 + lane; x < c.rw - 3; x += 32) {
-            const uint8_t *p = tile + y * BW + xo + x;
-            if (sb_fast_maybe(p, BW, t0)) {
-                const int s = sb_fast_score(p, BW);
-                if (s >= t0) sc[y * BW + xo + x] = (uint8_t)s;
+        for (int xb = 3; xb < c.rw - 3; xb += 32) {
+            const int x = xb + lane;
+            const bool m = x < c.rw - 3 && sb_fast_maybe(tile + y * BW + xo + x, BW, t0);
+            const unsigned bal = __ballot_sync(0xffffffffu, m);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_np, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (m) plist[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((y << 8) | x);
             }
         }
     __syncthreads();
-    for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
-        for (int x = 3 + lane; x < c.rw - 3; x += 32) {
-            const uint8_t *q = sc + y * BW + xo + x;
-            const int s = q[0];
-            if (s > 0 && s > q[-1] && s > q[1] && s > q[-BW - 1] && s > q[-BW] && s > q[-BW + 1] && s > q[BW - 1] &&
-                s > q[BW] && s > q[BW + 1]) {
-                const int i = atomicAdd(&s_n, 1);
-                if (i < SB_CELL_LIST_CAP) list[i] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
-                if (s >= a.iniTh) s_any = 1;
-            }
+    const int np = s_np;
+    // Phase 2: responses of the listed pixels
+    for (int i = tid; i < np; i += FAST_THREADS) {
+        const int y = plist[i] >> 8, x = plist[i] & 255;
+        const int s = sb_fast_score(tile + y * BW + xo + x, BW);
+        if (s >= t0) sc[y * BW + xo + x] = (uint8_t)s;
+    }
+    __syncthreads();
+    // Phase 3: 3x3 non-maximum suppression (only listed pixels can be maxima)
+    for (int i = tid; i < np; i += FAST_THREADS) {
+        const int y = plist[i] >> 8, x = plist[i] & 255;
+        const uint8_t *q = sc + y * BW + xo + x;
+        const int s = q[0];
+        if (s > 0 && s > q[-1] && s > q[1] && s > q[-BW - 1] && s > q[-BW] && s > q[-BW + 1] && s > q[BW - 1] &&
+            s > q[BW] && s > q[BW + 1]) {
+            const int k = atomicAdd(&s_n, 1);
+            if (k < SB_CELL_LIST_CAP) list[k] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+            if (s >= a.iniTh) s_any = 1;
         }
+    }
     __syncthreads();
     if (a.dbg && img == 0 && (int)blockIdx.x == a.dbg_cell) {
         for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) {
@@ -325,48 +342,70 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps ma
     __syncthreads();
     sb_mbar_wait(&bar, 0);
 
-    const bool interior_x = x0 >= 3 && x0 + BLUR_TW + 3 <= L.w;
-    // horizontal pass: tile row r <-> image row y0 - 3 + r (rows outside the image are never used)
-    for (int i = tid; i < BLUR_BH * BLUR_TW; i += 256) {
-        const int r = i / BLUR_TW, cx = i % BLUR_TW;
-        const uint8_t *row = tile + r * BLUR_BW + (BLUR_HX - 3);
-        unsigned v;
-        if (interior_x) {
-            v = sb_gauss_row(row[cx], row[cx + 1], row[cx + 2], row[cx + 3], row[cx + 4], row[cx + 5], row[cx + 6]);
-        } else {
-            int ix[7];
-#pragma unroll
-            for (int k = 0; k < 7; k++) {
-                int gx = x0 + cx + k - 3;
-                gx = sb_reflect101(gx, L.w);
-                ix[k] = min(max(gx - (x0 - 3), -(BLUR_HX - 3)), BLUR_BW - 1 - (BLUR_HX - 3));  // clamp only guards columns past the image (unused)
+    // BORDER_REFLECT_101: tiles on the image border complete their halo inside shared memory
+    // (columns first, then whole rows, so the corners come out right); interior tiles skip this.
+    const bool left = x0 == 0, right = x0 + BLUR_TW + 3 > L.w, top = y0 == 0, bottom = y0 + BLUR_TH + 3 > L.h;
+    if (left || right) {
+        for (int i = tid; i < BLUR_BH * 3; i += 256) {
+            const int r = i / 3, k = i % 3 + 1;
+            uint8_t *row = tile + r * BLUR_BW;
+            if (left) row[BLUR_HX - k] = row[BLUR_HX + k];
+            if (right) {
+                const int col = L.w - 1 + k - x0 + BLUR_HX, src = L.w - 1 - k - x0 + BLUR_HX;
+                if (col < BLUR_BW) row[col] = row[src];
             }
-            v = sb_gauss_row(row[ix[0]], row[ix[1]], row[ix[2]], row[ix[3]], row[ix[4]], row[ix[5]], row[ix[6]]);
         }
-        hrow[i] = (uint16_t)v;
+        __syncthreads();
+    }
+    if (top || bottom) {
+        for (int i = tid; i < 3 * BLUR_BW; i += 256) {
+            const int k = i / BLUR_BW + 1, c = i % BLUR_BW;
+            if (top) tile[(3 - k) * BLUR_BW + c] = tile[(3 + k) * BLUR_BW + c];
+            if (bottom) {
+                const int r = L.h - 1 + k - (y0 - 3), src = L.h - 1 - k - (y0 - 3);
+                if (r < BLUR_BH) tile[r * BLUR_BW + c] = tile[src * BLUR_BW + c];
+            }
+        }
+        __syncthreads();
+    }
+
+    // horizontal pass: 4 outputs per item from 12 tile bytes; each output is two 4-tap dot products (DP4A)
+    const uint32_t W0 = SB_G0 | (SB_G1 << 8) | (SB_G2 << 16) | (SB_G3 << 24), W1 = SB_G2 | (SB_G1 << 8) | (SB_G0 << 16);
+    for (int i = tid; i < BLUR_BH * (BLUR_TW / 4); i += 256) {
+        const int r = i / (BLUR_TW / 4), gq = i % (BLUR_TW / 4);
+        // output column cx reads tile columns (BLUR_HX - 3) + cx + 0..6; BLUR_HX - 3 = 13 = 12 + 1
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(tile + r * BLUR_BW + (BLUR_HX - 4) + 4 * gq);
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const uint32_t o0 = __dp4a(__funnelshift_r(w0, w1, 8), W0, __dp4a(__funnelshift_r(w1, w2, 8), W1, 0u));
+        const uint32_t o1 = __dp4a(__funnelshift_r(w0, w1, 16), W0, __dp4a(__funnelshift_r(w1, w2, 16), W1, 0u));
+        const uint32_t o2 = __dp4a(__funnelshift_r(w0, w1, 24), W0, __dp4a(__funnelshift_r(w1, w2, 24), W1, 0u));
+        const uint32_t o3 = __dp4a(w1, W0, __dp4a(w2, W1, 0u));
+        *reinterpret_cast<uint2 *>(hrow + r * BLUR_TW + 4 * gq) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));  // each <= 255 * 256
     }
     __syncthreads();
-    // vertical pass: one warp per output row, 4 pixels per lane
-    const int lane = tid & 31, warp = tid >> 5;
-    uint8_t *out = a.blur + (long long)img * a.slab + L.off;
-    for (int ry = warp; ry < BLUR_TH; ry += 8) {
-        const int y = y0 + ry;
-        if (y >= L.h) break;
-        int rr[7];
+    // vertical pass: a thread owns 4 columns x 4 output rows (10 input rows)
+    {
+        const int gq = tid & 31, seg = tid >> 5;
+        const int ry0 = seg * 4;
+        if (y0 + ry0 < L.h && x0 + 4 * gq < L.w) {
+            uint32_t h[10][4];
 #pragma unroll
-        for (int k = 0; k < 7; k++) rr[k] = sb_reflect101(y + k - 3, L.h) - (y0 - 3);
-        const int cx = lane * 4;
-        if (x0 + cx >= L.w) continue;
-        uint32_t o = 0;
+            for (int r = 0; r < 10; r++) {
+                const uint2 u = *reinterpret_cast<const uint2 *>(hrow + (ry0 + r) * BLUR_TW + 4 * gq);
+                h[r][0] = u.x & 0xffffu; h[r][1] = u.x >> 16; h[r][2] = u.y & 0xffffu; h[r][3] = u.y >> 16;
+            }
+            uint8_t *out = a.blur + (long long)img * a.slab + L.off + x0 + 4 * gq;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int c = cx + j;
-            o |= (uint32_t)sb_gauss_col(hrow[rr[0] * BLUR_TW + c], hrow[rr[1] * BLUR_TW + c], hrow[rr[2] * BLUR_TW + c],
-                                        hrow[rr[3] * BLUR_TW + c], hrow[rr[4] * BLUR_TW + c], hrow[rr[5] * BLUR_TW + c],
-                                        hrow[rr[6] * BLUR_TW + c])
-                 << (8 * j);
+            for (int ry = 0; ry < 4; ry++) {
+                const int y = y0 + ry0 + ry;
+                if (y >= L.h) break;
+                uint32_t o = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    o |= (uint32_t)sb_gauss_col(h[ry][j], h[ry + 1][j], h[ry + 2][j], h[ry + 3][j], h[ry + 4][j], h[ry + 5][j], h[ry + 6][j]) << (8 * j);
+                *reinterpret_cast<uint32_t *>(out + (long long)y * L.pitch) = o;
+            }
         }
-        *reinterpret_cast<uint32_t *>(out + (long long)y * L.pitch + x0 + cx) = o;
     }
 }
 
@@ -1024,7 +1063,7 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     fa.dbg = h->dbg_buf;
     fa.dbg_cell = h->dbg_cell;
     const int ncells = detect_only ? h->n_cells_l0 : h->n_cells;
-    const size_t fsmem = 2 * (size_t)h->fast_tile_bytes + SB_CELL_LIST_CAP * 4 + 128;
+    const size_t fsmem = 4 * (size_t)h->fast_tile_bytes + SB_CELL_LIST_CAP * 4 + 128;
     prof_begin(h, SB_STAGE_FAST, 1, h->stream);
     k_fast_cells<<<dim3(ncells, batch), FAST_THREADS, fsmem, h->stream>>>(h->fast_maps, h->geom, fa);
     prof_end(h, h->stream);

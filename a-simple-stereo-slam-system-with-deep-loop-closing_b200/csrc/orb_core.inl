@@ -18,6 +18,15 @@ SB_HD float sb_fdiv(float a, float b) { volatile float r = a / b; return r; }
 SB_HD int sb_rint(float a) { return (int)lrintf(a); }
 SB_HD int sb_min(int a, int b) { return a < b ? a : b; }
 SB_HD int sb_max(int a, int b) { return a > b ? a : b; }
+// host emulation of the packed 2 x int16 instructions the device build uses (VIADD.16x2, VIMNMX.S16x2, PRMT)
+SB_HD uint32_t sb_pack2(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+SB_HD int sb_lo2(uint32_t a) { return (int)(int16_t)(a & 0xffffu); }
+SB_HD int sb_hi2(uint32_t a) { return (int)(int16_t)(a >> 16); }
+SB_HD uint32_t sb_vadd2(uint32_t a, uint32_t b) { return sb_pack2(sb_lo2(a) + sb_lo2(b), sb_hi2(a) + sb_hi2(b)); }
+SB_HD uint32_t sb_vmin2(uint32_t a, uint32_t b) { return sb_pack2(sb_min(sb_lo2(a), sb_lo2(b)), sb_min(sb_hi2(a), sb_hi2(b))); }
+SB_HD uint32_t sb_vmax2(uint32_t a, uint32_t b) { return sb_pack2(sb_max(sb_lo2(a), sb_lo2(b)), sb_max(sb_hi2(a), sb_hi2(b))); }
+SB_HD uint32_t sb_vmin3_2(uint32_t a, uint32_t b, uint32_t c) { return sb_vmin2(sb_vmin2(a, b), c); }
+SB_HD uint32_t sb_vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return sb_vmax2(sb_vmax2(a, b), c); }
 #else
 #define SB_HD static __device__ __forceinline__
 SB_HD float sb_fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -27,6 +36,14 @@ SB_HD float sb_fdiv(float a, float b) { return __fdiv_rn(a, b); }
 SB_HD int sb_rint(float a) { return __float2int_rn(a); }  // cvRound: round half to even
 SB_HD int sb_min(int a, int b) { return min(a, b); }
 SB_HD int sb_max(int a, int b) { return max(a, b); }
+SB_HD uint32_t sb_pack2(int lo, int hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+SB_HD int sb_lo2(uint32_t a) { return (int)(short)(a & 0xffffu); }
+SB_HD int sb_hi2(uint32_t a) { return (int)a >> 16; }
+SB_HD uint32_t sb_vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }                             // VIADD.16x2
+SB_HD uint32_t sb_vmin2(uint32_t a, uint32_t b) { return __vmins2(a, b); }                            // VIMNMX.S16x2
+SB_HD uint32_t sb_vmax2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+SB_HD uint32_t sb_vmin3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_s16x2(a, b, c); }     // VIMNMX3.S16x2
+SB_HD uint32_t sb_vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 #endif
 
 #define SB_HALF_PATCH 15
@@ -53,31 +70,34 @@ SB_HD bool sb_fast_maybe(const uint8_t *p, int pitch, int t) {
 
 // Corner response = the largest threshold for which the pixel is still a FAST-9/16 corner:
 //   max over the 16 arcs of 9 contiguous ring pixels of  min(v - ring)  resp.  min(ring - v),  minus 1.
-// Running minima over windows 2, 4, 8 then 9 give all 16 arcs in 4 * 16 min per polarity.
-// Both polarities are written as minima of explicit differences (no "-max(...)"): ptxas 12.9 folds
-// max(a, -max3(...)) into VIMNMX3 for sm_100a and loses the negation (measured, tools/fast_probe.cu).
+// Both polarities ride in one register as 2 x int16 (low half: v - ring, high half: ring - v), so the
+// running minima over windows 2, 4 and 9 cost 16 + 16 + 16 packed instructions (VIMNMX.S16x2 /
+// VIMNMX3.S16x2) for all 16 arcs of both polarities, and no value is ever negated after a min/max
+// (ptxas 12.9 mis-folds max(a, -max3(...)) into VIMNMX3 on sm_100a — measured, tools/fast_probe.cu).
 SB_HD int sb_fast_score(const uint8_t *p, int pitch) {
     const int v = p[0];
-    int d[16], e[16];
+    const uint32_t vv = sb_pack2(v - 255, -v);
+    uint32_t d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        const int r = p[SB_RING_DY(k) * pitch + SB_RING_DX(k)];
-        d[k] = v - r;  // > t  <=> ring pixel darker than v - t
-        e[k] = r - v;  // > t  <=> ring pixel brighter than v + t
+        const uint32_t r = p[SB_RING_DY(k) * pitch + SB_RING_DX(k)];
+        d[k] = sb_vadd2(vv, r * 65535u + 255u);  // r * 65535 + 255 = (255 - r, r) without a borrow -> (v - r, r - v)
     }
-    int d2[16], e2[16], d4[16], e4[16];
+    uint32_t m2[16], m4[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) { d2[k] = sb_min(d[k], d[(k + 1) & 15]); e2[k] = sb_min(e[k], e[(k + 1) & 15]); }
+    for (int k = 0; k < 16; k++) m2[k] = sb_vmin2(d[k], d[(k + 1) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) { d4[k] = sb_min(d2[k], d2[(k + 2) & 15]); e4[k] = sb_min(e2[k], e2[(k + 2) & 15]); }
-    int best = -256;
+    for (int k = 0; k < 16; k++) m4[k] = sb_vmin2(m2[k], m2[(k + 2) & 15]);
+    uint32_t m9[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const int d9 = sb_min(sb_min(d4[k], d4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int e9 = sb_min(sb_min(e4[k], e4[(k + 4) & 15]), e[(k + 8) & 15]);
-        best = sb_max(best, sb_max(d9, e9));
-    }
-    return best - 1;
+    for (int k = 0; k < 16; k++) m9[k] = sb_vmin3_2(m4[k], m4[(k + 4) & 15], d[(k + 8) & 15]);
+    uint32_t b0 = sb_vmax3_2(m9[0], m9[1], m9[2]), b1 = sb_vmax3_2(m9[3], m9[4], m9[5]);
+    uint32_t b2 = sb_vmax3_2(m9[6], m9[7], m9[8]), b3 = sb_vmax3_2(m9[9], m9[10], m9[11]);
+    uint32_t b4 = sb_vmax3_2(m9[12], m9[13], m9[14]);
+    b0 = sb_vmax3_2(b0, b1, b2);
+    b3 = sb_vmax3_2(b3, b4, m9[15]);
+    b0 = sb_vmax2(b0, b3);
+    return sb_max(sb_lo2(b0), sb_hi2(b0)) - 1;
 }
 
 // ---- cv::resize INTER_LINEAR u8 (src/ORBextractor.cpp:1243-1244,1262) ----------------
