@@ -2,85 +2,157 @@
 //
 // Replaces cv::BFMatcher(NORM_HAMMING)::match as LoopClosing::MatchFeatures uses it (reference
 // src/loopclosing.cpp:33,172): for every query row the nearest train row, ties -> lowest trainIdx.
-// The work is xor + population count; there is nothing to put on tensor cores and HBM traffic is
-// negligible (64 KB per descriptor set), so the kernel is organised around the POPC issue rate:
-// each thread owns QPT query rows in registers, the train set streams through shared memory in
-// chunks and every shared-memory read is a warp-wide broadcast.
+// HBM traffic is negligible (64 KB per descriptor set); the work is 4 M distance evaluations per
+// 2000 x 2000 problem, done as an exact int8 tensor-core GEMM (see below).
 #include <string.h>
 
 #include "common.cuh"
 
-#define MATCH_THREADS 128
-#define MATCH_QPT 2                              // query rows per thread
-#define MATCH_QB (MATCH_THREADS * MATCH_QPT)     // query rows per CTA
-#define MATCH_CHUNK 256                          // train rows per shared-memory chunk
 
 struct sb_matcher {
     int device, max_batch, max_rows;
     cudaStream_t stream, own_stream;
     uint8_t *d_q, *d_t;
     int32_t *d_nq, *d_nt, *d_idx, *d_dist;
+    // tensor-core operands: 0/1-byte expansions of the two descriptor sets, train keys, query popcounts
+    int rows_pad;
+    uint8_t *d_xq, *d_xt;
+    uint32_t *d_tkey;
+    int32_t *d_pq;
 };
 
-// Partial 1-NN over one slice of the train set.  The result of a slice is folded into out_idx[] with
-// atomicMin on the key (distance << 22 | train index): the minimum key is the smallest distance and,
-// among equal distances, the lowest train index — exactly BFMatcher's tie rule, independent of the
-// order in which the slices finish.  k_hamming_decode then splits the key into (index, distance).
+// ---------------------------------------------------------------------------------------------------
+// Hamming distance on the tensor cores.  For bit vectors q, t:  |q xor t| = |q| + |t| - 2 <q, t>, and the
+// 2000 x 2000 x 256 table of dot products is GEMM-shaped, so the bits are widened to 0/1 bytes once
+// (k_expand) and the dot products come from int8 MMA (mma.sync m16n8k32 u8 x u8 -> s32, IMMA in SASS;
+// exact integer arithmetic).  Against the xor + POPC formulation this removes the POPC pipe (16
+// lanes/clk/SM) as the limit: one IMMA replaces 16 x 8 x 8 = 1024 POPCs.
+//
+// The reduction dimension may be permuted freely as long as both operands use the same permutation;
+// it is chosen so that every lane's operand bytes are 64 CONTIGUOUS bytes of an expanded row:
+//   MMA k-step s, fragment half h, lane column-group tig, byte b  <->  expanded byte 64 tig + 8 s + 4 h + b.
+// 1-NN: per query row minimise  |t| - 2 <q,t>  packed with the train index into one word
+//   key = (|t| + 512 - 2 <q,t>) << 22 | index      (10 + 22 bits)
+// so one IMAD + one unsigned min per accumulator keeps BFMatcher's "lowest trainIdx wins ties" rule,
+// and partial results of train slices merge with atomicMin.
+// ---------------------------------------------------------------------------------------------------
 #define MATCH_KEY_SHIFT 22
-__global__ void __launch_bounds__(MATCH_THREADS) k_hamming(const uint8_t *__restrict__ q, long long q_set_stride,
-                                                          const int32_t *__restrict__ nq_arr, int nq_stride,
-                                                          const uint8_t *__restrict__ t, long long t_set_stride,
-                                                          const int32_t *__restrict__ nt_arr, int nt_stride, int max_rows,
-                                                          uint32_t *__restrict__ out_key, long long out_stride, int nslices) {
-    __shared__ uint4 ts[MATCH_CHUNK * 2];
+#define MMA_QB 128          // query rows per CTA (4 warps x 2 m16 tiles)
+#define MMA_TC 64           // train rows per shared-memory chunk
+#define MMA_ROW 320         // padded expanded row in shared memory: 4 x (64 + 16) bytes, conflict-free LDS.128
+
+// Expanded operand rows: xq / xt [set][rows_pad][256] bytes (0/1), rows >= n are zero;
+// tkey[set][rows_pad] = (|t| + 512) << 22 | index  (0xffffffff for rows >= nt);  pq[set][rows_pad] = |q|.
+__global__ void __launch_bounds__(256) k_expand(const uint8_t *__restrict__ src, long long set_stride,
+                                               const int32_t *__restrict__ n_arr, int n_stride, int max_rows, int rows_pad,
+                                               uint8_t *__restrict__ dst, uint32_t *__restrict__ tkey, int32_t *__restrict__ pq) {
+    const int set = blockIdx.y;
+    const int n = min(n_arr[(long long)set * n_stride], max_rows);
+    const int row = blockIdx.x * 32 + (threadIdx.x >> 3), part = threadIdx.x & 7;  // 8 threads per row, one 32-bit word each
+    if (row >= rows_pad) return;
+    uint32_t w = 0;
+    if (row < n) w = reinterpret_cast<const uint32_t *>(src + (long long)set * set_stride + (long long)row * 32)[part];
+    uint4 lo, hi;  // bits 0..15 and 16..31 of the word as 0/1 bytes
+    lo.x = ((w >> 0) & 0xfu) * 0x00204081u & 0x01010101u;  lo.y = ((w >> 4) & 0xfu) * 0x00204081u & 0x01010101u;
+    lo.z = ((w >> 8) & 0xfu) * 0x00204081u & 0x01010101u;  lo.w = ((w >> 12) & 0xfu) * 0x00204081u & 0x01010101u;
+    hi.x = ((w >> 16) & 0xfu) * 0x00204081u & 0x01010101u; hi.y = ((w >> 20) & 0xfu) * 0x00204081u & 0x01010101u;
+    hi.z = ((w >> 24) & 0xfu) * 0x00204081u & 0x01010101u; hi.w = ((w >> 28) & 0xfu) * 0x00204081u & 0x01010101u;
+    uint4 *d = reinterpret_cast<uint4 *>(dst + ((long long)set * rows_pad + row) * 256 + part * 32);
+    d[0] = lo;
+    d[1] = hi;
+    int pc = __popc(w);
+    pc += __shfl_xor_sync(0xffffffffu, pc, 1);
+    pc += __shfl_xor_sync(0xffffffffu, pc, 2);
+    pc += __shfl_xor_sync(0xffffffffu, pc, 4);
+    if (part == 0) {
+        if (tkey) tkey[(long long)set * rows_pad + row] = row < n ? (((uint32_t)pc + 512u) << MATCH_KEY_SHIFT) | (uint32_t)row : 0xffffffffu;
+        if (pq) pq[(long long)set * rows_pad + row] = pc;
+    }
+}
+
+static __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// grid = (ceil(rows_pad / MMA_QB), nslices, batch); out_key pre-set to 0xffffffff.
+__global__ void __launch_bounds__(128) k_hamming_mma(const uint8_t *__restrict__ xq, const uint8_t *__restrict__ xt,
+                                                    const uint32_t *__restrict__ tkey, const int32_t *__restrict__ nq_arr,
+                                                    int nq_stride, const int32_t *__restrict__ nt_arr, int nt_stride,
+                                                    int max_rows, int rows_pad, uint32_t *__restrict__ out_key,
+                                                    long long out_stride, int nslices) {
+    __shared__ __align__(16) uint8_t ts[MMA_TC * MMA_ROW];
+    __shared__ uint32_t tk[MMA_TC];
     const int set = blockIdx.z;
     const int nq = min(nq_arr[(long long)set * nq_stride], max_rows);
     const int nt = min(nt_arr[(long long)set * nt_stride], max_rows);
-    const int q0 = blockIdx.x * MATCH_QB;
+    const int q0 = blockIdx.x * MMA_QB;
     if (q0 >= nq) return;
-    const int per = (((nt + nslices - 1) / nslices) + MATCH_CHUNK - 1) / MATCH_CHUNK * MATCH_CHUNK;  // rows per slice
+    const int per = (((nt + nslices - 1) / nslices) + MMA_TC - 1) / MMA_TC * MMA_TC;  // train rows per slice
     const int t_begin = blockIdx.y * per, t_end = min(nt, t_begin + per);
     if (t_begin >= t_end) return;
-    const uint4 *Q = reinterpret_cast<const uint4 *>(q + (long long)set * q_set_stride);
-    const uint4 *T = reinterpret_cast<const uint4 *>(t + (long long)set * t_set_stride);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+    const uint8_t *XQ = xq + (long long)set * rows_pad * 256, *XT = xt + (long long)set * rows_pad * 256;
+    const uint32_t *TK = tkey + (long long)set * rows_pad;
 
-    uint4 qa[MATCH_QPT], qb[MATCH_QPT];
-    int best[MATCH_QPT], bidx[MATCH_QPT];
+    // A fragments of this warp's 32 query rows, resident for the whole train loop: [tile][k-step][4]
+    uint32_t afr[2][8][4];
 #pragma unroll
-    for (int k = 0; k < MATCH_QPT; k++) {
-        const int qi = q0 + k * MATCH_THREADS + threadIdx.x;
-        const int qs = qi < nq ? qi : q0;  // idle lanes shadow a valid row; their result is not stored
-        qa[k] = Q[2 * qs];
-        qb[k] = Q[2 * qs + 1];
-        best[k] = 0x7fffffff;
-        bidx[k] = -1;
+    for (int m = 0; m < 2; m++) {
+        const int r0 = q0 + warp * 32 + m * 16 + g;  // rows r0 and r0 + 8 (always < rows_pad)
+        const uint4 *p0 = reinterpret_cast<const uint4 *>(XQ + (long long)r0 * 256 + 64 * tig);
+        const uint4 *p1 = reinterpret_cast<const uint4 *>(XQ + (long long)(r0 + 8) * 256 + 64 * tig);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {  // 16 bytes = k-steps 2i, 2i+1
+            const uint4 u = p0[i], v = p1[i];
+            afr[m][2 * i][0] = u.x; afr[m][2 * i][2] = u.y; afr[m][2 * i + 1][0] = u.z; afr[m][2 * i + 1][2] = u.w;
+            afr[m][2 * i][1] = v.x; afr[m][2 * i][3] = v.y; afr[m][2 * i + 1][1] = v.z; afr[m][2 * i + 1][3] = v.w;
+        }
     }
-    for (int c0 = t_begin; c0 < t_end; c0 += MATCH_CHUNK) {
-        const int cn = min(MATCH_CHUNK, t_end - c0);
+    uint32_t best[2][2] = {{0xffffffffu, 0xffffffffu}, {0xffffffffu, 0xffffffffu}};  // [tile][row g / row g + 8]
+
+    for (int c0 = t_begin; c0 < t_end; c0 += MMA_TC) {
         __syncthreads();
-        for (int i = threadIdx.x; i < cn * 2; i += MATCH_THREADS) ts[i] = T[2 * c0 + i];
+        // stage 64 expanded train rows (zero rows past nt come from k_expand's padding), re-pitched to MMA_ROW
+        for (int i = threadIdx.x; i < MMA_TC * 16; i += 128) {
+            const int r = i >> 4, q16 = i & 15;
+            const uint4 u = reinterpret_cast<const uint4 *>(XT + (long long)(c0 + r) * 256)[q16];
+            *reinterpret_cast<uint4 *>(ts + r * MMA_ROW + (q16 >> 2) * 80 + (q16 & 3) * 16) = u;
+        }
+        if (threadIdx.x < MMA_TC) tk[threadIdx.x] = c0 + threadIdx.x < t_end ? TK[c0 + threadIdx.x] : 0xffffffffu;
         __syncthreads();
-#pragma unroll 4
-        for (int j = 0; j < cn; j++) {
-            const uint4 ta = ts[2 * j], tb = ts[2 * j + 1];
+#pragma unroll 2
+        for (int n8 = 0; n8 < MMA_TC / 8; n8++) {
+            const uint4 *bp = reinterpret_cast<const uint4 *>(ts + (n8 * 8 + g) * MMA_ROW + tig * 80);
+            uint32_t bfr[16];
 #pragma unroll
-            for (int k = 0; k < MATCH_QPT; k++) {
-                const int d = __popc(qa[k].x ^ ta.x) + __popc(qa[k].y ^ ta.y) + __popc(qa[k].z ^ ta.z) +
-                              __popc(qa[k].w ^ ta.w) + __popc(qb[k].x ^ tb.x) + __popc(qb[k].y ^ tb.y) +
-                              __popc(qb[k].z ^ tb.z) + __popc(qb[k].w ^ tb.w);
-                if (d < best[k]) {  // strict: the first (lowest) train index wins ties
-                    best[k] = d;
-                    bidx[k] = c0 + j;
-                }
+            for (int i = 0; i < 4; i++) {
+                const uint4 u = bp[i];
+                bfr[4 * i] = u.x; bfr[4 * i + 1] = u.y; bfr[4 * i + 2] = u.z; bfr[4 * i + 3] = u.w;
+            }
+            const uint32_t k0 = tk[n8 * 8 + 2 * tig], k1 = tk[n8 * 8 + 2 * tig + 1];
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                int acc[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int s = 0; s < 8; s++) imma_16832(acc, afr[m][s], bfr[2 * s], bfr[2 * s + 1]);
+                // key - (dot << 23): rows past the slice carry 0xffffffff and a zero dot product
+                best[m][0] = min(best[m][0], min(k0 - ((uint32_t)acc[0] << 23), k1 - ((uint32_t)acc[1] << 23)));
+                best[m][1] = min(best[m][1], min(k0 - ((uint32_t)acc[2] << 23), k1 - ((uint32_t)acc[3] << 23)));
             }
         }
     }
 #pragma unroll
-    for (int k = 0; k < MATCH_QPT; k++) {
-        const int qi = q0 + k * MATCH_THREADS + threadIdx.x;
-        if (qi < nq && bidx[k] >= 0)
-            atomicMin(&out_key[(long long)set * out_stride + qi], ((uint32_t)best[k] << MATCH_KEY_SHIFT) | (uint32_t)bidx[k]);
-    }
+    for (int m = 0; m < 2; m++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            uint32_t b = best[m][h];
+            b = min(b, __shfl_xor_sync(0xffffffffu, b, 1));
+            b = min(b, __shfl_xor_sync(0xffffffffu, b, 2));
+            const int row = q0 + warp * 32 + m * 16 + h * 8 + g;
+            if (tig == 0 && row < nq && b != 0xffffffffu) atomicMin(&out_key[(long long)set * out_stride + row], b);
+        }
 }
 
 __global__ void k_hamming_init(const int32_t *__restrict__ nq_arr, int nq_stride, int max_rows, uint32_t *out_key,
@@ -89,20 +161,21 @@ __global__ void k_hamming_init(const int32_t *__restrict__ nq_arr, int nq_stride
     if (qi < min(nq_arr[(long long)set * nq_stride], max_rows)) out_key[(long long)set * out_stride + qi] = 0xffffffffu;
 }
 
-__global__ void k_hamming_decode(const int32_t *__restrict__ nq_arr, int nq_stride, int max_rows, int32_t *idx_key,
-                                 int32_t *out_dist, long long out_stride) {
+// key -> (train index, distance = |q| + (key >> 22) - 512)
+__global__ void k_hamming_decode(const int32_t *__restrict__ nq_arr, int nq_stride, int max_rows, int rows_pad,
+                                 const int32_t *__restrict__ pq, int32_t *idx_key, int32_t *out_dist, long long out_stride) {
     const int set = blockIdx.y, qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= min(nq_arr[(long long)set * nq_stride], max_rows)) return;
     const uint32_t key = (uint32_t)idx_key[(long long)set * out_stride + qi];
     const bool none = key == 0xffffffffu;
     idx_key[(long long)set * out_stride + qi] = none ? -1 : (int32_t)(key & ((1u << MATCH_KEY_SHIFT) - 1u));
-    out_dist[(long long)set * out_stride + qi] = none ? -1 : (int32_t)(key >> MATCH_KEY_SHIFT);
+    out_dist[(long long)set * out_stride + qi] = none ? -1 : (int32_t)(key >> MATCH_KEY_SHIFT) - 512 + pq[(long long)set * rows_pad + qi];
 }
 
 static void free_matcher(sb_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    void *ptrs[] = {m->d_q, m->d_t, m->d_nq, m->d_nt, m->d_idx, m->d_dist};
+    void *ptrs[] = {m->d_q, m->d_t, m->d_nq, m->d_nt, m->d_idx, m->d_dist, m->d_xq, m->d_xt, m->d_tkey, m->d_pq};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -128,6 +201,12 @@ extern "C" int sb_matcher_create(sb_matcher_t **out, int device, int max_batch, 
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_nt, (size_t)max_batch * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_idx, rows * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_dist, rows * 4);
+    m->rows_pad = (int)sb_align_up((size_t)max_rows, MMA_QB);
+    const size_t prow = (size_t)max_batch * m->rows_pad;
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_xq, prow * 256);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_xt, prow * 256);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_tkey, prow * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_pq, prow * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         sb_set_error("sb_matcher_create: %s", cudaGetErrorString(e));
@@ -166,17 +245,21 @@ extern "C" int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d
     SB_REQUIRE(((uintptr_t)d_q & 15) == 0 && ((uintptr_t)d_t & 15) == 0 && (q_set_stride & 15) == 0 && (t_set_stride & 15) == 0,
                "descriptor sets must be 16-byte aligned");
     SB_TRY(sb_use_device(m->device));
+    SB_REQUIRE(batch <= m->max_batch && max_rows <= m->max_rows, "batch / max_rows larger than given at create time");
+    const int rp = m->rows_pad;
+    k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_q, q_set_stride, d_nq, nq_stride, max_rows, rp, m->d_xq, nullptr, m->d_pq);
+    k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_t, t_set_stride, d_nt, nt_stride, max_rows, rp, m->d_xt, m->d_tkey, nullptr);
     // enough CTAs to fill 148 SMs: slice the train set when the batch alone does not
-    const int qblocks = sb_div_up(max_rows, MATCH_QB);
+    const int qblocks = sb_div_up(max_rows, MMA_QB);
     int nslices = 1;
-    while (nslices < 8 && (long long)qblocks * batch * nslices < 148 * 12 && max_rows / (nslices * 2) >= MATCH_CHUNK) nslices *= 2;
+    while (nslices < 16 && (long long)qblocks * batch * nslices < 148 * 8 && max_rows / (nslices * 2) >= MMA_TC) nslices *= 2;
     k_hamming_init<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows,
                                                                                  reinterpret_cast<uint32_t *>(d_train_idx), out_stride);
-    k_hamming<<<dim3(qblocks, nslices, batch), MATCH_THREADS, 0, m->stream>>>(d_q, q_set_stride, d_nq, nq_stride, d_t, t_set_stride,
-                                                                              d_nt, nt_stride, max_rows,
-                                                                              reinterpret_cast<uint32_t *>(d_train_idx), out_stride, nslices);
-    k_hamming_decode<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows, d_train_idx, d_dist,
-                                                                                   out_stride);
+    k_hamming_mma<<<dim3(qblocks, nslices, batch), 128, 0, m->stream>>>(m->d_xq, m->d_xt, m->d_tkey, d_nq, nq_stride, d_nt, nt_stride,
+                                                                        max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx),
+                                                                        out_stride, nslices);
+    k_hamming_decode<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows, rp, m->d_pq, d_train_idx,
+                                                                                   d_dist, out_stride);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }
