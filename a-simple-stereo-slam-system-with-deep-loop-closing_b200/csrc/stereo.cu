@@ -97,13 +97,17 @@ extern "C" int sb_stereo_submit(sb_stereo_t *h, int pairs, const uint8_t *images
     SB_REQUIRE(w >= 62 && w <= h->max_w && hgt >= 62 && hgt <= h->max_h && stride >= w, "bad image size / stride");
     SB_REQUIRE(!h->pending, "previous batch not waited for");
     SB_TRY(sb_use_device(h->device));
-    const size_t row = sb_align_up((size_t)w, 16), plane = row * hgt;
-    if ((size_t)stride == row && (size_t)view_pitch == plane && (size_t)frame_pitch == 2 * plane) {
+    // Staging: when the planes are equally spaced the whole batch is ONE contiguous copy (rows keep the
+    // caller's stride; the extractor's level-0 kernel re-pitches on the device — a 2-D copy with 1241-byte
+    // rows would cost one DMA descriptor per row).  Otherwise plane-by-plane 2-D copies.
+    const size_t row = sb_align_up((size_t)w, 16), plane_cap = sb_align_up((size_t)h->max_w, 16) * h->max_h;
+    size_t plane = row * hgt;
+    int dev_stride = (int)row;
+    if ((size_t)view_pitch == (size_t)stride * hgt && (size_t)frame_pitch == 2 * (size_t)view_pitch &&
+        (size_t)stride * hgt <= plane_cap) {
+        plane = (size_t)stride * hgt;
+        dev_stride = stride;
         SB_CUDA(cudaMemcpyAsync(h->d_img, images, (size_t)pairs * 2 * plane, cudaMemcpyHostToDevice, h->stream));
-    } else if ((size_t)view_pitch == (size_t)stride * hgt && (size_t)frame_pitch == 2 * (size_t)view_pitch) {
-        // all planes are equally spaced rows: one strided copy for the whole batch
-        SB_CUDA(cudaMemcpy2DAsync(h->d_img, row, images, (size_t)stride, (size_t)w, (size_t)hgt * 2 * pairs,
-                                  cudaMemcpyHostToDevice, h->stream));
     } else {
         for (int p = 0; p < pairs; p++)
             for (int v = 0; v < 2; v++)
@@ -111,7 +115,7 @@ extern "C" int sb_stereo_submit(sb_stereo_t *h, int pairs, const uint8_t *images
                                           (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, h->stream));
     }
     const int cap = h->cap;
-    SB_TRY(sb_orb_detect_and_compute_dev(h->orb, 2 * pairs, h->d_img, (int64_t)plane, nullptr, 0, w, hgt, (int)row, 0, h->d_kps,
+    SB_TRY(sb_orb_detect_and_compute_dev(h->orb, 2 * pairs, h->d_img, (int64_t)plane, nullptr, 0, w, hgt, dev_stride, 0, h->d_kps,
                                          h->d_desc, h->d_counts, cap));
     SB_TRY(sb_hamming_match_dev(h->mat, pairs, h->d_desc, (int64_t)2 * cap * 32, h->d_counts, 2, h->d_desc + (size_t)cap * 32,
                                 (int64_t)2 * cap * 32, h->d_counts + 1, 2, cap, h->d_midx, h->d_mdist, cap));
