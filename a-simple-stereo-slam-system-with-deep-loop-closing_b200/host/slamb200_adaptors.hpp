@@ -1,0 +1,337 @@
+// slamb200_adaptors.hpp — C++ host side above the C ABI (include/slamb200.h): drop-in replacements for the
+// operator classes of the reference's libmyslam.so, keeping their names, signatures, argument meaning and
+// error behaviour (silent return on empty input, no exceptions, no status codes) so that the three thread
+// classes (Frontend, Backend, LoopClosing) compile against them unchanged.
+//
+//   myslam::ORBextractor               include/myslam/ORBextractor.h:47-138  (src/ORBextractor.cpp)
+//   myslam::HammingMatcher::match      cv::DescriptorMatcher::match as used at src/loopclosing.cpp:33,172
+//   myslam::LocalBASolver              the g2o block of Backend::OptimizeActiveMap, src/backend.cpp:126-269
+//   myslam::DeepLCDScorer              DeepLCD::score + LoopClosing::DetectLoop, src/deeplcd.cpp:35-39,
+//                                      src/loopclosing.cpp:124-161
+//   myslam::PoseGraphSolver            the g2o block of LoopClosing::PoseGraphOptimization, :537-646
+//
+// With OpenCV present (the reference's build) the classes take cv::InputArray / cv::KeyPoint / cv::Mat.
+// Without it (this repository's CI, which has no OpenCV C++ headers) a minimal stand-in with the same
+// field layout is used so that the header still compiles and is exercised by tests/host_adaptor_test.cpp.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/slamb200.h"
+
+#if defined(SLAMB200_WITH_OPENCV) || (defined(__has_include) && __has_include(<opencv2/core.hpp>) && !defined(SLAMB200_NO_OPENCV))
+#include <opencv2/core.hpp>
+#define SLAMB200_CV 1
+#else
+#define SLAMB200_CV 0
+namespace cv {  // field-for-field stand-ins, only what the adaptors touch
+struct Point2f { float x = 0, y = 0; };
+struct KeyPoint {
+    Point2f pt;
+    float size = 0, angle = -1, response = 0;
+    int octave = 0, class_id = -1;
+};
+struct DMatch { int queryIdx = -1, trainIdx = -1, imgIdx = -1; float distance = 0; };
+struct Mat {  // CV_8UC1 view or owner
+    int rows = 0, cols = 0;
+    size_t step = 0;
+    uint8_t *data = nullptr;
+    std::shared_ptr<std::vector<uint8_t>> own;
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    void create(int r, int c) { own = std::make_shared<std::vector<uint8_t>>((size_t)r * c); data = own->data(); rows = r; cols = c; step = (size_t)c; }
+    void release() { own.reset(); data = nullptr; rows = cols = 0; step = 0; }
+    uint8_t *ptr(int r) { return data + (size_t)r * step; }
+    const uint8_t *ptr(int r) const { return data + (size_t)r * step; }
+};
+typedef const Mat &InputArray;
+typedef Mat &OutputArray;
+}  // namespace cv
+#endif
+
+namespace myslam {
+
+namespace detail {
+inline const cv::Mat &as_mat(const cv::Mat &m) { return m; }
+#if SLAMB200_CV
+inline cv::Mat as_mat(cv::InputArray a) { return a.getMat(); }
+#endif
+static_assert(sizeof(sb_keypoint) == 28, "sb_keypoint must mirror cv::KeyPoint");
+inline sb_keypoint to_sb(const cv::KeyPoint &k) { return sb_keypoint{k.pt.x, k.pt.y, k.size, k.angle, k.response, k.octave, k.class_id}; }
+inline cv::KeyPoint from_sb(const sb_keypoint &k) {
+    cv::KeyPoint o;
+    o.pt.x = k.x; o.pt.y = k.y; o.size = k.size; o.angle = k.angle; o.response = k.response; o.octave = k.octave; o.class_id = k.class_id;
+    return o;
+}
+// The reference logs with glog and carries on; the adaptors keep the last C-ABI status readable instead.
+inline int &last_status() { static thread_local int s = SB_OK; return s; }
+}  // namespace detail
+
+// -----------------------------------------------------------------------------------------------------
+class ORBextractor {
+public:
+    typedef std::shared_ptr<ORBextractor> Ptr;
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    // max_w / max_h bound the images this instance will see (device memory is reserved once); the
+    // reference has no such limit, so the default covers KITTI and EuRoC.
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int max_w = 1280, int max_h = 1024,
+                 int device = 0)
+        : nfeatures(nfeatures), scaleFactor(scaleFactor), nlevels(nlevels), iniThFAST(iniThFAST), minThFAST(minThFAST) {
+        // the reference shares one ORBextractor between the front-end thread (Detect) and the loop-closing
+        // thread (ScreenAndComputeKPsParams / CalcDescriptors), src/system.cpp:54,66: one handle per caller
+        for (sb_orb_t **h : {&h_detect_, &h_pyramid_}) {
+            int rc = sb_orb_create(h, device, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, max_w, max_h, 1);
+            if (rc != SB_OK) throw std::runtime_error(std::string("sb_orb_create: ") + sb_last_error());  // a constructor cannot return
+        }
+        int n = 0;
+        mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels); mvLevelSigma2.resize(nlevels);
+        mvInvLevelSigma2.resize(nlevels); mnFeaturesPerLevel.resize(nlevels);
+        sb_orb_get_tables(h_pyramid_, &n, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                          mvInvLevelSigma2.data(), mnFeaturesPerLevel.data());
+        cap_ = sb_orb_capacity(h_pyramid_);
+    }
+    ~ORBextractor() { sb_orb_destroy(h_detect_); sb_orb_destroy(h_pyramid_); }
+    ORBextractor(const ORBextractor &) = delete;
+    ORBextractor &operator=(const ORBextractor &) = delete;
+
+    // src/ORBextractor.cpp:922-985
+    void DetectAndCompute(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint> &keypoints, cv::OutputArray _descriptors) {
+        const cv::Mat image = detail::as_mat(_image), mask = detail::as_mat(_mask);
+        if (image.empty()) return;
+        run_pyramid(image, mask, keypoints, &_descriptors);
+    }
+    // :1135-1176
+    void DetectWithPyramid(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint> &keypoints) {
+        const cv::Mat image = detail::as_mat(_image), mask = detail::as_mat(_mask);
+        if (image.empty()) return;
+        run_pyramid(image, mask, keypoints, nullptr);
+    }
+    // :989-1074 — re-entrant with respect to the two methods below (own handle)
+    void Detect(cv::InputArray _image, cv::InputArray _mask, std::vector<cv::KeyPoint> &keypoints) {
+        const cv::Mat image = detail::as_mat(_image), mask = detail::as_mat(_mask);
+        if (image.empty() || mask.empty()) return;
+        std::vector<sb_keypoint> k((size_t)cap_);
+        int32_t n = 0;
+        const uint8_t *ip = image.data, *mp = mask.data;
+        detail::last_status() = sb_orb_detect(h_detect_, 1, &ip, &mp, image.cols, image.rows, (int)image.step, (int)mask.step, k.data(), &n, cap_);
+        keypoints.clear();
+        if (detail::last_status() != SB_OK) return;
+        for (int i = 0; i < n; i++) keypoints.push_back(detail::from_sb(k[i]));
+    }
+    // :1083-1129 — mutates _keypoints exactly like the reference
+    void ScreenAndComputeKPsParams(cv::InputArray _image, std::vector<cv::KeyPoint> &_keypoints, std::vector<cv::KeyPoint> &out_keypoints) {
+        const cv::Mat image = detail::as_mat(_image);
+        if (image.empty() || _keypoints.empty()) return;
+        std::vector<sb_keypoint> in(_keypoints.size()), out(_keypoints.size());
+        for (size_t i = 0; i < in.size(); i++) in[i] = detail::to_sb(_keypoints[i]);
+        int32_t n = 0;
+        detail::last_status() = sb_orb_screen_params(h_pyramid_, image.data, image.cols, image.rows, (int)image.step, in.data(), (int)in.size(), out.data(), &n);
+        out_keypoints.clear();
+        if (detail::last_status() != SB_OK) return;
+        for (size_t i = 0; i < in.size(); i++) _keypoints[i] = detail::from_sb(in[i]);
+        for (int i = 0; i < n; i++) out_keypoints.push_back(detail::from_sb(out[i]));
+    }
+    // :1180-1226
+    void CalcDescriptors(cv::InputArray _image, const std::vector<cv::KeyPoint> &_keypoints, cv::OutputArray _descriptors) {
+        const cv::Mat image = detail::as_mat(_image);
+        if (image.empty() || _keypoints.empty()) return;
+        std::vector<sb_keypoint> k(_keypoints.size());
+        for (size_t i = 0; i < k.size(); i++) k[i] = detail::to_sb(_keypoints[i]);
+        std::vector<uint8_t> d(k.size() * 32);
+        detail::last_status() = sb_orb_calc_descriptors(h_pyramid_, image.data, image.cols, image.rows, (int)image.step, k.data(), (int)k.size(), d.data());
+        if (detail::last_status() != SB_OK) return;
+        store_descriptors(_descriptors, d.data(), (int)k.size());
+    }
+
+    int GetLevels() { return nlevels; }
+    float GetScaleFactor() { return (float)scaleFactor; }
+    std::vector<float> GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+    // The reference exposes mvImagePyramid / mvMaskPyramid as public members; here the levels live on the
+    // device and are copied out on demand (which: 0 image, 1 blurred, 2 mask).
+    bool GetPyramidLevel(int level, int which, cv::Mat &out) {
+        int lw = 0, lh = 0;
+        if (sb_orb_debug_level(h_pyramid_, 0, level, which, nullptr, 0, &lw, &lh) != SB_OK) return false;
+        mat_create(out, lh, lw);
+        return sb_orb_debug_level(h_pyramid_, 0, level, which, out.data, lw * lh, &lw, &lh) == SB_OK;
+    }
+
+protected:
+    static void mat_create(cv::Mat &m, int rows, int cols) {
+#if SLAMB200_CV
+        m.create(rows, cols, CV_8UC1);
+#else
+        m.create(rows, cols);
+#endif
+    }
+    typedef std::remove_reference<cv::OutputArray>::type OutArrT;
+    static void store_descriptors(OutArrT &dst, const uint8_t *d, int n) {
+#if SLAMB200_CV
+        dst.create(n, 32, CV_8U);
+        cv::Mat m = dst.getMat();
+        for (int i = 0; i < n; i++) std::memcpy(m.ptr(i), d + (size_t)i * 32, 32);
+#else
+        dst.create(n, 32);
+        for (int i = 0; i < n; i++) std::memcpy(dst.ptr(i), d + (size_t)i * 32, 32);
+#endif
+    }
+    void run_pyramid(const cv::Mat &image, const cv::Mat &mask, std::vector<cv::KeyPoint> &keypoints, OutArrT *descriptors) {
+        std::vector<sb_keypoint> k((size_t)cap_);
+        std::vector<uint8_t> d(descriptors ? (size_t)cap_ * 32 : 0);
+        int32_t n = 0;
+        const uint8_t *ip = image.data, *mp = mask.empty() ? nullptr : mask.data;
+        detail::last_status() = sb_orb_detect_and_compute(h_pyramid_, 1, &ip, mp ? &mp : nullptr, image.cols, image.rows, (int)image.step,
+                                                          mp ? (int)mask.step : 0, k.data(), descriptors ? d.data() : nullptr, &n, cap_);
+        keypoints.clear();
+        if (detail::last_status() != SB_OK) return;
+        keypoints.reserve(n);
+        for (int i = 0; i < n; i++) keypoints.push_back(detail::from_sb(k[i]));
+        if (descriptors) {
+            if (n == 0) descriptors->release();
+            else store_descriptors(*descriptors, d.data(), n);
+        }
+    }
+
+    int nfeatures;
+    double scaleFactor;  // a double holding the float argument, like the reference (ORBextractor.h:125)
+    int nlevels, iniThFAST, minThFAST;
+    std::vector<int> mnFeaturesPerLevel;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+    sb_orb_t *h_detect_ = nullptr, *h_pyramid_ = nullptr;
+    int cap_ = 0;
+};
+
+// -----------------------------------------------------------------------------------------------------
+// cv::DescriptorMatcher::create("BruteForce-Hamming")->match(query, train, matches)  (src/loopclosing.cpp:33,172)
+class HammingMatcher {
+public:
+    explicit HammingMatcher(int max_rows = 8192, int device = 0) : max_rows_(max_rows) {
+        if (sb_matcher_create(&h_, device, 1, max_rows) != SB_OK) throw std::runtime_error(std::string("sb_matcher_create: ") + sb_last_error());
+    }
+    ~HammingMatcher() { sb_matcher_destroy(h_); }
+    void match(cv::InputArray _query, cv::InputArray _train, std::vector<cv::DMatch> &matches) {
+        const cv::Mat q = detail::as_mat(_query), t = detail::as_mat(_train);
+        matches.clear();
+        if (q.empty() || t.empty()) return;
+        const int cap = q.rows > t.rows ? q.rows : t.rows;
+        std::vector<uint8_t> qb((size_t)cap * 32), tb((size_t)cap * 32);
+        for (int i = 0; i < q.rows; i++) std::memcpy(&qb[(size_t)i * 32], q.ptr(i), 32);
+        for (int i = 0; i < t.rows; i++) std::memcpy(&tb[(size_t)i * 32], t.ptr(i), 32);
+        std::vector<int32_t> idx(cap), dist(cap);
+        const int32_t nq = q.rows, nt = t.rows;
+        detail::last_status() = sb_hamming_match(h_, 1, qb.data(), &nq, tb.data(), &nt, cap, idx.data(), dist.data());
+        if (detail::last_status() != SB_OK) return;
+        for (int i = 0; i < nq; i++) {
+            cv::DMatch m;
+            m.queryIdx = i; m.trainIdx = idx[i]; m.imgIdx = 0; m.distance = (float)dist[i];
+            matches.push_back(m);
+        }
+    }
+private:
+    sb_matcher_t *h_ = nullptr;
+    int max_rows_;
+};
+
+// -----------------------------------------------------------------------------------------------------
+// The solver of Backend::OptimizeActiveMap.  The Backend keeps its graph-building loops (src/backend.cpp:135-206)
+// but fills these flat arrays instead of g2o vertices/edges, calls Optimize(), and reads poses, points and the
+// per-edge chi2 back for its outlier handling and write-back (:236-266).
+struct LocalBAProblem {
+    std::vector<double> poses;       // [n_poses][7] qx qy qz qw tx ty tz  (Sophus::SE3d::data() order)
+    std::vector<double> points;      // [n_points][3]
+    std::vector<uint8_t> fixed;      // [n_points]
+    std::vector<int32_t> obs_pose, obs_point;
+    std::vector<double> uv;          // [n_obs][2]
+    double K[4] = {0, 0, 0, 0};      // fx fy cx cy
+    double cam_ext[7] = {0, 0, 0, 1, 0, 0, 0};
+    std::vector<double> chi2;        // out
+    std::vector<uint8_t> outlier;    // out
+    int info[4] = {0, 0, 0, 0};      // out: outer rounds, LM iterations, inliers, outliers
+};
+
+class LocalBASolver {
+public:
+    LocalBASolver(int max_poses = 7, int max_points = 4096, int max_obs = 32768, int device = 0)
+        : mp_(max_poses), ml_(max_points), mo_(max_obs) {
+        if (sb_ba_create(&h_, device, 1, max_poses, max_points, max_obs) != SB_OK) throw std::runtime_error(std::string("sb_ba_create: ") + sb_last_error());
+    }
+    ~LocalBASolver() { sb_ba_destroy(h_); }
+    // chi2_th 5.991, Huber delta 5.991, up to 5 rounds of optimize(10): src/backend.cpp:155,198-200,212-232
+    bool Optimize(LocalBAProblem &p, double huber_delta = 5.991, double chi2_th = 5.991, int outer_max = 5, int inner_iters = 10) {
+        const int32_t np = (int32_t)(p.poses.size() / 7), nl = (int32_t)(p.points.size() / 3), ne = (int32_t)p.obs_pose.size();
+        if (np > mp_ || nl > ml_ || ne > mo_) { detail::last_status() = SB_ERR_CAPACITY; return false; }
+        std::vector<double> poses((size_t)mp_ * 7, 0.0), points((size_t)ml_ * 3, 0.0), uv((size_t)mo_ * 2, 0.0), chi2((size_t)mo_);
+        std::vector<uint8_t> fixed((size_t)ml_, 0), outl((size_t)mo_);
+        std::vector<int32_t> op((size_t)mo_, 0), ol((size_t)mo_, 0);
+        std::copy(p.poses.begin(), p.poses.end(), poses.begin());
+        std::copy(p.points.begin(), p.points.end(), points.begin());
+        std::copy(p.fixed.begin(), p.fixed.end(), fixed.begin());
+        std::copy(p.obs_pose.begin(), p.obs_pose.end(), op.begin());
+        std::copy(p.obs_point.begin(), p.obs_point.end(), ol.begin());
+        std::copy(p.uv.begin(), p.uv.end(), uv.begin());
+        detail::last_status() = sb_ba_solve(h_, 1, &np, &nl, &ne, poses.data(), points.data(), fixed.data(), op.data(), ol.data(), uv.data(),
+                                            p.K, p.cam_ext, huber_delta, chi2_th, outer_max, inner_iters, chi2.data(), outl.data(), p.info);
+        if (detail::last_status() != SB_OK) return false;
+        std::copy(poses.begin(), poses.begin() + (size_t)np * 7, p.poses.begin());
+        std::copy(points.begin(), points.begin() + (size_t)nl * 3, p.points.begin());
+        p.chi2.assign(chi2.begin(), chi2.begin() + ne);
+        p.outlier.assign(outl.begin(), outl.begin() + ne);
+        return true;
+    }
+private:
+    sb_ba_t *h_ = nullptr;
+    int mp_, ml_, mo_;
+};
+
+// -----------------------------------------------------------------------------------------------------
+// DeepLCD::score over the database + the scan of LoopClosing::DetectLoop (src/loopclosing.cpp:124-161).
+class DeepLCDScorer {
+public:
+    explicit DeepLCDScorer(int capacity = 4096, bool fp16_database = true, int device = 0) {
+        if (sb_lcd_create(&h_, device, capacity, fp16_database ? SB_LCD_FP16 : SB_LCD_FP32, 1) != SB_OK)
+            throw std::runtime_error(std::string("sb_lcd_create: ") + sb_last_error());
+    }
+    ~DeepLCDScorer() { sb_lcd_destroy(h_); }
+    void AddToDatabase(unsigned long kfId, const float *descr1064) { detail::last_status() = sb_lcd_add(h_, (int64_t)kfId, descr1064); }
+    void Erase(unsigned long kfId) { detail::last_status() = sb_lcd_remove(h_, (int64_t)kfId); }
+    // returns true and the candidate id when the reference's DetectLoop would (thresholds: yaml LCD.similarityScoreThreshold.*)
+    bool DetectLoop(unsigned long curKFId, const float *descr1064, float thresHigh, float thresLow, unsigned long &bestId, float &maxScore) {
+        int found = 0, cnt = 0;
+        int64_t best = 0;
+        detail::last_status() = sb_lcd_detect_loop(h_, (int64_t)curKFId, descr1064, thresHigh, thresLow, 20, 3, &found, &best, &maxScore, &cnt);
+        bestId = (unsigned long)best;
+        return detail::last_status() == SB_OK && found != 0;
+    }
+private:
+    sb_lcd_t *h_ = nullptr;
+};
+
+// -----------------------------------------------------------------------------------------------------
+// The solver of LoopClosing::PoseGraphOptimization (src/loopclosing.cpp:537-646): vertices in ascending keyframe id.
+class PoseGraphSolver {
+public:
+    PoseGraphSolver(int max_vertices = 8192, int max_edges = 16384, int device = 0) {
+        if (sb_posegraph_create(&h_, device, max_vertices, max_edges) != SB_OK) throw std::runtime_error(std::string("sb_posegraph_create: ") + sb_last_error());
+    }
+    ~PoseGraphSolver() { sb_posegraph_destroy(h_); }
+    bool Optimize(std::vector<double> &poses7, const std::vector<uint8_t> &fixed, const std::vector<int32_t> &v0, const std::vector<int32_t> &v1,
+                  const std::vector<double> &meas7, int iters = 20) {
+        int32_t info[4];
+        double stats[2];
+        detail::last_status() = sb_posegraph_solve(h_, (int)(poses7.size() / 7), poses7.data(), fixed.data(), (int)v0.size(), v0.data(), v1.data(),
+                                                   meas7.data(), iters, info, stats);
+        return detail::last_status() == SB_OK;
+    }
+private:
+    sb_posegraph_t *h_ = nullptr;
+};
+
+}  // namespace myslam
