@@ -156,14 +156,17 @@ struct FastArgs {
 
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ TmaMaps maps,
                                                             const __grid_constant__ Geom g, FastArgs a) {
-    extern __shared__ uint8_t smem_raw[];
+    // dynamic shared memory: [tile | response plane | maxima list | candidate-pixel list]; the array keeps its
+    // shared address space through plain pointer arithmetic (an integer round trip would demote every
+    // access to generic LD/ST with 64-bit address math)
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int s_n, s_any, s_np;
-    uint8_t *tile = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);  // TMA destination
-    uint8_t *sc = tile + a.tile_bytes;
-    uint32_t *list = reinterpret_cast<uint32_t *>(tile + 2 * a.tile_bytes);
-    uint16_t *plist = reinterpret_cast<uint16_t *>(tile + 2 * a.tile_bytes + SB_CELL_LIST_CAP * 4);  // <= one entry per tile pixel
-
+    uint8_t *tile = smem;  // TMA destination, 128-byte aligned
+    uint8_t *sc = smem + a.tile_bytes;
+    uint32_t *list = reinterpret_cast<uint32_t *>(smem + 2 * a.tile_bytes);
+    uint16_t *plist = reinterpret_cast<uint16_t *>(smem + 2 * a.tile_bytes + SB_CELL_LIST_CAP * 4);  // <= one entry per tile pixel
+    if (threadIdx.x == 0 && (sb_smem_u32(tile) & 127u)) __trap();
     const Cell c = a.cells[blockIdx.x];
     const int img = blockIdx.y;
     const LevelGeom &L = g.lv[c.level];
@@ -432,20 +435,29 @@ static __device__ __forceinline__ float warp_ic_angle(const uint8_t *center, int
     return sb_fast_atan2((float)m01, (float)m10);
 }
 
+// The 256 test pairs as floats in shared memory, transposed so that lane i's j-th pair (pair 8i + j) sits
+// at [j * 32 + i]: conflict-free 16-byte loads, no int8 -> float conversions in the loop.
+static __device__ __forceinline__ void load_pattern(float4 *pat) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int8_t *q = d_pattern + 4 * i;
+        pat[(i & 7) * 32 + (i >> 3)] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
+    }
+}
+
 // computeOrbDescriptor (:59-98): lane i produces byte i (pairs 8i .. 8i+7).
 static __device__ __forceinline__ uint32_t warp_brief_byte(const uint8_t *center, int pitch, float angle_deg,
-                                                           const int8_t *pat, int lane) {
+                                                           const float4 *pat, int lane) {
     const float factorPI = (float)(3.14159265358979323846 / 180.f);
     const float ang = sb_fmul(angle_deg, factorPI);
     double sn, cs;
     sincos((double)ang, &sn, &cs);
     const float a = (float)cs, b = (float)sn;
-    const int8_t *q = pat + lane * 32;
     uint32_t val = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const int t0 = sb_brief_sample(center, pitch, a, b, (float)q[4 * j], (float)q[4 * j + 1]);
-        const int t1 = sb_brief_sample(center, pitch, a, b, (float)q[4 * j + 2], (float)q[4 * j + 3]);
+        const float4 q = pat[j * 32 + lane];
+        const int t0 = sb_brief_sample(center, pitch, a, b, q.x, q.y);
+        const int t1 = sb_brief_sample(center, pitch, a, b, q.z, q.w);
         val |= (uint32_t)(t0 < t1) << j;
     }
     return val;
@@ -480,8 +492,8 @@ struct DescArgs {
 };
 
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, DescArgs a) {
-    __shared__ int8_t pat[1024];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t *>(pat)[i] = reinterpret_cast<const uint32_t *>(d_pattern)[i];
+    __shared__ float4 pat[256];
+    load_pattern(pat);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int level = blockIdx.y, img = blockIdx.z;
@@ -592,8 +604,8 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_screen(const __grid_constan
 // CalcDescriptors (:1180-1226): row i = descriptor of keypoint i on the blurred level `octave`.
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_calc_desc(const __grid_constant__ Geom g, const uint8_t *blur,
                                                               const sb_keypoint *kps, int n, uint8_t *desc) {
-    __shared__ int8_t pat[1024];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint32_t *>(pat)[i] = reinterpret_cast<const uint32_t *>(d_pattern)[i];
+    __shared__ float4 pat[256];
+    load_pattern(pat);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
