@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     // access to generic LD/ST with 64-bit address math)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_n, s_any, s_np;
+    __shared__ int s_n, s_any, s_cnt[FAST_THREADS / 32];
     uint8_t *tile = smem;  // TMA destination, 128-byte aligned
     uint8_t *sc = smem + a.tile_bytes;
     uint32_t *list = reinterpret_cast<uint32_t *>(smem + 2 * a.tile_bytes);
@@ -177,7 +177,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     if (tid == 0) {
         s_n = 0;
         s_any = 0;
-        s_np = 0;
         sb_mbar_init(&bar, 1);
         sb_mbar_expect_tx(&bar, (uint32_t)(BW * BH));
         sb_tma_load_3d(tile, &maps.m[c.level], c.x0 - xo, c.y0, img, &bar);
@@ -188,35 +187,42 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
 
     // Phase 1: pixels that pass the cheap necessary test are compacted into a list, so that the response
     // (about 100 instructions) is later computed by full warps instead of a few lanes of every warp.
+    // Every warp appends to its own segment of the list with a warp-uniform running count: no atomics.
     const int t0 = min(a.iniTh, a.minTh);
-    for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
-        for (int xb = 3; xb < c.rw - 3; xb += 32) {
-            const int x = xb + lane;
-            const bool m = x < c.rw - 3 && sb_fast_maybe(tile + y * BW + xo + x, BW, t0);
-            const unsigned bal = __ballot_sync(0xffffffffu, m);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_np, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (m) plist[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)((y << 8) | x);
+    const int seg = a.tile_bytes >> 2;
+    {
+        uint16_t *mine = plist + warp * seg;
+        int cnt = 0;
+        const unsigned lt = (1u << lane) - 1u;
+        for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
+            for (int xb = 3; xb < c.rw - 3; xb += 32) {
+                const int x = xb + lane;
+                const bool m = x < c.rw - 3 && sb_fast_maybe(tile + y * BW + xo + x, BW, t0);
+                const unsigned bal = __ballot_sync(0xffffffffu, m);
+                if (m) mine[cnt + __popc(bal & lt)] = (uint16_t)((y << 8) | x);
+                cnt += __popc(bal);
             }
-        }
+        if (lane == 0) s_cnt[warp] = cnt;
+    }
     __syncthreads();
-    const int np = s_np;
+    const int c0 = s_cnt[0], c1 = c0 + s_cnt[1], c2 = c1 + s_cnt[2], np = c2 + s_cnt[3];
     // Phase 2: responses of the listed pixels
     for (int i = tid; i < np; i += FAST_THREADS) {
-        const int y = plist[i] >> 8, x = plist[i] & 255;
+        const int e = i < c0 ? plist[i] : i < c1 ? plist[seg + i - c0] : i < c2 ? plist[2 * seg + i - c1] : plist[3 * seg + i - c2];
+        const int y = e >> 8, x = e & 255;
         const int s = sb_fast_score(tile + y * BW + xo + x, BW);
         if (s >= t0) sc[y * BW + xo + x] = (uint8_t)s;
     }
     __syncthreads();
     // Phase 3: 3x3 non-maximum suppression (only listed pixels can be maxima)
     for (int i = tid; i < np; i += FAST_THREADS) {
-        const int y = plist[i] >> 8, x = plist[i] & 255;
+        const int e = i < c0 ? plist[i] : i < c1 ? plist[seg + i - c0] : i < c2 ? plist[2 * seg + i - c1] : plist[3 * seg + i - c2];
+        const int y = e >> 8, x = e & 255;
         const uint8_t *q = sc + y * BW + xo + x;
         const int s = q[0];
-        if (s > 0 && s > q[-1] && s > q[1] && s > q[-BW - 1] && s > q[-BW] && s > q[-BW + 1] && s > q[BW - 1] &&
-            s > q[BW] && s > q[BW + 1]) {
+        const int nb = max(max(max((int)q[-1], (int)q[1]), max((int)q[-BW - 1], (int)q[-BW])),
+                           max(max((int)q[-BW + 1], (int)q[BW - 1]), max((int)q[BW], (int)q[BW + 1])));
+        if (s > nb) {  // s > 0 follows: neighbours are >= 0
             const int k = atomicAdd(&s_n, 1);
             if (k < SB_CELL_LIST_CAP) list[k] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
             if (s >= a.iniTh) s_any = 1;
@@ -851,6 +857,11 @@ static int configure(sb_orb *h, int w, int hgt) {
     SB_REQUIRE(qt_smem_bytes(ncap_pyr > h->ncap_detect ? ncap_pyr : h->ncap_detect) <= 220 * 1024,
                "nfeatures too large for the on-chip quadtree");
     h->fast_tile_bytes = (int)sb_align_up(fast_tile, 128);
+    for (int l = 0; l < h->nlevels; l++) {  // per-warp segment of the candidate-pixel list (k_fast_cells phase 1)
+        const LevelGeom &L = g.lv[l];
+        const int need = sb_div_up(L.hCell, FAST_THREADS / 32) * sb_div_up(L.wCell, 32) * 32;
+        SB_REQUIRE(need <= h->fast_tile_bytes / 4, "internal: FAST candidate segment too small");
+    }
     h->n_cells = (int)cells.size();
     h->n_blur_tiles = (int)tiles.size();
     SB_REQUIRE((int)xofs.size() <= h->tab_cap && (int)yofs.size() <= h->tab_cap, "internal: table capacity");

@@ -59,13 +59,14 @@ SB_HD uint32_t sb_vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_
                        (k) == 13 ? 1 : (k) == 14 ? 2 : 3)
 
 // Necessary condition for "corner at threshold t": any 9 contiguous ring positions contain at least
-// two of the four compass positions 0, 4, 8, 12, and all of them must lie on the same side.
+// two of the four compass positions 0, 4, 8, 12, and all of them must lie on the same side.  "At least
+// two of four darker than v - t" <=> the second smallest of the four is; likewise for brighter.
 SB_HD bool sb_fast_maybe(const uint8_t *p, int pitch, int t) {
     const int v = p[0];
-    const int d0 = v - p[3 * pitch], d4 = v - p[3], d8 = v - p[-3 * pitch], d12 = v - p[-3];
-    const int darker = (d0 > t) + (d4 > t) + (d8 > t) + (d12 > t);       // ring pixel darker than centre
-    const int brighter = (d0 < -t) + (d4 < -t) + (d8 < -t) + (d12 < -t);
-    return darker >= 2 || brighter >= 2;
+    const int r0 = p[3 * pitch], r4 = p[3], r8 = p[-3 * pitch], r12 = p[-3];
+    const int m1 = sb_min(r0, r4), M1 = sb_max(r0, r4), m2 = sb_min(r8, r12), M2 = sb_max(r8, r12);
+    const int A = sb_max(m1, m2), B = sb_min(M1, M2);
+    return sb_min(A, B) < v - t || sb_max(A, B) > v + t;
 }
 
 // Corner response = the largest threshold for which the pixel is still a FAST-9/16 corner:
