@@ -108,29 +108,42 @@ __global__ void k_fill_level0(uint8_t *dst, long long slab, int pitch, int h, in
 }
 
 // cv::resize(level-1 -> level, INTER_LINEAR), fixed point.  4 destination pixels per thread.
+// xtab[dx] = (source column, c0 | c1 << 16).  The two source rows are read as aligned 32-bit words; a
+// funnel shift brings (S[sx], S[sx+1]) into the low bytes and one DP2A forms S[sx] * c0 + S[sx+1] * c1.
 __global__ void __launch_bounds__(256) k_resize(uint8_t *__restrict__ pyr, long long slab, LevelGeom src, LevelGeom dst,
-                                               const int *__restrict__ xofs, const short2 *__restrict__ xco,
-                                               const int *__restrict__ yofs, const short2 *__restrict__ yco) {
+                                               const int2 *__restrict__ xtab, const int2 *__restrict__ ytab) {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     if (x0 >= dst.w) return;
     uint8_t *base = pyr + (long long)blockIdx.z * slab;
-    const int sy = yofs[dst.ytab + y];
-    const short2 bc = yco[dst.ytab + y];
+    const int2 yt = ytab[dst.ytab + y];
+    const int sy = yt.x, b0 = yt.y & 0xffff, b1 = (unsigned)yt.y >> 16;
     const int sy0 = min(max(sy, 0), src.h - 1), sy1 = min(max(sy + 1, 0), src.h - 1);
     const uint8_t *S0 = base + src.off + (long long)sy0 * src.pitch;
     const uint8_t *S1 = base + src.off + (long long)sy1 * src.pitch;
-    uint32_t out = 0;
+    int2 xt[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int x = x0 + k;
-        if (x < dst.w) {
-            const int sx = xofs[dst.xtab + x];
-            const short2 ac = xco[dst.xtab + x];
-            const int sx1 = min(sx + 1, src.w - 1);
-            const int h0 = S0[sx] * ac.x + S0[sx1] * ac.y;
-            const int h1 = S1[sx] * ac.x + S1[sx1] * ac.y;
-            out |= (uint32_t)sb_lin_vert(h0, h1, bc.x, bc.y) << (8 * k);
+    for (int k = 0; k < 4; k++) xt[k] = xtab[dst.xtab + min(x0 + k, dst.w - 1)];
+    const int wb = xt[0].x >> 2;  // first source word
+    uint32_t out = 0;
+    if (xt[3].x + 1 - 4 * wb < 12) {  // the 4 pixels read at most 12 consecutive source bytes (any scale factor <= 2)
+        const uint32_t *W0 = reinterpret_cast<const uint32_t *>(S0) + wb, *W1 = reinterpret_cast<const uint32_t *>(S1) + wb;
+        const uint32_t a0 = W0[0], a1 = W0[1], a2 = W0[2], c0 = W1[0], c1 = W1[1], c2 = W1[2];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int o = xt[k].x - 4 * wb;  // 0 .. 10
+            const uint32_t p0 = o < 4 ? __funnelshift_r(a0, a1, 8 * o) : o < 8 ? __funnelshift_r(a1, a2, 8 * (o - 4)) : a2 >> (8 * (o - 8));
+            const uint32_t p1 = o < 4 ? __funnelshift_r(c0, c1, 8 * o) : o < 8 ? __funnelshift_r(c1, c2, 8 * (o - 4)) : c2 >> (8 * (o - 8));
+            const int h0 = (int)__dp2a_lo((unsigned)xt[k].y, p0, 0u);
+            const int h1 = (int)__dp2a_lo((unsigned)xt[k].y, p1, 0u);
+            out |= (uint32_t)sb_lin_vert(h0, h1, b0, b1) << (8 * k);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int sx = xt[k].x, sx1 = min(sx + 1, src.w - 1);
+            const int ca = xt[k].y & 0xffff, cb = (unsigned)xt[k].y >> 16;
+            out |= (uint32_t)sb_lin_vert(S0[sx] * ca + S0[sx1] * cb, S1[sx] * ca + S1[sx1] * cb, b0, b1) << (8 * k);
         }
     }
     *reinterpret_cast<uint32_t *>(base + dst.off + (long long)y * dst.pitch + x0) = out;
@@ -649,8 +662,7 @@ struct sb_orb {
     uint8_t *d_pyr, *d_blur, *d_mask;
     Cell *d_cells;
     BlurTile *d_tiles;
-    int *d_xofs, *d_yofs;
-    short2 *d_xco, *d_yco;
+    int2 *d_xtab, *d_ytab;  // resize tables: (source index, c0 | c1 << 16)
     uint32_t *d_cand, *d_sel;
     int *d_cand_cnt, *d_sel_cnt, *d_flags;
     int tab_cap, cell_cap, tile_cap;
@@ -690,8 +702,8 @@ static void prof_end(sb_orb *h, cudaStream_t s) {
 static void free_orb(sb_orb *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->d_pyr,  h->d_blur, h->d_mask,     h->d_cells,   h->d_tiles,   h->d_xofs,    h->d_yofs,
-                    h->d_xco,  h->d_yco,  h->d_cand,     h->d_sel,     h->d_cand_cnt, h->d_sel_cnt, h->d_flags,
+    void *ptrs[] = {h->d_pyr,  h->d_blur, h->d_mask,     h->d_cells,   h->d_tiles,   h->d_xtab,    h->d_ytab,
+                    h->d_cand,     h->d_sel,     h->d_cand_cnt, h->d_sel_cnt, h->d_flags,
                     h->d_in,   h->d_in_mask, h->d_desc_out, h->d_kps_out, h->d_counts_out, h->d_keep};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -774,8 +786,7 @@ static int configure(sb_orb *h, int w, int hgt) {
     memset(&g, 0, sizeof(g));
     g.nlevels = h->nlevels;
     memcpy(g.umax, h->umax, sizeof(g.umax));
-    std::vector<int> xofs, yofs;
-    std::vector<short2> xco, yco;
+    std::vector<int2> xtab, ytab;
     std::vector<Cell> cells;
     std::vector<BlurTile> tiles;
     long long off = 0;
@@ -823,19 +834,17 @@ static int configure(sb_orb *h, int w, int hgt) {
         }
         if (l == 0) h->n_cells_l0 = (int)cells.size();
         // resize tables for level l from level l-1 (unused for l == 0)
-        L.xtab = (int)xofs.size();
-        L.ytab = (int)yofs.size();
+        L.xtab = (int)xtab.size();
+        L.ytab = (int)ytab.size();
         if (l > 0) {
             const LevelGeom &S = g.lv[l - 1];
             for (int d = 0; d < L.w; d++) {
                 SbLinCoef c = sb_lin_coef(d, L.w, S.w, true);
-                xofs.push_back(c.s);
-                xco.push_back(make_short2(c.c0, c.c1));
+                xtab.push_back(make_int2(c.s, (int)((uint32_t)(uint16_t)c.c0 | ((uint32_t)(uint16_t)c.c1 << 16))));
             }
             for (int d = 0; d < L.h; d++) {
                 SbLinCoef c = sb_lin_coef(d, L.h, S.h, false);
-                yofs.push_back(c.s);
-                yco.push_back(make_short2(c.c0, c.c1));
+                ytab.push_back(make_int2(c.s, (int)((uint32_t)(uint16_t)c.c0 | ((uint32_t)(uint16_t)c.c1 << 16))));
             }
         }
         for (int ty = 0; ty < sb_div_up(L.h, BLUR_TH); ty++)
@@ -864,16 +873,14 @@ static int configure(sb_orb *h, int w, int hgt) {
     }
     h->n_cells = (int)cells.size();
     h->n_blur_tiles = (int)tiles.size();
-    SB_REQUIRE((int)xofs.size() <= h->tab_cap && (int)yofs.size() <= h->tab_cap, "internal: table capacity");
+    SB_REQUIRE((int)xtab.size() <= h->tab_cap && (int)ytab.size() <= h->tab_cap, "internal: table capacity");
     SB_REQUIRE(h->n_cells <= h->cell_cap && h->n_blur_tiles <= h->tile_cap, "internal: cell/tile capacity");
     cudaStream_t s = h->stream;
     // the previous geometry may still be in use by queued kernels
     SB_CUDA(cudaStreamSynchronize(s));
-    if (!xofs.empty()) {
-        SB_CUDA(cudaMemcpyAsync(h->d_xofs, xofs.data(), xofs.size() * 4, cudaMemcpyHostToDevice, s));
-        SB_CUDA(cudaMemcpyAsync(h->d_xco, xco.data(), xco.size() * 4, cudaMemcpyHostToDevice, s));
-        SB_CUDA(cudaMemcpyAsync(h->d_yofs, yofs.data(), yofs.size() * 4, cudaMemcpyHostToDevice, s));
-        SB_CUDA(cudaMemcpyAsync(h->d_yco, yco.data(), yco.size() * 4, cudaMemcpyHostToDevice, s));
+    if (!xtab.empty()) {
+        SB_CUDA(cudaMemcpyAsync(h->d_xtab, xtab.data(), xtab.size() * 8, cudaMemcpyHostToDevice, s));
+        SB_CUDA(cudaMemcpyAsync(h->d_ytab, ytab.data(), ytab.size() * 8, cudaMemcpyHostToDevice, s));
     }
     SB_CUDA(cudaMemcpyAsync(h->d_cells, cells.data(), cells.size() * sizeof(Cell), cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(h->d_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice, s));
@@ -957,10 +964,8 @@ extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float sc
     SB_ALLOC(h->d_blur, B * h->slab_cap);
     SB_ALLOC(h->d_cells, (size_t)h->cell_cap * sizeof(Cell));
     SB_ALLOC(h->d_tiles, (size_t)h->tile_cap * sizeof(BlurTile));
-    SB_ALLOC(h->d_xofs, (size_t)h->tab_cap * 4);
-    SB_ALLOC(h->d_yofs, (size_t)h->tab_cap * 4);
-    SB_ALLOC(h->d_xco, (size_t)h->tab_cap * 4);
-    SB_ALLOC(h->d_yco, (size_t)h->tab_cap * 4);
+    SB_ALLOC(h->d_xtab, (size_t)h->tab_cap * 8);
+    SB_ALLOC(h->d_ytab, (size_t)h->tab_cap * 8);
     SB_ALLOC(h->d_cand, B * nlevels * SB_CAND_CAP * 4);
     SB_ALLOC(h->d_sel, B * nlevels * h->selcap * 4);
     SB_ALLOC(h->d_cand_cnt, B * nlevels * 4);
@@ -1053,7 +1058,7 @@ static int launch_pyramid(sb_orb *h, uint8_t *pyr, const uint8_t *d_img, long lo
     for (int l = 1; l < nlevels_to_build; l++) {
         const LevelGeom &D = g.lv[l];
         dim3 grid(sb_div_up(sb_div_up(D.w, 4), 256), D.h, batch);
-        k_resize<<<grid, 256, 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_xofs, h->d_xco, h->d_yofs, h->d_yco);
+        k_resize<<<grid, 256, 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_xtab, h->d_ytab);
     }
     if (nlevels_to_build > 1) prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
