@@ -22,6 +22,12 @@
 
 #define BA_THREADS 256
 #define BA_MAX_POSES 16
+#ifdef BA_PROFILE
+__device__ long long g_ba_prof[16];
+#define BA_T(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) { long long t_ = clock64(); g_ba_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define BA_T(i) ((void)0)
+#endif
 
 struct sb_ba {
     int device, max_windows, max_poses, max_points, max_obs;
@@ -35,6 +41,7 @@ struct sb_ba {
     double *d_lm;        // [W][ML][18]: Hll(6) bl(3) Dinv(6) xl(3)
     double *d_ptbak;     // [W][ML][3]
     double *d_err;       // [W][2][MO][2]
+    double *d_hpl;       // [W][MO][18]: w A^T B of every edge to a free landmark (the Hpl block), rebuilt each iteration
 };
 
 struct BaArgs {
@@ -48,7 +55,7 @@ struct BaArgs {
     uint8_t *outlier;        // [W][MO] out
     int32_t *info;           // [W][4] out: outer rounds, LM iterations, inliers, outliers (or -1: bad input)
     int32_t *edge_of;
-    double *lm, *ptbak, *err;
+    double *lm, *ptbak, *err, *hpl;
     int MP, ML, MO;
     double fx, fy, cx, cy;
     double extR[9], extT[3];
@@ -183,6 +190,7 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
     int32_t *edge_of = a.edge_of + (size_t)w * a.ML * MP;
     double *lm = a.lm + (size_t)w * a.ML * 18;
     double *ptb = a.ptbak + (size_t)w * a.ML * 3;
+    double *hpl = a.hpl + (size_t)w * a.MO * 18;
     double *err = a.err + (size_t)w * a.MO * 4;   // errors of the last evaluation
     double *elin = err + (size_t)a.MO * 2;         // errors at the linearisation state
     int32_t *info = a.info + 4 * w;
@@ -213,13 +221,18 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
     EdgeCtx c;
     c.a = &a; c.Rt = Rt; c.pts = pts; c.uv = a.uv + (size_t)w * a.MO * 2; c.op = op; c.ol = ol;
 
+#ifdef BA_PROFILE
+    long long t_prev = clock64();
+#endif
     int rounds = 0, lm_total = 0, inl = 0, outl = 0;
     for (int outer = 0; outer < a.outer_max;) {  // src/backend.cpp:212-232
         // ================= optimizer.optimize(inner_iters): Levenberg-Marquardt =================
         double lambda = 0, ni = 2;
         bool terminated = false;
         for (int it = 0; it < a.inner_iters && !terminated; it++) {
+            BA_T(0);
             double currentChi = compute_errors(c, ne, err, elin, red);
+            BA_T(1);
             // ---- buildSystem.  Pose blocks: one warp per pose, lanes over the landmarks it observes.
             for (int i = wid; i < np; i += BA_THREADS / 32) {
                 double h[21], g[6];
@@ -270,6 +283,11 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                     g[2] += -wgt * (B[2] * r[0] + B[5] * r[1]);
                     H[0] += wgt * (B[0] * B[0] + B[3] * B[3]); H[1] += wgt * (B[0] * B[1] + B[3] * B[4]); H[2] += wgt * (B[0] * B[2] + B[3] * B[5]);
                     H[3] += wgt * (B[1] * B[1] + B[4] * B[4]); H[4] += wgt * (B[1] * B[2] + B[4] * B[5]); H[5] += wgt * (B[2] * B[2] + B[5] * B[5]);
+                    double *P = hpl + 18 * e;  // Hpl block of this edge: w A^T B (6x3)
+#pragma unroll
+                    for (int p = 0; p < 6; p++)
+#pragma unroll
+                        for (int q = 0; q < 3; q++) P[3 * p + q] = wgt * (A[p] * B[q] + A[6 + p] * B[3 + q]);
                 }
                 double *L = lm + 18 * j;
 #pragma unroll
@@ -277,6 +295,7 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                 L[6] = g[0]; L[7] = g[1]; L[8] = g[2];
             }
             __syncthreads();
+            BA_T(2);
             if (it == 0) {  // computeLambdaInit: 1e-5 * largest diagonal entry of H over the free vertices
                 double mx = 0;
                 for (int k = tid; k < n6; k += BA_THREADS) mx = fmax(mx, fabs(Hpp[36 * (k / 6) + 7 * (k % 6)]));
@@ -305,6 +324,7 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                     L[12] = (A0 * f - cc * cc) * id; L[13] = (b * cc - A0 * e) * id; L[14] = (A0 * d - b * b) * id;
                 }
                 int ok = !__syncthreads_or(bad);
+                BA_T(3);
                 // ---- Schur complement: S(i1,i2) = Hpp'(i1,i2) - sum_j Hpl(i1,j) Dinv_j Hpl(i2,j)^T, one warp per block
                 //      (upper triangle), lanes over landmarks; the diagonal pass also reduces b.
                 const int nblk = np * (np + 1) / 2;
@@ -323,39 +343,24 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                         if (e1 < 0 || e2 < 0) continue;
                         const double *L = lm + 18 * j;
                         const double D[9] = {L[9], L[10], L[11], L[10], L[12], L[13], L[11], L[13], L[14]};
-                        double A1[12], B1[6], r1[2], w1, A2[12], B2[6], r2[2], w2;
-                        edge_lin(c, e1, elin, A1, B1, r1, w1);
-                        if (e2 == e1) {
-#pragma unroll
-                            for (int k = 0; k < 12; k++) A2[k] = A1[k];
-#pragma unroll
-                            for (int k = 0; k < 6; k++) B2[k] = B1[k];
-                            w2 = w1;
-                        } else {
-                            edge_lin(c, e2, elin, A2, B2, r2, w2);
-                        }
-                        // M = w1 w2 B1 D B2^T (2x2);  Hpl(i1) D Hpl(i2)^T = A1^T M A2
-                        double BD[6];
-#pragma unroll
-                        for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-                            for (int k = 0; k < 3; k++) BD[3 * rr + k] = B1[3 * rr] * D[k] + B1[3 * rr + 1] * D[3 + k] + B1[3 * rr + 2] * D[6 + k];
-                        double M[4];
-#pragma unroll
-                        for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-                            for (int s2 = 0; s2 < 2; s2++)
-                                M[2 * rr + s2] = w1 * w2 * (BD[3 * rr] * B2[3 * s2] + BD[3 * rr + 1] * B2[3 * s2 + 1] + BD[3 * rr + 2] * B2[3 * s2 + 2]);
+                        const double *P1 = hpl + 18 * e1, *P2 = hpl + 18 * e2;
+                        double BD[18];  // Hpl(i1, j) Dinv_j
 #pragma unroll
                         for (int p = 0; p < 6; p++) {
-                            const double t0 = A1[p] * M[0] + A1[6 + p] * M[2], t1 = A1[p] * M[1] + A1[6 + p] * M[3];
-#pragma unroll
-                            for (int q = 0; q < 6; q++) acc[6 * p + q] += t0 * A2[q] + t1 * A2[6 + q];
+                            const double h0 = P1[3 * p], h1 = P1[3 * p + 1], h2 = P1[3 * p + 2];
+                            BD[3 * p] = h0 * D[0] + h1 * D[3] + h2 * D[6];
+                            BD[3 * p + 1] = h0 * D[1] + h1 * D[4] + h2 * D[7];
+                            BD[3 * p + 2] = h0 * D[2] + h1 * D[5] + h2 * D[8];
                         }
-                        if (i1 == i2) {  // b_schur(i1) -= Hpl(i1,j) Dinv_j bl_j = A1^T w1 (B1 Dinv bl)
-                            const double v0 = BD[0] * L[6] + BD[1] * L[7] + BD[2] * L[8], v1 = BD[3] * L[6] + BD[4] * L[7] + BD[5] * L[8];
 #pragma unroll
-                            for (int p = 0; p < 6; p++) gb[p] += w1 * (A1[p] * v0 + A1[6 + p] * v1);
+                        for (int q = 0; q < 6; q++) {
+                            const double g0 = P2[3 * q], g1 = P2[3 * q + 1], g2 = P2[3 * q + 2];
+#pragma unroll
+                            for (int p = 0; p < 6; p++) acc[6 * p + q] += BD[3 * p] * g0 + BD[3 * p + 1] * g1 + BD[3 * p + 2] * g2;
+                        }
+                        if (i1 == i2) {  // b_schur(i1) -= Hpl(i1, j) Dinv_j bl_j
+#pragma unroll
+                            for (int p = 0; p < 6; p++) gb[p] += BD[3 * p] * L[6] + BD[3 * p + 1] * L[7] + BD[3 * p + 2] * L[8];
                         }
                     }
 #pragma unroll
@@ -381,50 +386,56 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                     }
                 }
                 __syncthreads();
-                // ---- Cholesky of the reduced system (lower triangle, in place) and the two triangular solves
+                BA_T(4);
+                // ---- Cholesky of the reduced system (lower triangle, in place, left-looking) and the two triangular
+                //      solves, all by ONE warp with warp-level synchronisation only: the system is 42 x 42, and
+                //      block-wide barriers per column cost more than the arithmetic.
                 if (ok) {
-                    for (int j = 0; j < n6; j++) {
-                        if (tid == 0) {
-                            double d = S[j * n6 + j];
-                            s_bad = !(d > 0);
-                            S[j * n6 + j] = sqrt(d);
+                    if (wid == 0) {
+                        int bad_pivot = 0;
+                        for (int j = 0; j < n6; j++) {
+                            double v = 0;
+                            for (int k = lane; k < j; k += 32) v += S[j * n6 + k] * S[j * n6 + k];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            const double d = S[j * n6 + j] - v;
+                            if (!(d > 0)) { bad_pivot = 1; break; }
+                            const double dj = sqrt(d), inv = 1.0 / dj;
+                            for (int i = j + 1 + lane; i < n6; i += 32) {
+                                double sacc = S[i * n6 + j];
+                                for (int k = 0; k < j; k++) sacc -= S[i * n6 + k] * S[j * n6 + k];
+                                S[i * n6 + j] = sacc * inv;
+                            }
+                            __syncwarp();
+                            if (lane == 0) S[j * n6 + j] = dj;
+                            __syncwarp();
                         }
-                        __syncthreads();
-                        if (s_bad) break;
-                        const double dj = S[j * n6 + j];
-                        for (int i = j + 1 + tid; i < n6; i += BA_THREADS) S[i * n6 + j] /= dj;
-                        __syncthreads();
-                        // trailing update of the lower triangle
-                        const int m = n6 - j - 1;
-                        for (int k = tid; k < m * m; k += BA_THREADS) {
-                            const int r = j + 1 + k / m, cc = j + 1 + k % m;
-                            if (cc <= r) S[r * n6 + cc] -= S[r * n6 + j] * S[cc * n6 + j];
+                        if (!bad_pivot) {
+                            // forward substitution, column oriented: after y_j is final every lane updates its entries
+                            for (int j = 0; j < n6; j++) {
+                                const double yj = xs[j] / S[j * n6 + j];
+                                __syncwarp();
+                                if (lane == 0) xs[j] = yj;
+                                for (int i = j + 1 + lane; i < n6; i += 32) xs[i] -= S[i * n6 + j] * yj;
+                                __syncwarp();
+                            }
+                            // backward substitution with L^T: row j of L is column j of L^T
+                            for (int j = n6 - 1; j >= 0; j--) {
+                                const double xj = xs[j] / S[j * n6 + j];
+                                __syncwarp();
+                                if (lane == 0) xs[j] = xj;
+                                for (int i = lane; i < j; i += 32) xs[i] -= S[j * n6 + i] * xj;
+                                __syncwarp();
+                            }
                         }
-                        __syncthreads();
+                        if (lane == 0) s_bad = bad_pivot;
                     }
+                    __syncthreads();
                     ok = !s_bad;
                     __syncthreads();
                     if (tid == 0) s_bad = 0;
-                    if (ok && wid == 0) {  // forward / backward substitution by one warp
-                        for (int i = 0; i < n6; i++) {
-                            double v = 0;
-                            for (int k = lane; k < i; k += 32) v += S[i * n6 + k] * xs[k];
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                            if (lane == 0) xs[i] = (xs[i] - v) / S[i * n6 + i];
-                            __syncwarp();
-                        }
-                        for (int i = n6 - 1; i >= 0; i--) {
-                            double v = 0;
-                            for (int k = i + 1 + lane; k < n6; k += 32) v += S[k * n6 + i] * xs[k];
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                            if (lane == 0) xs[i] = (xs[i] - v) / S[i * n6 + i];
-                            __syncwarp();
-                        }
-                    }
-                    __syncthreads();
                 }
+                BA_T(5);
                 double scale = 0;
                 if (ok) {
                     // ---- landmark increments: xl = Dinv (bl - sum_i Hpl(i,j)^T xs_i), then the state update
@@ -435,13 +446,12 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                         for (int i = 0; i < np; i++) {
                             const int e = edge_of[j * MP + i];
                             if (e < 0) continue;
-                            double A[12], B[6], r[2], wgt;
-                            edge_lin(c, e, elin, A, B, r, wgt);
-                            double u0 = 0, u1 = 0;  // u = w A xs_i  (2)
+                            const double *P = hpl + 18 * e;  // v -= Hpl(i, j)^T xs_i
 #pragma unroll
-                            for (int p = 0; p < 6; p++) { u0 += A[p] * xs[6 * i + p]; u1 += A[6 + p] * xs[6 * i + p]; }
-                            u0 *= wgt; u1 *= wgt;
-                            v[0] -= B[0] * u0 + B[3] * u1; v[1] -= B[1] * u0 + B[4] * u1; v[2] -= B[2] * u0 + B[5] * u1;
+                            for (int p = 0; p < 6; p++) {
+                                const double xp = xs[6 * i + p];
+                                v[0] -= P[3 * p] * xp; v[1] -= P[3 * p + 1] * xp; v[2] -= P[3 * p + 2] * xp;
+                            }
                         }
                         const double x0 = L[9] * v[0] + L[10] * v[1] + L[11] * v[2];
                         const double x1 = L[10] * v[0] + L[12] * v[1] + L[13] * v[2];
@@ -459,7 +469,9 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                     for (int i = tid; i < np; i += BA_THREADS) pose_oplus(Rt + 12 * i, xs + 6 * i);
                     __syncthreads();
                 }
+                BA_T(6);
                 double tempChi = compute_errors(c, ne, err, nullptr, red);
+                BA_T(7);
                 if (!ok) tempChi = 1.7976931348623157e308;
                 rho = (currentChi - tempChi) / (scale + 1e-3);
                 if (rho > 0 && isfinite(tempChi)) {
@@ -518,7 +530,7 @@ static void free_ba(sb_ba *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_np, h->d_nl, h->d_ne, h->d_info, h->d_poses, h->d_points, h->d_uv, h->d_chi2, h->d_fixed,
-                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_lm, h->d_ptbak, h->d_err};
+                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_lm, h->d_ptbak, h->d_err, h->d_hpl};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -561,6 +573,7 @@ extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_
     BA_ALLOC(h->d_lm, W * ML * 18 * 8);
     BA_ALLOC(h->d_ptbak, W * ML * 3 * 8);
     BA_ALLOC(h->d_err, W * MO * 4 * 8);
+    BA_ALLOC(h->d_hpl, W * MO * 18 * 8);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_bytes(BA_MAX_POSES));
     if (e != cudaSuccess) {
@@ -614,7 +627,7 @@ extern "C" int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_pos
     a.np = d_n_poses; a.nl = d_n_points; a.ne = d_n_obs;
     a.poses = d_poses; a.points = d_points; a.fixed = d_fixed; a.op = d_obs_pose; a.ol = d_obs_point; a.uv = d_uv;
     a.chi2 = d_chi2; a.outlier = d_outlier; a.info = d_info;
-    a.edge_of = h->d_edge_of; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err;
+    a.edge_of = h->d_edge_of; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err; a.hpl = h->d_hpl;
     a.MP = h->max_poses; a.ML = h->max_points; a.MO = h->max_obs;
     a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
     quat7_to_ext(cam_ext7, a.extR, a.extT);
@@ -662,3 +675,13 @@ extern "C" int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, co
         }
     return SB_OK;
 }
+
+#ifdef BA_PROFILE
+extern "C" int sb_ba_debug_profile(long long *out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_ba_prof, sizeof(long long) * 16);
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_ba_prof, z, sizeof(z));
+    return 0;
+}
+#endif
