@@ -22,6 +22,7 @@
 
 #define PG_THREADS 256
 #define PG_MAX_LOOPS 64
+#define PG_CHUNK 16
 
 enum { PG_NONE = 0, PG_DIAG = 1, PG_CHAIN = 2, PG_LOOP = 3 };
 
@@ -142,6 +143,8 @@ static __device__ double pg_errors(const PgArgs &a, double *red) {
 
 __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant__ PgArgs a) {
     __shared__ double red[16];
+    __shared__ double w_B[36], w_G[36], w_M[36], w_I[36];  // 6x6 work blocks of the factorisation warp
+    __shared__ __align__(16) double w_stage[2 * PG_CHUNK * 36];           // G / (S^-1, B) of a chunk of chain steps
     __shared__ int s_nf, s_R, s_bad;
     const int tid = threadIdx.x;
     const int n = a.n, m = a.m;
@@ -175,11 +178,8 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
             a.inc_start[u0 + 1]++;
             a.inc_start[u1 + 1]++;
         }
-        if (!bad) {
+        if (!bad)
             for (int v = 0; v < n; v++) a.inc_start[v + 1] += a.inc_start[v];
-            // fill in edge order (stable): use Sinv's first ints as cursors? keep it simple: second pass with a scan
-            for (int v = 0; v < n; v++) a.fidx[v] = a.fidx[v];  // no-op, keeps the numbering
-        }
         s_nf = nf; s_R = R; s_bad = bad;
     }
     __syncthreads();
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
         return;
     }
     const int nf = s_nf, R = s_R, NC = 1 + 6 * R;
-    // incidence fill: vertex v's edges in ascending edge index (thread per vertex scans nothing; thread 0 fills serially)
+    // incidence lists: vertex v's edges in ascending edge index (serial fill keeps the order deterministic)
     if (tid == 0) {
         int *cursor = a.eloop + m;  // scratch of n ints behind eloop
         for (int v = 0; v < n; v++) cursor[v] = a.inc_start[v];
@@ -295,27 +295,65 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
         int qmax = 0;
         do {
             for (int k = tid; k < 12 * n; k += PG_THREADS) a.Rtb[k] = a.Rt[k];  // push()
-            // ---- block Thomas factorisation of T = tridiag(B, A + lambda I, B^T)
-            if (tid == 0) {
+            // ---- block Thomas factorisation of T = tridiag(B, A + lambda I, B^T): S_p = A_p - G_p B_p^T with
+            //      G_p = B_p S_{p-1}^-1.  The recurrence is serial in p; inside a step one warp works on the 6x6
+            //      blocks (18 lanes x 2 elements: rows r and r + 3 of column c), products and the Gauss-Jordan
+            //      inverse go through shared memory with warp-level synchronisation only.
+            if (tid < 32) {
+                const int l = tid, r = l / 6, cc = l % 6;  // lanes 0..17 own (r, cc) and (r + 3, cc)
+                const bool act = l < 18;
                 int bad = 0;
-                double Sprev_inv[36];
-                for (int p = 0; p < nf && !bad; p++) {
-                    double S[36], Gp[36];
-                    for (int k = 0; k < 36; k++) S[k] = a.A[36 * p + k];
-                    for (int k = 0; k < 6; k++) S[7 * k] += lambda;
-                    if (p > 0) {
-                        m6_mul(a.B + 36 * p, Sprev_inv, Gp);          // G_p = B_p S_{p-1}^-1
-                        double GB[36];
-                        m6_mul_bt(Gp, a.B + 36 * p, GB);              // G_p B_p^T
-                        for (int k = 0; k < 36; k++) { S[k] -= GB[k]; a.G[36 * p + k] = Gp[k]; }
+                for (int p = 0; p < nf; p++) {
+                    double e0 = 0, e1 = 0;
+                    if (act) {
+                        e0 = a.A[36 * p + 6 * r + cc] + (r == cc ? lambda : 0.0);
+                        e1 = a.A[36 * p + 6 * (r + 3) + cc] + (r + 3 == cc ? lambda : 0.0);
+                        if (p > 0) { w_B[6 * r + cc] = a.B[36 * p + 6 * r + cc]; w_B[6 * (r + 3) + cc] = a.B[36 * p + 6 * (r + 3) + cc]; }
                     }
-                    // symmetrise against round-off before the Cholesky-based inverse
-                    for (int i = 0; i < 6; i++)
-                        for (int j = i + 1; j < 6; j++) { const double s = 0.5 * (S[6 * i + j] + S[6 * j + i]); S[6 * i + j] = s; S[6 * j + i] = s; }
-                    if (!m6_inv_spd(S, Sprev_inv)) bad = 1;
-                    for (int k = 0; k < 36; k++) a.Sinv[36 * p + k] = Sprev_inv[k];
+                    __syncwarp();
+                    if (p > 0) {
+                        if (act) {  // G = B S_{p-1}^-1
+                            double g0 = 0, g1 = 0;
+#pragma unroll
+                            for (int k = 0; k < 6; k++) { g0 += w_B[6 * r + k] * w_I[6 * k + cc]; g1 += w_B[6 * (r + 3) + k] * w_I[6 * k + cc]; }
+                            w_G[6 * r + cc] = g0; w_G[6 * (r + 3) + cc] = g1;
+                            a.G[36 * p + 6 * r + cc] = g0; a.G[36 * p + 6 * (r + 3) + cc] = g1;
+                        }
+                        __syncwarp();
+                        if (act) {  // S = A - G B^T
+#pragma unroll
+                            for (int k = 0; k < 6; k++) { e0 -= w_G[6 * r + k] * w_B[6 * cc + k]; e1 -= w_G[6 * (r + 3) + k] * w_B[6 * cc + k]; }
+                        }
+                    }
+                    if (act) { w_M[6 * r + cc] = e0; w_M[6 * (r + 3) + cc] = e1; }
+                    __syncwarp();
+                    if (act) {  // symmetrise against round-off, start Gauss-Jordan on [M | I]
+                        e0 = 0.5 * (w_M[6 * r + cc] + w_M[6 * cc + r]);
+                        e1 = 0.5 * (w_M[6 * (r + 3) + cc] + w_M[6 * cc + r + 3]);
+                    }
+                    double i0 = r == cc ? 1.0 : 0.0, i1 = r + 3 == cc ? 1.0 : 0.0;
+                    __syncwarp();
+                    if (act) { w_M[6 * r + cc] = e0; w_M[6 * (r + 3) + cc] = e1; w_I[6 * r + cc] = i0; w_I[6 * (r + 3) + cc] = i1; }
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const double piv = w_M[7 * k];
+                        if (!(piv > 0)) bad = 1;  // positive definite blocks have positive pivots without pivoting
+                        const double ip = 1.0 / piv;
+                        double mk = 0, ik = 0, f0 = 0, f1 = 0;
+                        if (act) { mk = w_M[6 * k + cc] * ip; ik = w_I[6 * k + cc] * ip; f0 = w_M[6 * r + k]; f1 = w_M[6 * (r + 3) + k]; }
+                        __syncwarp();
+                        if (act) {
+                            e0 = r == k ? mk : e0 - f0 * mk;      i0 = r == k ? ik : i0 - f0 * ik;
+                            e1 = r + 3 == k ? mk : e1 - f1 * mk;  i1 = r + 3 == k ? ik : i1 - f1 * ik;
+                            w_M[6 * r + cc] = e0; w_M[6 * (r + 3) + cc] = e1; w_I[6 * r + cc] = i0; w_I[6 * (r + 3) + cc] = i1;
+                        }
+                        __syncwarp();
+                    }
+                    if (act) { a.Sinv[36 * p + 6 * r + cc] = i0; a.Sinv[36 * p + 6 * (r + 3) + cc] = i1; }
+                    if (__any_sync(0xffffffffu, bad)) break;
                 }
-                s_bad = bad;
+                if (tid == 0) s_bad = bad;
             }
             // ---- right-hand sides Q[p][c][6]: column 0 = b, column 1 + 6r + k = row k of J_loop,r (as a column of J^T)
             for (int idx = tid; idx < nf * NC * 6; idx += PG_THREADS) a.Q[idx] = 0;
@@ -334,50 +372,80 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
             int ok = !s_bad;
             __syncthreads();
             if (ok) {
-                // ---- T^-1 [b, J^T]: one thread per column, sequential over the chain
-                for (int c = tid; c < NC; c += PG_THREADS) {
-                    double y[6];
-                    for (int p = 0; p < nf; p++) {
-                        double *q = a.Q + ((size_t)p * NC + c) * 6;
-                        if (p > 0) {
-                            const double *Gp = a.G + 36 * p;
+                // ---- T^-1 [b, J^T]: one thread per column, sequential over the chain; the 6x6 blocks every column
+                //      needs (G_p forward, S_p^-1 and B_{p+1} backward) are staged through shared memory in chunks.
+                {
+                    const int ncol_iters = (NC + PG_THREADS - 1) / PG_THREADS;
+                    for (int ci = 0; ci < ncol_iters; ci++) {
+                        const int c = ci * PG_THREADS + tid;
+                        const bool on = c < NC;
+                        double y[6] = {0, 0, 0, 0, 0, 0};
+                        for (int p0 = 0; p0 < nf; p0 += PG_CHUNK) {
+                            const int pn = min(PG_CHUNK, nf - p0);
+                            __syncthreads();
+                            for (int k = tid; k < pn * 36; k += PG_THREADS) w_stage[k] = a.G[36 * p0 + k];
+                            __syncthreads();
+                            if (on)
+                                for (int pp = 0; pp < pn; pp++) {
+                                    const int p = p0 + pp;
+                                    double *q = a.Q + ((size_t)p * NC + c) * 6;
+                                    double v[6];
 #pragma unroll
-                            for (int i = 0; i < 6; i++) {
-                                double s = q[i];
+                                    for (int i = 0; i < 6; i++) v[i] = q[i];
+                                    if (p > 0) {
+                                        const double *Gp = w_stage + 36 * pp;
 #pragma unroll
-                                for (int k = 0; k < 6; k++) s -= Gp[6 * i + k] * y[k];
-                                q[i] = s;
+                                        for (int i = 0; i < 6; i++) {
+                                            double sacc = v[i];
+#pragma unroll
+                                            for (int k = 0; k < 6; k++) sacc -= Gp[6 * i + k] * y[k];
+                                            v[i] = sacc;
+                                        }
+#pragma unroll
+                                        for (int i = 0; i < 6; i++) q[i] = v[i];
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < 6; i++) y[i] = v[i];
+                                }
+                        }
+                        double xn[6] = {0, 0, 0, 0, 0, 0};
+                        for (int pend = nf; pend > 0; pend -= PG_CHUNK) {
+                            const int p0 = max(0, pend - PG_CHUNK), pn = pend - p0;
+                            __syncthreads();
+                            for (int k = tid; k < pn * 36; k += PG_THREADS) {
+                                w_stage[k] = a.Sinv[36 * p0 + k];
+                                w_stage[PG_CHUNK * 36 + k] = p0 + k / 36 + 1 < nf ? a.B[36 * (p0 + 1) + k] : 0.0;  // B_{p+1}
                             }
+                            __syncthreads();
+                            if (on)
+                                for (int pp = pn - 1; pp >= 0; pp--) {
+                                    const int p = p0 + pp;
+                                    double *q = a.Q + ((size_t)p * NC + c) * 6;
+                                    double r6[6];
+#pragma unroll
+                                    for (int i = 0; i < 6; i++) r6[i] = q[i];
+                                    if (p + 1 < nf) {
+                                        const double *Bn = w_stage + PG_CHUNK * 36 + 36 * pp;  // (B_{p+1})^T x_{p+1}
+#pragma unroll
+                                        for (int i = 0; i < 6; i++) {
+                                            double sacc = 0;
+#pragma unroll
+                                            for (int k = 0; k < 6; k++) sacc += Bn[6 * k + i] * xn[k];
+                                            r6[i] -= sacc;
+                                        }
+                                    }
+                                    const double *Si = w_stage + 36 * pp;
+#pragma unroll
+                                    for (int i = 0; i < 6; i++) {
+                                        double sacc = 0;
+#pragma unroll
+                                        for (int k = 0; k < 6; k++) sacc += Si[6 * i + k] * r6[k];
+                                        xn[i] = sacc;
+                                    }
+#pragma unroll
+                                    for (int i = 0; i < 6; i++) q[i] = xn[i];
+                                }
                         }
-#pragma unroll
-                        for (int i = 0; i < 6; i++) y[i] = q[i];
-                    }
-                    double xn[6] = {0, 0, 0, 0, 0, 0};
-                    for (int p = nf - 1; p >= 0; p--) {
-                        double *q = a.Q + ((size_t)p * NC + c) * 6;
-                        double r6[6];
-#pragma unroll
-                        for (int i = 0; i < 6; i++) r6[i] = q[i];
-                        if (p + 1 < nf) {
-                            const double *Bn = a.B + 36 * (p + 1);  // (B_{p+1})^T x_{p+1}
-#pragma unroll
-                            for (int i = 0; i < 6; i++) {
-                                double s = 0;
-#pragma unroll
-                                for (int k = 0; k < 6; k++) s += Bn[6 * k + i] * xn[k];
-                                r6[i] -= s;
-                            }
-                        }
-                        const double *Si = a.Sinv + 36 * p;
-#pragma unroll
-                        for (int i = 0; i < 6; i++) {
-                            double s = 0;
-#pragma unroll
-                            for (int k = 0; k < 6; k++) s += Si[6 * i + k] * r6[k];
-                            xn[i] = s;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 6; i++) q[i] = xn[i];
                     }
                 }
                 __syncthreads();
