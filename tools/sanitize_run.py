@@ -1,0 +1,33 @@
+"""One small invocation of every kernel family (for compute-sanitizer memcheck / racecheck / initcheck)."""
+import importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+PKG = "a-simple-stereo-slam-system-with-deep-loop-closing_b200"
+pkg = importlib.import_module(PKG)
+synth = importlib.import_module(PKG + ".synth")
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which in ("all", "orb"):
+    frames = synth.stereo_batch(0, 1)
+    fe = pkg.StereoFrontend(2000, 1.2, 8, 20, 7, max_pairs=1)
+    out = fe.extract_match(frames)
+    print("stereo", out["counts"].tolist(), int((out["mdist"][0, :out["counts"][0, 0]] <= 30).sum()))
+    ext = pkg.ORBextractor(300, 1.2, 8, 20, 7)
+    mask = np.full(frames[0, 0].shape, 255, np.uint8); mask[100:200, 300:600] = 0
+    k = ext.Detect(frames[0, 0], mask)
+    kin = np.repeat(k, 8); kin["octave"] = np.tile(np.arange(8), len(k))
+    _, ks = ext.ScreenAndComputeKPsParams(frames[0, 0], kin)
+    d = ext.CalcDescriptors(frames[0, 0], ks)
+    print("detect/screen/calc", len(k), len(ks), d.shape)
+if which in ("all", "ba"):
+    w = [synth.ba_window(s, n_points=60) for s in range(2)]
+    r = pkg.LocalBA(max_windows=2, max_poses=7, max_points=64, max_obs=512).solve(w, synth.KITTI_K)
+    print("ba", r[0][4].tolist())
+if which in ("all", "lcd"):
+    db = synth.lcd_database(0, n=100, pairs=[(90, 5)])
+    lcd = pkg.DeepLCDScorer(capacity=128, dtype=1, max_queries=4)
+    lcd.add_batch(np.arange(90), db[:90])
+    print("lcd", lcd.DetectLoop(90, db[90]), lcd.score(db[:3]).shape)
+if which in ("all", "pg"):
+    g = synth.pose_graph(1, n=50, n_loops=2)
+    p, info = pkg.PoseGraph(64, 128).solve(g["poses0"], g["fixed"], g["v0"], g["v1"], g["meas"], iters=5)
+    print("pg", info)
