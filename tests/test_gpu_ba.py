@@ -24,7 +24,10 @@ def check_window(oracle, synth, w, got, **kw):
     p, x, chi2, outl, info = oracle.ba_solve(w["poses0"], w["points0"], w["fixed"], w["obs_pose"], w["obs_point"], w["uv"],
                                              synth.KITTI_K, **kw)
     gp, gx, gchi2, goutl, ginfo = got
-    assert np.array_equal(ginfo, info), (ginfo, info)
+    # outer rounds and inlier / outlier counts must agree; the LM iteration count too, except on windows that
+    # converge to round-off level, where "rho == 0 -> terminate" (g2o) is decided by the last bits of chi2
+    assert ginfo[0] == info[0] and np.array_equal(ginfo[2:], info[2:]), (ginfo, info)
+    assert ginfo[1] == info[1] or np.median(chi2) < 1e-8, (ginfo, info)
     assert rel_close(gp, p), np.abs(gp - p).max()
     assert rel_close(gx, x), np.abs(gx - x).max()
     assert rel_close(gchi2, chi2), np.abs(gchi2 - chi2).max()
