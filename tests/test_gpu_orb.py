@@ -172,3 +172,35 @@ def test_errors_are_reported_not_thrown_away(pkg):
     with pytest.raises(pkg.SlamB200Error):
         g.DetectAndCompute(np.zeros((376, 1241), np.uint8))            # larger than max_w x max_h
     g.close()
+
+
+@pytest.mark.parametrize("params", [(1200, 1.5, 5, 20, 7), (800, 2.0, 3, 30, 10), (1500, 1.1, 6, 12, 5), (600, 1.2, 8, 40, 40)])
+def test_other_pyramid_and_threshold_parameters(pkg, oracle, synth, params):
+    left, right = synth.stereo_pair(33)
+    g = pkg.ORBextractor(*params, max_batch=2)
+    c = oracle.ORBextractor(*params)
+    assert np.array_equal(g.quota, c.quota) and np.array_equal(g.scale, c.scale) and np.array_equal(g.inv_scale, c.inv_scale)
+    for img, (gk, gd) in zip((left, right), g.DetectAndComputeBatch([left, right])):
+        wk, wd = c.DetectAndCompute(img)
+        assert_kps_equal(gk, wk, params)
+        assert np.array_equal(gd, wd)
+    g.close()
+
+
+def test_low_texture_images_exercise_the_threshold_fallback(pkg, oracle):
+    """Soft blobs only: most cells find nothing at iniThFAST = 20 and fall back to minThFAST = 7 (src/ORBextractor.cpp:858-865)."""
+    rng = np.random.default_rng(4)
+    yy, xx = np.mgrid[0:376, 0:1241]
+    img = np.full((376, 1241), 110.0)
+    for _ in range(300):
+        cx, cy, s, a = rng.uniform(0, 1241), rng.uniform(0, 376), rng.uniform(2, 5), rng.uniform(-35, 35)
+        img += a * np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * s * s))
+    img = np.clip(np.rint(img + rng.integers(-1, 2, img.shape)), 0, 255).astype(np.uint8)
+    g = pkg.ORBextractor(1000, 1.2, 8, 20, 7)
+    c = oracle.ORBextractor(1000, 1.2, 8, 20, 7)
+    gk, gd = g.DetectAndCompute(img)
+    wk, wd = c.DetectAndCompute(img)
+    assert_kps_equal(gk, wk)
+    assert np.array_equal(gd, wd)
+    assert 0 < len(gk) and (gk["response"] < 20).any() and (gk["response"] >= 20).any()
+    g.close()
