@@ -510,13 +510,13 @@ struct DescArgs {
     int nlevels, selcap, cap;
 };
 
+#define DESC_KPB 32  // keypoints per CTA of k_describe
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, DescArgs a) {
     __shared__ float4 pat[256];
+    __shared__ float s_ang[DESC_KPB], s_cos[DESC_KPB], s_sin[DESC_KPB];
     load_pattern(pat);
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int level = blockIdx.y, img = blockIdx.z;
-    const int k = blockIdx.x * DESC_WARPS + warp;
     const int *cnt = a.sel_cnt + img * a.nlevels;
     int offset = 0, total = 0;
     for (int l = 0; l < a.nlevels; l++) {
@@ -524,24 +524,55 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
         if (l < level) offset += c;
         total += c;
     }
-    if (level == 0 && k == 0 && lane == 0) {
+    if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
         a.counts[img] = min(total, a.cap);
         if (total > a.cap) a.flags[1] = 1;
     }
-    if (k >= cnt[level] || offset + k >= a.cap) return;
+    const int k0 = blockIdx.x * DESC_KPB;
+    const int nk = min(min(cnt[level], a.cap - offset) - k0, DESC_KPB);  // keypoints of this CTA
+    if (nk <= 0) return;
     const LevelGeom &L = g.lv[level];
-    const uint32_t w = a.sel[((long long)img * a.nlevels + level) * a.selcap + k];
-    const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;  // :895-896
-    const long long o = (long long)img * a.slab + L.off + (long long)y * L.pitch + x;
-    const float angle = warp_ic_angle(a.pyr + o, L.pitch, g.umax, lane);
-    const long long row = (long long)img * a.cap + offset + k;
-    if (a.desc) {
-        const uint32_t byte = warp_brief_byte(a.blur + o, L.pitch, angle, pat, lane);
-        a.desc[row * 32 + lane] = (uint8_t)byte;
+    const uint32_t *sel = a.sel + ((long long)img * a.nlevels + level) * a.selcap + k0;
+    const long long base = (long long)img * a.slab + L.off;
+    // phase A: orientation, one warp per keypoint (4 keypoints per warp)
+    for (int i = warp; i < nk; i += DESC_WARPS) {
+        const uint32_t w = sel[i];
+        const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;  // :895-896
+        const float angle = warp_ic_angle(a.pyr + base + (long long)y * L.pitch + x, L.pitch, g.umax, lane);
+        if (lane == 0) s_ang[i] = angle;
     }
-    float fx = (float)x, fy = (float)y;
-    if (level != 0) { fx = sb_fmul(fx, L.scale); fy = sb_fmul(fy, L.scale); }  // :975-981
-    warp_store_keypoint(a.kps + row, fx, fy, L.patch, angle, (float)(w >> 24), level, -1, lane);
+    __syncthreads();
+    // phase B: cos / sin in double, ONE THREAD per keypoint (as a warp-wide computation it would cost 32x)
+    if (a.desc && threadIdx.x < nk) {
+        const float factorPI = (float)(3.14159265358979323846 / 180.f);
+        double sn, cs;
+        sincos((double)sb_fmul(s_ang[threadIdx.x], factorPI), &sn, &cs);
+        s_cos[threadIdx.x] = (float)cs;
+        s_sin[threadIdx.x] = (float)sn;
+    }
+    __syncthreads();
+    // phase C: descriptor (lane i -> byte i) and the keypoint record
+    for (int i = warp; i < nk; i += DESC_WARPS) {
+        const uint32_t w = sel[i];
+        const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;
+        const long long row = (long long)img * a.cap + offset + k0 + i;
+        if (a.desc) {
+            const uint8_t *center = a.blur + base + (long long)y * L.pitch + x;
+            const float ca = s_cos[i], sb = s_sin[i];
+            uint32_t val = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float4 q = pat[j * 32 + lane];
+                const int t0 = sb_brief_sample(center, L.pitch, ca, sb, q.x, q.y);
+                const int t1 = sb_brief_sample(center, L.pitch, ca, sb, q.z, q.w);
+                val |= (uint32_t)(t0 < t1) << j;
+            }
+            a.desc[row * 32 + lane] = (uint8_t)val;
+        }
+        float fx = (float)x, fy = (float)y;
+        if (level != 0) { fx = sb_fmul(fx, L.scale); fy = sb_fmul(fy, L.scale); }  // :975-981
+        warp_store_keypoint(a.kps + row, fx, fy, L.patch, s_ang[i], (float)(w >> 24), level, -1, lane);
+    }
 }
 
 // Output of Detect (:1062-1073): FAST's size 7 / angle -1 / octave 0 are kept (quirk Q4).
@@ -1172,7 +1203,7 @@ extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8
     da.selcap = h->selcap;
     da.cap = cap;
     prof_begin(h, SB_STAGE_DESCRIBE, 1, h->stream);
-    k_describe<<<dim3(sb_div_up(h->ncap_pyr, DESC_WARPS), h->nlevels, batch), DESC_WARPS * 32, 0, h->stream>>>(h->geom, da);
+    k_describe<<<dim3(sb_div_up(h->ncap_pyr, DESC_KPB), h->nlevels, batch), DESC_WARPS * 32, 0, h->stream>>>(h->geom, da);
     prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
