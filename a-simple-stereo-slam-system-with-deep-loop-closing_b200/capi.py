@@ -483,3 +483,41 @@ class StereoFrontend:
         self.submit(images, out)
         self.wait()
         return out
+
+
+class PoseOnlyOptimizer:
+    """The g2o solve of Frontend::EstimateCurrentPose (src/frontend.cpp:176-276; pre_rounds=0) and
+    LoopClosing::OptimizeCurrentPose (src/loopclosing.cpp:339-433; pre_rounds=1), batched over frames."""
+
+    def __init__(self, max_frames=1, max_obs=2048, device=0):
+        self._h = C.c_void_p()
+        self.F, self.MO = max_frames, max_obs
+        _check(lib().sb_pose_create(C.byref(self._h), device, max_frames, max_obs))
+
+    def close(self):
+        if self._h:
+            lib().sb_pose_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, frames, K, huber_delta=1.0, chi2_th=5.991, pre_rounds=0, rounds=4, inner_iters=10):
+        """frames: list of dicts (pose0 [7], points [n,3], uv [n,2]) -> list of (pose, outlier, info)."""
+        n = len(frames)
+        cnt = np.array([len(f["points"]) for f in frames], np.int32)
+        poses = np.stack([np.asarray(f["pose0"], np.float64) for f in frames])
+        pts = np.zeros((n, self.MO, 3))
+        uv = np.zeros((n, self.MO, 2))
+        for k, f in enumerate(frames):
+            pts[k, :cnt[k]] = f["points"]
+            uv[k, :cnt[k]] = f["uv"]
+        K = np.ascontiguousarray(K, np.float64)
+        outl = np.zeros((n, self.MO), np.uint8)
+        info = np.zeros((n, 4), np.int32)
+        _check(lib().sb_pose_solve(self._h, n, _p(cnt), _p(poses), _p(pts), _p(uv), _p(K), C.c_double(huber_delta),
+                                   C.c_double(chi2_th), pre_rounds, rounds, inner_iters, _p(outl), _p(info)))
+        return [(poses[k].copy(), outl[k, :cnt[k]].copy(), info[k].copy()) for k in range(n)]

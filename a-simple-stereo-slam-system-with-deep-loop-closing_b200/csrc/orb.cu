@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
         const int y = e >> 8, x = e & 255;
         const uint8_t *q = sc + y * BW + xo + x;
         const int s = q[0];
+        if (s == 0) continue;  // listed by the pre-test but not a corner (the majority)
         const int nb = max(max(max((int)q[-1], (int)q[1]), max((int)q[-BW - 1], (int)q[-BW])),
                            max(max((int)q[-BW + 1], (int)q[BW - 1]), max((int)q[BW], (int)q[BW + 1])));
         if (s > nb) {  // s > 0 follows: neighbours are >= 0

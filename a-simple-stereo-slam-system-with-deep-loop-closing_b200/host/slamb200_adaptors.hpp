@@ -334,4 +334,34 @@ private:
     sb_posegraph_t *h_ = nullptr;
 };
 
+// -----------------------------------------------------------------------------------------------------
+// The solver of Frontend::EstimateCurrentPose (src/frontend.cpp:176-276, preRounds = 0) and of
+// LoopClosing::OptimizeCurrentPose (src/loopclosing.cpp:339-433, preRounds = 1).
+class PoseOnlySolver {
+public:
+    explicit PoseOnlySolver(int max_obs = 4096, int device = 0) : mo_(max_obs) {
+        if (sb_pose_create(&h_, device, 1, max_obs) != SB_OK) throw std::runtime_error(std::string("sb_pose_create: ") + sb_last_error());
+    }
+    ~PoseOnlySolver() { sb_pose_destroy(h_); }
+    // pose7: qx qy qz qw tx ty tz (in/out); points3 / uv2: one row per matched map point; returns the number of
+    // inliers (what the reference's functions return) and fills `outlier`.
+    int Optimize(double pose7[7], const std::vector<double> &points3, const std::vector<double> &uv2, const double K[4],
+                 std::vector<uint8_t> &outlier, int preRounds = 0, double chi2_th = 5.991) {
+        const int32_t n = (int32_t)(uv2.size() / 2);
+        if (n > mo_) { detail::last_status() = SB_ERR_CAPACITY; return -1; }
+        std::vector<double> p((size_t)mo_ * 3, 0.0), u((size_t)mo_ * 2, 0.0);
+        std::copy(points3.begin(), points3.end(), p.begin());
+        std::copy(uv2.begin(), uv2.end(), u.begin());
+        std::vector<uint8_t> o((size_t)mo_);
+        int32_t info[4];
+        detail::last_status() = sb_pose_solve(h_, 1, &n, pose7, p.data(), u.data(), K, 1.0, chi2_th, preRounds, 4, 10, o.data(), info);
+        if (detail::last_status() != SB_OK) return -1;
+        outlier.assign(o.begin(), o.begin() + n);
+        return info[0];
+    }
+private:
+    sb_pose_t *h_ = nullptr;
+    int mo_;
+};
+
 }  // namespace myslam

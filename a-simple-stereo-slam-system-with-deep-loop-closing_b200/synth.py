@@ -237,3 +237,18 @@ def _quat_to_R_np(q):
     return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def pose_only_frame(seed, n_points=250, pix_noise=0.7, outlier_frac=0.1, pose_noise=(0.01, 0.15)):
+    """One tracked frame for Frontend::EstimateCurrentPose: map points seen by a camera, noisy pixel observations
+    (float like cv::KeyPoint::pt), a fraction of gross outliers (LK mis-tracks), a perturbed starting pose.
+    Returns dict: pose0 [7], pose_gt [7], points [n,3], uv [n,2], planted [n] bool."""
+    w = ba_window(seed, n_poses=1, n_points=n_points, pix_noise=pix_noise, outlier_frac=0.0, pose_noise=pose_noise,
+                  point_noise=0.0, fixed_frac=1.0)
+    rng = np.random.default_rng(seed + 9999)
+    pts = w["points_gt"][w["obs_point"]]
+    uv = w["uv"].copy()
+    planted = rng.uniform(size=len(uv)) < outlier_frac
+    uv[planted] += rng.uniform(-40, 40, (int(planted.sum()), 2))
+    uv = uv.astype(np.float32).astype(np.float64)
+    return {"pose0": w["poses0"][0], "pose_gt": w["poses_gt"][0], "points": pts, "uv": uv, "planted": planted}

@@ -257,6 +257,29 @@ int sb_posegraph_solve_dev(sb_posegraph_t *h, int n_vertices, double *d_poses, c
                            const int32_t *d_v0, const int32_t *d_v1, const double *d_meas, int iters, int32_t *d_info,
                            double *d_stats);
 
+/* ---------------------------------------------------------------------------------------------
+ * Pose-only optimisation (SURVEY §8f "next" row 1) — replaces the g2o solve inside
+ * Frontend::EstimateCurrentPose (src/frontend.cpp:176-276) and LoopClosing::OptimizeCurrentPose
+ * (src/loopclosing.cpp:339-433): one pose, one EdgeProjectionPoseOnly (include/myslam/g2o_types.h:63-102)
+ * per matched map point, Huber kernel (g2o default delta 1.0), `pre_rounds` plain optimize(inner_iters)
+ * calls (loop closing: 1, front end: 0) and then `rounds` (4) rounds of optimize(inner_iters) + chi2
+ * classification (outliers sit out the next round; the robust kernels are removed after round rounds-2).
+ * A call solves `n_frames` independent frames:
+ *   poses [F][7] in/out (qx qy qz qw tx ty tz), points [F][max_obs][3] world positions of the matched map
+ *   points, uv [F][max_obs][2] their pixel observations, K = fx fy cx cy,
+ *   outlier [F][max_obs] out, info [F][4] = inliers (the functions' return value), LM iterations, rounds, 0.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sb_pose sb_pose_t;
+int sb_pose_create(sb_pose_t **h, int device, int max_frames, int max_obs);
+int sb_pose_destroy(sb_pose_t *h);
+int sb_pose_set_stream(sb_pose_t *h, void *stream);
+int sb_pose_solve(sb_pose_t *h, int n_frames, const int32_t *n_obs, double *poses, const double *points, const double *uv,
+                  const double *K, double huber_delta, double chi2_th, int pre_rounds, int rounds, int inner_iters,
+                  uint8_t *outlier, int32_t *info);
+int sb_pose_solve_dev(sb_pose_t *h, int n_frames, const int32_t *d_n_obs, double *d_poses, const double *d_points,
+                      const double *d_uv, const double *K, double huber_delta, double chi2_th, int pre_rounds, int rounds,
+                      int inner_iters, uint8_t *d_outlier, int32_t *d_info);
+
 #ifdef __cplusplus
 }
 #endif

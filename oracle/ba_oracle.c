@@ -411,3 +411,134 @@ int orc_ba_solve(int n_poses, int n_points, int n_obs, double *poses, double *po
     free(P.pose); free(P.err);
     return 0;
 }
+
+/* ==========================================================================================================
+ * Pose-only optimisation: Frontend::EstimateCurrentPose (src/frontend.cpp:176-276) and
+ * LoopClosing::OptimizeCurrentPose (src/loopclosing.cpp:339-433) — SURVEY §8(f) "next" row 1.
+ * One VertexPose, one EdgeProjectionPoseOnly per matched map point (include/myslam/g2o_types.h:63-102,
+ * no camera extrinsics), information I2, RobustKernelHuber with g2o's default delta 1.0, LinearSolverDense.
+ * `pre_rounds` un-classified optimize(inner) calls first (loop closing: 1, front end: 0), then `rounds`
+ * (4) rounds of { initializeOptimization(level 0); optimize(inner); classify }: an edge whose chi2 exceeds
+ * chi2_th becomes an outlier (level 1, left out of the next round), otherwise an inlier; outliers of the
+ * previous round are re-evaluated at the new pose first; after round rounds-2 the robust kernels are removed.
+ * chi2() of an active edge is that of g2o's last error evaluation (the last LM trial).
+ * ========================================================================================================== */
+static void po_error(const se3 *T, const double *pt, const double *uv, const double *K, double err[2]) {
+    double pc[3];
+    se3_apply(T, pt, pc);
+    const double px = K[0] * pc[0] + K[2] * pc[2], py = K[1] * pc[1] + K[3] * pc[2];
+    err[0] = uv[0] - px / pc[2];
+    err[1] = uv[1] - py / pc[2];
+}
+
+static double po_active_errors(const se3 *T, int n, const double *pts, const double *uv, const double *K,
+                               const uint8_t *level, int robust, double delta, double *err) {
+    double chi = 0;
+    for (int e = 0; e < n; e++) {
+        if (level[e]) continue;
+        po_error(T, pts + 3 * e, uv + 2 * e, K, err + 2 * e);
+        const double e2 = err[2 * e] * err[2 * e] + err[2 * e + 1] * err[2 * e + 1];
+        if (robust) { double rho[2]; huber(e2, delta, rho); chi += rho[0]; }
+        else chi += e2;
+    }
+    return chi;
+}
+
+static void po_optimize(se3 *T, int n, const double *pts, const double *uv, const double *K, const uint8_t *level,
+                        int robust, double delta, int iters, double *err, int *lm_done) {
+    int n_active = 0;
+    for (int e = 0; e < n; e++) n_active += !level[e];
+    if (n_active == 0) return; /* g2o: "0 vertices to optimize" -> optimize() returns without touching anything */
+    double lambda = 0, ni = 2;
+    int terminated = 0;
+    for (int it = 0; it < iters && !terminated; it++) {
+        double currentChi = po_active_errors(T, n, pts, uv, K, level, robust, delta, err);
+        double H[36], b[6];
+        memset(H, 0, sizeof(H)); memset(b, 0, sizeof(b));
+        for (int e = 0; e < n; e++) {
+            if (level[e]) continue;
+            double pc[3];
+            se3_apply(T, pts + 3 * e, pc);
+            const double X = pc[0], Y = pc[1], Z = pc[2], fx = K[0], fy = K[1];
+            const double Zinv = 1.0 / (Z + 1e-18), Zinv2 = Zinv * Zinv;
+            const double A[12] = {-fx * Zinv, 0, fx * X * Zinv2, fx * X * Y * Zinv2, -fx - fx * X * X * Zinv2, fx * Y * Zinv,
+                                  0, -fy * Zinv, fy * Y * Zinv2, fy + fy * Y * Y * Zinv2, -fy * X * Y * Zinv2, -fy * X * Zinv};
+            const double *r = err + 2 * e;
+            double w = 1.0;
+            if (robust) { double rho[2]; huber(r[0] * r[0] + r[1] * r[1], delta, rho); w = rho[1]; }
+            for (int a = 0; a < 6; a++) {
+                b[a] += -w * (A[a] * r[0] + A[6 + a] * r[1]);
+                for (int c = 0; c < 6; c++) H[6 * a + c] += w * (A[a] * A[c] + A[6 + a] * A[6 + c]);
+            }
+        }
+        if (it == 0) {
+            double mx = 0;
+            for (int a = 0; a < 6; a++) if (fabs(H[7 * a]) > mx) mx = fabs(H[7 * a]);
+            lambda = 1e-5 * mx;
+            ni = 2;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            const se3 bak = *T;
+            double S[36], x[6];
+            memcpy(S, H, sizeof(S)); memcpy(x, b, sizeof(x));
+            for (int a = 0; a < 6; a++) S[7 * a] += lambda;
+            int ok = chol_solve(S, x, 6);
+            if (ok) {
+                se3 E, N;
+                orc_se3_exp(x, E.R, E.t);
+                se3_mul(&E, T, &N);
+                *T = N;
+            }
+            double tempChi = po_active_errors(T, n, pts, uv, K, level, robust, delta, err);
+            if (!ok) tempChi = 1.7976931348623157e308;
+            double scale = 1e-3;
+            if (ok) for (int a = 0; a < 6; a++) scale += x[a] * (lambda * x[a] + b[a]);
+            rho = (currentChi - tempChi) / scale;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow(2 * rho - 1, 3);
+                if (alpha > 2. / 3.) alpha = 2. / 3.;
+                lambda *= alpha > 1. / 3. ? alpha : 1. / 3.;
+                ni = 2;
+                currentChi = tempChi;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                *T = bak;
+            }
+            qmax++;
+        } while (rho < 0 && qmax < 10);
+        (*lm_done)++;
+        if (qmax == 10 || rho == 0) terminated = 1;
+    }
+}
+
+/* pose7 in/out; points [n][3] (world), uv [n][2]; outlier_out [n]; info[4] = inliers, LM iterations, rounds, 0 */
+int orc_pose_only_solve(int n, double *pose7, const double *points, const double *uv, const double *K, double huber_delta,
+                        double chi2_th, int pre_rounds, int rounds, int inner_iters, uint8_t *outlier_out, int32_t *info) {
+    if (n < 0) return -1;
+    se3 T;
+    se3_from7(pose7, &T);
+    uint8_t *level = (uint8_t *)calloc((size_t)(n > 0 ? n : 1), 1);
+    uint8_t *is_out = (uint8_t *)calloc((size_t)(n > 0 ? n : 1), 1);
+    double *err = (double *)calloc((size_t)(n > 0 ? n : 1) * 2, sizeof(double));
+    int robust = 1, lm = 0, n_out = 0;
+    for (int r = 0; r < pre_rounds; r++) po_optimize(&T, n, points, uv, K, level, robust, huber_delta, inner_iters, err, &lm);
+    for (int round = 0; round < rounds; round++) {
+        po_optimize(&T, n, points, uv, K, level, robust, huber_delta, inner_iters, err, &lm);
+        n_out = 0;
+        for (int e = 0; e < n; e++) {
+            if (is_out[e]) po_error(&T, points + 3 * e, uv + 2 * e, K, err + 2 * e);
+            const double c = err[2 * e] * err[2 * e] + err[2 * e + 1] * err[2 * e + 1];
+            if (c > chi2_th) { is_out[e] = 1; level[e] = 1; n_out++; }
+            else { is_out[e] = 0; level[e] = 0; }
+        }
+        if (round == rounds - 2) robust = 0;
+    }
+    se3_to7(&T, pose7);
+    for (int e = 0; e < n; e++) outlier_out[e] = is_out[e];
+    if (info) { info[0] = n - n_out; info[1] = lm; info[2] = pre_rounds + rounds; info[3] = 0; }
+    free(level); free(is_out); free(err);
+    return 0;
+}

@@ -294,3 +294,18 @@ def lcd_detect_loop(db_ids, db_descr, cur_id, cur_descr, thres_high=0.94, thres_
     if max_score < np.float32(thres_high) or cnt > max_suspected:
         return False, best, float(max_score), cnt
     return True, best, float(max_score), cnt
+
+
+def pose_only_solve(pose0, points, uv, K, huber_delta=1.0, chi2_th=5.991, pre_rounds=0, rounds=4, inner_iters=10):
+    """Frontend::EstimateCurrentPose / LoopClosing::OptimizeCurrentPose solver -> (pose [7], outlier [n], info [4])."""
+    pose = np.ascontiguousarray(pose0, np.float64).copy()
+    pts = np.ascontiguousarray(points, np.float64)
+    uv = np.ascontiguousarray(uv, np.float64)
+    K = np.ascontiguousarray(K, np.float64)
+    outl = np.zeros(max(1, len(pts)), np.uint8)
+    info = np.zeros(4, np.int32)
+    lib().orc_pose_only_solve.restype = C.c_int
+    rc = lib().orc_pose_only_solve(len(pts), _p(pose), _p(pts), _p(uv), _p(K), C.c_double(huber_delta), C.c_double(chi2_th),
+                                   pre_rounds, rounds, inner_iters, _p(outl), _p(info))
+    assert rc == 0
+    return pose, outl[:len(pts)], info
