@@ -198,23 +198,60 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     __syncthreads();
     sb_mbar_wait(&bar, 0);
 
-    // Phase 1: pixels that pass the cheap necessary test are compacted into a list, so that the response
+    // Phase 1: pixels that pass the cheap necessary test (sb_fast_maybe's rule: at least two of the four compass
+    // ring pixels darker than v - t, or two brighter than v + t) are compacted into a list, so that the response
     // (about 100 instructions) is later computed by full warps instead of a few lanes of every warp.
-    // Every warp appends to its own segment of the list with a warp-uniform running count: no atomics.
+    // A work item is 4 horizontally adjacent pixels: five aligned 32-bit loads, two funnel shifts, then the
+    // order statistics for two pixels at a time in packed 2 x int16 arithmetic.  Every warp appends to its own
+    // segment of the list with a warp-uniform running count: no atomics.
     const int t0 = min(a.iniTh, a.minTh);
     const int seg = a.tile_bytes >> 2;
     {
         uint16_t *mine = plist + warp * seg;
         int cnt = 0;
         const unsigned lt = (1u << lane) - 1u;
-        for (int y = 3 + warp; y < c.rh - 3; y += FAST_THREADS / 32)
-            for (int xb = 3; xb < c.rw - 3; xb += 32) {
-                const int x = xb + lane;
-                const bool m = x < c.rw - 3 && sb_fast_maybe(tile + y * BW + xo + x, BW, t0);
+        // only the 4-pixel groups that overlap the tested ROI columns [3, rw - 3)
+        const int g0 = (xo + 3) >> 2, G = c.rw > 6 ? ((xo + c.rw - 4) >> 2) - g0 + 1 : 0, rows = c.rh - 6;
+        const int items = rows > 0 ? rows * G : 0;
+        const uint32_t Tp1 = (uint32_t)(t0 + 1) * 0x00010001u;
+        for (int it0 = warp * 32; it0 < items; it0 += FAST_THREADS) {
+            const int it = it0 + lane;
+            uint32_t hit = 0;  // bit j: pixel j of the item passes
+            int y = 0, col = 0;
+            if (it < items) {
+                y = 3 + it / G;
+                col = (g0 + it - (y - 3) * G) << 2;  // tile column of pixel 0
+                const uint32_t *pw = reinterpret_cast<const uint32_t *>(tile + y * BW + col);
+                const uint32_t C = pw[0], U = pw[-3 * (BW >> 2)], D = pw[3 * (BW >> 2)];
+                const uint32_t L = __funnelshift_r(pw[-1], C, 8), R = __funnelshift_r(C, pw[1], 24);
+#pragma unroll
+                for (int hpair = 0; hpair < 2; hpair++) {
+                    const uint32_t sel = hpair ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> two 16-bit halves
+                    const uint32_t v = __byte_perm(C, 0u, sel), r0 = __byte_perm(D, 0u, sel), r8 = __byte_perm(U, 0u, sel);
+                    const uint32_t r4 = __byte_perm(R, 0u, sel), r12 = __byte_perm(L, 0u, sel);
+                    const uint32_t m1 = __vmins2(r0, r4), M1 = __vmaxs2(r0, r4), m2 = __vmins2(r8, r12), M2 = __vmaxs2(r8, r12);
+                    const uint32_t A = __vmaxs2(m1, m2), B = __vmins2(M1, M2);
+                    const uint32_t s2 = __vmins2(A, B), s3 = __vmaxs2(A, B);  // 2nd smallest / 2nd largest of the four
+                    // s2 < v - t  <=>  s2 - v + t < 0 ;  s3 > v + t  <=>  v - s3 + t < 0   (x - y = x + ~y + 1 per half)
+                    const uint32_t dk = __vadd2(__vadd2(s2, ~v), Tp1), br = __vadd2(__vadd2(v, ~s3), Tp1);
+                    const uint32_t neg = (dk | br) & 0x80008000u;
+                    hit |= (((neg >> 15) & 1u) | ((neg >> 30) & 2u)) << (2 * hpair);
+                }
+                // only ROI columns [3, rw - 3) are tested by cv::FAST
+                const int x0 = col - xo;  // ROI column of pixel 0
+                uint32_t valid = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) valid |= (uint32_t)(x0 + j >= 3 && x0 + j < c.rw - 3) << j;
+                hit &= valid;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const bool m = (hit >> j) & 1u;
                 const unsigned bal = __ballot_sync(0xffffffffu, m);
-                if (m) mine[cnt + __popc(bal & lt)] = (uint16_t)((y << 8) | x);
+                if (m) mine[cnt + __popc(bal & lt)] = (uint16_t)((y << 8) | (col - xo + j));
                 cnt += __popc(bal);
             }
+        }
         if (lane == 0) s_cnt[warp] = cnt;
     }
     __syncthreads();
@@ -900,7 +937,7 @@ static int configure(sb_orb *h, int w, int hgt) {
     h->fast_tile_bytes = (int)sb_align_up(fast_tile, 128);
     for (int l = 0; l < h->nlevels; l++) {  // per-warp segment of the candidate-pixel list (k_fast_cells phase 1)
         const LevelGeom &L = g.lv[l];
-        const int need = sb_div_up(L.hCell, FAST_THREADS / 32) * sb_div_up(L.wCell, 32) * 32;
+        const int need = sb_div_up(L.hCell * (L.fast_bw / 4), FAST_THREADS) * 32 * 4;
         SB_REQUIRE(need <= h->fast_tile_bytes / 4, "internal: FAST candidate segment too small");
     }
     h->n_cells = (int)cells.size();
