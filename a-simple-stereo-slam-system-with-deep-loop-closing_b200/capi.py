@@ -521,3 +521,19 @@ class PoseOnlyOptimizer:
         _check(lib().sb_pose_solve(self._h, n, _p(cnt), _p(poses), _p(pts), _p(uv), _p(K), C.c_double(huber_delta),
                                    C.c_double(chi2_th), pre_rounds, rounds, inner_iters, _p(outl), _p(info)))
         return [(poses[k].copy(), outl[k, :cnt[k]].copy(), info[k].copy()) for k in range(n)]
+
+
+def triangulate(uv_left, uv_right, K_left, K_right, pose_left7, pose_right7, T_wc7=None, ratio_th=1e-2, device=0):
+    """myslam::triangulation (include/myslam/algorithm.h:16-33) + the callers' acceptance test, for n correspondences.
+    -> (points [n,3] float64, ok [n] bool)"""
+    ul = np.ascontiguousarray(uv_left, np.float32).reshape(-1, 2)
+    ur = np.ascontiguousarray(uv_right, np.float32).reshape(-1, 2)
+    n = len(ul)
+    pts = np.zeros((max(n, 1), 3))
+    ok = np.zeros(max(n, 1), np.uint8)
+    Kl, Kr = np.ascontiguousarray(K_left, np.float64), np.ascontiguousarray(K_right, np.float64)
+    pl, pr = np.ascontiguousarray(pose_left7, np.float64), np.ascontiguousarray(pose_right7, np.float64)
+    tw = np.ascontiguousarray(T_wc7, np.float64) if T_wc7 is not None else None
+    _check(lib().sb_triangulate(device, n, _p(ul), _p(ur), _p(Kl), _p(Kr), _p(pl), _p(pr), _p(tw), C.c_double(ratio_th),
+                                _p(pts), _p(ok)))
+    return pts[:n], ok[:n].astype(bool)

@@ -364,4 +364,18 @@ private:
     int mo_;
 };
 
+// -----------------------------------------------------------------------------------------------------
+// myslam::triangulation (include/myslam/algorithm.h:16-33) for all left/right correspondences of a frame at once,
+// including the callers' `&& p[2] > 0` (src/frontend.cpp:403,474); Twc7 != nullptr maps accepted points to the world.
+inline bool triangulation_batch(const std::vector<float> &uvLeft, const std::vector<float> &uvRight, const double Kl[4], const double Kr[4],
+                                const double poseLeft7[7], const double poseRight7[7], const double *Twc7,
+                                std::vector<double> &points3, std::vector<uint8_t> &ok, int device = 0) {
+    const int n = (int)(uvLeft.size() / 2);
+    points3.assign((size_t)n * 3, 0.0);
+    ok.assign((size_t)n, 0);
+    detail::last_status() = sb_triangulate(device, n, uvLeft.data(), uvRight.data(), Kl, Kr, poseLeft7, poseRight7, Twc7, 1e-2,
+                                           points3.data(), ok.data());
+    return detail::last_status() == SB_OK;
+}
+
 }  // namespace myslam

@@ -280,6 +280,22 @@ int sb_pose_solve_dev(sb_pose_t *h, int n_frames, const int32_t *d_n_obs, double
                       const double *d_uv, const double *K, double huber_delta, double chi2_th, int pre_rounds, int rounds,
                       int inner_iters, uint8_t *d_outlier, int32_t *d_info);
 
+/* ---------------------------------------------------------------------------------------------
+ * Stereo triangulation (SURVEY §8f "next" row 3) — replaces myslam::triangulation
+ * (include/myslam/algorithm.h:16-33) plus the callers' acceptance test (src/frontend.cpp:403,474) for n
+ * left/right correspondences that share the two camera poses (Camera::Pose() of the left and right
+ * camera): DLT by SVD of the 4x4 system, ok = sigma4 / sigma3 < ratio_th (reference: 1e-2) && z > 0;
+ * accepted and rejected points are both written (like the reference computes pt_world before testing),
+ * mapped by T_wc7 when given (currentPoseTwc * pcamera, src/frontend.cpp:477).
+ *   uv_left / uv_right [n][2] float pixels, K = fx fy cx cy, poses = qx qy qz qw tx ty tz.
+ * --------------------------------------------------------------------------------------------- */
+int sb_triangulate(int device, int n, const float *uv_left, const float *uv_right, const double *K_left,
+                   const double *K_right, const double *pose_left7, const double *pose_right7, const double *T_wc7,
+                   double ratio_th, double *points, uint8_t *ok);
+int sb_triangulate_dev(int device, void *stream, int n, const float *d_uv_left, const float *d_uv_right, const double *K_left,
+                       const double *K_right, const double *pose_left7, const double *pose_right7, const double *T_wc7,
+                       double ratio_th, double *d_points, uint8_t *d_ok);
+
 #ifdef __cplusplus
 }
 #endif

@@ -309,3 +309,29 @@ def pose_only_solve(pose0, points, uv, K, huber_delta=1.0, chi2_th=5.991, pre_ro
                                    pre_rounds, rounds, inner_iters, _p(outl), _p(info))
     assert rc == 0
     return pose, outl[:len(pts)], info
+
+
+def triangulate(uv_left, uv_right, K_left, K_right, pose_left7, pose_right7, T_wc7=None, ratio_th=1e-2):
+    """numpy restatement of myslam::triangulation (include/myslam/algorithm.h:16-33: A from the two 3x4 pose matrices
+    and the normalised points, SVD, V.col(3) / V(3,3)) and of the callers' test `ok && z > 0` (src/frontend.cpp:403,474)."""
+    from oracle import posegraph_oracle as PG
+    ul = np.asarray(uv_left, np.float32).reshape(-1, 2).astype(np.float64)
+    ur = np.asarray(uv_right, np.float32).reshape(-1, 2).astype(np.float64)
+    M = []
+    for p in (pose_left7, pose_right7):
+        R, t = PG.se3_from7(np.asarray(p, np.float64))
+        M.append(np.concatenate([R, t[:, None]], 1))
+    pts, ok = np.zeros((len(ul), 3)), np.zeros(len(ul), bool)
+    for i in range(len(ul)):
+        rows = []
+        for (u, v), K, m in ((ul[i], K_left, M[0]), (ur[i], K_right, M[1])):
+            x, y = (u - K[2]) / K[0], (v - K[3]) / K[1]          # Camera::pixel2camera, depth 1
+            rows += [x * m[2] - m[0], y * m[2] - m[1]]
+        _, s, vt = np.linalg.svd(np.array(rows))
+        p = vt[3, :3] / vt[3, 3]
+        ok[i] = (s[3] / s[2] < ratio_th) and p[2] > 0
+        pts[i] = p
+    if T_wc7 is not None:
+        R, t = PG.se3_from7(np.asarray(T_wc7, np.float64))
+        pts = pts @ R.T + t
+    return pts, ok
