@@ -537,3 +537,44 @@ def triangulate(uv_left, uv_right, K_left, K_right, pose_left7, pose_right7, T_w
     _check(lib().sb_triangulate(device, n, _p(ul), _p(ur), _p(Kl), _p(Kr), _p(pl), _p(pr), _p(tw), C.c_double(ratio_th),
                                 _p(pts), _p(ok)))
     return pts[:n], ok[:n].astype(bool)
+
+
+class LKTracker:
+    """cv::calcOpticalFlowPyrLK as Frontend::TrackLastFrame / FindFeaturesInRight call it (src/frontend.cpp:150-153,
+    :358-361), batched over image pairs."""
+
+    def __init__(self, max_w=1241, max_h=376, max_batch=1, max_pts=512, max_level=3, device=0):
+        self._h = C.c_void_p()
+        self.max_batch, self.max_pts = max_batch, max_pts
+        _check(lib().sb_lk_create(C.byref(self._h), device, max_w, max_h, max_batch, max_pts, max_level))
+
+    def close(self):
+        if self._h:
+            lib().sb_lk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def track(self, prev_imgs, next_imgs, prev_pts, next_pts0=None, win=11, max_count=30, eps=0.01, min_eig_th=1e-4):
+        """prev_imgs / next_imgs: lists of equally sized uint8 images; prev_pts: list of [n,2]; next_pts0: list of [n,2] or
+        None (no OPTFLOW_USE_INITIAL_FLOW).  -> list of (next_pts [n,2] float32, status [n] uint8)"""
+        B = len(prev_imgs)
+        prev_imgs = [np.ascontiguousarray(i, np.uint8) for i in prev_imgs]
+        next_imgs = [np.ascontiguousarray(i, np.uint8) for i in next_imgs]
+        h, w = prev_imgs[0].shape
+        cnt = np.array([len(p) for p in prev_pts], np.int32)
+        pp = np.zeros((B, self.max_pts, 2), np.float32)
+        npts = np.zeros((B, self.max_pts, 2), np.float32)
+        for b in range(B):
+            pp[b, :cnt[b]] = prev_pts[b]
+            npts[b, :cnt[b]] = next_pts0[b] if next_pts0 is not None else prev_pts[b]
+        status = np.zeros((B, self.max_pts), np.uint8)
+        PA = C.c_void_p * B
+        _check(lib().sb_lk_track(self._h, B, PA(*[i.ctypes.data for i in prev_imgs]), PA(*[i.ctypes.data for i in next_imgs]), w, h, w,
+                                 _p(cnt), _p(pp), _p(npts), _p(status), win, max_count, C.c_double(eps),
+                                 int(next_pts0 is not None), C.c_float(min_eig_th)))
+        return [(npts[b, :cnt[b]].copy(), status[b, :cnt[b]].copy()) for b in range(B)]

@@ -365,6 +365,37 @@ private:
 };
 
 // -----------------------------------------------------------------------------------------------------
+// cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, Size(11,11), 3, (COUNT+EPS, 30, 0.01),
+// OPTFLOW_USE_INITIAL_FLOW) as called at src/frontend.cpp:150-153 and :358-361.  nextPts carries the initial guess in
+// and the tracked position out; status[i] = 1 where the track succeeded.
+class LKTracker {
+public:
+    LKTracker(int max_w = 1280, int max_h = 1024, int max_pts = 4096, int device = 0) : mp_(max_pts) {
+        if (sb_lk_create(&h_, device, max_w, max_h, 1, max_pts, 3) != SB_OK) throw std::runtime_error(std::string("sb_lk_create: ") + sb_last_error());
+    }
+    ~LKTracker() { sb_lk_destroy(h_); }
+    bool calcOpticalFlowPyrLK(cv::InputArray _prev, cv::InputArray _next, const std::vector<float> &prevPts2, std::vector<float> &nextPts2,
+                              std::vector<uint8_t> &status) {
+        const cv::Mat prev = detail::as_mat(_prev), next = detail::as_mat(_next);
+        const int32_t n = (int32_t)(prevPts2.size() / 2);
+        if (prev.empty() || next.empty() || n > mp_) { detail::last_status() = SB_ERR_INVALID; return false; }
+        std::vector<float> pp((size_t)mp_ * 2, 0.f), np((size_t)mp_ * 2, 0.f);
+        std::copy(prevPts2.begin(), prevPts2.end(), pp.begin());
+        std::copy(nextPts2.begin(), nextPts2.begin() + 2 * n, np.begin());
+        std::vector<uint8_t> st((size_t)mp_);
+        const uint8_t *pi = prev.data, *ni = next.data;
+        detail::last_status() = sb_lk_track(h_, 1, &pi, &ni, prev.cols, prev.rows, (int)prev.step, &n, pp.data(), np.data(), st.data(), 11, 30, 0.01, 1, 1e-4f);
+        if (detail::last_status() != SB_OK) return false;
+        nextPts2.assign(np.begin(), np.begin() + 2 * n);
+        status.assign(st.begin(), st.begin() + n);
+        return true;
+    }
+private:
+    sb_lk_t *h_ = nullptr;
+    int mp_;
+};
+
+// -----------------------------------------------------------------------------------------------------
 // myslam::triangulation (include/myslam/algorithm.h:16-33) for all left/right correspondences of a frame at once,
 // including the callers' `&& p[2] > 0` (src/frontend.cpp:403,474); Twc7 != nullptr maps accepted points to the world.
 inline bool triangulation_batch(const std::vector<float> &uvLeft, const std::vector<float> &uvRight, const double Kl[4], const double Kr[4],

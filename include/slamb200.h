@@ -296,6 +296,26 @@ int sb_triangulate_dev(int device, void *stream, int n, const float *d_uv_left, 
                        const double *K_right, const double *pose_left7, const double *pose_right7, const double *T_wc7,
                        double ratio_th, double *d_points, uint8_t *d_ok);
 
+/* ---------------------------------------------------------------------------------------------
+ * Pyramidal Lucas-Kanade tracking (SURVEY §8f "next" row 1) — replaces cv::calcOpticalFlowPyrLK as called
+ * by Frontend::TrackLastFrame (src/frontend.cpp:150-153) and Frontend::FindFeaturesInRight (:358-361):
+ * winSize (win, win) = (11, 11), maxLevel (create time) = 3, criteria COUNT+EPS (max_count 30, eps 0.01),
+ * OPTFLOW_USE_INITIAL_FLOW, minEigThreshold 1e-4.  `batch` image pairs per call, up to max_pts points each:
+ *   prev_pts [batch][max_pts][2] float; next_pts [batch][max_pts][2] in (initial guess when
+ *   use_initial_flow) / out; status [batch][max_pts] (1 = tracked); n_pts [batch].
+ * The error output of the OpenCV call is not produced (the reference ignores it).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sb_lk sb_lk_t;
+int sb_lk_create(sb_lk_t **h, int device, int max_w, int max_h, int max_batch, int max_pts, int max_level);
+int sb_lk_destroy(sb_lk_t *h);
+int sb_lk_set_stream(sb_lk_t *h, void *stream);
+int sb_lk_track(sb_lk_t *h, int batch, const uint8_t *const *prev, const uint8_t *const *next, int w, int hgt, int stride,
+                const int32_t *n_pts, const float *prev_pts, float *next_pts, uint8_t *status, int win, int max_count,
+                double eps, int use_initial_flow, float min_eig_th);
+int sb_lk_track_dev(sb_lk_t *h, int batch, const uint8_t *d_prev_img, const uint8_t *d_next_img, int64_t img_pitch_bytes, int w,
+                    int hgt, int stride, const int32_t *d_n_pts, const float *d_prev_pts, float *d_next_pts, uint8_t *d_status,
+                    int win, int max_count, double eps, int use_initial_flow, float min_eig_th);
+
 #ifdef __cplusplus
 }
 #endif

@@ -335,3 +335,38 @@ def triangulate(uv_left, uv_right, K_left, K_right, pose_left7, pose_right7, T_w
         R, t = PG.se3_from7(np.asarray(T_wc7, np.float64))
         pts = pts @ R.T + t
     return pts, ok
+
+
+# ---------------------------------------------------------------------------------------------------
+# pyramidal Lucas-Kanade (oracle/lk_oracle.c)
+# ---------------------------------------------------------------------------------------------------
+def pyr_down(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().orc_pyr_down_u8(_p(img), w, h, img.strides[0], _p(out), out.strides[0])
+    return out
+
+
+def scharr(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = np.empty((h, w, 2), np.int16)
+    lib().orc_scharr_u8(_p(img), w, h, img.strides[0], _p(out))
+    return out
+
+
+def lk_track(prev, nxt, prev_pts, next_pts0=None, win=11, max_level=3, max_count=30, eps=0.01, min_eig_th=1e-4):
+    """cv::calcOpticalFlowPyrLK as the front end calls it (src/frontend.cpp:150-153).  next_pts0 given ->
+    OPTFLOW_USE_INITIAL_FLOW.  -> (next_pts [n,2] float32, status [n] uint8)"""
+    prev = np.ascontiguousarray(prev, np.uint8)
+    nxt = np.ascontiguousarray(nxt, np.uint8)
+    pp = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+    use_init = next_pts0 is not None
+    npts = np.ascontiguousarray(next_pts0, np.float32).reshape(-1, 2).copy() if use_init else pp.copy()
+    status = np.zeros(max(1, len(pp)), np.uint8)
+    lib().orc_lk_track.restype = C.c_int
+    rc = lib().orc_lk_track(_p(prev), _p(nxt), prev.shape[1], prev.shape[0], prev.strides[0], len(pp), _p(pp), _p(npts),
+                            _p(status), win, max_level, max_count, C.c_double(eps), int(use_init), C.c_float(min_eig_th))
+    assert rc == 0
+    return npts, status[:len(pp)]
