@@ -578,3 +578,107 @@ class LKTracker:
                                  _p(cnt), _p(pp), _p(npts), _p(status), win, max_count, C.c_double(eps),
                                  int(next_pts0 is not None), C.c_float(min_eig_th)))
         return [(npts[b, :cnt[b]].copy(), status[b, :cnt[b]].copy()) for b in range(B)]
+
+
+class CalcLayer(C.Structure):
+    """sb_calc_layer (include/slamb200.h)."""
+    _fields_ = [("type", C.c_int32), ("num_output", C.c_int32), ("kernel", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("local_size", C.c_int32), ("alpha", C.c_float), ("beta", C.c_float), ("k", C.c_float)]
+
+
+# deploy.prototxt of the reference's DeepLCD model restated as a layer list (absent from the reference tree: CALC's
+# published architecture, which yields the 1064 outputs src/deeplcd.cpp:82 asserts)
+CALC_LAYERS = (
+    dict(type=0, num_output=64, kernel=5, stride=2, pad=4), dict(type=1),
+    dict(type=2, kernel=3, stride=2, pad=0), dict(type=3, local_size=5, alpha=1e-4, beta=0.75, k=1.0),
+    dict(type=0, num_output=128, kernel=4, stride=1, pad=2), dict(type=1),
+    dict(type=2, kernel=3, stride=2, pad=0), dict(type=3, local_size=5, alpha=1e-4, beta=0.75, k=1.0),
+    dict(type=0, num_output=4, kernel=3, stride=1, pad=0), dict(type=1),
+)
+
+
+def parse_caffe(prototxt, caffemodel):
+    """(layers, weights, (in_h, in_w)) of a Caffe deploy.prototxt + .caffemodel pair (sb_calc_parse_caffe; no device needed)."""
+    nl, nw, shape = C.c_int(), C.c_int64(), (C.c_int * 2)()
+    a, b = os.fsencode(prototxt), os.fsencode(caffemodel)
+    _check(lib().sb_calc_parse_caffe(a, b, None, 0, C.byref(nl), None, C.c_int64(0), C.byref(nw), shape))
+    arr = (CalcLayer * nl.value)()
+    w = np.empty(nw.value, np.float32)
+    _check(lib().sb_calc_parse_caffe(a, b, arr, nl.value, C.byref(nl), _p(w), C.c_int64(w.size), C.byref(nw), shape))
+    layers = [dict(type=L.type, num_output=L.num_output, kernel=L.kernel, stride=L.stride, pad=L.pad, local_size=L.local_size,
+                   alpha=L.alpha, beta=L.beta, k=L.k) for L in arr]
+    return layers, w, (shape[0], shape[1])
+
+
+class DeepLCD:
+    """myslam::DeepLCD (include/myslam/deeplcd.h:20-48) with the network given as (layers, weights) instead of
+    (deploy.prototxt, calc.caffemodel): calcDescrOriginalImg / calcDescr / score, batched."""
+
+    def __init__(self, weights, layers=CALC_LAYERS, in_h=120, in_w=160, max_batch=1, max_img_w=1241, max_img_h=376, device=0):
+        self._h = C.c_void_p()
+        arr = (CalcLayer * len(layers))()
+        for i, L in enumerate(layers):
+            arr[i] = CalcLayer(L["type"], L.get("num_output", 0), L.get("kernel", 0), L.get("stride", 0), L.get("pad", 0),
+                               L.get("local_size", 0), L.get("alpha", 0.0), L.get("beta", 0.0), L.get("k", 0.0))
+        w = np.ascontiguousarray(weights, np.float32)
+        _check(lib().sb_calc_create(C.byref(self._h), device, in_h, in_w, arr, len(layers), _p(w), C.c_int64(w.size), max_batch,
+                                    max_img_w, max_img_h))
+        self.dim = lib().sb_calc_descr_dim(self._h)
+        self.in_h, self.in_w, self.max_batch = in_h, in_w, max_batch
+
+    @classmethod
+    def from_caffe(cls, prototxt="calc_model/deploy.prototxt", caffemodel="calc_model/calc.caffemodel", gpu_id=0, **kw):
+        """DeepLCD(network_definition_file, pre_trained_model_file, gpu_id) (include/myslam/deeplcd.h:35)."""
+        layers, weights, (in_h, in_w) = parse_caffe(prototxt, caffemodel)
+        return cls(weights, layers=layers, in_h=in_h, in_w=in_w, device=gpu_id, **kw)
+
+    def close(self):
+        if self._h:
+            lib().sb_calc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream_ptr):
+        _check(lib().sb_calc_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def calcDescrOriginalImgBatch(self, images, in_place=True):
+        """Returns descriptors [n][dim]; with in_place the images (writable u8 arrays) come back blurred, as the
+        reference leaves KeyFrame::mImageLeft (src/deeplcd.cpp:46)."""
+        imgs = [np.asarray(i) for i in images]
+        h, w = imgs[0].shape
+        for i in imgs:
+            assert i.dtype == np.uint8 and i.shape == (h, w) and i.strides[1] == 1
+        stride = imgs[0].strides[0]
+        assert all(i.strides[0] == stride for i in imgs)
+        ptrs = (C.c_void_p * len(imgs))(*[i.ctypes.data for i in imgs])
+        descr = np.empty((len(imgs), self.dim), np.float32)
+        _check(lib().sb_calc_descr_original(self._h, len(imgs), ptrs, w, h, stride, _p(descr), ptrs if in_place else None))
+        return descr
+
+    def calcDescrOriginalImg(self, image, in_place=True):
+        return self.calcDescrOriginalImgBatch([image], in_place)[0]
+
+    def calcDescrBatch(self, images):
+        imgs = [np.ascontiguousarray(i, np.uint8) for i in images]
+        for i in imgs:
+            assert i.shape == (self.in_h, self.in_w)
+        ptrs = (C.c_void_p * len(imgs))(*[i.ctypes.data for i in imgs])
+        descr = np.empty((len(imgs), self.dim), np.float32)
+        _check(lib().sb_calc_descr(self._h, len(imgs), ptrs, self.in_w, _p(descr)))
+        return descr
+
+    def calcDescr(self, image):
+        return self.calcDescrBatch([image])[0]
+
+    def descr_original_dev(self, batch, d_img, img_pitch, w, h, stride, d_descr, d_blurred=None):
+        _check(lib().sb_calc_descr_original_dev(self._h, batch, _dev_ptr(d_img), C.c_int64(img_pitch), w, h, stride, _dev_ptr(d_descr),
+                                                _dev_ptr(d_blurred)))
+
+    @staticmethod
+    def score(d1, d2):
+        raise NotImplementedError("scoring runs on the keyframe database: DeepLCDScorer.score / DetectLoop")

@@ -1,0 +1,509 @@
+// calc.cu — DeepLCD whole-image descriptor (the CALC auto-encoder's encoder) on B200 (sm_100a).
+//
+// SURVEY §8f "next" row 2.  Replaces DeepLCD::calcDescrOriginalImg / DeepLCD::calcDescr (reference
+// src/deeplcd.cpp:43-91) for a BATCH of keyframe images per call:
+//   cv::GaussianBlur(img, img, Size(7,7), 0)  :46   -> k_calc_blur    (u8 fixed point, kernel [8 28 56 72 56 28 8] / 256,
+//                                                                      REFLECT_101; the blurred image can be handed back:
+//                                                                      the reference blurs the caller's image in place)
+//   cv::resize(img, 160 x 120)                :49-50 -> k_calc_resize  (fixed-point bilinear) fused with
+//   im.convertTo(CV_32FC1, 1/255)             :66                      the u8 -> float * (1/255) conversion
+//   autoencoder->Forward()                    :69   -> k_calc_conv / k_calc_pool / k_calc_lrn, one launch per Caffe layer
+//                                                      (ReLU fused into the convolution that precedes it)
+//   descriptor /= descriptor.norm()           :88   -> k_calc_normalize
+// The network is DATA: the layer list (what deploy.prototxt says) and one flat fp32 weight buffer in Caffe's blob order
+// (what calc.caffemodel holds) are given at create time.  Caffe's layer rules are restated in oracle/calc_oracle.py.
+// Activations live in HBM as fp32 [batch][C][H][W], two ping-pong buffers sized for the largest blob.
+// Convolutions run as implicit GEMM in fp32 on the CUDA cores (64 pixels x 64 output channels per CTA, K in chunks of
+// 16 through shared memory): the reference computes in fp32 and its two score thresholds are 0.02 apart.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "orb_core.inl"
+
+#define CALC_MAX_LAYERS 32
+#define CONV_TP 64   // output pixels per CTA
+#define CONV_TC 64   // output channels per CTA
+#define CONV_KC 16   // reduction chunk
+#define BLUR_W 128
+#define BLUR_H 16
+
+struct CalcLayer {
+    int type;
+    int ic, ih, iw, oc, oh, ow;
+    int kernel, stride, pad;
+    int relu;            // convolution followed by a ReLU layer (fused)
+    int local_size;
+    float alpha, beta, k;
+    size_t w_off, b_off; // into d_wt: transposed weights [K][ocp], bias [ocp]
+    int ocp, K;          // oc rounded up to CONV_TC, ic * kernel^2
+    size_t kt_off;       // into d_ktab
+};
+
+struct sb_calc {
+    int device, in_h, in_w, max_batch, max_img_w, max_img_h, dim;
+    cudaStream_t stream, own_stream;
+    std::vector<CalcLayer> *plan;
+    float *d_wt;
+    int2 *d_ktab;
+    float *d_act[2];
+    size_t act_elems;    // per image
+    uint8_t *d_img, *d_blur;   // [max_batch][max_img_h][row]
+    float *d_descr;
+    int2 *d_xtab, *d_ytab;     // resize tables for (cur_w, cur_h) -> (in_w, in_h)
+    int cur_w, cur_h;
+    float *h_descr;            // pinned
+};
+
+// ================================================================================================
+// kernels
+// ================================================================================================
+
+// cv::GaussianBlur 7x7, sigma 0 (OpenCV's built-in table), u8 fixed point.  One CTA = 128 x 16 output pixels.
+__global__ void __launch_bounds__(256) k_calc_blur(const uint8_t *__restrict__ src, long long src_img, int src_stride,
+                                                  uint8_t *__restrict__ dst, long long dst_img, int dst_stride, int w, int h) {
+    __shared__ uint8_t raw[BLUR_H + 6][BLUR_W + 8];
+    __shared__ uint16_t rows[BLUR_H + 6][BLUR_W];
+    const int x0 = blockIdx.x * BLUR_W, y0 = blockIdx.y * BLUR_H;
+    const uint8_t *S = src + (long long)blockIdx.z * src_img;
+    for (int i = threadIdx.x; i < (BLUR_H + 6) * (BLUR_W + 6); i += 256) {
+        const int ry = i / (BLUR_W + 6), rx = i - ry * (BLUR_W + 6);
+        const int sy = sb_reflect101(y0 + ry - 3, h), sx = sb_reflect101(x0 + rx - 3, w);
+        raw[ry][rx] = S[(long long)sy * src_stride + sx];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (BLUR_H + 6) * BLUR_W; i += 256) {
+        const int ry = i / BLUR_W, rx = i - ry * BLUR_W;
+        const uint8_t *p = &raw[ry][rx];
+        rows[ry][rx] = (uint16_t)(8u * (p[0] + p[6]) + 28u * (p[1] + p[5]) + 56u * (p[2] + p[4]) + 72u * p[3]);  // 8.8, <= 255 * 256
+    }
+    __syncthreads();
+    uint8_t *D = dst + (long long)blockIdx.z * dst_img;
+    for (int i = threadIdx.x; i < BLUR_H * BLUR_W; i += 256) {
+        const int ry = i / BLUR_W, rx = i - ry * BLUR_W;
+        const int x = x0 + rx, y = y0 + ry;
+        if (x >= w || y >= h) continue;
+        const unsigned acc = 8u * (rows[ry][rx] + rows[ry + 6][rx]) + 28u * (rows[ry + 1][rx] + rows[ry + 5][rx]) +
+                             56u * (rows[ry + 2][rx] + rows[ry + 4][rx]) + 72u * rows[ry + 3][rx];
+        D[(long long)y * dst_stride + x] = (uint8_t)((acc + 32768u) >> 16);
+    }
+}
+
+// cv::resize(INTER_LINEAR) to the net's input size + convertTo(CV_32F, 1/255).  xtab/ytab: (source index, c0 | c1 << 16).
+__global__ void __launch_bounds__(256) k_calc_resize(const uint8_t *__restrict__ src, long long src_img, int src_stride, int sw, int sh,
+                                                    const int2 *__restrict__ xtab, const int2 *__restrict__ ytab, float *__restrict__ out,
+                                                    long long out_img, int ow, int oh) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= ow * oh) return;
+    const int y = i / ow, x = i - y * ow;
+    const uint8_t *S = src + (long long)blockIdx.y * src_img;
+    const int2 xt = xtab[x], yt = ytab[y];
+    const int sx = xt.x, sx1 = min(sx + 1, sw - 1), ca = xt.y & 0xffff, cb = (unsigned)xt.y >> 16;
+    const int sy0 = min(max(yt.x, 0), sh - 1), sy1 = min(max(yt.x + 1, 0), sh - 1), b0 = yt.y & 0xffff, b1 = (unsigned)yt.y >> 16;
+    const uint8_t *R0 = S + (long long)sy0 * src_stride, *R1 = S + (long long)sy1 * src_stride;
+    const int v = sb_lin_vert(R0[sx] * ca + R0[sx1] * cb, R1[sx] * ca + R1[sx1] * cb, b0, b1);
+    out[(long long)blockIdx.y * out_img + i] = __fmul_rn((float)v, 1.0f / 255.0f);
+}
+
+// calcDescr on an image that already has the net's input size: convertTo only.
+__global__ void k_calc_u8_to_float(const uint8_t *__restrict__ src, long long src_img, int src_stride, float *__restrict__ out,
+                                   long long out_img, int w, int h) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= w * h) return;
+    const int y = i / w, x = i - y * w;
+    out[(long long)blockIdx.y * out_img + i] = __fmul_rn((float)src[(long long)blockIdx.y * src_img + (long long)y * src_stride + x], 1.0f / 255.0f);
+}
+
+// Caffe Convolution (+ fused ReLU) as implicit GEMM: out[p][c] = bias[c] + sum_k A[p][k] * Wt[k][c], p = output pixel,
+// k = (ci, ky, kx).  grid = (pixel tiles, channel tiles, batch); 256 threads, each 4 pixels x 4 channels.
+struct ConvArgs {
+    const float *in;
+    float *out;
+    const float *wt, *bias;
+    const int2 *ktab;   // k -> (ci * ih * iw + ky * iw + kx, ky | kx << 8)
+    long long in_img, out_img;
+    int ih, iw, oc, ocp, oh, ow, K, stride, pad;
+};
+
+template <bool RELU>
+__global__ void __launch_bounds__(256) k_calc_conv(const __grid_constant__ ConvArgs a) {
+    __shared__ __align__(16) float As[CONV_KC][CONV_TP];
+    __shared__ __align__(16) float Bs[CONV_KC][CONV_TC];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int p0 = blockIdx.x * CONV_TP, c0 = blockIdx.y * CONV_TC, npix = a.oh * a.ow;
+    const float *in = a.in + (long long)blockIdx.z * a.in_img;
+    // this thread's im2col gather: one pixel, 4 reduction indices per chunk
+    const int pa = tid & 63, ka = tid >> 6;
+    const int p = p0 + pa;
+    const bool pvalid = p < npix;
+    const int oy = pvalid ? p / a.ow : 0, ox = pvalid ? p - oy * a.ow : 0;
+    const int iy0 = oy * a.stride - a.pad, ix0 = ox * a.stride - a.pad;
+    const int base = iy0 * a.iw + ix0;
+    // weight tile: row tid >> 4, 4 channels at (tid & 15) * 4
+    const float *wrow = a.wt + c0 + tx * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < a.K; k0 += CONV_KC) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int kk = ka + 4 * i, k = k0 + kk;
+            float v = 0.f;
+            if (pvalid && k < a.K) {
+                const int2 t = a.ktab[k];
+                const int iy = iy0 + (t.y & 255), ix = ix0 + (t.y >> 8);
+                if ((unsigned)iy < (unsigned)a.ih && (unsigned)ix < (unsigned)a.iw) v = in[base + t.x];
+            }
+            As[kk][pa] = v;
+        }
+        {
+            const int k = k0 + ty;
+            float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < a.K) w4 = *reinterpret_cast<const float4 *>(wrow + (size_t)k * a.ocp);
+            *reinterpret_cast<float4 *>(&Bs[ty][tx * 4]) = w4;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CONV_KC; kk++) {
+            const float4 av = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *out = a.out + (long long)blockIdx.z * a.out_img;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int c = c0 + tx * 4 + j;
+        if (c >= a.oc) continue;
+        const float b = a.bias[c];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = p0 + ty * 4 + i;
+            if (q >= npix) continue;
+            float v = acc[i][j] + b;
+            if (RELU) v = fmaxf(v, 0.f);
+            out[(size_t)c * npix + q] = v;
+        }
+    }
+}
+
+// Caffe Pooling MAX: windows clipped to the image.  One thread per output element.
+__global__ void k_calc_pool(const float *__restrict__ in, float *__restrict__ out, long long in_img, long long out_img, int c, int ih, int iw,
+                            int oh, int ow, int kernel, int stride, int pad) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= c * oh * ow) return;
+    const int ch = i / (oh * ow), r = i - ch * oh * ow, oy = r / ow, ox = r - oy * ow;
+    const int y0 = max(oy * stride - pad, 0), y1 = min(oy * stride - pad + kernel, ih);
+    const int x0 = max(ox * stride - pad, 0), x1 = min(ox * stride - pad + kernel, iw);
+    const float *P = in + (long long)blockIdx.y * in_img + (size_t)ch * ih * iw;
+    float m = -3.402823466e+38f;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) m = fmaxf(m, P[y * iw + x]);
+    out[(long long)blockIdx.y * out_img + i] = m;
+}
+
+// Caffe LRN, ACROSS_CHANNELS: y_c = x_c * (k + alpha / n * sum_{c' in window} x_c'^2) ^ -beta.
+__global__ void k_calc_lrn(const float *__restrict__ in, float *__restrict__ out, long long img, int c, int hw, int n, float alpha_over_n,
+                           float beta, float k) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= c * hw) return;
+    const int ch = i / hw, r = i - ch * hw;
+    const float *P = in + (long long)blockIdx.y * img;
+    float s = 0.f;
+    const int lo = max(ch - n / 2, 0), hi = min(ch - n / 2 + n - 1, c - 1);
+    for (int cc = lo; cc <= hi; cc++) {
+        const float v = P[(size_t)cc * hw + r];
+        s = fmaf(v, v, s);
+    }
+    out[(long long)blockIdx.y * img + i] = P[i] * powf(k + alpha_over_n * s, -beta);
+}
+
+// descriptor /= descriptor.norm() — one CTA per image, fixed-order reduction.
+__global__ void __launch_bounds__(256) k_calc_normalize(const float *__restrict__ in, long long in_img, float *__restrict__ out, int dim) {
+    __shared__ float red[8];
+    const float *P = in + (long long)blockIdx.x * in_img;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < dim; i += 256) s = fmaf(P[i], P[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t += red[k];
+    const float nrm = sqrtf(t);
+    for (int i = threadIdx.x; i < dim; i += 256) out[(size_t)blockIdx.x * dim + i] = P[i] / nrm;
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+static void free_calc(sb_calc *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    void *ptrs[] = {h->d_wt, h->d_ktab, h->d_act[0], h->d_act[1], h->d_img, h->d_blur, h->d_descr, h->d_xtab, h->d_ytab};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_descr) cudaFreeHost(h->h_descr);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h->plan;
+    delete h;
+}
+
+static size_t calc_row(const sb_calc *h) { return sb_align_up((size_t)h->max_img_w, 16); }
+
+extern "C" int sb_calc_create(sb_calc_t **out, int device, int in_h, int in_w, const sb_calc_layer *layers, int n_layers,
+                              const float *weights, int64_t n_weights, int max_batch, int max_img_w, int max_img_h) {
+    sb_clear_error();
+    SB_REQUIRE(out, "null handle pointer");
+    *out = nullptr;
+    SB_REQUIRE(layers && weights, "null pointer");
+    SB_REQUIRE(n_layers >= 1 && n_layers <= CALC_MAX_LAYERS, "n_layers out of range [1, 32]");
+    SB_REQUIRE(in_h >= 1 && in_h <= 4096 && in_w >= 1 && in_w <= 4096, "net input size out of range");
+    SB_REQUIRE(max_batch >= 1 && max_batch <= 4096, "max_batch out of range [1, 4096]");
+    SB_REQUIRE(max_img_w >= in_w && max_img_w <= 8192 && max_img_h >= in_h && max_img_h <= 8192, "max image size out of range");
+    // ---- shape inference with Caffe's rules, weight layout
+    std::vector<CalcLayer> plan;
+    std::vector<float> wt;
+    std::vector<int2> ktab;
+    int c = 1, hh = in_h, ww = in_w;
+    size_t consumed = 0, max_elems = (size_t)in_h * in_w;
+    for (int i = 0; i < n_layers; i++) {
+        const sb_calc_layer &S = layers[i];
+        CalcLayer L;
+        memset(&L, 0, sizeof(L));
+        L.type = S.type; L.ic = c; L.ih = hh; L.iw = ww;
+        if (S.type == SB_CALC_CONV) {
+            SB_REQUIRE(S.num_output >= 1 && S.num_output <= 4096 && S.kernel >= 1 && S.kernel <= 15 && S.stride >= 1 && S.pad >= 0 && S.pad < 128,
+                       "convolution parameters out of range");
+            L.kernel = S.kernel; L.stride = S.stride; L.pad = S.pad;
+            L.oc = S.num_output;
+            SB_REQUIRE(hh + 2 * S.pad >= S.kernel && ww + 2 * S.pad >= S.kernel, "convolution kernel larger than its padded input");
+            L.oh = (hh + 2 * S.pad - S.kernel) / S.stride + 1;
+            L.ow = (ww + 2 * S.pad - S.kernel) / S.stride + 1;
+            L.K = c * S.kernel * S.kernel;
+            L.ocp = (int)sb_align_up((size_t)L.oc, CONV_TC);
+            const size_t nw = (size_t)L.oc * L.K;
+            SB_REQUIRE((int64_t)(consumed + nw + L.oc) <= n_weights, "weight buffer shorter than the layer list needs");
+            L.w_off = wt.size();
+            wt.resize(wt.size() + (size_t)L.K * L.ocp, 0.f);
+            for (int o = 0; o < L.oc; o++)
+                for (int k = 0; k < L.K; k++) wt[L.w_off + (size_t)k * L.ocp + o] = weights[consumed + (size_t)o * L.K + k];
+            consumed += nw;
+            L.b_off = wt.size();
+            wt.resize(wt.size() + L.ocp, 0.f);
+            for (int o = 0; o < L.oc; o++) wt[L.b_off + o] = weights[consumed + o];
+            consumed += L.oc;
+            L.kt_off = ktab.size();
+            for (int ci = 0; ci < c; ci++)
+                for (int ky = 0; ky < S.kernel; ky++)
+                    for (int kx = 0; kx < S.kernel; kx++) ktab.push_back(make_int2(ci * hh * ww + ky * ww + kx, ky | (kx << 8)));
+            L.relu = (i + 1 < n_layers && layers[i + 1].type == SB_CALC_RELU) ? 1 : 0;
+        } else if (S.type == SB_CALC_RELU) {
+            SB_REQUIRE(i > 0 && layers[i - 1].type == SB_CALC_CONV, "a ReLU layer must follow a Convolution layer");
+            continue;  // fused into the convolution before it
+        } else if (S.type == SB_CALC_POOL_MAX) {
+            SB_REQUIRE(S.kernel >= 1 && S.kernel <= 15 && S.stride >= 1 && S.pad >= 0 && S.pad < S.kernel, "pooling parameters out of range");
+            SB_REQUIRE(hh + 2 * S.pad >= S.kernel && ww + 2 * S.pad >= S.kernel, "pooling kernel larger than its padded input");
+            L.kernel = S.kernel; L.stride = S.stride; L.pad = S.pad;
+            L.oc = c;
+            L.oh = (hh + 2 * S.pad - S.kernel + S.stride - 1) / S.stride + 1;
+            L.ow = (ww + 2 * S.pad - S.kernel + S.stride - 1) / S.stride + 1;
+            if (S.pad > 0) {
+                if ((L.oh - 1) * S.stride >= hh + S.pad) L.oh--;
+                if ((L.ow - 1) * S.stride >= ww + S.pad) L.ow--;
+            }
+        } else if (S.type == SB_CALC_LRN) {
+            SB_REQUIRE(S.local_size >= 1 && (S.local_size & 1) && S.local_size <= 255, "LRN local_size must be odd, 1..255");
+            L.local_size = S.local_size; L.alpha = S.alpha; L.beta = S.beta; L.k = S.k;
+            L.oc = c; L.oh = hh; L.ow = ww;
+        } else {
+            SB_REQUIRE(false, "unknown layer type");
+        }
+        c = L.oc; hh = L.oh; ww = L.ow;
+        if ((size_t)c * hh * ww > max_elems) max_elems = (size_t)c * hh * ww;
+        plan.push_back(L);
+    }
+    SB_REQUIRE((int64_t)consumed == n_weights, "weight buffer longer than the layer list needs");
+    SB_REQUIRE(!plan.empty(), "the layer list has no computing layer");
+    SB_TRY(sb_use_device(device));
+    sb_calc *h = new sb_calc();
+    memset(h, 0, sizeof(*h));
+    h->device = device; h->in_h = in_h; h->in_w = in_w; h->max_batch = max_batch; h->max_img_w = max_img_w; h->max_img_h = max_img_h;
+    h->dim = c * hh * ww;
+    h->act_elems = sb_align_up(max_elems, 64);
+    h->plan = new std::vector<CalcLayer>(plan);
+    h->cur_w = h->cur_h = -1;
+    const size_t B = max_batch, plane = calc_row(h) * max_img_h;
+    cudaError_t e = cudaMalloc((void **)&h->d_wt, (wt.size() + 4) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_ktab, (ktab.size() + 1) * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_act[0], B * h->act_elems * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_act[1], B * h->act_elems * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_img, B * plane);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_blur, B * plane);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_descr, B * h->dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_xtab, (size_t)in_w * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_ytab, (size_t)in_h * sizeof(int2));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_descr, B * h->dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess && !wt.empty()) e = cudaMemcpy(h->d_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !ktab.empty()) e = cudaMemcpy(h->d_ktab, ktab.data(), ktab.size() * sizeof(int2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        sb_set_error("sb_calc_create: %s", cudaGetErrorString(e));
+        free_calc(h);
+        return SB_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return SB_OK;
+}
+
+extern "C" int sb_calc_destroy(sb_calc_t *h) {
+    if (h) {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        free_calc(h);
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_calc_set_stream(sb_calc_t *h, void *stream) {
+    SB_REQUIRE(h, "null handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return SB_OK;
+}
+
+extern "C" int sb_calc_descr_dim(const sb_calc_t *h) { return h ? h->dim : SB_ERR_INVALID; }
+
+// Net::Forward over d_act[0] (the input blobs) + normalisation into d_descr.
+static int run_net(sb_calc *h, int batch, float *d_descr) {
+    cudaStream_t s = h->stream;
+    int cur = 0;
+    const long long img = (long long)h->act_elems;
+    for (const CalcLayer &L : *h->plan) {
+        const float *in = h->d_act[cur];
+        float *out = h->d_act[cur ^ 1];
+        if (L.type == SB_CALC_CONV) {
+            ConvArgs a;
+            a.in = in; a.out = out; a.wt = h->d_wt + L.w_off; a.bias = h->d_wt + L.b_off; a.ktab = h->d_ktab + L.kt_off;
+            a.in_img = img; a.out_img = img;
+            a.ih = L.ih; a.iw = L.iw; a.oc = L.oc; a.ocp = L.ocp; a.oh = L.oh; a.ow = L.ow; a.K = L.K; a.stride = L.stride; a.pad = L.pad;
+            const dim3 grid(sb_div_up(L.oh * L.ow, CONV_TP), L.ocp / CONV_TC, batch);
+            if (L.relu) k_calc_conv<true><<<grid, 256, 0, s>>>(a);
+            else k_calc_conv<false><<<grid, 256, 0, s>>>(a);
+        } else if (L.type == SB_CALC_POOL_MAX) {
+            k_calc_pool<<<dim3(sb_div_up(L.oc * L.oh * L.ow, 256), batch), 256, 0, s>>>(in, out, img, img, L.oc, L.ih, L.iw, L.oh, L.ow, L.kernel,
+                                                                                      L.stride, L.pad);
+        } else {
+            k_calc_lrn<<<dim3(sb_div_up(L.oc * L.oh * L.ow, 256), batch), 256, 0, s>>>(in, out, img, L.oc, L.oh * L.ow, L.local_size,
+                                                                                     L.alpha / (float)L.local_size, L.beta, L.k);
+        }
+        cur ^= 1;
+    }
+    k_calc_normalize<<<batch, 256, 0, s>>>(h->d_act[cur], img, d_descr, h->dim);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+}
+
+static int ensure_tables(sb_calc *h, int w, int hgt) {
+    if (h->cur_w == w && h->cur_h == hgt) return SB_OK;
+    std::vector<int2> xt(h->in_w), yt(h->in_h);
+    for (int x = 0; x < h->in_w; x++) {
+        const SbLinCoef c = sb_lin_coef(x, h->in_w, w, true);
+        xt[x] = make_int2(c.s, (int)(((unsigned)(unsigned short)c.c1 << 16) | (unsigned short)c.c0));
+    }
+    for (int y = 0; y < h->in_h; y++) {
+        const SbLinCoef c = sb_lin_coef(y, h->in_h, hgt, false);
+        yt[y] = make_int2(c.s, (int)(((unsigned)(unsigned short)c.c1 << 16) | (unsigned short)c.c0));
+    }
+    // the stream may still be reading the previous tables
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    SB_CUDA(cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    SB_CUDA(cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    h->cur_w = w; h->cur_h = hgt;
+    return SB_OK;
+}
+
+// DeepLCD::calcDescrOriginalImg on device images: image b at d_img + b * img_pitch_bytes, rows `stride` bytes.
+// d_blurred (nullable, same layout) receives the blurred images — what the reference leaves in the caller's cv::Mat.
+extern "C" int sb_calc_descr_original_dev(sb_calc_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes, int w, int hgt, int stride,
+                                          float *d_descr, uint8_t *d_blurred) {
+    sb_clear_error();
+    SB_REQUIRE(h && d_img && d_descr, "null pointer");
+    SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
+    SB_REQUIRE(w >= 1 && hgt >= 1 && w <= h->max_img_w && hgt <= h->max_img_h && stride >= w, "image larger than the handle's maximum or bad stride");
+    SB_TRY(sb_use_device(h->device));
+    SB_TRY(ensure_tables(h, w, hgt));
+    cudaStream_t s = h->stream;
+    uint8_t *blur = d_blurred ? d_blurred : h->d_blur;
+    const long long bimg = d_blurred ? img_pitch_bytes : (long long)(calc_row(h) * h->max_img_h);
+    const int bstride = d_blurred ? stride : (int)calc_row(h);
+    k_calc_blur<<<dim3(sb_div_up(w, BLUR_W), sb_div_up(hgt, BLUR_H), batch), 256, 0, s>>>(d_img, img_pitch_bytes, stride, blur, bimg, bstride, w, hgt);
+    k_calc_resize<<<dim3(sb_div_up(h->in_w * h->in_h, 256), batch), 256, 0, s>>>(blur, bimg, bstride, w, hgt, h->d_xtab, h->d_ytab, h->d_act[0],
+                                                                               (long long)h->act_elems, h->in_w, h->in_h);
+    return run_net(h, batch, d_descr);
+}
+
+// DeepLCD::calcDescr on device images that already have the net's input size.
+extern "C" int sb_calc_descr_dev(sb_calc_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes, int stride, float *d_descr) {
+    sb_clear_error();
+    SB_REQUIRE(h && d_img && d_descr, "null pointer");
+    SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
+    SB_REQUIRE(stride >= h->in_w, "bad stride");
+    SB_TRY(sb_use_device(h->device));
+    k_calc_u8_to_float<<<dim3(sb_div_up(h->in_w * h->in_h, 256), batch), 256, 0, h->stream>>>(d_img, img_pitch_bytes, stride, h->d_act[0],
+                                                                                            (long long)h->act_elems, h->in_w, h->in_h);
+    return run_net(h, batch, d_descr);
+}
+
+// Host-pointer forms.  descr [batch][dim]; blurred_out: null, or `batch` pointers (entries may be null) to images with
+// the input's geometry that receive the blurred input (pass the input pointers to reproduce the reference's in-place blur).
+extern "C" int sb_calc_descr_original(sb_calc_t *h, int batch, const uint8_t *const *img, int w, int hgt, int stride, float *descr,
+                                      uint8_t *const *blurred_out) {
+    sb_clear_error();
+    SB_REQUIRE(h && img && descr, "null pointer");
+    SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
+    SB_REQUIRE(w >= 1 && hgt >= 1 && w <= h->max_img_w && hgt <= h->max_img_h && stride >= w, "image larger than the handle's maximum or bad stride");
+    for (int b = 0; b < batch; b++) SB_REQUIRE(img[b], "null image");
+    SB_TRY(sb_use_device(h->device));
+    cudaStream_t s = h->stream;
+    const size_t row = calc_row(h), plane = row * h->max_img_h;
+    for (int b = 0; b < batch; b++)
+        SB_CUDA(cudaMemcpy2DAsync(h->d_img + b * plane, row, img[b], (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, s));
+    SB_TRY(sb_calc_descr_original_dev(h, batch, h->d_img, (int64_t)plane, w, hgt, (int)row, h->d_descr, h->d_blur));
+    SB_CUDA(cudaMemcpyAsync(h->h_descr, h->d_descr, (size_t)batch * h->dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (blurred_out)
+        for (int b = 0; b < batch; b++)
+            if (blurred_out[b])
+                SB_CUDA(cudaMemcpy2DAsync(blurred_out[b], (size_t)stride, h->d_blur + b * plane, row, (size_t)w, (size_t)hgt, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    memcpy(descr, h->h_descr, (size_t)batch * h->dim * sizeof(float));
+    return SB_OK;
+}
+
+extern "C" int sb_calc_descr(sb_calc_t *h, int batch, const uint8_t *const *img, int stride, float *descr) {
+    sb_clear_error();
+    SB_REQUIRE(h && img && descr, "null pointer");
+    SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
+    SB_REQUIRE(stride >= h->in_w, "bad stride");
+    for (int b = 0; b < batch; b++) SB_REQUIRE(img[b], "null image");
+    SB_TRY(sb_use_device(h->device));
+    cudaStream_t s = h->stream;
+    const size_t row = calc_row(h), plane = row * h->max_img_h;
+    for (int b = 0; b < batch; b++)
+        SB_CUDA(cudaMemcpy2DAsync(h->d_img + b * plane, row, img[b], (size_t)stride, (size_t)h->in_w, (size_t)h->in_h, cudaMemcpyHostToDevice, s));
+    SB_TRY(sb_calc_descr_dev(h, batch, h->d_img, (int64_t)plane, (int)row, h->d_descr));
+    SB_CUDA(cudaMemcpyAsync(h->h_descr, h->d_descr, (size_t)batch * h->dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaStreamSynchronize(s));
+    memcpy(descr, h->h_descr, (size_t)batch * h->dim * sizeof(float));
+    return SB_OK;
+}

@@ -8,6 +8,7 @@
 //   myslam::LocalBASolver              the g2o block of Backend::OptimizeActiveMap, src/backend.cpp:126-269
 //   myslam::DeepLCDScorer              DeepLCD::score + LoopClosing::DetectLoop, src/deeplcd.cpp:35-39,
 //                                      src/loopclosing.cpp:124-161
+//   myslam::DeepLCD                    include/myslam/deeplcd.h:20-48 (src/deeplcd.cpp:10-91): the CALC CNN forward
 //   myslam::PoseGraphSolver            the g2o block of LoopClosing::PoseGraphOptimization, :537-646
 //
 // With OpenCV present (the reference's build) the classes take cv::InputArray / cv::KeyPoint / cv::Mat.
@@ -312,6 +313,59 @@ public:
     }
 private:
     sb_lcd_t *h_ = nullptr;
+};
+
+// -----------------------------------------------------------------------------------------------------
+// myslam::DeepLCD (include/myslam/deeplcd.h:20-48, src/deeplcd.cpp): same constructor arguments and method names.
+// DescrVector is Eigen::Matrix<float, 1064, 1> in the reference; here any contiguous float container of
+// descrDim() entries (std::vector<float> by default; Eigen::Map it where Eigen is present).  gpu_id = -1 ("CPU" in
+// the reference) selects device 0: there is no CPU path.
+class DeepLCD {
+public:
+    typedef std::vector<float> DescrVector;
+    typedef std::shared_ptr<DeepLCD> Ptr;
+    DeepLCD(const std::string &network_definition_file = "calc_model/deploy.prototxt",
+            const std::string &pre_trained_model_file = "calc_model/calc.caffemodel", int gpu_id = -1, int max_img_w = 2048, int max_img_h = 1024) {
+        if (sb_calc_create_from_caffe(&h_, gpu_id < 0 ? 0 : gpu_id, network_definition_file.c_str(), pre_trained_model_file.c_str(), 1, max_img_w,
+                                      max_img_h) != SB_OK)
+            throw std::runtime_error(std::string("sb_calc_create_from_caffe: ") + sb_last_error());
+    }
+    // the network as data (what the two files hold)
+    DeepLCD(const std::vector<sb_calc_layer> &layers, const std::vector<float> &weights, int in_h, int in_w, int gpu_id = 0, int max_img_w = 2048,
+            int max_img_h = 1024) {
+        if (sb_calc_create(&h_, gpu_id < 0 ? 0 : gpu_id, in_h, in_w, layers.data(), (int)layers.size(), weights.data(), (int64_t)weights.size(), 1,
+                           max_img_w, max_img_h) != SB_OK)
+            throw std::runtime_error(std::string("sb_calc_create: ") + sb_last_error());
+    }
+    ~DeepLCD() { sb_calc_destroy(h_); }
+    DeepLCD(const DeepLCD &) = delete;
+    DeepLCD &operator=(const DeepLCD &) = delete;
+    int descrDim() const { return sb_calc_descr_dim(h_); }
+    // src/deeplcd.cpp:35-39
+    float score(const DescrVector &d1, const DescrVector &d2) const {
+        float r = 0.f;
+        for (size_t i = 0; i < d1.size() && i < d2.size(); i++) r += d1[i] * d2[i];
+        return r;
+    }
+    // :43-52 — like the reference, the caller's image comes back blurred (cv::GaussianBlur(originalImg, originalImg, ...))
+    DescrVector calcDescrOriginalImg(const cv::Mat &originalImg) {
+        DescrVector d((size_t)descrDim(), 0.f);
+        if (originalImg.empty()) { detail::last_status() = SB_ERR_INVALID; return d; }
+        const uint8_t *in = originalImg.data;
+        uint8_t *out = originalImg.data;
+        detail::last_status() = sb_calc_descr_original(h_, 1, &in, originalImg.cols, originalImg.rows, (int)originalImg.step, d.data(), &out);
+        return d;
+    }
+    // :55-91 — the image must already have the net's input size
+    DescrVector calcDescr(const cv::Mat &im) {
+        DescrVector d((size_t)descrDim(), 0.f);
+        if (im.empty()) { detail::last_status() = SB_ERR_INVALID; return d; }
+        const uint8_t *in = im.data;
+        detail::last_status() = sb_calc_descr(h_, 1, &in, (int)im.step, d.data());
+        return d;
+    }
+private:
+    sb_calc_t *h_ = nullptr;
 };
 
 // -----------------------------------------------------------------------------------------------------

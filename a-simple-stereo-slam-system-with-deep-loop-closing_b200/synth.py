@@ -252,3 +252,19 @@ def pose_only_frame(seed, n_points=250, pix_noise=0.7, outlier_frac=0.1, pose_no
     uv[planted] += rng.uniform(-40, 40, (int(planted.sum()), 2))
     uv = uv.astype(np.float32).astype(np.float64)
     return {"pose0": w["poses0"][0], "pose_gt": w["poses_gt"][0], "points": pts, "uv": uv, "planted": planted}
+
+
+# ---------------------------------------------------------------------------------------------------
+# DeepLCD CNN ("next" row 2).  The trained calc.caffemodel is a configure-time download of the reference
+# (get_model.sh) and absent: tests and bench use seeded random weights of the same architecture.
+CALC_CONVS = ((64, 1, 5), (128, 64, 4), (4, 128, 3))  # (Cout, Cin, k) of the three Convolution layers
+
+
+def calc_weights(seed=0, convs=CALC_CONVS):
+    """Flat fp32 buffer in Caffe blob order: per Convolution layer W [Cout][Cin][k][k] then bias [Cout]."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for co, ci, k in convs:
+        out.append((rng.standard_normal(co * ci * k * k) * np.sqrt(2.0 / (ci * k * k))).astype(np.float32))
+        out.append((rng.standard_normal(co) * 0.05).astype(np.float32))
+    return np.concatenate(out)

@@ -39,6 +39,9 @@ STAGES = ["copy_level0", "resize_pyramid", "fast_cells", "quadtree", "gauss_blur
 BA_CAPS = dict(max_poses=7, max_points=320, max_obs=2304)
 
 
+CALC_MACS = 64 * 62 * 82 * 25 + 128 * 32 * 42 * 1024 + 4 * 14 * 19 * 1152   # multiply-adds of the three convolutions per image
+
+
 def pyramid_bytes():
     """Bytes of the 8 pyramid levels of one image."""
     inv = [np.float32(1.0)]
@@ -420,6 +423,21 @@ def main():
         lms = a0.elapsed_time(a1) / 10
         extras["lcd_score_queries_per_s"] = n_kf / (lms * 1e-3)
         extras["lcd_score_gbs"] = n_kf * n_kf * 1088 * 2 / (lms * 1e-3) / 1e9
+        # DeepLCD CNN forward ("next" row 2): whole-image descriptors of 64 keyframes per call (seeded random weights of the
+        # CALC architecture; the trained model is a configure-time download of the reference)
+        nb = 64
+        net = pkg.DeepLCD(synth.calc_weights(0), max_batch=nb, max_img_w=W, max_img_h=H, device=local_rank)
+        net.set_stream(sl.cuda_stream)
+        ddescr = torch.zeros((nb, net.dim), dtype=torch.float32, device="cuda")
+        net.descr_original_dev(nb, pool[:, 0], 2 * H * W, W, H, W, ddescr)
+        a0.record(sl)
+        for r in range(10):
+            net.descr_original_dev(nb, pool[(r % (P // nb)) * nb:, 0], 2 * H * W, W, H, W, ddescr)
+        a1.record(sl)
+        torch.cuda.synchronize()
+        cms = a0.elapsed_time(a1) / 10
+        extras["calc_descr_keyframes_per_s"] = nb / (cms * 1e-3)
+        extras["calc_descr_tflops_fp32"] = nb * 2 * CALC_MACS / (cms * 1e-3) / 1e12
     except Exception as ex:   # the extras never invalidate the headline measurement
         extras["error"] = repr(ex)
 

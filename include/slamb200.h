@@ -316,6 +316,53 @@ int sb_lk_track_dev(sb_lk_t *h, int batch, const uint8_t *d_prev_img, const uint
                     int hgt, int stride, const int32_t *d_n_pts, const float *d_prev_pts, float *d_next_pts, uint8_t *d_status,
                     int win, int max_count, double eps, int use_initial_flow, float min_eig_th);
 
+/* ---------------------------------------------------------------------------------------------
+ * DeepLCD whole-image descriptor (SURVEY §8f "next" row 2) — replaces DeepLCD::calcDescrOriginalImg
+ * (src/deeplcd.cpp:43-52: 7x7 sigma-0 Gaussian blur IN PLACE on the caller's image, resize to 160x120)
+ * and DeepLCD::calcDescr (:55-91: u8 -> float / 255, Caffe Net::Forward, descriptor /= norm) for a
+ * batch of images.  The network is data: `layers` restates deploy.prototxt (Convolution / ReLU /
+ * Pooling MAX / LRN across channels, Caffe's shape rules; the trailing Flatten is implicit) and
+ * `weights` is one flat fp32 buffer in Caffe's blob order — per Convolution layer W [Cout][Cin][k][k]
+ * then bias [Cout] — i.e. the contents of calc.caffemodel (DeepLCD::DeepLCD, src/deeplcd.cpp:10-31).
+ * The reference's network (1 x 120 x 160 in, 1064 out) is listed in INTEGRATION.md.
+ * --------------------------------------------------------------------------------------------- */
+#define SB_CALC_CONV 0
+#define SB_CALC_RELU 1
+#define SB_CALC_POOL_MAX 2
+#define SB_CALC_LRN 3
+typedef struct sb_calc_layer {
+    int32_t type;                          /* SB_CALC_* */
+    int32_t num_output, kernel, stride, pad; /* Convolution; Pooling uses kernel, stride, pad */
+    int32_t local_size;                    /* LRN */
+    float alpha, beta, k;                  /* LRN */
+} sb_calc_layer;
+typedef struct sb_calc sb_calc_t;
+int sb_calc_create(sb_calc_t **h, int device, int in_h, int in_w, const sb_calc_layer *layers, int n_layers,
+                   const float *weights, int64_t n_weights, int max_batch, int max_img_w, int max_img_h);
+int sb_calc_destroy(sb_calc_t *h);
+int sb_calc_set_stream(sb_calc_t *h, void *stream);
+/* autoencoder_output->channels() (src/deeplcd.cpp:72): 1064 for the reference's network. */
+int sb_calc_descr_dim(const sb_calc_t *h);
+/* calcDescrOriginalImg: img = `batch` pointers to w x hgt u8 images; descr [batch][dim];
+ * blurred_out = null, or `batch` pointers (entries may be null) that receive the blurred image —
+ * pass the input pointers to reproduce the reference's in-place blur of KeyFrame::mImageLeft. */
+int sb_calc_descr_original(sb_calc_t *h, int batch, const uint8_t *const *img, int w, int hgt, int stride, float *descr,
+                           uint8_t *const *blurred_out);
+/* calcDescr: images that already have the net's input size. */
+int sb_calc_descr(sb_calc_t *h, int batch, const uint8_t *const *img, int stride, float *descr);
+int sb_calc_descr_original_dev(sb_calc_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes, int w, int hgt, int stride,
+                               float *d_descr, uint8_t *d_blurred);
+int sb_calc_descr_dev(sb_calc_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes, int stride, float *d_descr);
+/* DeepLCD::DeepLCD(network_definition_file, pre_trained_model_file, gpu_id) (src/deeplcd.cpp:10-31): reads
+ * deploy.prototxt (protobuf text format) and calc.caffemodel (protobuf wire format of caffe.proto's
+ * NetParameter; weights matched to layers by name like CopyTrainedLayersFrom) without Caffe or protobuf.
+ * sb_calc_parse_caffe needs no device: layers / weights may be null to query n_layers / n_weights;
+ * shape [2] = net input height, width. */
+int sb_calc_parse_caffe(const char *prototxt_path, const char *caffemodel_path, sb_calc_layer *layers, int cap_layers, int *n_layers,
+                        float *weights, int64_t cap_weights, int64_t *n_weights, int *shape);
+int sb_calc_create_from_caffe(sb_calc_t **h, int device, const char *prototxt_path, const char *caffemodel_path, int max_batch,
+                              int max_img_w, int max_img_h);
+
 #ifdef __cplusplus
 }
 #endif

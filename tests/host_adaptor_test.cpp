@@ -52,5 +52,20 @@ int main(int argc, char **argv) {
     std::vector<cv::KeyPoint> all; cv::Mat d2;
     ext.DetectAndCompute(img, mask, all, d2);
     std::printf("DetectAndCompute: %zu keypoints\n", all.size());
-    return all.size() > 200 ? 0 : 5;
+    if (all.size() <= 200) return 5;
+    // LoopClosing::ProcessNewKF: the whole-image descriptor; the keyframe image comes back blurred (src/deeplcd.cpp:46)
+    std::vector<sb_calc_layer> layers = {{SB_CALC_CONV, 8, 5, 2, 4, 0, 0, 0, 0}, {SB_CALC_RELU, 0, 0, 0, 0, 0, 0, 0, 0},
+                                         {SB_CALC_POOL_MAX, 0, 3, 2, 0, 0, 0, 0, 0}, {SB_CALC_LRN, 0, 0, 0, 0, 5, 1e-4f, 0.75f, 1.f}};
+    std::vector<float> weights(8 * 25 + 8);
+    for (size_t i = 0; i < weights.size(); i++) { s = s * 1664525u + 1013904223u; weights[i] = ((int)((s >> 8) % 2001) - 1000) * 1e-4f; }
+    myslam::DeepLCD lcd(layers, weights, 120, 160);
+    cv::Mat kf;
+    kf.create(376, 1241);
+    std::memcpy(kf.data, img.data, (size_t)376 * 1241);
+    myslam::DeepLCD::DescrVector d1 = lcd.calcDescrOriginalImg(kf), dsame = lcd.calcDescrOriginalImg(img);
+    const float self = lcd.score(d1, d1);
+    std::printf("DeepLCD: dim %d, self score %.6f, image blurred in place: %s\n", lcd.descrDim(), self,
+                std::memcmp(kf.data, img.data, (size_t)376 * 1241) == 0 ? "both" : "?");
+    if (lcd.descrDim() != 8 * 31 * 41 || self < 0.9999f || self > 1.0001f) return 6;
+    return 0;
 }
