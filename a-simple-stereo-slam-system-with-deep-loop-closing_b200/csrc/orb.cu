@@ -26,8 +26,9 @@
 
 #define SB_MAX_LEVELS 12
 #define SB_CAND_CAP 16384       // FAST candidates one (image, level) can hand to the quadtree
-#define SB_CELL_LIST_CAP 1024   // local maxima one FAST cell can hold (a cell has < 60 x 60 tested pixels)
-#define FAST_THREADS 128
+#define SB_FAST_KMAX 8          // FAST cells one CTA handles (a horizontal run of one grid row)
+#define SB_FAST_SPAN 160        // ... as many as fit this many tested columns
+#define FAST_THREADS 256
 #define QT_THREADS 256
 #define BLUR_TW 128
 #define BLUR_TH 32
@@ -61,8 +62,13 @@ struct Geom {
     int umax[16];
 };
 
-struct Cell {  // one cv::FAST call of the reference's grid loop
-    short level, x0, y0, rw, rh, offx, offy, pad;
+struct CellGroup {  // up to SB_FAST_KMAX horizontally adjacent cv::FAST calls of the reference's grid loop (one CTA)
+    short level, x0, y0;   // first cell's ROI origin (iniX, iniY) in level pixels
+    short rw, rh;          // ROI span of the whole group: last cell's maxX - first cell's iniX, maxY - iniY
+    short offx, offy;      // j0 * wCell, i * hCell: what the reference adds to the ROI coordinates
+    short ncells, wCell;
+    short G;               // 4-pixel items per row
+    int rcpG, rcpW;        // ceil(2^20 / G), ceil(2^20 / wCell): exact division of the small indices used
 };
 
 struct TmaMaps {
@@ -150,20 +156,23 @@ __global__ void __launch_bounds__(256) k_resize(uint8_t *__restrict__ pyr, long 
 }
 
 // cv::FAST(cell ROI, iniTh, nms) with the minTh fallback (ComputeKeyPointsOctTree :838-883 /
-// Detect :1015-1060), one CTA per cell.  The corner response does not depend on the threshold and
-// "corner at t" <=> response >= t, so one response plane serves both thresholds; 3x3 non-maximum
-// suppression is threshold independent for the survivors (a neighbour below t is also below the
-// survivor).  Only the ROI's inner [3, rw-3) x [3, rh-3) box is tested, outside counts as 0 —
-// exactly the per-cell semantics of the reference.
+// Detect :1015-1060).  One CTA per GROUP of up to SB_FAST_KMAX horizontally adjacent cells of one grid
+// row: the tested pixels of adjacent cells tile the row without gaps (cell j tests ROI columns
+// [3 + j * wCell, 3 + (j + 1) * wCell)), so one TMA box and one pass over ~5 000 pixels serve all of them.
+// The corner response does not depend on the threshold and "corner at t" <=> response >= t, so one
+// response plane serves both thresholds; 3x3 non-maximum suppression is threshold independent for the
+// survivors (a neighbour below t is also below the survivor).  Per-cell semantics of the reference are
+// kept exactly: a neighbour that belongs to the next cell counts as 0 in the suppression, and the
+// 20 -> 7 fallback is decided per cell from "did any maximum of this cell reach iniTh".
 struct FastArgs {
-    const Cell *cells;
+    const CellGroup *groups;
     const uint8_t *mask_pyr;  // null: no mask
     uint32_t *cand;           // [batch][nlevels][SB_CAND_CAP]
     int *cand_cnt;            // [batch][nlevels]
     int *flags;               // [0] overflow
     long long slab;
-    int nlevels, iniTh, minTh, tile_bytes;
-    uint8_t *dbg;  // inspection: tile + response plane of cell `dbg_cell` of image 0 (null in production calls)
+    int nlevels, iniTh, minTh, tile_bytes, list_cap, seg;
+    uint8_t *dbg;  // inspection: tile + response plane of group `dbg_cell` of image 0 (null in production calls)
     int dbg_cell;
 };
 
@@ -174,13 +183,13 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     // access to generic LD/ST with 64-bit address math)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_n, s_any, s_cnt[FAST_THREADS / 32];
+    __shared__ int s_n, s_any[SB_FAST_KMAX], s_cnt[FAST_THREADS / 32];
     uint8_t *tile = smem;  // TMA destination, 128-byte aligned
     uint8_t *sc = smem + a.tile_bytes;
     uint32_t *list = reinterpret_cast<uint32_t *>(smem + 2 * a.tile_bytes);
-    uint16_t *plist = reinterpret_cast<uint16_t *>(smem + 2 * a.tile_bytes + SB_CELL_LIST_CAP * 4);  // <= one entry per tile pixel
+    uint16_t *plist = reinterpret_cast<uint16_t *>(smem + 2 * a.tile_bytes + a.list_cap * 4);
     if (threadIdx.x == 0 && (sb_smem_u32(tile) & 127u)) __trap();
-    const Cell c = a.cells[blockIdx.x];
+    const CellGroup c = a.groups[blockIdx.x];
     const int img = blockIdx.y;
     const LevelGeom &L = g.lv[c.level];
     const int BW = L.fast_bw, BH = L.fast_bh;
@@ -189,46 +198,49 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
 
     if (tid == 0) {
         s_n = 0;
-        s_any = 0;
         sb_mbar_init(&bar, 1);
         sb_mbar_expect_tx(&bar, (uint32_t)(BW * BH));
         sb_tma_load_3d(tile, &maps.m[c.level], c.x0 - xo, c.y0, img, &bar);
     }
+    if (tid < SB_FAST_KMAX) s_any[tid] = 0;
     for (int i = tid; i < (BW * BH) >> 2; i += FAST_THREADS) reinterpret_cast<uint32_t *>(sc)[i] = 0u;
     __syncthreads();
     sb_mbar_wait(&bar, 0);
 
     // Phase 1: pixels that pass the cheap necessary test (sb_fast_maybe's rule: at least two of the four compass
     // ring pixels darker than v - t, or two brighter than v + t) are compacted into a list, so that the response
-    // (about 100 instructions) is later computed by full warps instead of a few lanes of every warp.
+    // (about 80 instructions) is later computed by full warps instead of a few lanes of every warp.
     // A work item is 4 horizontally adjacent pixels: five aligned 32-bit loads, two funnel shifts, then the
     // order statistics for two pixels at a time in packed 2 x int16 arithmetic.  Every warp appends to its own
-    // segment of the list with a warp-uniform running count: no atomics.
+    // segment of the list with a warp-uniform running count: no atomics.  Pixels of the first / last item of a
+    // row that fall outside the tested columns [3, rw - 3) are listed too and dropped in phase 2.
     const int t0 = min(a.iniTh, a.minTh);
-    const int seg = a.tile_bytes >> 2;
+    uint16_t *mine = plist + warp * a.seg;
+    int cnt = 0;
     {
-        uint16_t *mine = plist + warp * seg;
-        int cnt = 0;
         const unsigned lt = (1u << lane) - 1u;
         // only the 4-pixel groups that overlap the tested ROI columns [3, rw - 3)
-        const int g0 = (xo + 3) >> 2, G = c.rw > 6 ? ((xo + c.rw - 4) >> 2) - g0 + 1 : 0, rows = c.rh - 6;
-        const int items = rows > 0 ? rows * G : 0;
+        const int g0 = (xo + 3) >> 2, G = c.G, rows = c.rh - 6;
+        const int items = (rows > 0 && c.rw > 6) ? rows * G : 0;
         const uint32_t Tp1 = (uint32_t)(t0 + 1) * 0x00010001u;
+        const int bw4 = BW >> 2;
         for (int it0 = warp * 32; it0 < items; it0 += FAST_THREADS) {
             const int it = it0 + lane;
             uint32_t hit = 0;  // bit j: pixel j of the item passes
-            int y = 0, col = 0;
+            int e0 = 0;
             if (it < items) {
-                y = 3 + it / G;
-                col = (g0 + it - (y - 3) * G) << 2;  // tile column of pixel 0
+                const int yy = (int)(((uint32_t)it * (uint32_t)c.rcpG) >> 20);  // it / G
+                const int y = 3 + yy;
+                const int col = (g0 + it - yy * G) << 2;  // tile column of pixel 0
+                e0 = (y << 8) + col - xo;
                 const uint32_t *pw = reinterpret_cast<const uint32_t *>(tile + y * BW + col);
-                const uint32_t C = pw[0], U = pw[-3 * (BW >> 2)], D = pw[3 * (BW >> 2)];
-                const uint32_t L = __funnelshift_r(pw[-1], C, 8), R = __funnelshift_r(C, pw[1], 24);
+                const uint32_t C = pw[0], U = pw[-3 * bw4], D = pw[3 * bw4];
+                const uint32_t Lw = __funnelshift_r(pw[-1], C, 8), R = __funnelshift_r(C, pw[1], 24);
 #pragma unroll
                 for (int hpair = 0; hpair < 2; hpair++) {
                     const uint32_t sel = hpair ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> two 16-bit halves
                     const uint32_t v = __byte_perm(C, 0u, sel), r0 = __byte_perm(D, 0u, sel), r8 = __byte_perm(U, 0u, sel);
-                    const uint32_t r4 = __byte_perm(R, 0u, sel), r12 = __byte_perm(L, 0u, sel);
+                    const uint32_t r4 = __byte_perm(R, 0u, sel), r12 = __byte_perm(Lw, 0u, sel);
                     const uint32_t m1 = __vmins2(r0, r4), M1 = __vmaxs2(r0, r4), m2 = __vmins2(r8, r12), M2 = __vmaxs2(r8, r12);
                     const uint32_t A = __vmaxs2(m1, m2), B = __vmins2(M1, M2);
                     const uint32_t s2 = __vmins2(A, B), s3 = __vmaxs2(A, B);  // 2nd smallest / 2nd largest of the four
@@ -237,46 +249,45 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
                     const uint32_t neg = (dk | br) & 0x80008000u;
                     hit |= (((neg >> 15) & 1u) | ((neg >> 30) & 2u)) << (2 * hpair);
                 }
-                // only ROI columns [3, rw - 3) are tested by cv::FAST
-                const int x0 = col - xo;  // ROI column of pixel 0
-                uint32_t valid = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) valid |= (uint32_t)(x0 + j >= 3 && x0 + j < c.rw - 3) << j;
-                hit &= valid;
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const bool m = (hit >> j) & 1u;
                 const unsigned bal = __ballot_sync(0xffffffffu, m);
-                if (m) mine[cnt + __popc(bal & lt)] = (uint16_t)((y << 8) | (col - xo + j));
+                if (m) mine[cnt + __popc(bal & lt)] = (uint16_t)(e0 + j);  // (y << 8) | ROI column
                 cnt += __popc(bal);
             }
         }
-        if (lane == 0) s_cnt[warp] = cnt;
     }
-    __syncthreads();
-    const int c0 = s_cnt[0], c1 = c0 + s_cnt[1], c2 = c1 + s_cnt[2], np = c2 + s_cnt[3];
-    // Phase 2: responses of the listed pixels
-    for (int i = tid; i < np; i += FAST_THREADS) {
-        const int e = i < c0 ? plist[i] : i < c1 ? plist[seg + i - c0] : i < c2 ? plist[2 * seg + i - c1] : plist[3 * seg + i - c2];
+    __syncwarp();
+    // Phase 2: responses of the listed pixels; every warp walks its own segment.  Only ROI columns [3, rw - 3)
+    // are tested by cv::FAST: the response plane stays 0 elsewhere.
+    for (int i = lane; i < cnt; i += 32) {
+        const int e = mine[i];
         const int y = e >> 8, x = e & 255;
+        if (x < 3 || x >= c.rw - 3) continue;
         const int s = sb_fast_score(tile + y * BW + xo + x, BW);
         if (s >= t0) sc[y * BW + xo + x] = (uint8_t)s;
     }
     __syncthreads();
-    // Phase 3: 3x3 non-maximum suppression (only listed pixels can be maxima)
-    for (int i = tid; i < np; i += FAST_THREADS) {
-        const int e = i < c0 ? plist[i] : i < c1 ? plist[seg + i - c0] : i < c2 ? plist[2 * seg + i - c1] : plist[3 * seg + i - c2];
+    // Phase 3: 3x3 non-maximum suppression (only listed pixels can be maxima).  Tested columns only; a neighbour
+    // in the adjacent cell counts as 0, exactly as if each cell had been given to cv::FAST on its own.
+    const int wC = c.wCell;
+    for (int i = lane; i < cnt; i += 32) {
+        const int e = mine[i];
         const int y = e >> 8, x = e & 255;
         const uint8_t *q = sc + y * BW + xo + x;
         const int s = q[0];
         if (s == 0) continue;  // listed by the pre-test but not a corner (the majority)
-        const int nb = max(max(max((int)q[-1], (int)q[1]), max((int)q[-BW - 1], (int)q[-BW])),
-                           max(max((int)q[-BW + 1], (int)q[BW - 1]), max((int)q[BW], (int)q[BW + 1])));
+        const int jl = (int)(((uint32_t)(x - 3) * (uint32_t)c.rcpW) >> 20);  // cell of the group
+        const int xr = x - 3 - jl * wC;
+        int nb = max((int)q[-BW], (int)q[BW]);
+        if (xr != 0) nb = max(nb, max(max((int)q[-1], (int)q[-BW - 1]), (int)q[BW - 1]));
+        if (xr != wC - 1) nb = max(nb, max(max((int)q[1], (int)q[-BW + 1]), (int)q[BW + 1]));
         if (s > nb) {  // s > 0 follows: neighbours are >= 0
             const int k = atomicAdd(&s_n, 1);
-            if (k < SB_CELL_LIST_CAP) list[k] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
-            if (s >= a.iniTh) s_any = 1;
+            if (k < a.list_cap) list[k] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+            if (s >= a.iniTh) s_any[jl] = 1;
         }
     }
     __syncthreads();
@@ -288,24 +299,39 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
         if (tid == 0) {
             int *info = reinterpret_cast<int *>(a.dbg + 2 * a.tile_bytes);
             info[0] = BW; info[1] = BH; info[2] = xo; info[3] = c.x0; info[4] = c.y0; info[5] = c.rw; info[6] = c.rh;
-            info[7] = s_n; info[8] = s_any; info[9] = c.level;
+            info[7] = s_n; info[8] = s_any[0]; info[9] = c.level; info[10] = c.ncells; info[11] = c.wCell;
         }
     }
-    const int n = min(s_n, SB_CELL_LIST_CAP);
-    const int th = s_any ? a.iniTh : a.minTh;  // the reference's second cv::FAST call only if the first found nothing
+    const int n = min(s_n, a.list_cap);
     const int slot = img * a.nlevels + c.level;
-    for (int i = tid; i < n; i += FAST_THREADS) {
-        const uint32_t w = list[i];
-        const int s = (int)(w >> 24);
-        if (s < th) continue;
-        const int x = (int)(w & 0xfff) + c.offx, y = (int)((w >> 12) & 0xfff) + c.offy;  // border-relative
-        // quirk Q1 (:871-877): the mask is read at the border-relative coordinates
-        if (a.mask_pyr && a.mask_pyr[(long long)img * a.slab + L.off + (long long)y * L.pitch + x] == 0) continue;
-        const int pos = atomicAdd(&a.cand_cnt[slot], 1);
-        if (pos < SB_CAND_CAP)
-            a.cand[(long long)slot * SB_CAND_CAP + pos] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
-        else
-            a.flags[0] = 1;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += FAST_THREADS) {  // one global atomic per warp
+        const int i = base + tid;
+        bool ok = false;
+        uint32_t out = 0;
+        if (i < n) {
+            const uint32_t w = list[i];
+            const int s = (int)(w >> 24), xl = (int)(w & 0xfff);
+            const int jl = (int)(((uint32_t)(xl - 3) * (uint32_t)c.rcpW) >> 20);
+            // the reference's second cv::FAST call (minTh) only if the first (iniTh) found nothing in this cell
+            ok = s >= (s_any[jl] ? a.iniTh : a.minTh);
+            const int x = xl + c.offx, y = (int)((w >> 12) & 0xfff) + c.offy;  // border-relative
+            // quirk Q1 (:871-877): the mask is read at the border-relative coordinates
+            if (ok && a.mask_pyr && a.mask_pyr[(long long)img * a.slab + L.off + (long long)y * L.pitch + x] == 0) ok = false;
+            out = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (bal) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&a.cand_cnt[slot], __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & lt);
+            if (ok) {
+                if (pos < SB_CAND_CAP)
+                    a.cand[(long long)slot * SB_CAND_CAP + pos] = out;
+                else
+                    a.flags[0] = 1;
+            }
+        }
     }
 }
 
@@ -722,14 +748,14 @@ struct sb_orb {
     int cur_w, cur_h;
     Geom geom;
     TmaMaps fast_maps, blur_maps, blur_maps_mask_unused;
-    int n_cells, n_cells_l0, n_blur_tiles;
-    int fast_tile_bytes;
+    int n_cells, n_cells_l0, n_blur_tiles;  // n_cells: FAST cell groups (CTAs)
+    int fast_tile_bytes, fast_list_cap, fast_seg;
     int selcap, ncap_pyr, ncap_detect;
     long long slab_cap;  // bytes reserved per image
     int kp_cap;          // sb_orb_capacity()
     // device memory
     uint8_t *d_pyr, *d_blur, *d_mask;
-    Cell *d_cells;
+    CellGroup *d_cells;
     BlurTile *d_tiles;
     int2 *d_xtab, *d_ytab;  // resize tables: (source index, c0 | c1 << 16)
     uint32_t *d_cand, *d_sel;
@@ -840,6 +866,10 @@ static long long slab_bytes(const sb_orb *h, int w, int hgt) {
     return off;
 }
 
+static size_t fast_smem_bytes(const sb_orb *h) {
+    return 2 * (size_t)h->fast_tile_bytes + (size_t)h->fast_list_cap * 4 + (size_t)(FAST_THREADS / 32) * h->fast_seg * 2 + 128;
+}
+
 static int quadtree_ncap(int N, int bw, int bh) {
     const int nIni = (int)roundf((float)bw / (float)bh);
     const int a = 4 * (nIni > 0 ? nIni : 1), b = N + 3;
@@ -856,10 +886,10 @@ static int configure(sb_orb *h, int w, int hgt) {
     g.nlevels = h->nlevels;
     memcpy(g.umax, h->umax, sizeof(g.umax));
     std::vector<int2> xtab, ytab;
-    std::vector<Cell> cells;
+    std::vector<CellGroup> cells;
     std::vector<BlurTile> tiles;
     long long off = 0;
-    int fast_tile = 0, selcap = 0, ncap_pyr = 0, kp_cap = 0;
+    int fast_tile = 0, fast_list = 0, fast_items = 0, selcap = 0, ncap_pyr = 0, kp_cap = 0;
     for (int l = 0; l < h->nlevels; l++) {
         LevelGeom &L = g.lv[l];
         level_size(h, w, hgt, l, &L.w, &L.h);
@@ -880,24 +910,46 @@ static int configure(sb_orb *h, int w, int hgt) {
         L.wCell = (int)ceilf(width / L.nCols);
         L.hCell = (int)ceilf(height / L.nRows);
         SB_REQUIRE(L.wCell + 6 <= 72 && L.hCell + 6 <= 72, "FAST cell larger than supported");
-        L.fast_bw = (int)sb_align_up(L.wCell + 6 + 15, 16);
+        // cells per CTA: runs of K adjacent cells of a grid row, K * wCell <= SB_FAST_SPAN, rows split evenly
+        int K = SB_FAST_SPAN / L.wCell;
+        K = K < 1 ? 1 : K > SB_FAST_KMAX ? SB_FAST_KMAX : K;
+        const int runs = sb_div_up(L.nCols, K);
+        K = sb_div_up(L.nCols, runs);
+        L.fast_bw = (int)sb_align_up(K * L.wCell + 6 + 15, 16);
         L.fast_bh = L.hCell + 6;
         if (L.fast_bw * L.fast_bh > fast_tile) fast_tile = L.fast_bw * L.fast_bh;
+        if (K * L.wCell * L.hCell / 4 + 8 > fast_list) fast_list = K * L.wCell * L.hCell / 4 + 8;  // maxima: at most 1 per 2 x 2
         const int minB = SB_EDGE - 3, maxBX = L.w - SB_EDGE + 3, maxBY = L.h - SB_EDGE + 3;
         for (int i = 0; i < L.nRows; i++) {
             const int iniY = minB + i * L.hCell;
             int maxY = iniY + L.hCell + 6;
             if (iniY >= maxBY - 3) continue;
             if (maxY > maxBY) maxY = maxBY;
-            for (int j = 0; j < L.nCols; j++) {
-                const int iniX = minB + j * L.wCell;
-                int maxX = iniX + L.wCell + 6;
-                if (iniX >= maxBX - 6) continue;
-                if (maxX > maxBX) maxX = maxBX;
-                Cell c;
+            for (int j0 = 0; j0 < L.nCols; j0 += K) {
+                CellGroup c;
+                memset(&c, 0, sizeof(c));
+                int endX = 0;
+                for (int j = j0; j < L.nCols && j < j0 + K; j++) {  // the reference's column loop (:849-855)
+                    const int iniX = minB + j * L.wCell;
+                    int maxX = iniX + L.wCell + 6;
+                    if (iniX >= maxBX - 6) continue;
+                    if (maxX > maxBX) maxX = maxBX;
+                    c.ncells++;
+                    endX = maxX;
+                }
+                if (c.ncells == 0) continue;
+                const int iniX = minB + j0 * L.wCell;
                 c.level = (short)l; c.x0 = (short)iniX; c.y0 = (short)iniY;
-                c.rw = (short)(maxX - iniX); c.rh = (short)(maxY - iniY);
-                c.offx = (short)(j * L.wCell); c.offy = (short)(i * L.hCell); c.pad = 0;
+                c.rw = (short)(endX - iniX); c.rh = (short)(maxY - iniY);
+                c.offx = (short)(j0 * L.wCell); c.offy = (short)(i * L.hCell);
+                c.wCell = (short)L.wCell;
+                const int xo = iniX & 15;
+                const int G = c.rw > 6 ? ((xo + c.rw - 4) >> 2) - ((xo + 3) >> 2) + 1 : 1;
+                c.G = (short)G;
+                c.rcpG = ((1 << 20) + G - 1) / G;
+                c.rcpW = ((1 << 20) + L.wCell - 1) / L.wCell;
+                const int items = c.rh > 6 ? (c.rh - 6) * G : 0;
+                if (items > fast_items) fast_items = items;
                 cells.push_back(c);
             }
         }
@@ -935,11 +987,9 @@ static int configure(sb_orb *h, int w, int hgt) {
     SB_REQUIRE(qt_smem_bytes(ncap_pyr > h->ncap_detect ? ncap_pyr : h->ncap_detect) <= 220 * 1024,
                "nfeatures too large for the on-chip quadtree");
     h->fast_tile_bytes = (int)sb_align_up(fast_tile, 128);
-    for (int l = 0; l < h->nlevels; l++) {  // per-warp segment of the candidate-pixel list (k_fast_cells phase 1)
-        const LevelGeom &L = g.lv[l];
-        const int need = sb_div_up(L.hCell * (L.fast_bw / 4), FAST_THREADS) * 32 * 4;
-        SB_REQUIRE(need <= h->fast_tile_bytes / 4, "internal: FAST candidate segment too small");
-    }
+    h->fast_list_cap = (int)sb_align_up(fast_list, 32);
+    h->fast_seg = sb_div_up(fast_items, FAST_THREADS) * 32 * 4;  // per-warp segment of the candidate-pixel list (phase 1)
+    SB_REQUIRE(fast_smem_bytes(h) <= 200 * 1024, "internal: FAST shared memory");
     h->n_cells = (int)cells.size();
     h->n_blur_tiles = (int)tiles.size();
     SB_REQUIRE((int)xtab.size() <= h->tab_cap && (int)ytab.size() <= h->tab_cap, "internal: table capacity");
@@ -951,7 +1001,7 @@ static int configure(sb_orb *h, int w, int hgt) {
         SB_CUDA(cudaMemcpyAsync(h->d_xtab, xtab.data(), xtab.size() * 8, cudaMemcpyHostToDevice, s));
         SB_CUDA(cudaMemcpyAsync(h->d_ytab, ytab.data(), ytab.size() * 8, cudaMemcpyHostToDevice, s));
     }
-    SB_CUDA(cudaMemcpyAsync(h->d_cells, cells.data(), cells.size() * sizeof(Cell), cudaMemcpyHostToDevice, s));
+    SB_CUDA(cudaMemcpyAsync(h->d_cells, cells.data(), cells.size() * sizeof(CellGroup), cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(h->d_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaStreamSynchronize(s));
     for (int l = 0; l < h->nlevels; l++) {
@@ -1031,7 +1081,7 @@ extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float sc
     const size_t B = (size_t)max_batch;
     SB_ALLOC(h->d_pyr, B * h->slab_cap);
     SB_ALLOC(h->d_blur, B * h->slab_cap);
-    SB_ALLOC(h->d_cells, (size_t)h->cell_cap * sizeof(Cell));
+    SB_ALLOC(h->d_cells, (size_t)h->cell_cap * sizeof(CellGroup));
     SB_ALLOC(h->d_tiles, (size_t)h->tile_cap * sizeof(BlurTile));
     SB_ALLOC(h->d_xtab, (size_t)h->tab_cap * 8);
     SB_ALLOC(h->d_ytab, (size_t)h->tab_cap * 8);
@@ -1048,6 +1098,7 @@ extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float sc
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
         sb_set_error("sb_orb_create: %s", cudaGetErrorString(e));
         free_orb(h);
@@ -1147,7 +1198,7 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     const int nl = h->nlevels;
     SB_CUDA(cudaMemsetAsync(h->d_cand_cnt, 0, (size_t)batch * nl * 4, h->stream));
     FastArgs fa;
-    fa.cells = h->d_cells;
+    fa.groups = h->d_cells;
     fa.mask_pyr = use_mask ? h->d_mask : nullptr;
     fa.cand = h->d_cand;
     fa.cand_cnt = h->d_cand_cnt;
@@ -1157,10 +1208,12 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     fa.iniTh = h->iniTh;
     fa.minTh = h->minTh;
     fa.tile_bytes = h->fast_tile_bytes;
+    fa.list_cap = h->fast_list_cap;
+    fa.seg = h->fast_seg;
     fa.dbg = h->dbg_buf;
     fa.dbg_cell = h->dbg_cell;
     const int ncells = detect_only ? h->n_cells_l0 : h->n_cells;
-    const size_t fsmem = 4 * (size_t)h->fast_tile_bytes + SB_CELL_LIST_CAP * 4 + 128;
+    const size_t fsmem = fast_smem_bytes(h);
     prof_begin(h, SB_STAGE_FAST, 1, h->stream);
     k_fast_cells<<<dim3(ncells, batch), FAST_THREADS, fsmem, h->stream>>>(h->fast_maps, h->geom, fa);
     prof_end(h, h->stream);

@@ -71,34 +71,32 @@ SB_HD bool sb_fast_maybe(const uint8_t *p, int pitch, int t) {
 
 // Corner response = the largest threshold for which the pixel is still a FAST-9/16 corner:
 //   max over the 16 arcs of 9 contiguous ring pixels of  min(v - ring)  resp.  min(ring - v),  minus 1.
-// Both polarities ride in one register as 2 x int16 (low half: v - ring, high half: ring - v), so the
-// running minima over windows 2, 4 and 9 cost 16 + 16 + 16 packed instructions (VIMNMX.S16x2 /
-// VIMNMX3.S16x2) for all 16 arcs of both polarities, and no value is ever negated after a min/max
+// Both polarities ride in one register as 2 x int16: high half ring - v, low half v - ring + 256 (the bias
+// keeps the low half positive, so ONE 32-bit multiply-add  ring * 65535 + c(v)  builds the pair without a
+// borrow into the high half).  A window of 9 is min3 of three windows of 3 (VIMNMX3.S16x2): 16 + 16
+// packed instructions for all 16 arcs of both polarities.  No value is ever negated after a min/max
 // (ptxas 12.9 mis-folds max(a, -max3(...)) into VIMNMX3 on sm_100a — measured, tools/fast_probe.cu).
 SB_HD int sb_fast_score(const uint8_t *p, int pitch) {
-    const int v = p[0];
-    const uint32_t vv = sb_pack2(v - 255, -v);
+    const uint32_t v = p[0];
+    const uint32_t cv = (0u - (v << 16)) + v + 256u;  // ((-v) << 16) + (v + 256)
     uint32_t d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         const uint32_t r = p[SB_RING_DY(k) * pitch + SB_RING_DX(k)];
-        d[k] = sb_vadd2(vv, r * 65535u + 255u);  // r * 65535 + 255 = (255 - r, r) without a borrow -> (v - r, r - v)
+        d[k] = r * 65535u + cv;  // (r << 16) - r + cv = ((r - v) << 16) + (v - r + 256), low half in [1, 511]
     }
-    uint32_t m2[16], m4[16];
+    uint32_t m3[16], m9[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) m2[k] = sb_vmin2(d[k], d[(k + 1) & 15]);
+    for (int k = 0; k < 16; k++) m3[k] = sb_vmin3_2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; k++) m4[k] = sb_vmin2(m2[k], m2[(k + 2) & 15]);
-    uint32_t m9[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) m9[k] = sb_vmin3_2(m4[k], m4[(k + 4) & 15], d[(k + 8) & 15]);
+    for (int k = 0; k < 16; k++) m9[k] = sb_vmin3_2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
     uint32_t b0 = sb_vmax3_2(m9[0], m9[1], m9[2]), b1 = sb_vmax3_2(m9[3], m9[4], m9[5]);
     uint32_t b2 = sb_vmax3_2(m9[6], m9[7], m9[8]), b3 = sb_vmax3_2(m9[9], m9[10], m9[11]);
     uint32_t b4 = sb_vmax3_2(m9[12], m9[13], m9[14]);
     b0 = sb_vmax3_2(b0, b1, b2);
     b3 = sb_vmax3_2(b3, b4, m9[15]);
     b0 = sb_vmax2(b0, b3);
-    return sb_max(sb_lo2(b0), sb_hi2(b0)) - 1;
+    return sb_max(sb_lo2(b0) - 256, sb_hi2(b0)) - 1;
 }
 
 // ---- cv::resize INTER_LINEAR u8 (src/ORBextractor.cpp:1243-1244,1262) ----------------
