@@ -28,6 +28,7 @@
 #define SB_CAND_CAP 16384       // FAST candidates one (image, level) can hand to the quadtree
 #define SB_FAST_KMAX 8          // FAST cells one CTA handles (a horizontal run of one grid row)
 #define SB_FAST_SPAN 160        // ... as many as fit this many tested columns
+#define SB_FAST_BW 192          // TMA box width of every FAST tile (compile time: ring offsets fold into the LDS immediates)
 #define FAST_THREADS 256
 #define QT_THREADS 256
 #define BLUR_TW 128
@@ -186,13 +187,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     __shared__ int s_n, s_any[SB_FAST_KMAX], s_cnt[FAST_THREADS / 32];
     uint8_t *tile = smem;  // TMA destination, 128-byte aligned
     uint8_t *sc = smem + a.tile_bytes;
-    uint32_t *list = reinterpret_cast<uint32_t *>(smem + 2 * a.tile_bytes);
-    uint16_t *plist = reinterpret_cast<uint16_t *>(smem + 2 * a.tile_bytes + a.list_cap * 4);
+    uint32_t *list = reinterpret_cast<uint32_t *>(smem);  // maxima list: reuses the tile, which is dead after phase 2
+    uint16_t *plist = reinterpret_cast<uint16_t *>(smem + 2 * a.tile_bytes);
     if (threadIdx.x == 0 && (sb_smem_u32(tile) & 127u)) __trap();
     const CellGroup c = a.groups[blockIdx.x];
     const int img = blockIdx.y;
     const LevelGeom &L = g.lv[c.level];
-    const int BW = L.fast_bw, BH = L.fast_bh;
+    constexpr int BW = SB_FAST_BW;
+    const int BH = L.fast_bh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int xo = c.x0 & 15;  // the innermost TMA coordinate must be 16-byte aligned: ROI column x is tile column xo + x
 
@@ -222,8 +224,10 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
         // only the 4-pixel groups that overlap the tested ROI columns [3, rw - 3)
         const int g0 = (xo + 3) >> 2, G = c.G, rows = c.rh - 6;
         const int items = (rows > 0 && c.rw > 6) ? rows * G : 0;
-        const uint32_t Tp1 = (uint32_t)(t0 + 1) * 0x00010001u;
-        const int bw4 = BW >> 2;
+        // per 16-bit half: s2 + t + 512 - v in [257, 1022], "< 512" <=> bit 9 clear; no borrow crosses the halves,
+        // so one 32-bit IADD3 does both pixels (there is no packed 16-bit integer add on sm_100a: __vadd2 is 5 ops)
+        const uint32_t Tb = (uint32_t)(t0 + 512) * 0x00010001u;
+        constexpr int bw4 = BW >> 2;
         for (int it0 = warp * 32; it0 < items; it0 += FAST_THREADS) {
             const int it = it0 + lane;
             uint32_t hit = 0;  // bit j: pixel j of the item passes
@@ -244,10 +248,10 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
                     const uint32_t m1 = __vmins2(r0, r4), M1 = __vmaxs2(r0, r4), m2 = __vmins2(r8, r12), M2 = __vmaxs2(r8, r12);
                     const uint32_t A = __vmaxs2(m1, m2), B = __vmins2(M1, M2);
                     const uint32_t s2 = __vmins2(A, B), s3 = __vmaxs2(A, B);  // 2nd smallest / 2nd largest of the four
-                    // s2 < v - t  <=>  s2 - v + t < 0 ;  s3 > v + t  <=>  v - s3 + t < 0   (x - y = x + ~y + 1 per half)
-                    const uint32_t dk = __vadd2(__vadd2(s2, ~v), Tp1), br = __vadd2(__vadd2(v, ~s3), Tp1);
-                    const uint32_t neg = (dk | br) & 0x80008000u;
-                    hit |= (((neg >> 15) & 1u) | ((neg >> 30) & 2u)) << (2 * hpair);
+                    // darker: s2 < v - t  <=>  s2 + t - v < 0 ;  brighter: s3 > v + t  <=>  v + t - s3 < 0
+                    const uint32_t dk = s2 + Tb - v, br = v + Tb - s3;
+                    const uint32_t neg = ~(dk & br) & 0x02000200u;  // bit 9 of a half clear in either
+                    hit |= (((neg >> 9) & 1u) | ((neg >> 24) & 2u)) << (2 * hpair);
                 }
             }
 #pragma unroll
@@ -270,6 +274,10 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
         if (s >= t0) sc[y * BW + xo + x] = (uint8_t)s;
     }
     __syncthreads();
+    if (a.dbg && img == 0 && (int)blockIdx.x == a.dbg_cell) {
+        for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) a.dbg[i] = tile[i];
+        __syncthreads();
+    }
     // Phase 3: 3x3 non-maximum suppression (only listed pixels can be maxima).  Tested columns only; a neighbour
     // in the adjacent cell counts as 0, exactly as if each cell had been given to cv::FAST on its own.
     const int wC = c.wCell;
@@ -292,10 +300,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     }
     __syncthreads();
     if (a.dbg && img == 0 && (int)blockIdx.x == a.dbg_cell) {
-        for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) {
-            a.dbg[i] = tile[i];
-            a.dbg[a.tile_bytes + i] = sc[i];
-        }
+        for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) a.dbg[a.tile_bytes + i] = sc[i];
         if (tid == 0) {
             int *info = reinterpret_cast<int *>(a.dbg + 2 * a.tile_bytes);
             info[0] = BW; info[1] = BH; info[2] = xo; info[3] = c.x0; info[4] = c.y0; info[5] = c.rw; info[6] = c.rh;
@@ -867,7 +872,7 @@ static long long slab_bytes(const sb_orb *h, int w, int hgt) {
 }
 
 static size_t fast_smem_bytes(const sb_orb *h) {
-    return 2 * (size_t)h->fast_tile_bytes + (size_t)h->fast_list_cap * 4 + (size_t)(FAST_THREADS / 32) * h->fast_seg * 2 + 128;
+    return 2 * (size_t)h->fast_tile_bytes + (size_t)(FAST_THREADS / 32) * h->fast_seg * 2 + 128;
 }
 
 static int quadtree_ncap(int N, int bw, int bh) {
@@ -915,7 +920,8 @@ static int configure(sb_orb *h, int w, int hgt) {
         K = K < 1 ? 1 : K > SB_FAST_KMAX ? SB_FAST_KMAX : K;
         const int runs = sb_div_up(L.nCols, K);
         K = sb_div_up(L.nCols, runs);
-        L.fast_bw = (int)sb_align_up(K * L.wCell + 6 + 15, 16);
+        SB_REQUIRE(K * L.wCell + 6 + 15 <= SB_FAST_BW, "internal: FAST tile width");
+        L.fast_bw = SB_FAST_BW;
         L.fast_bh = L.hCell + 6;
         if (L.fast_bw * L.fast_bh > fast_tile) fast_tile = L.fast_bw * L.fast_bh;
         if (K * L.wCell * L.hCell / 4 + 8 > fast_list) fast_list = K * L.wCell * L.hCell / 4 + 8;  // maxima: at most 1 per 2 x 2
@@ -988,6 +994,7 @@ static int configure(sb_orb *h, int w, int hgt) {
                "nfeatures too large for the on-chip quadtree");
     h->fast_tile_bytes = (int)sb_align_up(fast_tile, 128);
     h->fast_list_cap = (int)sb_align_up(fast_list, 32);
+    SB_REQUIRE(h->fast_list_cap * 4 <= h->fast_tile_bytes, "internal: FAST maxima list does not fit the tile");
     h->fast_seg = sb_div_up(fast_items, FAST_THREADS) * 32 * 4;  // per-warp segment of the candidate-pixel list (phase 1)
     SB_REQUIRE(fast_smem_bytes(h) <= 200 * 1024, "internal: FAST shared memory");
     h->n_cells = (int)cells.size();
