@@ -53,6 +53,7 @@ struct LevelGeom {
     int nCols, nRows, wCell, hCell;
     int quota;                 // mnFeaturesPerLevel[level]
     int xtab, ytab;            // offsets into the resize tables
+    int qtab;                  // offset into the quad table, -1: this level needs the generic k_resize
     float scale, patch;        // mvScaleFactor[level], (float)(int)(31 * scale)
 };
 
@@ -154,6 +155,62 @@ __global__ void __launch_bounds__(256) k_resize(uint8_t *__restrict__ pyr, long 
         }
     }
     *reinterpret_cast<uint32_t *>(base + dst.off + (long long)y * dst.pitch + x0) = out;
+}
+
+// The same resize for scale factors <= 2: the 4 destination pixels of a thread read at most 8 consecutive source
+// bytes starting at S[sx of the first pixel]; three aligned words per source row and two funnel shifts form that
+// window, and one PRMT with a precomputed selector per pixel brings (S[sx], S[sx + 1]) into place for the DP2A.
+// A thread keeps its column table in registers and walks RESIZE_ROWS rows.
+struct __align__(16) ResizeQuad {
+    int wb;           // first source word of the quad
+    uint32_t sels;    // 4 x 8-bit PRMT selectors: bytes (o, o + 1) of the 8-byte window
+    uint32_t c[4];    // c0 | c1 << 16 per pixel
+    int sh;           // 8 * (first source byte & 3): the window starts this many bits into word wb
+    int pad;
+};
+#define RESIZE_ROWS 4
+__global__ void __launch_bounds__(256) k_resize_quads(uint8_t *__restrict__ pyr, long long slab, LevelGeom src, LevelGeom dst,
+                                                     const ResizeQuad *__restrict__ qtab, const int2 *__restrict__ ytab, int nquads) {
+    const int q = blockIdx.x * 32 + threadIdx.x;
+    if (q >= nquads) return;
+    const int4 t0 = __ldg(reinterpret_cast<const int4 *>(qtab + q));
+    const int4 t1 = __ldg(reinterpret_cast<const int4 *>(qtab + q) + 1);
+    const int sh = t1.z;
+    const uint32_t sels = (uint32_t)t0.y, cA = (uint32_t)t0.z, cB = (uint32_t)t0.w, cC = (uint32_t)t1.x, cD = (uint32_t)t1.y;
+    uint8_t *base = pyr + (long long)blockIdx.z * slab;
+    const uint32_t *sp = reinterpret_cast<const uint32_t *>(base + src.off) + t0.x;
+    uint8_t *dp = base + dst.off + 4 * q;
+    const int spw = src.pitch >> 2;
+#pragma unroll
+    for (int r = 0; r < RESIZE_ROWS; r++) {
+        const int y = blockIdx.y * (8 * RESIZE_ROWS) + r * 8 + threadIdx.y;
+        if (y >= dst.h) break;
+        const int2 yt = __ldg(ytab + dst.ytab + y);
+        const int b0 = yt.y & 0xffff, b1 = (unsigned)yt.y >> 16;
+        const int sy0 = min(max(yt.x, 0), src.h - 1), sy1 = min(max(yt.x + 1, 0), src.h - 1);
+        const uint32_t *W0 = sp + sy0 * spw, *W1 = sp + sy1 * spw;
+        const uint32_t u0 = W0[0], u1 = W0[1], u2 = W0[2], v0 = W1[0], v1 = W1[1], v2 = W1[2];
+        const uint32_t a0 = __funnelshift_r(u0, u1, sh), a1 = __funnelshift_r(u1, u2, sh);
+        const uint32_t e0 = __funnelshift_r(v0, v1, sh), e1 = __funnelshift_r(v1, v2, sh);
+        uint32_t out;
+        {
+            const int h0 = (int)__dp2a_lo(cA, __byte_perm(a0, a1, sels), 0u), h1 = (int)__dp2a_lo(cA, __byte_perm(e0, e1, sels), 0u);
+            out = (uint32_t)sb_lin_vert(h0, h1, b0, b1);
+        }
+        {
+            const int h0 = (int)__dp2a_lo(cB, __byte_perm(a0, a1, sels >> 8), 0u), h1 = (int)__dp2a_lo(cB, __byte_perm(e0, e1, sels >> 8), 0u);
+            out |= (uint32_t)sb_lin_vert(h0, h1, b0, b1) << 8;
+        }
+        {
+            const int h0 = (int)__dp2a_lo(cC, __byte_perm(a0, a1, sels >> 16), 0u), h1 = (int)__dp2a_lo(cC, __byte_perm(e0, e1, sels >> 16), 0u);
+            out |= (uint32_t)sb_lin_vert(h0, h1, b0, b1) << 16;
+        }
+        {
+            const int h0 = (int)__dp2a_lo(cD, __byte_perm(a0, a1, sels >> 24), 0u), h1 = (int)__dp2a_lo(cD, __byte_perm(e0, e1, sels >> 24), 0u);
+            out |= (uint32_t)sb_lin_vert(h0, h1, b0, b1) << 24;
+        }
+        *reinterpret_cast<uint32_t *>(dp + (long long)y * dst.pitch) = out;
+    }
 }
 
 // cv::FAST(cell ROI, iniTh, nms) with the minTh fallback (ComputeKeyPointsOctTree :838-883 /
@@ -500,20 +557,34 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps ma
     }
 }
 
-// IC_Angle (:27-55): moments over the radius-15 disc, one warp, lane = column u.
-static __device__ __forceinline__ float warp_ic_angle(const uint8_t *center, int pitch, const int *umax, int lane) {
+// IC_Angle (:27-55): moments over the radius-15 disc, one warp, lane = column u.  Column u holds the rows
+// |v| <= nv(u) = #{v >= 1 : |u| <= umax[v]} (ic_rows, computed once per thread); the row pair (+v, -v) is read
+// through two running pointers, and m10 = u * (sum of the column) is formed once at the end.
+static __device__ __forceinline__ int ic_rows(const int *umax, int lane) {
+    if (lane >= 31) return -1;
+    const int au = abs(lane - SB_HALF_PATCH);
+    int nv = 0;
+#pragma unroll
+    for (int v = 1; v <= SB_HALF_PATCH; v++) nv += au <= umax[v];
+    return nv;
+}
+static __device__ __forceinline__ float warp_ic_angle(const uint8_t *center, int pitch, int nv, int lane) {
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - SB_HALF_PATCH, au = abs(u);
-        m10 = u * center[u];
+    if (nv >= 0) {
+        const int u = lane - SB_HALF_PATCH;
+        const uint8_t *pu = center + u, *pd = pu;
+        int col = pu[0];
 #pragma unroll 5
         for (int v = 1; v <= SB_HALF_PATCH; v++) {
-            if (au <= umax[v]) {
-                const int vp = center[u + v * pitch], vm = center[u - v * pitch];
-                m10 += u * (vp + vm);
+            pu += pitch;
+            pd -= pitch;
+            if (v <= nv) {
+                const int vp = *pu, vm = *pd;
+                col += vp + vm;
                 m01 += v * (vp - vm);
             }
         }
+        m10 = u * col;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -604,10 +675,11 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     const uint32_t *sel = a.sel + ((long long)img * a.nlevels + level) * a.selcap + k0;
     const long long base = (long long)img * a.slab + L.off;
     // phase A: orientation, one warp per keypoint (4 keypoints per warp)
+    const int nv = ic_rows(g.umax, lane);
     for (int i = warp; i < nk; i += DESC_WARPS) {
         const uint32_t w = sel[i];
         const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;  // :895-896
-        const float angle = warp_ic_angle(a.pyr + base + (long long)y * L.pitch + x, L.pitch, g.umax, lane);
+        const float angle = warp_ic_angle(a.pyr + base + (long long)y * L.pitch + x, L.pitch, nv, lane);
         if (lane == 0) s_ang[i] = angle;
     }
     __syncthreads();
@@ -709,7 +781,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_screen(const __grid_constan
             const uint8_t *c = pyr + L.off + (long long)sb_rint(y) * L.pitch + sb_rint(x);
             ok = is_fast_corner_at(c, L.pitch, minTh);
             if (ok) {
-                angle = warp_ic_angle(c, L.pitch, g.umax, lane);
+                angle = warp_ic_angle(c, L.pitch, ic_rows(g.umax, lane), lane);
                 size = sb_fmul(31.f, L.scale);
             }
         }
@@ -763,6 +835,7 @@ struct sb_orb {
     CellGroup *d_cells;
     BlurTile *d_tiles;
     int2 *d_xtab, *d_ytab;  // resize tables: (source index, c0 | c1 << 16)
+    ResizeQuad *d_qtab;
     uint32_t *d_cand, *d_sel;
     int *d_cand_cnt, *d_sel_cnt, *d_flags;
     int tab_cap, cell_cap, tile_cap;
@@ -802,7 +875,7 @@ static void prof_end(sb_orb *h, cudaStream_t s) {
 static void free_orb(sb_orb *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->d_pyr,  h->d_blur, h->d_mask,     h->d_cells,   h->d_tiles,   h->d_xtab,    h->d_ytab,
+    void *ptrs[] = {h->d_pyr,  h->d_blur, h->d_mask,     h->d_cells,   h->d_tiles,   h->d_xtab,    h->d_ytab,    h->d_qtab,
                     h->d_cand,     h->d_sel,     h->d_cand_cnt, h->d_sel_cnt, h->d_flags,
                     h->d_in,   h->d_in_mask, h->d_desc_out, h->d_kps_out, h->d_counts_out, h->d_keep};
     for (void *p : ptrs)
@@ -891,6 +964,7 @@ static int configure(sb_orb *h, int w, int hgt) {
     g.nlevels = h->nlevels;
     memcpy(g.umax, h->umax, sizeof(g.umax));
     std::vector<int2> xtab, ytab;
+    std::vector<ResizeQuad> qtab;
     std::vector<CellGroup> cells;
     std::vector<BlurTile> tiles;
     long long off = 0;
@@ -973,6 +1047,26 @@ static int configure(sb_orb *h, int w, int hgt) {
                 SbLinCoef c = sb_lin_coef(d, L.h, S.h, false);
                 ytab.push_back(make_int2(c.s, (int)((uint32_t)(uint16_t)c.c0 | ((uint32_t)(uint16_t)c.c1 << 16))));
             }
+            // quad table (k_resize_quads): usable when every group of 4 destination pixels reads <= 8 consecutive source bytes
+            const size_t q_start = qtab.size();
+            L.qtab = (int)q_start;
+            const int nq = sb_div_up(L.w, 4);
+            for (int q = 0; q < nq && L.qtab >= 0; q++) {
+                ResizeQuad e;
+                memset(&e, 0, sizeof(e));
+                const int2 *xt = &xtab[L.xtab];
+                e.wb = xt[4 * q].x >> 2;
+                e.sh = 8 * (xt[4 * q].x & 3);
+                for (int k = 0; k < 4; k++) {
+                    const int2 t = xt[4 * q + k < L.w ? 4 * q + k : L.w - 1];
+                    const int o = t.x - xt[4 * q].x;
+                    if (o < 0 || o + 1 > 7) { L.qtab = -1; break; }  // scale factor > 2: generic kernel
+                    e.sels |= (uint32_t)(o | ((o + 1) << 4)) << (8 * k);
+                    e.c[k] = (uint32_t)t.y;
+                }
+                qtab.push_back(e);
+            }
+            if (L.qtab < 0) qtab.resize(q_start);
         }
         for (int ty = 0; ty < sb_div_up(L.h, BLUR_TH); ty++)
             for (int tx = 0; tx < sb_div_up(L.w, BLUR_TW); tx++) {
@@ -1004,6 +1098,10 @@ static int configure(sb_orb *h, int w, int hgt) {
     cudaStream_t s = h->stream;
     // the previous geometry may still be in use by queued kernels
     SB_CUDA(cudaStreamSynchronize(s));
+    if (!qtab.empty()) {
+        SB_REQUIRE((int)qtab.size() <= h->tab_cap, "internal: quad table capacity");
+        SB_CUDA(cudaMemcpyAsync(h->d_qtab, qtab.data(), qtab.size() * sizeof(ResizeQuad), cudaMemcpyHostToDevice, s));
+    }
     if (!xtab.empty()) {
         SB_CUDA(cudaMemcpyAsync(h->d_xtab, xtab.data(), xtab.size() * 8, cudaMemcpyHostToDevice, s));
         SB_CUDA(cudaMemcpyAsync(h->d_ytab, ytab.data(), ytab.size() * 8, cudaMemcpyHostToDevice, s));
@@ -1092,6 +1190,7 @@ extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float sc
     SB_ALLOC(h->d_tiles, (size_t)h->tile_cap * sizeof(BlurTile));
     SB_ALLOC(h->d_xtab, (size_t)h->tab_cap * 8);
     SB_ALLOC(h->d_ytab, (size_t)h->tab_cap * 8);
+    SB_ALLOC(h->d_qtab, (size_t)h->tab_cap * sizeof(ResizeQuad));
     SB_ALLOC(h->d_cand, B * nlevels * SB_CAND_CAP * 4);
     SB_ALLOC(h->d_sel, B * nlevels * h->selcap * 4);
     SB_ALLOC(h->d_cand_cnt, B * nlevels * 4);
@@ -1184,8 +1283,14 @@ static int launch_pyramid(sb_orb *h, uint8_t *pyr, const uint8_t *d_img, long lo
     if (nlevels_to_build > 1) prof_begin(h, SB_STAGE_RESIZE, nlevels_to_build - 1, h->stream);
     for (int l = 1; l < nlevels_to_build; l++) {
         const LevelGeom &D = g.lv[l];
-        dim3 grid(sb_div_up(sb_div_up(D.w, 4), 256), D.h, batch);
-        k_resize<<<grid, 256, 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_xtab, h->d_ytab);
+        if (D.qtab >= 0) {
+            const int nq = sb_div_up(D.w, 4);
+            dim3 grid(sb_div_up(nq, 32), sb_div_up(D.h, 8 * RESIZE_ROWS), batch);
+            k_resize_quads<<<grid, dim3(32, 8), 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_qtab + D.qtab, h->d_ytab, nq);
+        } else {
+            dim3 grid(sb_div_up(sb_div_up(D.w, 4), 256), D.h, batch);
+            k_resize<<<grid, 256, 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_xtab, h->d_ytab);
+        }
     }
     if (nlevels_to_build > 1) prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
