@@ -23,7 +23,8 @@ class SlamB200Error(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libslamb200.so")
+    # SLAMB200_LIB: development hook to load an experimental build of the same library (tools/)
+    return os.environ.get("SLAMB200_LIB") or os.path.join(_HERE, "libslamb200.so")
 
 
 def lib():

@@ -32,6 +32,8 @@ __device__ long long g_ba_prof[16];
 struct sb_ba {
     int device, max_windows, max_poses, max_points, max_obs;
     cudaStream_t stream, own_stream;
+    const int32_t *pending_info;  // host `info` of the batch in flight (sb_ba_submit .. sb_ba_wait), else null
+    int pending_windows;
     // device copies of the batch (host-pointer entry point) and per-window workspace
     int32_t *d_np, *d_nl, *d_ne, *d_info;
     double *d_poses, *d_points, *d_uv, *d_chi2;
@@ -42,6 +44,9 @@ struct sb_ba {
     double *d_ptbak;     // [W][ML][3]
     double *d_err;       // [W][2][MO][2]
     double *d_hpl;       // [W][MO][18]: w A^T B of every edge to a free landmark (the Hpl block), rebuilt each iteration
+    double *d_ybd;       // [W][MO][18]: Hpl Dinv of the same edges (rebuilt for every lambda)
+    int2 *d_pairs;       // [W][MP (MP + 1) / 2][ML]: per pose-block pair (i1 <= i2) the (edge to i1, edge to i2) of every free
+                         //                           landmark both observe — the structure of the Schur complement, built once
 };
 
 struct BaArgs {
@@ -55,7 +60,8 @@ struct BaArgs {
     uint8_t *outlier;        // [W][MO] out
     int32_t *info;           // [W][4] out: outer rounds, LM iterations, inliers, outliers (or -1: bad input)
     int32_t *edge_of;
-    double *lm, *ptbak, *err, *hpl;
+    double *lm, *ptbak, *err, *hpl, *ybd;
+    int2 *pairs;
     int MP, ML, MO;
     double fx, fy, cx, cy;
     double extR[9], extT[3];
@@ -127,6 +133,21 @@ static __device__ __forceinline__ void edge_lin(const EdgeCtx &c, int e, const d
     huber(r[0] * r[0] + r[1] * r[1], a.delta, rho0, w);
 }
 
+// ---- warp reduction of 32 values at once: after the call lane l holds the warp-wide sum of v[l].  A butterfly that
+//      halves the number of live values per stage: 31 shuffles + adds instead of 32 x 5, in a fixed order.
+static __device__ __forceinline__ double warp_reduce32(double (&v)[32], int lane) {
+#pragma unroll
+    for (int n = 16; n >= 1; n >>= 1) {
+        const bool up = lane & n;
+#pragma unroll
+        for (int k = 0; k < n; k++) {
+            const double keep = up ? v[k + n] : v[k], send = up ? v[k] : v[k + n];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return v[0];
+}
+
 // ---- block-wide deterministic reductions ----------------------------------------------------------------
 static __device__ double block_sum(double v, double *red) {
 #pragma unroll
@@ -182,7 +203,9 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
     double *xs = bp + 6 * MP;           // [6 MP]
     double *S = xs + 6 * MP;            // [(6 MP)^2]
     double *red = S + 36 * MP * MP;     // [16]
-    __shared__ int s_bad;
+    double *dinv = red + 16;            // [6 MP] reciprocal pivots of the Cholesky factor
+    int *pcnt = reinterpret_cast<int *>(dinv + 6 * MP);  // [MP (MP + 1) / 2] entries of each pair list
+    __shared__ int s_bad, s_next;
     double *poses = a.poses + (size_t)w * MP * 7;
     double *pts = a.points + (size_t)w * a.ML * 3;
     const uint8_t *fixed = a.fixed + (size_t)w * a.ML;
@@ -191,6 +214,8 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
     double *lm = a.lm + (size_t)w * a.ML * 18;
     double *ptb = a.ptbak + (size_t)w * a.ML * 3;
     double *hpl = a.hpl + (size_t)w * a.MO * 18;
+    double *ybd = a.ybd + (size_t)w * a.MO * 18;
+    int2 *pairs = a.pairs + (size_t)w * (MP * (MP + 1) / 2) * a.ML;
     double *err = a.err + (size_t)w * a.MO * 4;   // errors of the last evaluation
     double *elin = err + (size_t)a.MO * 2;         // errors at the linearisation state
     int32_t *info = a.info + 4 * w;
@@ -215,6 +240,26 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
     for (int i = tid; i < np; i += BA_THREADS) {
         quat_to_R(poses + 7 * i, Rt + 12 * i);
         Rt[12 * i + 9] = poses[7 * i + 4]; Rt[12 * i + 10] = poses[7 * i + 5]; Rt[12 * i + 11] = poses[7 * i + 6];
+    }
+    // ---- structure of the Schur complement: for every pose-block pair the landmarks that couple them, compacted in
+    //      ascending landmark order (one warp per pair; ballot compaction keeps it deterministic)
+    const int nblk = np * (np + 1) / 2;
+    for (int blk = wid; blk < nblk; blk += BA_THREADS / 32) {
+        int i1 = 0, rem = blk;
+        while (rem >= np - i1) { rem -= np - i1; i1++; }
+        const int i2 = i1 + rem;
+        int2 *pl = pairs + (size_t)blk * a.ML;
+        int cnt = 0;
+        for (int j0 = 0; j0 < nl; j0 += 32) {
+            const int j = j0 + lane;
+            int e1 = -1, e2 = -1;
+            if (j < nl && !fixed[j]) { e1 = edge_of[j * MP + i1]; e2 = edge_of[j * MP + i2]; }
+            const bool ok = e1 >= 0 && e2 >= 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) pl[cnt + __popc(bal & ((1u << lane) - 1u))] = make_int2(e1, e2);
+            cnt += __popc(bal);
+        }
+        if (lane == 0) pcnt[blk] = cnt;
     }
     __syncthreads();
 
@@ -324,34 +369,46 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                     L[12] = (A0 * f - cc * cc) * id; L[13] = (b * cc - A0 * e) * id; L[14] = (A0 * d - b * b) * id;
                 }
                 int ok = !__syncthreads_or(bad);
+                // ---- Y_e = Hpl_e Dinv_j for every edge to a free landmark (one thread per edge)
+                if (tid == 0) s_next = BA_THREADS / 32;
+                if (ok)
+                    for (int e = tid; e < ne; e += BA_THREADS) {
+                        const int j = ol[e];
+                        if (fixed[j]) continue;
+                        const double *L = lm + 18 * j;
+                        const double D0 = L[9], D1 = L[10], D2 = L[11], D4 = L[12], D5 = L[13], D8 = L[14];
+                        const double *P = hpl + 18 * e;
+                        double *Y = ybd + 18 * e;
+#pragma unroll
+                        for (int p = 0; p < 6; p++) {
+                            const double h0 = P[3 * p], h1 = P[3 * p + 1], h2 = P[3 * p + 2];
+                            Y[3 * p] = h0 * D0 + h1 * D1 + h2 * D2;
+                            Y[3 * p + 1] = h0 * D1 + h1 * D4 + h2 * D5;
+                            Y[3 * p + 2] = h0 * D2 + h1 * D5 + h2 * D8;
+                        }
+                    }
+                __syncthreads();
                 BA_T(3);
-                // ---- Schur complement: S(i1,i2) = Hpp'(i1,i2) - sum_j Hpl(i1,j) Dinv_j Hpl(i2,j)^T, one warp per block
-                //      (upper triangle), lanes over landmarks; the diagonal pass also reduces b.
-                const int nblk = np * (np + 1) / 2;
-                for (int blk = wid; blk < nblk && ok; blk += BA_THREADS / 32) {
+                // ---- Schur complement: S(i1,i2) = Hpp'(i1,i2) - sum_j Y(i1,j) Hpl(i2,j)^T over the pair's list, one warp per
+                //      block (upper triangle, taken from a shared counter: the blocks differ in size), lanes over the list;
+                //      the diagonal pass also reduces b.
+                for (int blk = wid; blk < nblk && ok;) {
                     int i1 = 0, rem = blk;
                     while (rem >= np - i1) { rem -= np - i1; i1++; }
                     const int i2 = i1 + rem;
+                    const int2 *pl = pairs + (size_t)blk * a.ML;
+                    const int cnt = pcnt[blk];
                     double acc[36], gb[6];
 #pragma unroll
                     for (int k = 0; k < 36; k++) acc[k] = 0;
 #pragma unroll
                     for (int k = 0; k < 6; k++) gb[k] = 0;
-                    for (int j = lane; j < nl; j += 32) {
-                        if (fixed[j]) continue;
-                        const int e1 = edge_of[j * MP + i1], e2 = edge_of[j * MP + i2];
-                        if (e1 < 0 || e2 < 0) continue;
-                        const double *L = lm + 18 * j;
-                        const double D[9] = {L[9], L[10], L[11], L[10], L[12], L[13], L[11], L[13], L[14]};
-                        const double *P1 = hpl + 18 * e1, *P2 = hpl + 18 * e2;
-                        double BD[18];  // Hpl(i1, j) Dinv_j
+                    for (int t = lane; t < cnt; t += 32) {
+                        const int2 ee = pl[t];
+                        const double *Y = ybd + 18 * ee.x, *P2 = hpl + 18 * ee.y;
+                        double BD[18];
 #pragma unroll
-                        for (int p = 0; p < 6; p++) {
-                            const double h0 = P1[3 * p], h1 = P1[3 * p + 1], h2 = P1[3 * p + 2];
-                            BD[3 * p] = h0 * D[0] + h1 * D[3] + h2 * D[6];
-                            BD[3 * p + 1] = h0 * D[1] + h1 * D[4] + h2 * D[7];
-                            BD[3 * p + 2] = h0 * D[2] + h1 * D[5] + h2 * D[8];
-                        }
+                        for (int k = 0; k < 18; k++) BD[k] = Y[k];
 #pragma unroll
                         for (int q = 0; q < 6; q++) {
                             const double g0 = P2[3 * q], g1 = P2[3 * q + 1], g2 = P2[3 * q + 2];
@@ -359,81 +416,94 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                             for (int p = 0; p < 6; p++) acc[6 * p + q] += BD[3 * p] * g0 + BD[3 * p + 1] * g1 + BD[3 * p + 2] * g2;
                         }
                         if (i1 == i2) {  // b_schur(i1) -= Hpl(i1, j) Dinv_j bl_j
+                            const double *L = lm + 18 * ol[ee.x];
+                            const double b0 = L[6], b1 = L[7], b2 = L[8];
 #pragma unroll
-                            for (int p = 0; p < 6; p++) gb[p] += BD[3 * p] * L[6] + BD[3 * p + 1] * L[7] + BD[3 * p + 2] * L[8];
+                            for (int p = 0; p < 6; p++) gb[p] += BD[3 * p] * b0 + BD[3 * p + 1] * b1 + BD[3 * p + 2] * b2;
                         }
                     }
+                    // entries 0..31 by the butterfly (lane l ends with entry l), 32..35 and b by plain trees
+                    double head[32];
 #pragma unroll
-                    for (int k = 0; k < 36; k++)
+                    for (int k = 0; k < 32; k++) head[k] = acc[k];
+                    const double mine = warp_reduce32(head, lane);
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], o);
+                    for (int k = 32; k < 36; k++)
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+                    {
+                        const int p = lane / 6, q = lane - 6 * p;
+                        double v = -mine;
+                        if (i1 == i2) v += Hpp[36 * i1 + 6 * p + q] + (p == q ? lambda : 0.0);
+                        S[(6 * i1 + p) * n6 + 6 * i2 + q] = v;
+                        if (i1 != i2) S[(6 * i2 + q) * n6 + 6 * i1 + p] = v;  // a diagonal block holds both (p,q) and (q,p) itself
+                    }
+                    if (lane < 4) {
+                        const int q = 2 + lane;  // entries 32..35 = row 5, columns 2..5
+                        double v = -(lane == 0 ? acc[32] : lane == 1 ? acc[33] : lane == 2 ? acc[34] : acc[35]);
+                        if (i1 == i2) v += Hpp[36 * i1 + 30 + q] + (q == 5 ? lambda : 0.0);
+                        S[(6 * i1 + 5) * n6 + 6 * i2 + q] = v;
+                        if (i1 != i2) S[(6 * i2 + q) * n6 + 6 * i1 + 5] = v;
+                    }
                     if (i1 == i2) {
 #pragma unroll
                         for (int k = 0; k < 6; k++)
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) gb[k] += __shfl_down_sync(0xffffffffu, gb[k], o);
+                            for (int o = 16; o > 0; o >>= 1) gb[k] += __shfl_xor_sync(0xffffffffu, gb[k], o);
+                        if (lane < 6) {
+                            const double g = lane == 0 ? gb[0] : lane == 1 ? gb[1] : lane == 2 ? gb[2] : lane == 3 ? gb[3] : lane == 4 ? gb[4] : gb[5];
+                            xs[6 * i1 + lane] = bp[6 * i1 + lane] - g;
+                        }
                     }
-                    if (lane == 0) {
-                        for (int p = 0; p < 6; p++)
-                            for (int q = 0; q < 6; q++) {
-                                double v = -acc[6 * p + q];
-                                if (i1 == i2) v += Hpp[36 * i1 + 6 * p + q] + (p == q ? lambda : 0.0);
-                                S[(6 * i1 + p) * n6 + 6 * i2 + q] = v;
-                                S[(6 * i2 + q) * n6 + 6 * i1 + p] = v;
-                            }
-                        if (i1 == i2)
-                            for (int p = 0; p < 6; p++) xs[6 * i1 + p] = bp[6 * i1 + p] - gb[p];
-                    }
+                    blk = 0;
+                    if (lane == 0) blk = atomicAdd(&s_next, 1);
+                    blk = __shfl_sync(0xffffffffu, blk, 0);
                 }
                 __syncthreads();
                 BA_T(4);
-                // ---- Cholesky of the reduced system (lower triangle, in place, left-looking) and the two triangular
-                //      solves, all by ONE warp with warp-level synchronisation only: the system is 42 x 42, and
-                //      block-wide barriers per column cost more than the arithmetic.
+                // ---- Cholesky of the reduced system, right-looking, by the whole CTA with one barrier per column:
+                //      column j of L goes to ROW j of the upper triangle (S[j][i], i > j: contiguous for the substitutions),
+                //      the trailing update works on the lower triangle, the pivots are kept as reciprocals.  The order of
+                //      the subtractions per entry is the same as in the left-looking form (k = 0, 1, ...).
                 if (ok) {
-                    if (wid == 0) {
-                        int bad_pivot = 0;
-                        for (int j = 0; j < n6; j++) {
-                            double v = 0;
-                            for (int k = lane; k < j; k += 32) v += S[j * n6 + k] * S[j * n6 + k];
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                            const double d = S[j * n6 + j] - v;
-                            if (!(d > 0)) { bad_pivot = 1; break; }
-                            const double dj = sqrt(d), inv = 1.0 / dj;
-                            for (int i = j + 1 + lane; i < n6; i += 32) {
-                                double sacc = S[i * n6 + j];
-                                for (int k = 0; k < j; k++) sacc -= S[i * n6 + k] * S[j * n6 + k];
-                                S[i * n6 + j] = sacc * inv;
-                            }
-                            __syncwarp();
-                            if (lane == 0) S[j * n6 + j] = dj;
-                            __syncwarp();
+                    int bad_pivot = 0;
+                    const int r0 = tid >> 3, c0 = tid & 7;
+                    for (int j = 0; j < n6; j++) {
+                        const double d = S[j * n6 + j];
+                        if (!(d > 0)) { bad_pivot = 1; break; }   // uniform: every thread reads the same entry
+                        const double inv = rsqrt(d);
+                        if (tid == 0) dinv[j] = inv;
+                        for (int i = j + 1 + r0; i < n6; i += BA_THREADS / 8) {
+                            const double lij = S[i * n6 + j] * inv;
+                            if (c0 == 0) S[j * n6 + i] = lij;
+                            for (int k = j + 1 + c0; k <= i; k += 8) S[i * n6 + k] -= lij * (S[k * n6 + j] * inv);
                         }
-                        if (!bad_pivot) {
-                            // forward substitution, column oriented: after y_j is final every lane updates its entries
-                            for (int j = 0; j < n6; j++) {
-                                const double yj = xs[j] / S[j * n6 + j];
-                                __syncwarp();
-                                if (lane == 0) xs[j] = yj;
-                                for (int i = j + 1 + lane; i < n6; i += 32) xs[i] -= S[i * n6 + j] * yj;
-                                __syncwarp();
-                            }
-                            // backward substitution with L^T: row j of L is column j of L^T
-                            for (int j = n6 - 1; j >= 0; j--) {
-                                const double xj = xs[j] / S[j * n6 + j];
-                                __syncwarp();
-                                if (lane == 0) xs[j] = xj;
-                                for (int i = lane; i < j; i += 32) xs[i] -= S[j * n6 + i] * xj;
-                                __syncwarp();
-                            }
+                        __syncthreads();
+                    }
+                    if (!bad_pivot && wid == 0) {
+                        // substitutions by one warp, the unknowns in registers (n6 <= 96: three per lane)
+                        double x0 = lane < n6 ? xs[lane] : 0, x1 = lane + 32 < n6 ? xs[lane + 32] : 0, x2 = lane + 64 < n6 ? xs[lane + 64] : 0;
+                        for (int j = 0; j < n6; j++) {  // forward, column oriented: L(i, j) = S[j][i]
+                            const double src = j < 32 ? x0 : j < 64 ? x1 : x2;
+                            const double yj = __shfl_sync(0xffffffffu, src, j & 31) * dinv[j];
+                            const double *row = S + j * n6;
+                            if (lane == j) x0 = yj; else if (lane > j && lane < n6) x0 -= row[lane] * yj;
+                            if (lane + 32 == j) x1 = yj; else if (lane + 32 > j && lane + 32 < n6) x1 -= row[lane + 32] * yj;
+                            if (lane + 64 == j) x2 = yj; else if (lane + 64 > j && lane + 64 < n6) x2 -= row[lane + 64] * yj;
                         }
-                        if (lane == 0) s_bad = bad_pivot;
+                        for (int j = n6 - 1; j >= 0; j--) {  // backward with L^T: L^T(i, j) = L(j, i) = S[i][j], i < j
+                            const double src = j < 32 ? x0 : j < 64 ? x1 : x2;
+                            const double xj = __shfl_sync(0xffffffffu, src, j & 31) * dinv[j];
+                            if (lane == j) x0 = xj; else if (lane < j) x0 -= S[lane * n6 + j] * xj;
+                            if (lane + 32 == j) x1 = xj; else if (lane + 32 < j) x1 -= S[(lane + 32) * n6 + j] * xj;
+                            if (lane + 64 == j) x2 = xj; else if (lane + 64 < j) x2 -= S[(lane + 64) * n6 + j] * xj;
+                        }
+                        if (lane < n6) xs[lane] = x0;
+                        if (lane + 32 < n6) xs[lane + 32] = x1;
+                        if (lane + 64 < n6) xs[lane + 64] = x2;
                     }
                     __syncthreads();
-                    ok = !s_bad;
-                    __syncthreads();
-                    if (tid == 0) s_bad = 0;
+                    ok = !bad_pivot;
                 }
                 BA_T(5);
                 double scale = 0;
@@ -524,13 +594,15 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
 // ================================================================================================
 // host side
 // ================================================================================================
-static size_t ba_smem_bytes(int MP) { return sizeof(double) * (size_t)(12 * MP * 2 + 36 * MP + 6 * MP * 2 + 36 * MP * MP + 16); }
+static size_t ba_smem_bytes(int MP) {
+    return sizeof(double) * (size_t)(12 * MP * 2 + 36 * MP + 6 * MP * 2 + 36 * MP * MP + 16 + 6 * MP) + sizeof(int) * (size_t)(MP * (MP + 1) / 2 + 2);
+}
 
 static void free_ba(sb_ba *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_np, h->d_nl, h->d_ne, h->d_info, h->d_poses, h->d_points, h->d_uv, h->d_chi2, h->d_fixed,
-                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_lm, h->d_ptbak, h->d_err, h->d_hpl};
+                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_lm, h->d_ptbak, h->d_err, h->d_hpl, h->d_ybd, h->d_pairs};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -574,6 +646,8 @@ extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_
     BA_ALLOC(h->d_ptbak, W * ML * 3 * 8);
     BA_ALLOC(h->d_err, W * MO * 4 * 8);
     BA_ALLOC(h->d_hpl, W * MO * 18 * 8);
+    BA_ALLOC(h->d_ybd, W * MO * 18 * 8);
+    BA_ALLOC(h->d_pairs, W * (MP * (MP + 1) / 2) * ML * sizeof(int2));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_bytes(BA_MAX_POSES));
     if (e != cudaSuccess) {
@@ -627,7 +701,7 @@ extern "C" int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_pos
     a.np = d_n_poses; a.nl = d_n_points; a.ne = d_n_obs;
     a.poses = d_poses; a.points = d_points; a.fixed = d_fixed; a.op = d_obs_pose; a.ol = d_obs_point; a.uv = d_uv;
     a.chi2 = d_chi2; a.outlier = d_outlier; a.info = d_info;
-    a.edge_of = h->d_edge_of; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err; a.hpl = h->d_hpl;
+    a.edge_of = h->d_edge_of; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err; a.hpl = h->d_hpl; a.ybd = h->d_ybd; a.pairs = h->d_pairs;
     a.MP = h->max_poses; a.ML = h->max_points; a.MO = h->max_obs;
     a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
     quat7_to_ext(cam_ext7, a.extR, a.extT);
@@ -637,13 +711,17 @@ extern "C" int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_pos
     return SB_OK;
 }
 
-extern "C" int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t *n_points,
-                           const int32_t *n_obs, double *poses, double *points, const uint8_t *fixed,
-                           const int32_t *obs_pose, const int32_t *obs_point, const double *uv, const double *K,
-                           const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
-                           double *chi2, uint8_t *outlier, int32_t *info) {
+// Asynchronous host-pointer form: the reference's Backend runs in its own thread beside the front end
+// (src/backend.cpp:29-45), so the caller enqueues a batch of windows and collects it later.  Host arrays
+// must stay valid (and should be pinned) until sb_ba_wait returns.
+extern "C" int sb_ba_submit(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t *n_points,
+                            const int32_t *n_obs, double *poses, double *points, const uint8_t *fixed,
+                            const int32_t *obs_pose, const int32_t *obs_point, const double *uv, const double *K,
+                            const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
+                            double *chi2, uint8_t *outlier, int32_t *info) {
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
+    SB_REQUIRE(!h->pending_info, "a batch is already in flight: call sb_ba_wait first");
     SB_REQUIRE(n_windows >= 1 && n_windows <= h->max_windows, "n_windows out of range [1, max_windows]");
     SB_REQUIRE(n_poses && n_points && n_obs && poses && points && fixed && obs_pose && obs_point && uv && chi2 && outlier && info,
                "null pointer");
@@ -667,13 +745,36 @@ extern "C" int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, co
     SB_CUDA(cudaMemcpyAsync(chi2, h->d_chi2, W * MO * 8, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaMemcpyAsync(outlier, h->d_outlier, W * MO, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaMemcpyAsync(info, h->d_info, W * 16, cudaMemcpyDeviceToHost, s));
-    SB_CUDA(cudaStreamSynchronize(s));
+    h->pending_info = info;
+    h->pending_windows = n_windows;
+    return SB_OK;
+}
+
+extern "C" int sb_ba_wait(sb_ba_t *h) {
+    sb_clear_error();
+    SB_REQUIRE(h, "null handle");
+    SB_REQUIRE(h->pending_info, "no batch in flight");
+    SB_TRY(sb_use_device(h->device));
+    const int32_t *info = h->pending_info;
+    const size_t W = (size_t)h->pending_windows;
+    h->pending_info = nullptr;
+    SB_CUDA(cudaStreamSynchronize(h->stream));
     for (size_t w = 0; w < W; w++)
         if (info[4 * w] < 0) {
             sb_set_error("window %zu: %s", w, info[4 * w + 1] == -2 ? "a keyframe observes the same landmark twice" : "counts or indices out of range");
             return SB_ERR_INVALID;
         }
     return SB_OK;
+}
+
+extern "C" int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t *n_points,
+                           const int32_t *n_obs, double *poses, double *points, const uint8_t *fixed,
+                           const int32_t *obs_pose, const int32_t *obs_point, const double *uv, const double *K,
+                           const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
+                           double *chi2, uint8_t *outlier, int32_t *info) {
+    SB_TRY(sb_ba_submit(h, n_windows, n_poses, n_points, n_obs, poses, points, fixed, obs_pose, obs_point, uv, K, cam_ext7,
+                        huber_delta, chi2_th, outer_max, inner_iters, chi2, outlier, info));
+    return sb_ba_wait(h);
 }
 
 #ifdef BA_PROFILE

@@ -199,6 +199,15 @@ int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t
                 double *poses, double *points, const uint8_t *fixed, const int32_t *obs_pose, const int32_t *obs_point,
                 const double *uv, const double *K, const double *cam_ext7, double huber_delta, double chi2_th,
                 int outer_max, int inner_iters, double *chi2, uint8_t *outlier, int32_t *info);
+/* Asynchronous host-pointer form — the reference's Backend optimises in its own thread beside the front end
+ * (src/backend.cpp:29-45, BackendLoop): sb_ba_submit enqueues copies + solve + copies back on the handle's stream and
+ * returns; sb_ba_wait blocks until the batch is complete and reports invalid windows.  One batch in flight per handle;
+ * host arrays must stay valid (pinned for true overlap) until sb_ba_wait returns.  sb_ba_solve = submit + wait. */
+int sb_ba_submit(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t *n_points, const int32_t *n_obs,
+                 double *poses, double *points, const uint8_t *fixed, const int32_t *obs_pose, const int32_t *obs_point,
+                 const double *uv, const double *K, const double *cam_ext7, double huber_delta, double chi2_th,
+                 int outer_max, int inner_iters, double *chi2, uint8_t *outlier, int32_t *info);
+int sb_ba_wait(sb_ba_t *h);
 /* Same with every array on the device (K and cam_ext7 stay host pointers); asynchronous. */
 int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_poses, const int32_t *d_n_points,
                     const int32_t *d_n_obs, double *d_poses, double *d_points, const uint8_t *d_fixed,

@@ -10,7 +10,7 @@ ws = [synth.ba_window(s) for s in range(8)]
 ba.solve(ws, synth.KITTI_K)
 prof = (C.c_longlong * 16)()
 pkg.lib().sb_ba_debug_profile(prof)
-ba.solve(ws[:1], synth.KITTI_K)
+res = ba.solve(ws[:1], synth.KITTI_K); print("info", res[0][4])
 pkg.lib().sb_ba_debug_profile(prof)
 names = ["loop/accept", "errors", "build", "lambda+push+Dinv", "schur", "cholesky+solve", "xl+update", "errors(trial)"]
 tot = sum(prof[:8])
