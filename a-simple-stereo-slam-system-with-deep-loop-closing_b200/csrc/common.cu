@@ -39,8 +39,8 @@ typedef CUresult (*sb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuin
                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                        CUtensorMapFloatOOBfill);
 
-int sb_make_tensor_map_u8(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
-                          const uint64_t *strides_bytes, const uint32_t *box) {
+static int make_tensor_map_u8(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                              const uint32_t *box, CUtensorMapSwizzle swizzle) {
     static sb_encode_tiled_fn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -61,12 +61,22 @@ int sb_make_tensor_map_u8(CUtensorMap *map, const void *base, int rank, const ui
         if (i + 1 < rank) gstr[i] = strides_bytes[i];
     }
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void *>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         sb_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu, box %u x %u)", (int)r, rank,
                      (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 1), box[0], rank > 1 ? box[1] : 1);
         return SB_ERR_CUDA;
     }
     return SB_OK;
+}
+
+int sb_make_tensor_map_u8(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                          const uint32_t *box) {
+    return make_tensor_map_u8(map, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+}
+
+// 128-byte swizzle: the shared-memory image a tcgen05 K-major SWIZZLE_128B operand descriptor expects (box[0] = 128 bytes)
+int sb_make_tensor_map_u8_sw128(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                                const uint32_t *box) {
+    return make_tensor_map_u8(map, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }

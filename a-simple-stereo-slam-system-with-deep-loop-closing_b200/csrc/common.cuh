@@ -48,6 +48,9 @@ int sb_use_device(int device);
 int sb_make_tensor_map_u8(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
                           const uint64_t *strides_bytes, const uint32_t *box);
 
+int sb_make_tensor_map_u8_sw128(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
+                                const uint64_t *strides_bytes, const uint32_t *box);
+
 #ifdef __CUDACC__
 // ---- mbarrier + TMA (cp.async.bulk.tensor) -------------------------------------------------------
 static __device__ __forceinline__ uint32_t sb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -4,6 +4,7 @@
 // src/loopclosing.cpp:33,172): for every query row the nearest train row, ties -> lowest trainIdx.
 // HBM traffic is negligible (64 KB per descriptor set); the work is 4 M distance evaluations per
 // 2000 x 2000 problem, done as an exact int8 tensor-core GEMM (see below).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -19,6 +20,8 @@ struct sb_matcher {
     uint8_t *d_xq, *d_xt;
     uint32_t *d_tkey;
     int32_t *d_pq;
+    CUtensorMap map_q, map_t;  // expanded operands as [rows][256] u8, 128-byte swizzle; boxes 128 x UM_M / 128 x UM_N
+    int legacy;                // SLAMB200_MATCH=mma: the mma.sync kernel (development comparison only)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -172,6 +175,167 @@ __global__ void k_hamming_decode(const int32_t *__restrict__ nq_arr, int nq_stri
     out_dist[(long long)set * out_stride + qi] = none ? -1 : (int32_t)(key >> MATCH_KEY_SHIFT) - 512 + pq[(long long)set * rows_pad + qi];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same GEMM on the 5th-generation tensor cores: tcgen05.mma kind::i8 (u8 x u8 -> s32), operands staged by TMA
+// into 128-byte-swizzled shared memory, accumulators in tensor memory, 1-NN reduction fused into the epilogue.
+//   CTA  = 128 query rows (the M of one UMMA) x one slice of the train set, walked in tiles of 256 train rows (N);
+//   K    = 256 expanded bytes = 8 instructions of K = 32; an operand tile is two 128-byte-wide swizzle panels;
+//   TMEM = 2 accumulators of 128 lanes x 256 columns: the MMAs of tile t + 1 overlap the epilogue of tile t;
+//   warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one lane), warps 2-5 = epilogue (lane quadrant = warp % 4):
+//          one thread per query row reads its accumulator row with tcgen05.ld and folds key - (dot << 23) into a min.
+// ---------------------------------------------------------------------------------------------------
+#define UM_M 128
+#define UM_N 256
+#define UM_THREADS 192
+#define UM_A_BYTES (UM_M * 256)
+#define UM_B_BYTES (UM_N * 256)
+#define UM_SMEM (UM_A_BYTES + 2 * UM_B_BYTES + 1024)
+
+static __device__ __forceinline__ void um_tma_load_2d(void *smem_dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     sb_smem_u32(smem_dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(sb_smem_u32(bar))
+                 : "memory");
+}
+static __device__ __forceinline__ void um_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sb_smem_u32(bar)) : "memory");
+}
+static __device__ __forceinline__ void um_commit(uint64_t *bar) {  // arrives on `bar` when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sb_smem_u32(bar)) : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), descriptor version 1
+static __device__ __forceinline__ uint64_t um_smem_desc(const void *p) {
+    const uint64_t addr = (uint64_t)((sb_smem_u32(p) & 0x3ffffu) >> 4);
+    return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+static __device__ __forceinline__ void um_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+static __device__ __forceinline__ void um_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// grid = (rows_pad / UM_M, nslices, batch); out_key pre-set to 0xffffffff; rows_pad is a multiple of UM_N.
+__global__ void __launch_bounds__(UM_THREADS, 1) k_hamming_umma(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+                                                               const uint32_t *__restrict__ tkey, const int32_t *__restrict__ nq_arr,
+                                                               int nq_stride, const int32_t *__restrict__ nt_arr, int nt_stride,
+                                                               int max_rows, int rows_pad, uint32_t *__restrict__ out_key,
+                                                               long long out_stride, int nslices) {
+    extern __shared__ uint8_t um_raw[];
+    __shared__ __align__(8) uint64_t a_full, b_full[2], b_empty[2], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    const int set = blockIdx.z;
+    const int nq = min(nq_arr[(long long)set * nq_stride], max_rows);
+    const int nt = min(nt_arr[(long long)set * nt_stride], max_rows);
+    const int q0 = blockIdx.x * UM_M;
+    if (q0 >= nq) return;
+    const int per = (((nt + nslices - 1) / nslices) + UM_N - 1) / UM_N * UM_N;  // train rows per slice
+    const int t_begin = blockIdx.y * per, t_end = min(nt, t_begin + per);
+    if (t_begin >= t_end) return;
+    const int ntiles = (t_end - t_begin + UM_N - 1) / UM_N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *smem = um_raw + ((1024u - (sb_smem_u32(um_raw) & 1023u)) & 1023u);  // swizzle panels need 1024-byte alignment
+    uint8_t *sA = smem, *sB = smem + UM_A_BYTES;
+
+    if (threadIdx.x == 0) {
+        sb_mbar_init(&a_full, 1);
+        for (int i = 0; i < 2; i++) {
+            sb_mbar_init(&b_full[i], 1);
+            sb_mbar_init(&b_empty[i], 1);
+            sb_mbar_init(&acc_full[i], 1);
+            sb_mbar_init(&acc_empty[i], 4);
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb_smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer
+            const int rowq = set * rows_pad + q0, rowt = set * rows_pad + t_begin;
+            sb_mbar_expect_tx(&a_full, UM_A_BYTES);
+            um_tma_load_2d(sA, &map_q, 0, rowq, &a_full);
+            um_tma_load_2d(sA + UM_A_BYTES / 2, &map_q, 128, rowq, &a_full);
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t & 1;
+                if (t >= 2) sb_mbar_wait(&b_empty[s], ((t >> 1) - 1) & 1);
+                sb_mbar_expect_tx(&b_full[s], UM_B_BYTES);
+                um_tma_load_2d(sB + s * UM_B_BYTES, &map_t, 0, rowt + t * UM_N, &b_full[s]);
+                um_tma_load_2d(sB + s * UM_B_BYTES + UM_B_BYTES / 2, &map_t, 128, rowt + t * UM_N, &b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer
+            // instruction descriptor: D = s32 (2 << 4), A = B = u8 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(UM_N >> 3) << 17) | ((uint32_t)(UM_M >> 4) << 24);
+            sb_mbar_wait(&a_full, 0);
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t & 1;
+                sb_mbar_wait(&b_full[s], (t >> 1) & 1);
+                if (t >= 2) sb_mbar_wait(&acc_empty[s], ((t >> 1) - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint64_t ad = um_smem_desc(sA + (k >> 2) * (UM_A_BYTES / 2) + (k & 3) * 32);
+                    const uint64_t bd = um_smem_desc(sB + s * UM_B_BYTES + (k >> 2) * (UM_B_BYTES / 2) + (k & 3) * 32);
+                    um_mma_i8(tmem + s * UM_N, ad, bd, idesc, k > 0);
+                }
+                um_commit(&b_empty[s]);
+                um_commit(&acc_full[s]);
+            }
+        }
+    } else {  // ===== epilogue: one thread per query row
+        const int quad = warp & 3;
+        const int row = q0 + quad * 32 + lane;
+        const uint32_t *TK = tkey + (long long)set * rows_pad + t_begin;
+        uint32_t best = 0xffffffffu;
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t & 1;
+            sb_mbar_wait(&acc_full[s], (t >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < UM_N / 32; c++) {
+                uint32_t v[32];
+                um_tmem_ld32(tmem + (((uint32_t)quad * 32u) << 16) + (uint32_t)(s * UM_N + c * 32), v);
+                const uint4 *tk4 = reinterpret_cast<const uint4 *>(TK + t * UM_N + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint4 k4 = __ldg(tk4 + j);  // rows past the train set carry 0xffffffff and a zero dot product
+                    best = min(best, min(min(k4.x - (v[4 * j] << 23), k4.y - (v[4 * j + 1] << 23)),
+                                         min(k4.z - (v[4 * j + 2] << 23), k4.w - (v[4 * j + 3] << 23))));
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) um_mbar_arrive(&acc_empty[s]);
+        }
+        if (row < nq && best != 0xffffffffu) atomicMin(&out_key[(long long)set * out_stride + row], best);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 static void free_matcher(sb_matcher *m) {
     if (!m) return;
     cudaSetDevice(m->device);
@@ -201,18 +365,31 @@ extern "C" int sb_matcher_create(sb_matcher_t **out, int device, int max_batch, 
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_nt, (size_t)max_batch * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_idx, rows * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_dist, rows * 4);
-    m->rows_pad = (int)sb_align_up((size_t)max_rows, MMA_QB);
+    m->rows_pad = (int)sb_align_up((size_t)max_rows, 256);  // UM_N: train tiles never cross a set
     const size_t prow = (size_t)max_batch * m->rows_pad;
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_xq, prow * 256);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_xt, prow * 256);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_tkey, prow * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&m->d_pq, prow * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_hamming_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, UM_SMEM);
     if (e != cudaSuccess) {
         sb_set_error("sb_matcher_create: %s", cudaGetErrorString(e));
         free_matcher(m);
         return SB_ERR_CUDA;
     }
+    {
+        const uint64_t dims[2] = {256, (uint64_t)prow}, strides[1] = {256};
+        const uint32_t boxq[2] = {128, UM_M}, boxt[2] = {128, UM_N};
+        int rc = sb_make_tensor_map_u8_sw128(&m->map_q, m->d_xq, 2, dims, strides, boxq);
+        if (rc == SB_OK) rc = sb_make_tensor_map_u8_sw128(&m->map_t, m->d_xt, 2, dims, strides, boxt);
+        if (rc != SB_OK) {
+            free_matcher(m);
+            return rc;
+        }
+    }
+    const char *mode = getenv("SLAMB200_MATCH");
+    m->legacy = mode && !strcmp(mode, "mma");
     m->stream = m->own_stream;
     *out = m;
     return SB_OK;
@@ -251,13 +428,21 @@ extern "C" int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d
     k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_t, t_set_stride, d_nt, nt_stride, max_rows, rp, m->d_xt, m->d_tkey, nullptr);
     // enough CTAs to fill 148 SMs: slice the train set when the batch alone does not
     const int qblocks = sb_div_up(max_rows, MMA_QB);
-    int nslices = 1;
-    while (nslices < 16 && (long long)qblocks * batch * nslices < 148 * 8 && max_rows / (nslices * 2) >= MMA_TC) nslices *= 2;
     k_hamming_init<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows,
                                                                                  reinterpret_cast<uint32_t *>(d_train_idx), out_stride);
-    k_hamming_mma<<<dim3(qblocks, nslices, batch), 128, 0, m->stream>>>(m->d_xq, m->d_xt, m->d_tkey, d_nq, nq_stride, d_nt, nt_stride,
-                                                                        max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx),
-                                                                        out_stride, nslices);
+    if (m->legacy) {
+        int nslices = 1;
+        while (nslices < 16 && (long long)qblocks * batch * nslices < 148 * 8 && max_rows / (nslices * 2) >= MMA_TC) nslices *= 2;
+        k_hamming_mma<<<dim3(qblocks, nslices, batch), 128, 0, m->stream>>>(m->d_xq, m->d_xt, m->d_tkey, d_nq, nq_stride, d_nt, nt_stride,
+                                                                            max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx),
+                                                                            out_stride, nslices);
+    } else {
+        int nslices = 1;  // one CTA per SM (160 KB of shared memory, all of TMEM)
+        while (nslices < 16 && (long long)qblocks * batch * nslices < 148 && max_rows / (nslices * 2) >= UM_N) nslices *= 2;
+        k_hamming_umma<<<dim3(qblocks, nslices, batch), UM_THREADS, UM_SMEM, m->stream>>>(
+            m->map_q, m->map_t, m->d_tkey, d_nq, nq_stride, d_nt, nt_stride, max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx),
+            out_stride, nslices);
+    }
     k_hamming_decode<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows, rp, m->d_pq, d_train_idx,
                                                                                    d_dist, out_stride);
     SB_CUDA(cudaGetLastError());
