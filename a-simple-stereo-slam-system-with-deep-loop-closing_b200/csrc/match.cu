@@ -21,28 +21,21 @@ struct sb_matcher {
     uint32_t *d_tkey;
     int32_t *d_pq;
     CUtensorMap map_q, map_t;  // expanded operands as [rows][256] u8, 128-byte swizzle; boxes 128 x UM_M / 128 x UM_N
-    int legacy;                // SLAMB200_MATCH=mma: the mma.sync kernel (development comparison only)
 };
 
 // ---------------------------------------------------------------------------------------------------
 // Hamming distance on the tensor cores.  For bit vectors q, t:  |q xor t| = |q| + |t| - 2 <q, t>, and the
 // 2000 x 2000 x 256 table of dot products is GEMM-shaped, so the bits are widened to 0/1 bytes once
-// (k_expand) and the dot products come from int8 MMA (mma.sync m16n8k32 u8 x u8 -> s32, IMMA in SASS;
-// exact integer arithmetic).  Against the xor + POPC formulation this removes the POPC pipe (16
-// lanes/clk/SM) as the limit: one IMMA replaces 16 x 8 x 8 = 1024 POPCs.
-//
-// The reduction dimension may be permuted freely as long as both operands use the same permutation;
-// it is chosen so that every lane's operand bytes are 64 CONTIGUOUS bytes of an expanded row:
-//   MMA k-step s, fragment half h, lane column-group tig, byte b  <->  expanded byte 64 tig + 8 s + 4 h + b.
+// (k_expand) and the dot products come from the 5th-generation tensor cores (tcgen05.mma kind::i8,
+// u8 x u8 -> s32: exact integer arithmetic).  Against the xor + POPC formulation this removes the POPC
+// pipe (16 lanes/clk/SM) as the limit; against the mma.sync (IMMA m16n8k32) version this library used
+// first it is 2.7x faster (199 -> 75 us for 64 problems of 2000 x 2000, profiles/).
 // 1-NN: per query row minimise  |t| - 2 <q,t>  packed with the train index into one word
 //   key = (|t| + 512 - 2 <q,t>) << 22 | index      (10 + 22 bits)
 // so one IMAD + one unsigned min per accumulator keeps BFMatcher's "lowest trainIdx wins ties" rule,
 // and partial results of train slices merge with atomicMin.
 // ---------------------------------------------------------------------------------------------------
 #define MATCH_KEY_SHIFT 22
-#define MMA_QB 128          // query rows per CTA (4 warps x 2 m16 tiles)
-#define MMA_TC 64           // train rows per shared-memory chunk
-#define MMA_ROW 320         // padded expanded row in shared memory: 4 x (64 + 16) bytes, conflict-free LDS.128
 
 // Expanded operand rows: xq / xt [set][rows_pad][256] bytes (0/1), rows >= n are zero;
 // tkey[set][rows_pad] = (|t| + 512) << 22 | index  (0xffffffff for rows >= nt);  pq[set][rows_pad] = |q|.
@@ -73,91 +66,6 @@ __global__ void __launch_bounds__(256) k_expand(const uint8_t *__restrict__ src,
     }
 }
 
-static __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// grid = (ceil(rows_pad / MMA_QB), nslices, batch); out_key pre-set to 0xffffffff.
-__global__ void __launch_bounds__(128) k_hamming_mma(const uint8_t *__restrict__ xq, const uint8_t *__restrict__ xt,
-                                                    const uint32_t *__restrict__ tkey, const int32_t *__restrict__ nq_arr,
-                                                    int nq_stride, const int32_t *__restrict__ nt_arr, int nt_stride,
-                                                    int max_rows, int rows_pad, uint32_t *__restrict__ out_key,
-                                                    long long out_stride, int nslices) {
-    __shared__ __align__(16) uint8_t ts[MMA_TC * MMA_ROW];
-    __shared__ uint32_t tk[MMA_TC];
-    const int set = blockIdx.z;
-    const int nq = min(nq_arr[(long long)set * nq_stride], max_rows);
-    const int nt = min(nt_arr[(long long)set * nt_stride], max_rows);
-    const int q0 = blockIdx.x * MMA_QB;
-    if (q0 >= nq) return;
-    const int per = (((nt + nslices - 1) / nslices) + MMA_TC - 1) / MMA_TC * MMA_TC;  // train rows per slice
-    const int t_begin = blockIdx.y * per, t_end = min(nt, t_begin + per);
-    if (t_begin >= t_end) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
-    const uint8_t *XQ = xq + (long long)set * rows_pad * 256, *XT = xt + (long long)set * rows_pad * 256;
-    const uint32_t *TK = tkey + (long long)set * rows_pad;
-
-    // A fragments of this warp's 32 query rows, resident for the whole train loop: [tile][k-step][4]
-    uint32_t afr[2][8][4];
-#pragma unroll
-    for (int m = 0; m < 2; m++) {
-        const int r0 = q0 + warp * 32 + m * 16 + g;  // rows r0 and r0 + 8 (always < rows_pad)
-        const uint4 *p0 = reinterpret_cast<const uint4 *>(XQ + (long long)r0 * 256 + 64 * tig);
-        const uint4 *p1 = reinterpret_cast<const uint4 *>(XQ + (long long)(r0 + 8) * 256 + 64 * tig);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {  // 16 bytes = k-steps 2i, 2i+1
-            const uint4 u = p0[i], v = p1[i];
-            afr[m][2 * i][0] = u.x; afr[m][2 * i][2] = u.y; afr[m][2 * i + 1][0] = u.z; afr[m][2 * i + 1][2] = u.w;
-            afr[m][2 * i][1] = v.x; afr[m][2 * i][3] = v.y; afr[m][2 * i + 1][1] = v.z; afr[m][2 * i + 1][3] = v.w;
-        }
-    }
-    uint32_t best[2][2] = {{0xffffffffu, 0xffffffffu}, {0xffffffffu, 0xffffffffu}};  // [tile][row g / row g + 8]
-
-    for (int c0 = t_begin; c0 < t_end; c0 += MMA_TC) {
-        __syncthreads();
-        // stage 64 expanded train rows (zero rows past nt come from k_expand's padding), re-pitched to MMA_ROW
-        for (int i = threadIdx.x; i < MMA_TC * 16; i += 128) {
-            const int r = i >> 4, q16 = i & 15;
-            const uint4 u = reinterpret_cast<const uint4 *>(XT + (long long)(c0 + r) * 256)[q16];
-            *reinterpret_cast<uint4 *>(ts + r * MMA_ROW + (q16 >> 2) * 80 + (q16 & 3) * 16) = u;
-        }
-        if (threadIdx.x < MMA_TC) tk[threadIdx.x] = c0 + threadIdx.x < t_end ? TK[c0 + threadIdx.x] : 0xffffffffu;
-        __syncthreads();
-#pragma unroll 2
-        for (int n8 = 0; n8 < MMA_TC / 8; n8++) {
-            const uint4 *bp = reinterpret_cast<const uint4 *>(ts + (n8 * 8 + g) * MMA_ROW + tig * 80);
-            uint32_t bfr[16];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint4 u = bp[i];
-                bfr[4 * i] = u.x; bfr[4 * i + 1] = u.y; bfr[4 * i + 2] = u.z; bfr[4 * i + 3] = u.w;
-            }
-            const uint32_t k0 = tk[n8 * 8 + 2 * tig], k1 = tk[n8 * 8 + 2 * tig + 1];
-#pragma unroll
-            for (int m = 0; m < 2; m++) {
-                int acc[4] = {0, 0, 0, 0};
-#pragma unroll
-                for (int s = 0; s < 8; s++) imma_16832(acc, afr[m][s], bfr[2 * s], bfr[2 * s + 1]);
-                // key - (dot << 23): rows past the slice carry 0xffffffff and a zero dot product
-                best[m][0] = min(best[m][0], min(k0 - ((uint32_t)acc[0] << 23), k1 - ((uint32_t)acc[1] << 23)));
-                best[m][1] = min(best[m][1], min(k0 - ((uint32_t)acc[2] << 23), k1 - ((uint32_t)acc[3] << 23)));
-            }
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < 2; m++)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            uint32_t b = best[m][h];
-            b = min(b, __shfl_xor_sync(0xffffffffu, b, 1));
-            b = min(b, __shfl_xor_sync(0xffffffffu, b, 2));
-            const int row = q0 + warp * 32 + m * 16 + h * 8 + g;
-            if (tig == 0 && row < nq && b != 0xffffffffu) atomicMin(&out_key[(long long)set * out_stride + row], b);
-        }
-}
-
 __global__ void k_hamming_init(const int32_t *__restrict__ nq_arr, int nq_stride, int max_rows, uint32_t *out_key,
                                long long out_stride) {
     const int set = blockIdx.y, qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -180,16 +88,24 @@ __global__ void k_hamming_decode(const int32_t *__restrict__ nq_arr, int nq_stri
 // into 128-byte-swizzled shared memory, accumulators in tensor memory, 1-NN reduction fused into the epilogue.
 //   CTA  = 128 query rows (the M of one UMMA) x one slice of the train set, walked in tiles of 256 train rows (N);
 //   K    = 256 expanded bytes = 8 instructions of K = 32; an operand tile is two 128-byte-wide swizzle panels;
-//   TMEM = 2 accumulators of 128 lanes x 256 columns: the MMAs of tile t + 1 overlap the epilogue of tile t;
-//   warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one lane), warps 2-5 = epilogue (lane quadrant = warp % 4):
-//          one thread per query row reads its accumulator row with tcgen05.ld and folds key - (dot << 23) into a min.
+//   smem = the query tile (32 KB) + a 2-deep ring of train tiles (64 KB each) filled by TMA ahead of the MMAs;
+//   TMEM = 2 accumulators of 128 lanes x 256 columns: the MMAs of tile t + 1 overlap the epilogue of tile t
+//          (measured: 128-row tiles with a 5-deep ring are slower — the epilogue, not the operand feed, is the limit);
+//   warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one lane), warps 2-17 = epilogue (lane quadrant = warp % 4,
+//          column quarter = (warp - 2) / 4): a thread reads 64 columns of its accumulator row with tcgen05.ld (two loads
+//          in flight) and folds key - (dot << 23) into a min; the tile's 256 train keys are staged in shared memory.
+//          16 epilogue warps: the epilogue is ~1.75 instructions per (query, train) pair and must hide the TMEM latency.
 // ---------------------------------------------------------------------------------------------------
 #define UM_M 128
 #define UM_N 256
-#define UM_THREADS 192
+#define UM_BST 2   // train tiles in flight in shared memory
+#define UM_AST 2   // accumulators in tensor memory (UM_AST * UM_N = 512 columns)
+#define UM_THREADS 576
+#define UM_EPI_THREADS 512
+#define UM_COLS_PER_WARP (UM_N / (UM_EPI_THREADS / 128))   // 64
 #define UM_A_BYTES (UM_M * 256)
 #define UM_B_BYTES (UM_N * 256)
-#define UM_SMEM (UM_A_BYTES + 2 * UM_B_BYTES + 1024)
+#define UM_SMEM (UM_A_BYTES + UM_BST * UM_B_BYTES + 1024)
 
 static __device__ __forceinline__ void um_tma_load_2d(void *smem_dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -218,7 +134,7 @@ static __device__ __forceinline__ void um_mma_i8(uint32_t tmem_d, uint64_t adesc
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-static __device__ __forceinline__ void um_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+static __device__ __forceinline__ void um_tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
         "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -227,7 +143,28 @@ static __device__ __forceinline__ void um_tmem_ld32(uint32_t taddr, uint32_t (&v
           "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// The loaded registers are valid only after tcgen05.wait::ld; they are passed through the wait as in/out operands so that
+// the compiler cannot schedule their uses above it.
+static __device__ __forceinline__ void um_tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+static __device__ __forceinline__ uint32_t um_fold32(uint32_t best, const uint32_t (&v)[32], const uint32_t *tk) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 k4 = *reinterpret_cast<const uint4 *>(tk + 4 * j);  // rows past the train set carry 0xffffffff and a zero dot product
+        // key - (dot << 23) as one IMAD, two 3-input minima (VIMNMX3) per four columns
+        const uint32_t NEG = 0u - (1u << 23);
+        best = __vimin3_u32(best, v[4 * j] * NEG + k4.x, v[4 * j + 1] * NEG + k4.y);
+        best = __vimin3_u32(best, v[4 * j + 2] * NEG + k4.z, v[4 * j + 3] * NEG + k4.w);
+    }
+    return best;
 }
 
 // grid = (rows_pad / UM_M, nslices, batch); out_key pre-set to 0xffffffff; rows_pad is a multiple of UM_N.
@@ -237,8 +174,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_hamming_umma(const __grid_con
                                                                int max_rows, int rows_pad, uint32_t *__restrict__ out_key,
                                                                long long out_stride, int nslices) {
     extern __shared__ uint8_t um_raw[];
-    __shared__ __align__(8) uint64_t a_full, b_full[2], b_empty[2], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t a_full, b_full[UM_BST], b_empty[UM_BST], acc_full[UM_AST], acc_empty[UM_AST];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) uint32_t s_tk[UM_AST][UM_N];
     const int set = blockIdx.z;
     const int nq = min(nq_arr[(long long)set * nq_stride], max_rows);
     const int nt = min(nt_arr[(long long)set * nt_stride], max_rows);
@@ -254,11 +192,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_hamming_umma(const __grid_con
 
     if (threadIdx.x == 0) {
         sb_mbar_init(&a_full, 1);
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < UM_BST; i++) {
             sb_mbar_init(&b_full[i], 1);
             sb_mbar_init(&b_empty[i], 1);
+        }
+        for (int i = 0; i < UM_AST; i++) {
             sb_mbar_init(&acc_full[i], 1);
-            sb_mbar_init(&acc_empty[i], 4);
+            sb_mbar_init(&acc_empty[i], UM_EPI_THREADS / 32);
         }
     }
     if (warp == 1) {
@@ -277,8 +217,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_hamming_umma(const __grid_con
             um_tma_load_2d(sA, &map_q, 0, rowq, &a_full);
             um_tma_load_2d(sA + UM_A_BYTES / 2, &map_q, 128, rowq, &a_full);
             for (int t = 0; t < ntiles; t++) {
-                const int s = t & 1;
-                if (t >= 2) sb_mbar_wait(&b_empty[s], ((t >> 1) - 1) & 1);
+                const int s = t % UM_BST, u = t / UM_BST;
+                if (u >= 1) sb_mbar_wait(&b_empty[s], (u - 1) & 1);
                 sb_mbar_expect_tx(&b_full[s], UM_B_BYTES);
                 um_tma_load_2d(sB + s * UM_B_BYTES, &map_t, 0, rowt + t * UM_N, &b_full[s]);
                 um_tma_load_2d(sB + s * UM_B_BYTES + UM_B_BYTES / 2, &map_t, 128, rowt + t * UM_N, &b_full[s]);
@@ -290,44 +230,50 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_hamming_umma(const __grid_con
             const uint32_t idesc = (2u << 4) | ((uint32_t)(UM_N >> 3) << 17) | ((uint32_t)(UM_M >> 4) << 24);
             sb_mbar_wait(&a_full, 0);
             for (int t = 0; t < ntiles; t++) {
-                const int s = t & 1;
-                sb_mbar_wait(&b_full[s], (t >> 1) & 1);
-                if (t >= 2) sb_mbar_wait(&acc_empty[s], ((t >> 1) - 1) & 1);
+                const int s = t % UM_BST, a = t % UM_AST, ua = t / UM_AST;
+                sb_mbar_wait(&b_full[s], (t / UM_BST) & 1);
+                if (ua >= 1) sb_mbar_wait(&acc_empty[a], (ua - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const uint64_t ad = um_smem_desc(sA + (k >> 2) * (UM_A_BYTES / 2) + (k & 3) * 32);
                     const uint64_t bd = um_smem_desc(sB + s * UM_B_BYTES + (k >> 2) * (UM_B_BYTES / 2) + (k & 3) * 32);
-                    um_mma_i8(tmem + s * UM_N, ad, bd, idesc, k > 0);
+                    um_mma_i8(tmem + a * UM_N, ad, bd, idesc, k > 0);
                 }
                 um_commit(&b_empty[s]);
-                um_commit(&acc_full[s]);
+                um_commit(&acc_full[a]);
             }
         }
-    } else {  // ===== epilogue: one thread per query row
-        const int quad = warp & 3;
+    } else {  // ===== epilogue: two threads per query row (128 columns each)
+        const int quad = warp & 3, part = (warp - 2) >> 2;
         const int row = q0 + quad * 32 + lane;
+        const int et = threadIdx.x - 64;  // 0 .. UM_EPI_THREADS - 1
         const uint32_t *TK = tkey + (long long)set * rows_pad + t_begin;
         uint32_t best = 0xffffffffu;
+        uint32_t tk_next = et < UM_N ? __ldg(TK + et) : 0u;  // prefetched one tile ahead (rows_pad covers the last tile)
         for (int t = 0; t < ntiles; t++) {
-            const int s = t & 1;
-            sb_mbar_wait(&acc_full[s], (t >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int c = 0; c < UM_N / 32; c++) {
-                uint32_t v[32];
-                um_tmem_ld32(tmem + (((uint32_t)quad * 32u) << 16) + (uint32_t)(s * UM_N + c * 32), v);
-                const uint4 *tk4 = reinterpret_cast<const uint4 *>(TK + t * UM_N + c * 32);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint4 k4 = __ldg(tk4 + j);  // rows past the train set carry 0xffffffff and a zero dot product
-                    best = min(best, min(min(k4.x - (v[4 * j] << 23), k4.y - (v[4 * j + 1] << 23)),
-                                         min(k4.z - (v[4 * j + 2] << 23), k4.w - (v[4 * j + 3] << 23))));
-                }
+            const int a = t % UM_AST;
+            // the tile's train keys: s_tk[a] was last read for tile t - UM_AST, and every epilogue thread has passed the
+            // named barriers of the tiles in between since then
+            if (et < UM_N) {
+                s_tk[a][et] = tk_next;
+                if (t + 1 < ntiles) tk_next = __ldg(TK + (t + 1) * UM_N + et);
             }
+            asm volatile("bar.sync 1, %0;" ::"n"(UM_EPI_THREADS) : "memory");
+            sb_mbar_wait(&acc_full[a], (t / UM_AST) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tbase = tmem + (((uint32_t)quad * 32u) << 16) + (uint32_t)(a * UM_N + part * UM_COLS_PER_WARP);
+            const uint32_t *tk = s_tk[a] + part * UM_COLS_PER_WARP;
+            uint32_t va[32], vb[32];
+            um_tmem_ld32_issue(tbase, va);
+            um_tmem_ld32_issue(tbase + 32, vb);
+            um_tmem_ld_wait(va);
+            um_tmem_ld_wait(vb);
+            best = um_fold32(best, va, tk);
+            best = um_fold32(best, vb, tk + 32);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) um_mbar_arrive(&acc_empty[s]);
+            if (lane == 0) um_mbar_arrive(&acc_empty[a]);
         }
         if (row < nq && best != 0xffffffffu) atomicMin(&out_key[(long long)set * out_stride + row], best);
     }
@@ -388,8 +334,6 @@ extern "C" int sb_matcher_create(sb_matcher_t **out, int device, int max_batch, 
             return rc;
         }
     }
-    const char *mode = getenv("SLAMB200_MATCH");
-    m->legacy = mode && !strcmp(mode, "mma");
     m->stream = m->own_stream;
     *out = m;
     return SB_OK;
@@ -427,22 +371,14 @@ extern "C" int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d
     k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_q, q_set_stride, d_nq, nq_stride, max_rows, rp, m->d_xq, nullptr, m->d_pq);
     k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_t, t_set_stride, d_nt, nt_stride, max_rows, rp, m->d_xt, m->d_tkey, nullptr);
     // enough CTAs to fill 148 SMs: slice the train set when the batch alone does not
-    const int qblocks = sb_div_up(max_rows, MMA_QB);
+    const int qblocks = sb_div_up(max_rows, UM_M);
     k_hamming_init<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows,
                                                                                  reinterpret_cast<uint32_t *>(d_train_idx), out_stride);
-    if (m->legacy) {
-        int nslices = 1;
-        while (nslices < 16 && (long long)qblocks * batch * nslices < 148 * 8 && max_rows / (nslices * 2) >= MMA_TC) nslices *= 2;
-        k_hamming_mma<<<dim3(qblocks, nslices, batch), 128, 0, m->stream>>>(m->d_xq, m->d_xt, m->d_tkey, d_nq, nq_stride, d_nt, nt_stride,
-                                                                            max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx),
-                                                                            out_stride, nslices);
-    } else {
-        int nslices = 1;  // one CTA per SM (160 KB of shared memory, all of TMEM)
-        while (nslices < 16 && (long long)qblocks * batch * nslices < 148 && max_rows / (nslices * 2) >= UM_N) nslices *= 2;
-        k_hamming_umma<<<dim3(qblocks, nslices, batch), UM_THREADS, UM_SMEM, m->stream>>>(
-            m->map_q, m->map_t, m->d_tkey, d_nq, nq_stride, d_nt, nt_stride, max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx),
-            out_stride, nslices);
-    }
+    int nslices = 1;  // one CTA per SM (160 KB of shared memory, all of TMEM)
+    while (nslices < 16 && (long long)qblocks * batch * nslices < 148 && max_rows / (nslices * 2) >= UM_N) nslices *= 2;
+    k_hamming_umma<<<dim3(qblocks, nslices, batch), UM_THREADS, UM_SMEM, m->stream>>>(
+        m->map_q, m->map_t, m->d_tkey, d_nq, nq_stride, d_nt, nt_stride, max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx),
+        out_stride, nslices);
     k_hamming_decode<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows, rp, m->d_pq, d_train_idx,
                                                                                    d_dist, out_stride);
     SB_CUDA(cudaGetLastError());
