@@ -1306,7 +1306,11 @@ static int launch_blur(sb_orb *h, int batch, cudaStream_t s) {
     return SB_OK;
 }
 
-static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool detect_only) {
+static int launch_blur(sb_orb *h, int batch, cudaStream_t s);
+
+// blur_beside_quadtree: the Gaussian blur of the same batch is forked onto the side stream right after the FAST
+// kernel, so that it fills the issue slots the latency-bound quadtree leaves idle (FAST itself is issue bound).
+static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool detect_only, bool blur_beside_quadtree = false) {
     const int nl = h->nlevels;
     SB_CUDA(cudaMemsetAsync(h->d_cand_cnt, 0, (size_t)batch * nl * 4, h->stream));
     FastArgs fa;
@@ -1329,6 +1333,12 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     prof_begin(h, SB_STAGE_FAST, 1, h->stream);
     k_fast_cells<<<dim3(ncells, batch), FAST_THREADS, fsmem, h->stream>>>(h->fast_maps, h->geom, fa);
     prof_end(h, h->stream);
+    if (blur_beside_quadtree) {
+        SB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+        SB_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        SB_TRY(launch_blur(h, batch, h->side_stream));
+        SB_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+    }
     QtArgs qa;
     qa.cand = h->d_cand;
     qa.cand_cnt = h->d_cand_cnt;
@@ -1384,13 +1394,8 @@ extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8
         SB_TRY(ensure_mask_buffer(h));
         SB_TRY(launch_pyramid(h, h->d_mask, d_mask, mask_pitch_bytes, mstride, batch, h->nlevels));
     }
-    if (d_desc) {  // the blur only depends on the pyramid: run it beside FAST + quadtree
-        SB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
-        SB_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-        SB_TRY(launch_blur(h, batch, h->side_stream));
-        SB_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
-    }
-    SB_TRY(launch_fast_and_quadtree(h, batch, d_mask != nullptr, false));
+    // the blur only depends on the pyramid: it runs on the side stream beside the quadtree
+    SB_TRY(launch_fast_and_quadtree(h, batch, d_mask != nullptr, false, d_desc != nullptr));
     if (d_desc) SB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     DescArgs da;
     da.pyr = h->d_pyr;
