@@ -61,3 +61,27 @@ def test_left_right_descriptors_of_a_stereo_pair(pkg, matcher, oracle, synth):
     pairs = oracle.match_filter(idx, dist, np.arange(len(kl), dtype=np.int32), np.arange(len(kr), dtype=np.int32))
     assert len(pairs) > 500
     ext.close()
+
+
+def test_long_train_set_and_ties_across_tiles(pkg, oracle):
+    """More train rows than one CTA slice / many 256-row tiles: the mbarrier phases of the TMA ring and of the two TMEM
+    accumulators wrap several times; equal distances in different tiles and slices must still pick the lowest index."""
+    rng = np.random.default_rng(7)
+    m = pkg.HammingMatcher(max_batch=2, max_rows=6144)
+    q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (6000, 32), dtype=np.uint8)
+    for k in (5, 300, 1023, 1024, 2999, 5999):      # copies of query rows spread over tiles and slices
+        t[k] = q[17]
+    t[4000:4100] = q[200]
+    idx, dist = m.match(q, t)
+    widx, wdist = oracle.hamming_match(q, t)
+    assert np.array_equal(idx, widx) and np.array_equal(dist, wdist)
+    assert idx[17] == 5 and dist[17] == 0 and idx[200] == 4000
+    same = np.tile(rng.integers(0, 256, (1, 32), dtype=np.uint8), (5000, 1))   # every train row identical
+    idx, dist = m.match(q, same)
+    assert (idx == 0).all()
+    res = m.match_batch([q, q[:129]], [t[:257], t])                            # two problems of different shape in one launch
+    for (qq, tt), (i2, d2) in zip([(q, t[:257]), (q[:129], t)], res):
+        wi, wd = oracle.hamming_match(qq, tt)
+        assert np.array_equal(i2, wi) and np.array_equal(d2, wd)
+    m.close()

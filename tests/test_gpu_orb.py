@@ -141,7 +141,10 @@ def test_screen_params_and_calc_descriptors(pkg, oracle, synth):
     g.close()
 
 
-@pytest.mark.parametrize("shape,nlevels", [((480, 640), 8), ((200, 333), 4), ((376, 1241), 1)])
+# (64, 70): one FAST cell per level-0 grid row; (62, 400): a single grid row of cells; (300, 1000): runs of 5 cells + a rest;
+# (97, 131): cells wider than 40 px (short runs)
+@pytest.mark.parametrize("shape,nlevels", [((480, 640), 8), ((200, 333), 4), ((376, 1241), 1), ((64, 70), 1), ((62, 400), 1),
+                                           ((300, 1000), 3), ((97, 131), 2)])
 def test_other_image_sizes(pkg, oracle, shape, nlevels):
     rng = np.random.default_rng(shape[0])
     img = np.full(shape, 120, np.uint8)
