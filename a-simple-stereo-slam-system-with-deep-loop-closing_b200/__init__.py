@@ -5,4 +5,4 @@ The product is the shared library built from ``csrc/`` (C ABI declared in ``incl
 the C++ adaptor classes in ``host/``.  This package only binds the C ABI with ctypes for the tests,
 ``bench.py`` and ``__graft_entry__``; it contains no compute of its own and no CPU fallback.
 """
-from .capi import (KP_DTYPE, SlamB200Error, ORBextractor, HammingMatcher, LocalBA, DeepLCDScorer, PoseGraph, StereoFrontend, PoseOnlyOptimizer, LKTracker, DeepLCD, CALC_LAYERS, parse_caffe, triangulate, lib, lib_path, last_error)  # noqa: F401
+from .capi import (KP_DTYPE, SlamB200Error, ORBextractor, HammingMatcher, LocalBA, DeepLCDScorer, PoseGraph, StereoFrontend, PoseOnlyOptimizer, PnPRansac, LKTracker, DeepLCD, CALC_LAYERS, parse_caffe, triangulate, lib, lib_path, last_error)  # noqa: F401

@@ -540,6 +540,46 @@ def triangulate(uv_left, uv_right, K_left, K_right, pose_left7, pose_right7, T_w
     return pts[:n], ok[:n].astype(bool)
 
 
+class PnPRansac:
+    """cv::solvePnPRansac as LoopClosing::ComputeCorrectPose calls it (src/loopclosing.cpp:259-268), batched over loop
+    candidates: hypotheses in parallel, inliers of the best one, Levenberg-Marquardt refinement on them."""
+
+    def __init__(self, max_problems=1, max_points=2048, device=0):
+        self._h = C.c_void_p()
+        self.P, self.MP = max_problems, max_points
+        _check(lib().sb_pnp_create(C.byref(self._h), device, max_problems, max_points))
+
+    def close(self):
+        if self._h:
+            lib().sb_pnp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, problems, K, iterations=100, reproj_err=5.991, seed=0):
+        """problems: list of (obj [n,3], img [n,2]) -> list of dicts (found, pose7, rvec, tvec, inliers [n] bool, info [4])."""
+        n = len(problems)
+        cnt = np.array([len(o) for o, _ in problems], np.int32)
+        obj = np.zeros((n, self.MP, 3), np.float32)
+        img = np.zeros((n, self.MP, 2), np.float32)
+        for k, (o, m) in enumerate(problems):
+            obj[k, :cnt[k]] = o
+            img[k, :cnt[k]] = m
+        K = np.ascontiguousarray(K, np.float64)
+        pose = np.zeros((n, 7))
+        rt = np.zeros((n, 6))
+        inl = np.zeros((n, self.MP), np.uint8)
+        info = np.zeros((n, 4), np.int32)
+        _check(lib().sb_pnp_ransac(self._h, n, _p(cnt), _p(obj), _p(img), _p(K), int(iterations), C.c_double(reproj_err),
+                                   C.c_uint64(seed), _p(pose), _p(rt), _p(inl), _p(info)))
+        return [dict(found=bool(info[k, 0]), pose7=pose[k].copy(), rvec=rt[k, :3].copy(), tvec=rt[k, 3:].copy(),
+                     inliers=inl[k, :cnt[k]].astype(bool), info=info[k].copy()) for k in range(n)]
+
+
 class LKTracker:
     """cv::calcOpticalFlowPyrLK as Frontend::TrackLastFrame / FindFeaturesInRight call it (src/frontend.cpp:150-153,
     :358-361), batched over image pairs."""

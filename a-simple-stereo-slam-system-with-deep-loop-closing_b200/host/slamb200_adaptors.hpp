@@ -15,12 +15,15 @@
 // Without it (this repository's CI, which has no OpenCV C++ headers) a minimal stand-in with the same
 // field layout is used so that the header still compiles and is exercised by tests/host_adaptor_test.cpp.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/slamb200.h"
@@ -461,6 +464,130 @@ inline bool triangulation_batch(const std::vector<float> &uvLeft, const std::vec
     detail::last_status() = sb_triangulate(device, n, uvLeft.data(), uvRight.data(), Kl, Kr, poseLeft7, poseRight7, Twc7, 1e-2,
                                            points3.data(), ok.data());
     return detail::last_status() == SB_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// SE(3) helpers on the host for the two decisions below (Sophus storage order qx qy qz qw tx ty tz; T = [R | t]).
+namespace detail {
+struct Rt { double R[9], t[3]; };
+inline Rt rt_from_pose7(const double p[7]) {
+    const double n = std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+    const double x = p[0] / n, y = p[1] / n, z = p[2] / n, w = p[3] / n;
+    Rt o;
+    o.R[0] = 1 - 2 * (y * y + z * z); o.R[1] = 2 * (x * y - z * w);     o.R[2] = 2 * (x * z + y * w);
+    o.R[3] = 2 * (x * y + z * w);     o.R[4] = 1 - 2 * (x * x + z * z); o.R[5] = 2 * (y * z - x * w);
+    o.R[6] = 2 * (x * z - y * w);     o.R[7] = 2 * (y * z + x * w);     o.R[8] = 1 - 2 * (x * x + y * y);
+    o.t[0] = p[4]; o.t[1] = p[5]; o.t[2] = p[6];
+    return o;
+}
+inline Rt rt_mul(const Rt &A, const Rt &B) {
+    Rt C;
+    for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) C.R[3 * i + j] = A.R[3 * i] * B.R[j] + A.R[3 * i + 1] * B.R[3 + j] + A.R[3 * i + 2] * B.R[6 + j];
+        C.t[i] = A.R[3 * i] * B.t[0] + A.R[3 * i + 1] * B.t[1] + A.R[3 * i + 2] * B.t[2] + A.t[i];
+    }
+    return C;
+}
+inline Rt rt_inv(const Rt &A) {
+    Rt C;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C.R[3 * i + j] = A.R[3 * j + i];
+    for (int i = 0; i < 3; i++) C.t[i] = -(C.R[3 * i] * A.t[0] + C.R[3 * i + 1] * A.t[1] + C.R[3 * i + 2] * A.t[2]);
+    return C;
+}
+// |SE3::log(T)| (the 6-vector [upsilon, omega], Sophus' formulas)
+inline double rt_log_norm(const Rt &T) {
+    const double c = std::min(1.0, std::max(-1.0, 0.5 * (T.R[0] + T.R[4] + T.R[8] - 1.0)));
+    const double th = std::acos(c);
+    double w[3] = {T.R[7] - T.R[5], T.R[2] - T.R[6], T.R[3] - T.R[1]};
+    if (th < 1e-10) { for (double &v : w) v *= 0.5; }
+    else if (3.14159265358979323846 - th < 1e-6) {  // angle ~ pi: axis from the diagonal
+        double ax[3] = {std::sqrt(std::max(0.0, 0.5 * (T.R[0] + 1))), std::sqrt(std::max(0.0, 0.5 * (T.R[4] + 1))), std::sqrt(std::max(0.0, 0.5 * (T.R[8] + 1)))};
+        if (T.R[1] + T.R[3] < 0) ax[1] = -ax[1];
+        if (T.R[2] + T.R[6] < 0) ax[2] = -ax[2];
+        for (int i = 0; i < 3; i++) w[i] = th * ax[i];
+    } else { const double k = th / (2.0 * std::sin(th)); for (double &v : w) v *= k; }
+    const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    double coef;
+    if (th2 < 1e-20) coef = 1.0 / 12.0;
+    else { const double t1 = std::sqrt(th2), half = 0.5 * t1; coef = (1.0 - t1 * std::cos(half) / (2.0 * std::sin(half))) / th2; }
+    const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+    double u[3];
+    for (int i = 0; i < 3; i++) {
+        u[i] = 0;
+        for (int j = 0; j < 3; j++) {
+            const double w2 = W[3 * i] * W[j] + W[3 * i + 1] * W[3 + j] + W[3 * i + 2] * W[6 + j];
+            u[i] += ((i == j ? 1.0 : 0.0) - 0.5 * W[3 * i + j] + coef * w2) * T.t[j];
+        }
+    }
+    return std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + th2);
+}
+}  // namespace detail
+
+// -----------------------------------------------------------------------------------------------------
+// LoopClosing::ComputeCorrectPose (src/loopclosing.cpp:207-293) without the map walking: the caller collects, for the
+// valid feature matches whose loop feature has a map point, the map point positions (cv::Point3f) and the current
+// keyframe's keypoints (cv::Point2f).  solvePnPRansac (:263-264) -> OptimizeCurrentPose (:275, :339-433) ->
+// "fewer than 10 inliers: reject" (:279-281) -> need-correct test |log(T_current * T_corrected^-1)| > 1 (:284-289).
+struct LoopVerification {
+    bool accepted = false;      // ComputeCorrectPose's return value
+    bool needCorrect = false;   // _mbNeedCorrect
+    int inliers = 0;            // OptimizeCurrentPose's return value
+    double correctedPose[7] = {0, 0, 0, 1, 0, 0, 0};  // _mseCorrectedCurrentPose (T_cw)
+    std::vector<uint8_t> outlier;                      // matches OptimizeCurrentPose erases from _msetValidFeatureMatches
+};
+class LoopVerifier {
+public:
+    explicit LoopVerifier(int max_points = 4096, int device = 0) : mp_(max_points), refine_(max_points, device) {
+        if (sb_pnp_create(&h_, device, 1, max_points) != SB_OK) throw std::runtime_error(std::string("sb_pnp_create: ") + sb_last_error());
+    }
+    ~LoopVerifier() { sb_pnp_destroy(h_); }
+    LoopVerification ComputeCorrectPose(const std::vector<float> &loopPoints3, const std::vector<float> &currentPoints2, const double K[4],
+                                        const double currentPose7[7], uint64_t seed = 0) {
+        LoopVerification out;
+        const int32_t n = (int32_t)(currentPoints2.size() / 2);
+        if (n < 10) return out;                                                        // :255-256
+        if (n > mp_) { detail::last_status() = SB_ERR_CAPACITY; return out; }
+        std::vector<float> obj((size_t)mp_ * 3, 0.f), img((size_t)mp_ * 2, 0.f);
+        std::copy(loopPoints3.begin(), loopPoints3.begin() + 3 * (size_t)n, obj.begin());
+        std::copy(currentPoints2.begin(), currentPoints2.begin() + 2 * (size_t)n, img.begin());
+        std::vector<uint8_t> inl((size_t)mp_);
+        double rt[6];
+        int32_t info[4];
+        detail::last_status() = sb_pnp_ransac(h_, 1, &n, obj.data(), img.data(), K, 100, 5.991, seed, out.correctedPose, rt, inl.data(), info);
+        if (detail::last_status() != SB_OK || !info[0]) return out;                    // the reference's try / catch (:262-267)
+        std::vector<double> p3((size_t)n * 3), uv((size_t)n * 2);
+        for (size_t i = 0; i < p3.size(); i++) p3[i] = loopPoints3[i];
+        for (size_t i = 0; i < uv.size(); i++) uv[i] = currentPoints2[i];
+        out.inliers = refine_.Optimize(out.correctedPose, p3, uv, K, out.outlier, /*preRounds=*/1);
+        if (out.inliers < 10) return out;                                              // :279-281
+        const detail::Rt d = detail::rt_mul(detail::rt_from_pose7(currentPose7), detail::rt_inv(detail::rt_from_pose7(out.correctedPose)));
+        out.needCorrect = detail::rt_log_norm(d) > 1.0;                                // :284-289
+        out.accepted = true;
+        return out;
+    }
+private:
+    sb_pnp_t *h_ = nullptr;
+    int mp_;
+    PoseOnlySolver refine_;
+};
+
+// -----------------------------------------------------------------------------------------------------
+// Map::RemoveOldActiveKeyframe (src/map.cpp:78-120), the choice only: which active keyframe leaves the sliding window.
+// poses: (keyframe id, T_cw as pose7) of the active keyframes other than the current one, in the container's order;
+// returns the id to remove (the reference's quirks kept: "else if" means a keyframe that raises the maximum is never
+// considered for the minimum, and the ids start out as 0).
+inline unsigned long SelectActiveKeyframeToRemove(const std::vector<std::pair<unsigned long, const double *>> &poses, const double currentPose7[7]) {
+    double maxDis = 0, minDis = 9999;
+    unsigned long maxKFId = 0, minKFId = 0;
+    const detail::Rt Twc = detail::rt_inv(detail::rt_from_pose7(currentPose7));
+    for (const auto &kf : poses) {
+        const double dis = detail::rt_log_norm(detail::rt_mul(detail::rt_from_pose7(kf.second), Twc));
+        if (dis > maxDis) { maxDis = dis; maxKFId = kf.first; }
+        else if (dis < minDis) { minDis = dis; minKFId = kf.first; }
+    }
+    const double minDisTh = 0.2;
+    return minDis < minDisTh ? minKFId : maxKFId;
 }
 
 }  // namespace myslam

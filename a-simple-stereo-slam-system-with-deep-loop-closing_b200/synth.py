@@ -254,6 +254,29 @@ def pose_only_frame(seed, n_points=250, pix_noise=0.7, outlier_frac=0.1, pose_no
     return {"pose0": w["poses0"][0], "pose_gt": w["poses_gt"][0], "points": pts, "uv": uv, "planted": planted}
 
 
+def pnp_problem(seed, n_points=400, pix_noise=0.7, outlier_frac=0.3):
+    """One loop candidate for LoopClosing::ComputeCorrectPose (src/loopclosing.cpp:207-268): map points of the loop
+    keyframe (float32 like cv::Point3f) and their matched keypoints in the current keyframe (float32 pixels) under an
+    unknown pose; `outlier_frac` of the matches are wrong (uniformly random pixels).
+    Returns dict: obj [n,3] f32, img [n,2] f32, pose_gt [7], planted [n] bool."""
+    rng = np.random.default_rng(50000 + seed)
+    R = _so3_exp(rng.normal(size=3) * 0.3)
+    t = rng.normal(size=3) * np.array([2.0, 0.5, 2.0])
+    fx, fy, cx, cy = KITTI_K
+    pts = []
+    while len(pts) < n_points:                      # points in front of the camera that project inside the image
+        pc = np.array([rng.uniform(-25, 25), rng.uniform(-6, 6), rng.uniform(4, 60)])
+        u, v = fx * pc[0] / pc[2] + cx, fy * pc[1] / pc[2] + cy
+        if 0 <= u < KITTI_W and 0 <= v < KITTI_H:
+            pts.append(R.T @ (pc - t))
+    obj = np.array(pts)
+    pc = obj @ R.T + t
+    img = np.stack([fx * pc[:, 0] / pc[:, 2] + cx, fy * pc[:, 1] / pc[:, 2] + cy], 1) + rng.normal(size=(n_points, 2)) * pix_noise
+    planted = rng.uniform(size=n_points) < outlier_frac
+    img[planted] = np.stack([rng.uniform(0, KITTI_W, int(planted.sum())), rng.uniform(0, KITTI_H, int(planted.sum()))], 1)
+    return {"obj": obj.astype(np.float32), "img": img.astype(np.float32), "pose_gt": pose7(R, t), "planted": planted}
+
+
 # ---------------------------------------------------------------------------------------------------
 # DeepLCD CNN ("next" row 2).  The trained calc.caffemodel is a configure-time download of the reference
 # (get_model.sh) and absent: tests and bench use seeded random weights of the same architecture.

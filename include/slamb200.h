@@ -372,6 +372,33 @@ int sb_calc_parse_caffe(const char *prototxt_path, const char *caffemodel_path, 
 int sb_calc_create_from_caffe(sb_calc_t **h, int device, const char *prototxt_path, const char *caffemodel_path, int max_batch,
                               int max_img_w, int max_img_h);
 
+/* ---------------------------------------------------------------------------------------------
+ * PnP with RANSAC (SURVEY §8f "next" row 4) — replaces cv::solvePnPRansac as LoopClosing::ComputeCorrectPose
+ * calls it (src/loopclosing.cpp:259-268: objectPoints = map points seen by the loop keyframe, imagePoints =
+ * matched keypoints of the current keyframe, K, no distortion, no extrinsic guess, iterationsCount 100,
+ * reprojectionError 5.991, confidence 0.99, SOLVEPNP_ITERATIVE).  A call solves `n_problems` loop candidates:
+ *   obj [P][max_points][3] float (cv::Point3f), img [P][max_points][2] float (cv::Point2f), K = fx fy cx cy;
+ *   `iterations` hypotheses from minimal samples (P3P + a fourth point), all evaluated in parallel (OpenCV
+ *   stops early at `confidence`: a subset of these), inlier <=> squared reprojection error <= reproj_err^2,
+ *   best = most inliers, then Levenberg-Marquardt on the inliers of the best model;
+ *   pose7 [P][7] = qx qy qz qw tx ty tz of T_cw (what cv::Rodrigues + Sophus::SE3d(R, t) give, :269-272),
+ *   rvec_tvec [P][6] = cv's rvec, tvec; inlier [P][max_points] = 1 for the inliers of the best hypothesis;
+ *   info [P][4] = found (0: fewer than 4 points or no hypothesis with >= 4 inliers — the reference's
+ *   try/catch path, :262-267), inliers, hypotheses that had a solution, refinement iterations.
+ * The samples come from a counter-based generator seeded by `seed`: the result is a deterministic function of
+ * the arguments (cv::RNG state is not).  The follow-up OptimizeCurrentPose (:339-433) is sb_pose_solve.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct sb_pnp sb_pnp_t;
+int sb_pnp_create(sb_pnp_t **h, int device, int max_problems, int max_points);
+int sb_pnp_destroy(sb_pnp_t *h);
+int sb_pnp_set_stream(sb_pnp_t *h, void *stream);
+int sb_pnp_ransac(sb_pnp_t *h, int n_problems, const int32_t *n_points, const float *obj, const float *img, const double *K,
+                  int iterations, double reproj_err, uint64_t seed, double *pose7, double *rvec_tvec, uint8_t *inlier,
+                  int32_t *info);
+int sb_pnp_ransac_dev(sb_pnp_t *h, int n_problems, const int32_t *d_n_points, const float *d_obj, const float *d_img,
+                      int max_points, const double *K, int iterations, double reproj_err, uint64_t seed, double *d_pose7,
+                      double *d_rvec_tvec, uint8_t *d_inlier, int32_t *d_info);
+
 #ifdef __cplusplus
 }
 #endif

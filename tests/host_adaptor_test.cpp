@@ -4,11 +4,23 @@
 #define SLAMB200_NO_OPENCV
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include "../a-simple-stereo-slam-system-with-deep-loop-closing_b200/host/slamb200_adaptors.hpp"
 
 int main(int argc, char **argv) {
     const bool gpu = argc > 1 && !std::strcmp(argv[1], "gpu");
+    {   // host-only logic: Map::RemoveOldActiveKeyframe's choice (src/map.cpp:78-120)
+        const double cur[7] = {0, 0, 0, 1, 0, 0, -10.0};           // T_cw of a camera at z = 10
+        const double near_[7] = {0, 0, 0, 1, 0, 0, -9.9}, mid[7] = {0, 0, 0, 1, 0, 0, -6.0}, far_[7] = {0, 0, 0, 1, 0, 0, 0.0};
+        std::vector<std::pair<unsigned long, const double *>> kfs = {{3, far_}, {5, mid}, {7, near_}};
+        if (myslam::SelectActiveKeyframeToRemove(kfs, cur) != 7) return 20;   // a keyframe closer than 0.2 goes first
+        kfs.pop_back();
+        if (myslam::SelectActiveKeyframeToRemove(kfs, cur) != 3) return 21;   // otherwise the farthest one
+        const double rot[7] = {0, std::sin(0.25), 0, std::cos(0.25), 0, 0, 0};  // 0.5 rad about y
+        const double nrm = myslam::detail::rt_log_norm(myslam::detail::rt_from_pose7(rot));
+        if (std::fabs(nrm - 0.5) > 1e-12) return 22;
+    }
     if (!gpu) {
         try {
             myslam::ORBextractor e(300, 1.2f, 8, 20, 7);
@@ -67,5 +79,29 @@ int main(int argc, char **argv) {
     std::printf("DeepLCD: dim %d, self score %.6f, image blurred in place: %s\n", lcd.descrDim(), self,
                 std::memcmp(kf.data, img.data, (size_t)376 * 1241) == 0 ? "both" : "?");
     if (lcd.descrDim() != 8 * 31 * 41 || self < 0.9999f || self > 1.0001f) return 6;
+    {   // LoopClosing::ComputeCorrectPose: 300 map points seen under a pose 2 m away from the drifted current pose
+        const double K[4] = {718.856, 718.856, 607.1928, 185.2157};
+        const double truth[7] = {0, std::sin(0.05), 0, std::cos(0.05), 0.5, 0.0, 2.0}, drifted[7] = {0, 0, 0, 1, 0, 0, 0};
+        const myslam::detail::Rt T = myslam::detail::rt_from_pose7(truth);
+        std::vector<float> p3, p2;
+        for (int i = 0; i < 300; i++) {
+            s = s * 1664525u + 1013904223u; const double xc = ((s >> 8) % 4000) / 100.0 - 20.0;
+            s = s * 1664525u + 1013904223u; const double yc = ((s >> 8) % 800) / 100.0 - 4.0;
+            s = s * 1664525u + 1013904223u; const double zc = ((s >> 8) % 4000) / 100.0 + 6.0;
+            const double c[3] = {xc - T.t[0], yc - T.t[1], zc - T.t[2]};             // world = R^T (cam - t)
+            for (int k = 0; k < 3; k++) p3.push_back((float)(T.R[k] * c[0] + T.R[3 + k] * c[1] + T.R[6 + k] * c[2]));
+            const bool wrong = i % 4 == 0;                                            // 25 % wrong matches
+            s = s * 1664525u + 1013904223u;
+            p2.push_back(wrong ? (float)((s >> 8) % 1241) : (float)(K[0] * xc / zc + K[2]));
+            s = s * 1664525u + 1013904223u;
+            p2.push_back(wrong ? (float)((s >> 8) % 376) : (float)(K[1] * yc / zc + K[3]));
+        }
+        myslam::LoopVerifier verifier;
+        const myslam::LoopVerification v = verifier.ComputeCorrectPose(p3, p2, K, drifted);
+        std::printf("ComputeCorrectPose: accepted %d, inliers %d, needCorrect %d, t = %.3f %.3f %.3f\n", (int)v.accepted, v.inliers,
+                    (int)v.needCorrect, v.correctedPose[4], v.correctedPose[5], v.correctedPose[6]);
+        if (!v.accepted || v.inliers < 200 || !v.needCorrect) return 7;
+        if (std::fabs(v.correctedPose[4] - 0.5) > 0.02 || std::fabs(v.correctedPose[6] - 2.0) > 0.02) return 8;
+    }
     return 0;
 }

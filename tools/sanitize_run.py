@@ -31,3 +31,7 @@ if which in ("all", "pg"):
     g = synth.pose_graph(1, n=50, n_loops=2)
     p, info = pkg.PoseGraph(64, 128).solve(g["poses0"], g["fixed"], g["v0"], g["v1"], g["meas"], iters=5)
     print("pg", info)
+if which in ("all", "pnp"):
+    pr = [synth.pnp_problem(s, n_points=200) for s in range(2)]
+    r = pkg.PnPRansac(max_problems=2, max_points=256).solve([(p["obj"], p["img"]) for p in pr], synth.KITTI_K)
+    print("pnp", [x["info"].tolist() for x in r])
