@@ -297,8 +297,8 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     __syncthreads();
     sb_mbar_wait(&bar, 0);
 
-    // Phase 1: pixels that pass the cheap necessary test (sb_fast_maybe's rule: at least two of the four compass
-    // ring pixels darker than v - t, or two brighter than v + t) are compacted into a list, so that the response
+    // Phase 1: pixels that pass the cheap necessary test (sb_fast_maybe's rule on the four compass ring pixels: one
+    // of each opposite pair darker than v - t, or one of each pair brighter than v + t) are compacted into a list, so that the response
     // (about 80 instructions) is later computed by full warps instead of a few lanes of every warp.
     // A work item is 4 horizontally adjacent pixels: five aligned 32-bit loads, two funnel shifts, then the
     // order statistics for two pixels at a time in packed 2 x int16 arithmetic.  Every warp appends to its own
@@ -333,9 +333,10 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
                     const uint32_t sel = hpair ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> two 16-bit halves
                     const uint32_t v = __byte_perm(C, 0u, sel), r0 = __byte_perm(D, 0u, sel), r8 = __byte_perm(U, 0u, sel);
                     const uint32_t r4 = __byte_perm(R, 0u, sel), r12 = __byte_perm(Lw, 0u, sel);
-                    const uint32_t m1 = __vmins2(r0, r4), M1 = __vmaxs2(r0, r4), m2 = __vmins2(r8, r12), M2 = __vmaxs2(r8, r12);
-                    const uint32_t A = __vmaxs2(m1, m2), B = __vmins2(M1, M2);
-                    const uint32_t s2 = __vmins2(A, B), s3 = __vmaxs2(A, B);  // 2nd smallest / 2nd largest of the four
+                    // a 9-arc holds at least one pixel of each opposite pair (0, 8) and (4, 12): the brighter of the two
+                    // pair minima must be darker than v - t, or the darker of the two pair maxima brighter than v + t
+                    const uint32_t s2 = __vmaxs2(__vmins2(r0, r8), __vmins2(r4, r12));
+                    const uint32_t s3 = __vmins2(__vmaxs2(r0, r8), __vmaxs2(r4, r12));
                     // darker: s2 < v - t  <=>  s2 + t - v < 0 ;  brighter: s3 > v + t  <=>  v + t - s3 < 0
                     const uint32_t dk = s2 + Tb - v, br = v + Tb - s3;
                     const uint32_t neg = ~(dk & br) & 0x02000200u;  // bit 9 of a half clear in either

@@ -58,15 +58,15 @@ SB_HD uint32_t sb_vmax3_2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_
                        (k) == 7 ? -3 : (k) == 8 ? -3 : (k) == 9 ? -3 : (k) == 10 ? -2 : (k) == 11 ? -1 : (k) == 12 ? 0 :        \
                        (k) == 13 ? 1 : (k) == 14 ? 2 : 3)
 
-// Necessary condition for "corner at threshold t": any 9 contiguous ring positions contain at least
-// two of the four compass positions 0, 4, 8, 12, and all of them must lie on the same side.  "At least
-// two of four darker than v - t" <=> the second smallest of the four is; likewise for brighter.
+// Necessary condition for "corner at threshold t": any 9 contiguous ring positions contain at least one of the
+// opposite positions (0, 8) and at least one of (4, 12), and all of them lie on the same side.  So the brighter of
+// the two pair minima must be darker than v - t, or the darker of the two pair maxima brighter than v + t
+// (28 % of the synthetic pyramid's pixels pass; "two of the four compass pixels" passes 35 %).
 SB_HD bool sb_fast_maybe(const uint8_t *p, int pitch, int t) {
     const int v = p[0];
     const int r0 = p[3 * pitch], r4 = p[3], r8 = p[-3 * pitch], r12 = p[-3];
-    const int m1 = sb_min(r0, r4), M1 = sb_max(r0, r4), m2 = sb_min(r8, r12), M2 = sb_max(r8, r12);
-    const int A = sb_max(m1, m2), B = sb_min(M1, M2);
-    return sb_min(A, B) < v - t || sb_max(A, B) > v + t;
+    const int dk = sb_max(sb_min(r0, r8), sb_min(r4, r12)), br = sb_min(sb_max(r0, r8), sb_max(r4, r12));
+    return dk < v - t || br > v + t;
 }
 
 // Corner response = the largest threshold for which the pixel is still a FAST-9/16 corner:
