@@ -218,6 +218,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = importlib.import_module(PKG)
     synth = importlib.import_module(PKG + ".synth")
