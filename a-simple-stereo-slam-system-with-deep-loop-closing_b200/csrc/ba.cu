@@ -461,22 +461,80 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                 }
                 __syncthreads();
                 BA_T(4);
-                // ---- Cholesky of the reduced system, right-looking, by the whole CTA with one barrier per column:
-                //      column j of L goes to ROW j of the upper triangle (S[j][i], i > j: contiguous for the substitutions),
-                //      the trailing update works on the lower triangle, the pivots are kept as reciprocals.  The order of
-                //      the subtractions per entry is the same as in the left-looking form (k = 0, 1, ...).
+                // ---- Cholesky of the reduced system, right-looking by 6 x 6 pose blocks (two barriers per block column instead
+                //      of one per column): every thread of the first three warps factors the diagonal block in registers (the
+                //      same 21 values: no broadcast needed), thread t then solves row t of the panel below it, and the whole
+                //      CTA applies the rank-6 update to the trailing lower triangle.  Column j of L goes to ROW j of the
+                //      upper triangle (S[j][i], i > j: contiguous for the substitutions), the pivots are kept as
+                //      reciprocals.  Per entry the subtractions happen in the same order as in the left-looking form.
                 if (ok) {
                     int bad_pivot = 0;
-                    const int r0 = tid >> 3, c0 = tid & 7;
-                    for (int j = 0; j < n6; j++) {
-                        const double d = S[j * n6 + j];
-                        if (!(d > 0)) { bad_pivot = 1; break; }   // uniform: every thread reads the same entry
-                        const double inv = rsqrt(d);
-                        if (tid == 0) dinv[j] = inv;
-                        for (int i = j + 1 + r0; i < n6; i += BA_THREADS / 8) {
-                            const double lij = S[i * n6 + j] * inv;
-                            if (c0 == 0) S[j * n6 + i] = lij;
-                            for (int k = j + 1 + c0; k <= i; k += 8) S[i * n6 + k] -= lij * (S[k * n6 + j] * inv);
+                    if (tid == 0) s_bad = 0;
+                    __syncthreads();
+                    for (int J = 0; J < n6; J += 6) {
+                        const int below = n6 - J - 6;  // rows under the diagonal block
+                        if (tid < 96) {  // n6 - 6 <= 90 panel rows (16 poses)
+                            double Lb[21], inv[6];  // lower triangle of the block, row-major packed: (r, c) at r (r + 1) / 2 + c
+                            bool bad = false;
+#pragma unroll
+                            for (int r = 0; r < 6; r++)
+#pragma unroll
+                                for (int c = 0; c <= r; c++) Lb[r * (r + 1) / 2 + c] = S[(J + r) * n6 + J + c];
+#pragma unroll
+                            for (int c = 0; c < 6; c++) {
+                                double d = Lb[c * (c + 1) / 2 + c];
+#pragma unroll
+                                for (int k = 0; k < c; k++) d -= Lb[c * (c + 1) / 2 + k] * Lb[c * (c + 1) / 2 + k];
+                                if (!(d > 0)) bad = true;
+                                inv[c] = rsqrt(d);
+#pragma unroll
+                                for (int r = c + 1; r < 6; r++) {
+                                    double v = Lb[r * (r + 1) / 2 + c];
+#pragma unroll
+                                    for (int k = 0; k < c; k++) v -= Lb[r * (r + 1) / 2 + k] * Lb[c * (c + 1) / 2 + k];
+                                    Lb[r * (r + 1) / 2 + c] = v * inv[c];
+                                }
+                            }
+                            if (tid == 0) {
+                                if (bad) s_bad = 1;
+#pragma unroll
+                                for (int c = 0; c < 6; c++) {
+                                    dinv[J + c] = inv[c];
+#pragma unroll
+                                    for (int r = c + 1; r < 6; r++) S[(J + c) * n6 + J + r] = Lb[r * (r + 1) / 2 + c];
+                                }
+                            }
+                            if (tid < below && !bad) {  // panel row i: x L_JJ^T = S(i, J..J+5)
+                                const int i = J + 6 + tid;
+                                double x[6];
+#pragma unroll
+                                for (int c = 0; c < 6; c++) {
+                                    double v = S[i * n6 + J + c];
+#pragma unroll
+                                    for (int k = 0; k < c; k++) v -= x[k] * Lb[c * (c + 1) / 2 + k];
+                                    x[c] = v * inv[c];
+                                }
+#pragma unroll
+                                for (int c = 0; c < 6; c++) {
+                                    S[i * n6 + J + c] = x[c];    // read by the trailing update
+                                    S[(J + c) * n6 + i] = x[c];  // L^T for the substitutions
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        if (s_bad) { bad_pivot = 1; break; }
+                        {
+                            const int r0 = tid >> 3, c0 = tid & 7;
+                            for (int i = J + 6 + r0; i < n6; i += BA_THREADS / 8) {
+                                const double *li = S + i * n6 + J;
+                                const double l0 = li[0], l1 = li[1], l2 = li[2], l3 = li[3], l4 = li[4], l5 = li[5];
+                                for (int k = J + 6 + c0; k <= i; k += 8) {
+                                    const double *lk = S + k * n6 + J;
+                                    double v = S[i * n6 + k];
+                                    v -= l0 * lk[0]; v -= l1 * lk[1]; v -= l2 * lk[2]; v -= l3 * lk[3]; v -= l4 * lk[4]; v -= l5 * lk[5];
+                                    S[i * n6 + k] = v;
+                                }
+                            }
                         }
                         __syncthreads();
                     }
@@ -504,6 +562,7 @@ __global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__
                     }
                     __syncthreads();
                     ok = !bad_pivot;
+                    if (tid == 0) s_bad = 0;
                 }
                 BA_T(5);
                 double scale = 0;
