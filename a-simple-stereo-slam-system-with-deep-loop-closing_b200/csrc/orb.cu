@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     // access to generic LD/ST with 64-bit address math)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int s_n, s_any[SB_FAST_KMAX], s_cnt[FAST_THREADS / 32];
+    __shared__ int s_n, s_any[SB_FAST_KMAX];
     uint8_t *tile = smem;  // TMA destination, 128-byte aligned
     uint8_t *sc = smem + a.tile_bytes;
     uint32_t *list = reinterpret_cast<uint32_t *>(smem);  // maxima list: reuses the tile, which is dead after phase 2

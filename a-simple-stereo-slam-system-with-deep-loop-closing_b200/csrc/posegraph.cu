@@ -50,56 +50,6 @@ struct PgArgs {
     int32_t *fidx, *vof, *ecls, *eloop, *inc_start, *inc_edge, *loop_edge;
 };
 
-// ---- 6x6 helpers (row major) ---------------------------------------------------------------------------
-static __device__ __forceinline__ void m6_mul(const double *A, const double *B, double *C) {  // C = A B
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) {
-            double s = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) s += A[6 * i + k] * B[6 * k + j];
-            C[6 * i + j] = s;
-        }
-}
-static __device__ __forceinline__ void m6_mul_bt(const double *A, const double *B, double *C) {  // C = A B^T
-    for (int i = 0; i < 6; i++)
-        for (int j = 0; j < 6; j++) {
-            double s = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) s += A[6 * i + k] * B[6 * j + k];
-            C[6 * i + j] = s;
-        }
-}
-// inverse of a symmetric positive definite 6x6 by Cholesky; returns false if a pivot is not positive
-static __device__ bool m6_inv_spd(const double *S, double *Inv) {
-    double L[36];
-    for (int j = 0; j < 6; j++) {
-        double d = S[6 * j + j];
-        for (int k = 0; k < j; k++) d -= L[6 * j + k] * L[6 * j + k];
-        if (!(d > 0)) return false;
-        d = sqrt(d);
-        L[6 * j + j] = d;
-        for (int i = j + 1; i < 6; i++) {
-            double v = S[6 * i + j];
-            for (int k = 0; k < j; k++) v -= L[6 * i + k] * L[6 * j + k];
-            L[6 * i + j] = v / d;
-        }
-    }
-    for (int c = 0; c < 6; c++) {  // solve L L^T x = e_c
-        double y[6];
-        for (int i = 0; i < 6; i++) {
-            double v = (i == c) ? 1.0 : 0.0;
-            for (int k = 0; k < i; k++) v -= L[6 * i + k] * y[k];
-            y[i] = v / L[6 * i + i];
-        }
-        for (int i = 5; i >= 0; i--) {
-            double v = y[i];
-            for (int k = i + 1; k < 6; k++) v -= L[6 * k + i] * Inv[6 * k + c];
-            Inv[6 * i + c] = v / L[6 * i + i];
-        }
-    }
-    return true;
-}
-
 static __device__ double pg_block_sum(double v, double *red) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
