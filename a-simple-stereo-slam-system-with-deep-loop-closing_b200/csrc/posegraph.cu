@@ -23,8 +23,16 @@
 #define PG_THREADS 256
 #define PG_MAX_LOOPS 64
 #define PG_CHUNK 16
+#define PG_PF 4     // chain steps whose right-hand sides are fetched ahead (PG_CHUNK is a multiple)
 
 enum { PG_NONE = 0, PG_DIAG = 1, PG_CHAIN = 2, PG_LOOP = 3 };
+
+#ifdef PG_PROFILE  // per-phase clock64 totals (tools/pg_profile.py); the product build has no trace of it
+__device__ long long g_pg_prof[16];
+#define PG_T(i) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); g_pg_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define PG_T(i) ((void)0)
+#endif
 
 struct sb_posegraph {
     int device, max_vertices, max_edges;
@@ -96,6 +104,7 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
     __shared__ double w_B[36], w_G[36], w_M[36], w_I[36];  // 6x6 work blocks of the factorisation warp
     __shared__ __align__(16) double w_stage[2 * PG_CHUNK * 36];           // G / (S^-1, B) of a chunk of chain steps
     __shared__ int s_nf, s_R, s_bad;
+    __shared__ double s_diag[6 * PG_MAX_LOOPS];  // diagonal of the capacitance matrix' Cholesky factor
     const int tid = threadIdx.x;
     const int n = a.n, m = a.m;
 
@@ -162,8 +171,13 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
     double lambda = 0, ni = 2, chi_start = 0, chi_end = 0;
     int lm_iters = 0, trials = 0;
     bool terminated = false;
+#ifdef PG_PROFILE
+    long long t_prev = clock64();
+#endif
     for (int it = 0; it < a.iters && !terminated; it++) {
+        PG_T(7);
         double currentChi = pg_errors(a, red);
+        PG_T(0);
         if (it == 0) chi_start = currentChi;
         chi_end = currentChi;
         if (nf == 0) break;
@@ -190,6 +204,7 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
             for (int r = 0; r < 6; r++) J[6 * r + d] = scalar * (ep[r] - em[r]);
         }
         __syncthreads();
+        PG_T(1);
         // ---- assembly, one thread per free vertex (gather over its incident edges, ascending edge index)
         double mx = 0;
         for (int p = tid; p < nf; p += PG_THREADS) {
@@ -243,7 +258,9 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
 
         double rho = 0;
         int qmax = 0;
+        PG_T(2);
         do {
+            PG_T(7);
             for (int k = tid; k < 12 * n; k += PG_THREADS) a.Rtb[k] = a.Rt[k];  // push()
             // ---- block Thomas factorisation of T = tridiag(B, A + lambda I, B^T): S_p = A_p - G_p B_p^T with
             //      G_p = B_p S_{p-1}^-1.  The recurrence is serial in p; inside a step one warp works on the 6x6
@@ -253,12 +270,20 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
                 const int l = tid, r = l / 6, cc = l % 6;  // lanes 0..17 own (r, cc) and (r + 3, cc)
                 const bool act = l < 18;
                 int bad = 0;
+                // the blocks of step p + 1 are loaded during step p: the recurrence is a chain of dependent 6 x 6 operations,
+                // and a global load at the head of every step would sit on its critical path
+                double nA0 = 0, nA1 = 0, nB0 = 0, nB1 = 0;
+                if (act && nf > 0) { nA0 = a.A[6 * r + cc]; nA1 = a.A[6 * (r + 3) + cc]; }
                 for (int p = 0; p < nf; p++) {
                     double e0 = 0, e1 = 0;
                     if (act) {
-                        e0 = a.A[36 * p + 6 * r + cc] + (r == cc ? lambda : 0.0);
-                        e1 = a.A[36 * p + 6 * (r + 3) + cc] + (r + 3 == cc ? lambda : 0.0);
-                        if (p > 0) { w_B[6 * r + cc] = a.B[36 * p + 6 * r + cc]; w_B[6 * (r + 3) + cc] = a.B[36 * p + 6 * (r + 3) + cc]; }
+                        e0 = nA0 + (r == cc ? lambda : 0.0);
+                        e1 = nA1 + (r + 3 == cc ? lambda : 0.0);
+                        if (p > 0) { w_B[6 * r + cc] = nB0; w_B[6 * (r + 3) + cc] = nB1; }
+                        if (p + 1 < nf) {
+                            nA0 = a.A[36 * (p + 1) + 6 * r + cc]; nA1 = a.A[36 * (p + 1) + 6 * (r + 3) + cc];
+                            nB0 = a.B[36 * (p + 1) + 6 * r + cc]; nB1 = a.B[36 * (p + 1) + 6 * (r + 3) + cc];
+                        }
                     }
                     __syncwarp();
                     if (p > 0) {
@@ -282,29 +307,32 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
                         e1 = 0.5 * (w_M[6 * (r + 3) + cc] + w_M[6 * cc + r + 3]);
                     }
                     double i0 = r == cc ? 1.0 : 0.0, i1 = r + 3 == cc ? 1.0 : 0.0;
-                    __syncwarp();
-                    if (act) { w_M[6 * r + cc] = e0; w_M[6 * (r + 3) + cc] = e1; w_I[6 * r + cc] = i0; w_I[6 * (r + 3) + cc] = i1; }
-                    __syncwarp();
+                    // Gauss-Jordan on [M | I] in registers: the pivot row and the pivot column travel by warp shuffles
+                    // (element (r, cc) lives in lane 6 r + cc, rows 3..5 in the second register of lanes 0..17)
+                    const int col_src = act ? 6 * r : 0;
 #pragma unroll
                     for (int k = 0; k < 6; k++) {
-                        const double piv = w_M[7 * k];
+                        const double rowm = k < 3 ? e0 : e1, rowi = k < 3 ? i0 : i1;
+                        const double piv = __shfl_sync(0xffffffffu, rowm, 6 * (k % 3) + k);
+                        double mk = __shfl_sync(0xffffffffu, rowm, 6 * (k % 3) + cc);
+                        double ik = __shfl_sync(0xffffffffu, rowi, 6 * (k % 3) + cc);
+                        const double f0 = __shfl_sync(0xffffffffu, e0, col_src + k), f1 = __shfl_sync(0xffffffffu, e1, col_src + k);
                         if (!(piv > 0)) bad = 1;  // positive definite blocks have positive pivots without pivoting
                         const double ip = 1.0 / piv;
-                        double mk = 0, ik = 0, f0 = 0, f1 = 0;
-                        if (act) { mk = w_M[6 * k + cc] * ip; ik = w_I[6 * k + cc] * ip; f0 = w_M[6 * r + k]; f1 = w_M[6 * (r + 3) + k]; }
-                        __syncwarp();
-                        if (act) {
-                            e0 = r == k ? mk : e0 - f0 * mk;      i0 = r == k ? ik : i0 - f0 * ik;
-                            e1 = r + 3 == k ? mk : e1 - f1 * mk;  i1 = r + 3 == k ? ik : i1 - f1 * ik;
-                            w_M[6 * r + cc] = e0; w_M[6 * (r + 3) + cc] = e1; w_I[6 * r + cc] = i0; w_I[6 * (r + 3) + cc] = i1;
-                        }
-                        __syncwarp();
+                        mk *= ip;
+                        ik *= ip;
+                        e0 = r == k ? mk : e0 - f0 * mk;      i0 = r == k ? ik : i0 - f0 * ik;
+                        e1 = r + 3 == k ? mk : e1 - f1 * mk;  i1 = r + 3 == k ? ik : i1 - f1 * ik;
                     }
+                    __syncwarp();
+                    if (act) { w_I[6 * r + cc] = i0; w_I[6 * (r + 3) + cc] = i1; }
+                    __syncwarp();
                     if (act) { a.Sinv[36 * p + 6 * r + cc] = i0; a.Sinv[36 * p + 6 * (r + 3) + cc] = i1; }
                     if (__any_sync(0xffffffffu, bad)) break;
                 }
                 if (tid == 0) s_bad = bad;
             }
+            PG_T(3);
             // ---- right-hand sides Q[p][c][6]: column 0 = b, column 1 + 6r + k = row k of J_loop,r (as a column of J^T)
             for (int idx = tid; idx < nf * NC * 6; idx += PG_THREADS) a.Q[idx] = 0;
             __syncthreads();
@@ -321,6 +349,7 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
             __syncthreads();
             int ok = !s_bad;
             __syncthreads();
+            PG_T(4);
             if (ok) {
                 // ---- T^-1 [b, J^T]: one thread per column, sequential over the chain; the 6x6 blocks every column
                 //      needs (G_p forward, S_p^-1 and B_{p+1} backward) are staged through shared memory in chunks.
@@ -329,36 +358,64 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
                     for (int ci = 0; ci < ncol_iters; ci++) {
                         const int c = ci * PG_THREADS + tid;
                         const bool on = c < NC;
+                        // The recurrences only carry y (forward) and x (backward); the right-hand sides live in L2 (3.6 MB for
+                        // KITTI-00), ~700 cycles away.  They are therefore fetched a block of PG_PF steps ahead of their use —
+                        // without this every step waits for its own loads behind the previous step's stores.
                         double y[6] = {0, 0, 0, 0, 0, 0};
+                        double cur[PG_PF][6], nxt[PG_PF][6];
+#pragma unroll
+                        for (int s4 = 0; s4 < PG_PF; s4++)
+#pragma unroll
+                            for (int i = 0; i < 6; i++) cur[s4][i] = (on && s4 < nf) ? a.Q[((size_t)s4 * NC + c) * 6 + i] : 0.0;
                         for (int p0 = 0; p0 < nf; p0 += PG_CHUNK) {
                             const int pn = min(PG_CHUNK, nf - p0);
                             __syncthreads();
                             for (int k = tid; k < pn * 36; k += PG_THREADS) w_stage[k] = a.G[36 * p0 + k];
                             __syncthreads();
                             if (on)
-                                for (int pp = 0; pp < pn; pp++) {
-                                    const int p = p0 + pp;
-                                    double *q = a.Q + ((size_t)p * NC + c) * 6;
-                                    double v[6];
+                                for (int pb = 0; pb < pn; pb += PG_PF) {
 #pragma unroll
-                                    for (int i = 0; i < 6; i++) v[i] = q[i];
-                                    if (p > 0) {
-                                        const double *Gp = w_stage + 36 * pp;
+                                    for (int s4 = 0; s4 < PG_PF; s4++) {  // the block after this one
+                                        const int pnx = p0 + pb + PG_PF + s4;
 #pragma unroll
-                                        for (int i = 0; i < 6; i++) {
-                                            double sacc = v[i];
-#pragma unroll
-                                            for (int k = 0; k < 6; k++) sacc -= Gp[6 * i + k] * y[k];
-                                            v[i] = sacc;
-                                        }
-#pragma unroll
-                                        for (int i = 0; i < 6; i++) q[i] = v[i];
+                                        for (int i = 0; i < 6; i++) nxt[s4][i] = pnx < nf ? a.Q[((size_t)pnx * NC + c) * 6 + i] : 0.0;
                                     }
 #pragma unroll
-                                    for (int i = 0; i < 6; i++) y[i] = v[i];
+                                    for (int s4 = 0; s4 < PG_PF; s4++) {
+                                        const int pp = pb + s4, p = p0 + pp;
+                                        if (pp < pn) {
+                                            double v[6];
+#pragma unroll
+                                            for (int i = 0; i < 6; i++) v[i] = cur[s4][i];
+                                            if (p > 0) {
+                                                const double *Gp = w_stage + 36 * pp;
+#pragma unroll
+                                                for (int i = 0; i < 6; i++) {
+                                                    double sacc = v[i];
+#pragma unroll
+                                                    for (int k = 0; k < 6; k++) sacc -= Gp[6 * i + k] * y[k];
+                                                    v[i] = sacc;
+                                                }
+                                                double *q = a.Q + ((size_t)p * NC + c) * 6;
+#pragma unroll
+                                                for (int i = 0; i < 6; i++) q[i] = v[i];
+                                            }
+#pragma unroll
+                                            for (int i = 0; i < 6; i++) y[i] = v[i];
+                                        }
+                                    }
+#pragma unroll
+                                    for (int s4 = 0; s4 < PG_PF; s4++)
+#pragma unroll
+                                        for (int i = 0; i < 6; i++) cur[s4][i] = nxt[s4][i];
                                 }
                         }
                         double xn[6] = {0, 0, 0, 0, 0, 0};
+                        // backward: block s4 = 0 is the highest step; the forward pass' stores are visible to this thread
+#pragma unroll
+                        for (int s4 = 0; s4 < PG_PF; s4++)
+#pragma unroll
+                            for (int i = 0; i < 6; i++) cur[s4][i] = (on && nf - 1 - s4 >= 0) ? a.Q[((size_t)(nf - 1 - s4) * NC + c) * 6 + i] : 0.0;
                         for (int pend = nf; pend > 0; pend -= PG_CHUNK) {
                             const int p0 = max(0, pend - PG_CHUNK), pn = pend - p0;
                             __syncthreads();
@@ -368,37 +425,53 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
                             }
                             __syncthreads();
                             if (on)
-                                for (int pp = pn - 1; pp >= 0; pp--) {
-                                    const int p = p0 + pp;
-                                    double *q = a.Q + ((size_t)p * NC + c) * 6;
-                                    double r6[6];
+                                for (int pb = pn - 1; pb >= 0; pb -= PG_PF) {
 #pragma unroll
-                                    for (int i = 0; i < 6; i++) r6[i] = q[i];
-                                    if (p + 1 < nf) {
-                                        const double *Bn = w_stage + PG_CHUNK * 36 + 36 * pp;  // (B_{p+1})^T x_{p+1}
+                                    for (int s4 = 0; s4 < PG_PF; s4++) {  // the block below this one
+                                        const int pnx = p0 + pb - PG_PF - s4;
 #pragma unroll
-                                        for (int i = 0; i < 6; i++) {
-                                            double sacc = 0;
+                                        for (int i = 0; i < 6; i++) nxt[s4][i] = pnx >= 0 ? a.Q[((size_t)pnx * NC + c) * 6 + i] : 0.0;
+                                    }
 #pragma unroll
-                                            for (int k = 0; k < 6; k++) sacc += Bn[6 * k + i] * xn[k];
-                                            r6[i] -= sacc;
+                                    for (int s4 = 0; s4 < PG_PF; s4++) {
+                                        const int pp = pb - s4, p = p0 + pp;
+                                        if (pp >= 0) {
+                                            double r6[6];
+#pragma unroll
+                                            for (int i = 0; i < 6; i++) r6[i] = cur[s4][i];
+                                            if (p + 1 < nf) {
+                                                const double *Bn = w_stage + PG_CHUNK * 36 + 36 * pp;  // (B_{p+1})^T x_{p+1}
+#pragma unroll
+                                                for (int i = 0; i < 6; i++) {
+                                                    double sacc = 0;
+#pragma unroll
+                                                    for (int k = 0; k < 6; k++) sacc += Bn[6 * k + i] * xn[k];
+                                                    r6[i] -= sacc;
+                                                }
+                                            }
+                                            const double *Si = w_stage + 36 * pp;
+#pragma unroll
+                                            for (int i = 0; i < 6; i++) {
+                                                double sacc = 0;
+#pragma unroll
+                                                for (int k = 0; k < 6; k++) sacc += Si[6 * i + k] * r6[k];
+                                                xn[i] = sacc;
+                                            }
+                                            double *q = a.Q + ((size_t)p * NC + c) * 6;
+#pragma unroll
+                                            for (int i = 0; i < 6; i++) q[i] = xn[i];
                                         }
                                     }
-                                    const double *Si = w_stage + 36 * pp;
 #pragma unroll
-                                    for (int i = 0; i < 6; i++) {
-                                        double sacc = 0;
+                                    for (int s4 = 0; s4 < PG_PF; s4++)
 #pragma unroll
-                                        for (int k = 0; k < 6; k++) sacc += Si[6 * i + k] * r6[k];
-                                        xn[i] = sacc;
-                                    }
-#pragma unroll
-                                    for (int i = 0; i < 6; i++) q[i] = xn[i];
+                                        for (int i = 0; i < 6; i++) cur[s4][i] = nxt[s4][i];
                                 }
                         }
                     }
                 }
                 __syncthreads();
+                PG_T(5);
                 const int n6r = 6 * R;
                 if (R > 0) {
                     // ---- capacitance matrix M = I + J Z and right-hand side v = J x0
@@ -417,43 +490,43 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
                         else a.M[(size_t)row * n6r + col] = s + (row == col ? 1.0 : 0.0);
                     }
                     __syncthreads();
-                    // ---- dense Cholesky of M (lower, in place) and the solve M y = v
-                    for (int j = 0; j < n6r; j++) {
-                        if (tid == 0) {
+                    // ---- dense Cholesky of M, right-looking with one barrier per column: every thread reads the pivot and
+                    //      forms the scaled column entries it needs itself; column j of L goes to ROW j of the upper triangle
+                    //      (M[j][i], i > j), the trailing update works on the lower triangle, the diagonal of L is kept apart.
+                    {
+                        const int r0 = tid >> 3, c0 = tid & 7;
+                        for (int j = 0; j < n6r; j++) {
                             const double d = a.M[(size_t)j * n6r + j];
-                            if (!(d > 0)) s_bad = 1;
-                            a.M[(size_t)j * n6r + j] = sqrt(d);
+                            if (!(d > 0)) { if (tid == 0) s_bad = 1; break; }  // uniform: every thread reads the same entry
+                            const double dj = sqrt(d), inv = 1.0 / dj;
+                            if (tid == 0) s_diag[j] = dj;
+                            for (int i = j + 1 + r0; i < n6r; i += PG_THREADS / 8) {
+                                const double lij = a.M[(size_t)i * n6r + j] * inv;
+                                if (c0 == 0) a.M[(size_t)j * n6r + i] = lij;
+                                for (int k = j + 1 + c0; k <= i; k += 8) a.M[(size_t)i * n6r + k] -= lij * (a.M[(size_t)k * n6r + j] * inv);
+                            }
+                            __syncthreads();
                         }
-                        __syncthreads();
-                        if (s_bad) break;
-                        const double dj = a.M[(size_t)j * n6r + j];
-                        for (int i = j + 1 + tid; i < n6r; i += PG_THREADS) a.M[(size_t)i * n6r + j] /= dj;
-                        __syncthreads();
-                        const int mm = n6r - j - 1;
-                        for (int k = tid; k < mm * mm; k += PG_THREADS) {
-                            const int r = j + 1 + k / mm, cc = j + 1 + k % mm;
-                            if (cc <= r) a.M[(size_t)r * n6r + cc] -= a.M[(size_t)r * n6r + j] * a.M[(size_t)cc * n6r + j];
-                        }
-                        __syncthreads();
                     }
+                    __syncthreads();
                     ok = !s_bad;
                     __syncthreads();
-                    if (ok && tid < 32) {
+                    if (ok && tid < 32) {  // M y = v by one warp: L(i, k) = M[k][i]
                         const int lane = tid;
                         for (int i = 0; i < n6r; i++) {
                             double v = 0;
-                            for (int k = lane; k < i; k += 32) v += a.M[(size_t)i * n6r + k] * a.yv[k];
+                            for (int k = lane; k < i; k += 32) v += a.M[(size_t)k * n6r + i] * a.yv[k];
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                            if (lane == 0) a.yv[i] = (a.yv[i] - v) / a.M[(size_t)i * n6r + i];
+                            if (lane == 0) a.yv[i] = (a.yv[i] - v) / s_diag[i];
                             __syncwarp();
                         }
                         for (int i = n6r - 1; i >= 0; i--) {
                             double v = 0;
-                            for (int k = i + 1 + lane; k < n6r; k += 32) v += a.M[(size_t)k * n6r + i] * a.yv[k];
+                            for (int k = i + 1 + lane; k < n6r; k += 32) v += a.M[(size_t)i * n6r + k] * a.yv[k];
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                            if (lane == 0) a.yv[i] = (a.yv[i] - v) / a.M[(size_t)i * n6r + i];
+                            if (lane == 0) a.yv[i] = (a.yv[i] - v) / s_diag[i];
                             __syncwarp();
                         }
                     }
@@ -472,6 +545,7 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
                 }
             }
             __syncthreads();
+            PG_T(6);
             if (tid == 0) s_bad = 0;
             double scale = 0;
             if (ok) {
@@ -650,3 +724,13 @@ extern "C" int sb_posegraph_solve(sb_posegraph_t *h, int n_vertices, double *pos
     }
     return SB_OK;
 }
+
+#ifdef PG_PROFILE
+extern "C" int sb_posegraph_debug_profile(long long *out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_pg_prof, sizeof(long long) * 16);
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_pg_prof, z, sizeof(z));
+    return 0;
+}
+#endif
