@@ -167,6 +167,29 @@ def cpu_reference_fps(frames, windows, cores):
     return len(frames) / ref.run(frames, windows)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line.  Native libraries (NCCL prints its version from C) write to fd 1 too, so fd 1
+    is pointed at stderr for the whole run and the JSON line goes to a private copy of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(out):
+    line = (json.dumps(out) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, line)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -189,7 +212,7 @@ def run_reference(args, rank, world):
                                       "ORBextractor::DetectAndCompute + BFMatcher + the g2o-faithful LM/Schur BA; the reference "
                                       "itself needs OpenCV/g2o and cannot be built here), one frame per thread"},
            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def main():
@@ -203,6 +226,7 @@ def main():
     ap.add_argument("--no-ba", action="store_true", help="config 2 only: extract + match")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -218,8 +242,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = importlib.import_module(PKG)
     synth = importlib.import_module(PKG + ".synth")
@@ -530,7 +552,7 @@ def main():
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                    "sample": f"{len(sample)} of the same synthetic stereo frames (+ one BA window each) through "
                                              "oracle/ (C restatement of the reference's OpenCV/g2o-based path), one frame per thread"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
