@@ -41,7 +41,8 @@ struct sb_matcher {
 // tkey[set][rows_pad] = (|t| + 512) << 22 | index  (0xffffffff for rows >= nt);  pq[set][rows_pad] = |q|.
 __global__ void __launch_bounds__(256) k_expand(const uint8_t *__restrict__ src, long long set_stride,
                                                const int32_t *__restrict__ n_arr, int n_stride, int max_rows, int rows_pad,
-                                               uint8_t *__restrict__ dst, uint32_t *__restrict__ tkey, int32_t *__restrict__ pq) {
+                                               uint8_t *__restrict__ dst, uint32_t *__restrict__ tkey, int32_t *__restrict__ pq,
+                                               uint32_t *__restrict__ init_key, long long init_stride) {
     const int set = blockIdx.y;
     const int n = min(n_arr[(long long)set * n_stride], max_rows);
     const int row = blockIdx.x * 32 + (threadIdx.x >> 3), part = threadIdx.x & 7;  // 8 threads per row, one 32-bit word each
@@ -63,13 +64,8 @@ __global__ void __launch_bounds__(256) k_expand(const uint8_t *__restrict__ src,
     if (part == 0) {
         if (tkey) tkey[(long long)set * rows_pad + row] = row < n ? (((uint32_t)pc + 512u) << MATCH_KEY_SHIFT) | (uint32_t)row : 0xffffffffu;
         if (pq) pq[(long long)set * rows_pad + row] = pc;
+        if (init_key && row < n) init_key[(long long)set * init_stride + row] = 0xffffffffu;  // the atomicMin target of the query row
     }
-}
-
-__global__ void k_hamming_init(const int32_t *__restrict__ nq_arr, int nq_stride, int max_rows, uint32_t *out_key,
-                               long long out_stride) {
-    const int set = blockIdx.y, qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi < min(nq_arr[(long long)set * nq_stride], max_rows)) out_key[(long long)set * out_stride + qi] = 0xffffffffu;
 }
 
 // key -> (train index, distance = |q| + (key >> 22) - 512)
@@ -368,12 +364,12 @@ extern "C" int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d
     SB_TRY(sb_use_device(m->device));
     SB_REQUIRE(batch <= m->max_batch && max_rows <= m->max_rows, "batch / max_rows larger than given at create time");
     const int rp = m->rows_pad;
-    k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_q, q_set_stride, d_nq, nq_stride, max_rows, rp, m->d_xq, nullptr, m->d_pq);
-    k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_t, t_set_stride, d_nt, nt_stride, max_rows, rp, m->d_xt, m->d_tkey, nullptr);
+    k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_q, q_set_stride, d_nq, nq_stride, max_rows, rp, m->d_xq, nullptr, m->d_pq,
+                                                                    reinterpret_cast<uint32_t *>(d_train_idx), out_stride);
+    k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_t, t_set_stride, d_nt, nt_stride, max_rows, rp, m->d_xt, m->d_tkey, nullptr,
+                                                                    nullptr, 0);
     // enough CTAs to fill 148 SMs: slice the train set when the batch alone does not
     const int qblocks = sb_div_up(max_rows, UM_M);
-    k_hamming_init<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows,
-                                                                                 reinterpret_cast<uint32_t *>(d_train_idx), out_stride);
     int nslices = 1;  // one CTA per SM (160 KB of shared memory, all of TMEM)
     while (nslices < 16 && (long long)qblocks * batch * nslices < 148 && max_rows / (nslices * 2) >= UM_N) nslices *= 2;
     k_hamming_umma<<<dim3(qblocks, nslices, batch), UM_THREADS, UM_SMEM, m->stream>>>(

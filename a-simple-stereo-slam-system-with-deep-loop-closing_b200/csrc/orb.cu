@@ -682,7 +682,7 @@ struct DescArgs {
     int nlevels, selcap, cap;
 };
 
-#define DESC_KPB 32  // keypoints per CTA of k_describe
+#define DESC_KPB 64  // keypoints per CTA of k_describe
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, DescArgs a) {
     __shared__ float4 pat[256];
     __shared__ float s_ang[DESC_KPB], s_cos[DESC_KPB], s_sin[DESC_KPB];
