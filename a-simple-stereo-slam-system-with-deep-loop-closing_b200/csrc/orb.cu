@@ -27,8 +27,8 @@
 #define SB_MAX_LEVELS 12
 #define SB_CAND_CAP 16384       // FAST candidates one (image, level) can hand to the quadtree
 #define SB_FAST_KMAX 8          // FAST cells one CTA handles (a horizontal run of one grid row)
-#define SB_FAST_SPAN 160        // ... as many as fit this many tested columns
-#define SB_FAST_BW 192          // TMA box width of every FAST tile (compile time: ring offsets fold into the LDS immediates)
+#define SB_FAST_SPAN 224        // ... as many as fit this many tested columns
+#define SB_FAST_BW 256          // TMA box width of every FAST tile (compile time: ring offsets fold into the LDS immediates)
 #define FAST_THREADS 256
 #define QT_THREADS 256
 #define BLUR_TW 128
