@@ -45,8 +45,8 @@ CALC_MACS = 64 * 62 * 82 * 25 + 128 * 32 * 42 * 1024 + 4 * 14 * 19 * 1152   # mu
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of 128 images (64 stereo pairs), from the committed
 # `ncu --set full` capture of this same command (profiles/): traffic ~ algorithmic bytes => no wasted re-reads
 NCU_SOURCE = "profiles/r1_ncu_full_final.csv (ncu --set full, one launch of 128 images)"
-NCU_DRAM_BYTES_PER_LAUNCH = {"fast_cells": 189.6e6, "gauss_blur": 356.1e6, "describe": 380.9e6, "copy_level0": 80.0e6,
-                             "quadtree": 8.5e6, "hamming_match": 78.8e6, "resize_pyramid": 212.9e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {"fast_cells": 188.2e6, "gauss_blur": 356.9e6, "describe": 381.1e6, "copy_level0": 79.5e6,
+                             "quadtree": 8.5e6, "hamming_match": 78.2e6, "resize_pyramid": 212.5e6}
 
 
 def pyramid_bytes():
