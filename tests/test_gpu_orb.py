@@ -177,7 +177,10 @@ def test_errors_are_reported_not_thrown_away(pkg):
     g.close()
 
 
-@pytest.mark.parametrize("params", [(1200, 1.5, 5, 20, 7), (800, 2.0, 3, 30, 10), (1500, 1.1, 6, 12, 5), (600, 1.2, 8, 40, 40)])
+# scale factor 2.5: four destination pixels span more than 8 source bytes, so the pyramid falls back from k_resize_quads to
+# the generic k_resize
+@pytest.mark.parametrize("params", [(1200, 1.5, 5, 20, 7), (800, 2.0, 3, 30, 10), (1500, 1.1, 6, 12, 5), (600, 1.2, 8, 40, 40),
+                                    (500, 2.5, 2, 20, 7)])
 def test_other_pyramid_and_threshold_parameters(pkg, oracle, synth, params):
     left, right = synth.stereo_pair(33)
     g = pkg.ORBextractor(*params, max_batch=2)
