@@ -497,7 +497,7 @@ def main():
         stage_ms = {s: float(ms[i]) for i, s in enumerate(STAGES)}
         stage_ms["hamming_match"] = match_ms
         stage_launches = {s: int(launches[i]) for i, s in enumerate(STAGES)}
-        stage_launches["hamming_match"] = args.steps
+        stage_launches["hamming_match"] = 4 * args.steps   # k_expand x 2, k_hamming_umma, k_hamming_decode
         if with_ba:
             stage_ms["local_ba"] = ba_ms
             stage_launches["local_ba"] = args.steps
@@ -517,7 +517,7 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        groups = stage_launches[top] / (7 if top == "resize_pyramid" else 1)
+        groups = stage_launches[top] / (7 if top == "resize_pyramid" else 4 if top == "hamming_match" else 1)
         per_group_ms = stage_ms[top] / max(groups, 1)
         achieved = abytes(top) / (per_group_ms * 1e-3) / 1e9
         roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
