@@ -563,17 +563,26 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps ma
         *reinterpret_cast<uint2 *>(hrow + r * BLUR_TW + 4 * gq) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));  // each <= 255 * 256
     }
     __syncthreads();
-    // vertical pass: a thread owns 4 columns x 4 output rows (10 input rows)
+    // vertical pass: a thread owns 4 columns x 4 output rows (10 input rows).  Vertically adjacent 16-bit row sums of one
+    // column are paired in a word (PRMT) so that a 7-tap column is four DP2As against the byte pairs (18, 34), (48, 56),
+    // (48, 34), (18, 0); output rows 0 / 2 use the pairs that start on even input rows, rows 1 / 3 those on odd rows.
     {
         const int gq = tid & 31, seg = tid >> 5;
         const int ry0 = seg * 4;
         if (y0 + ry0 < L.h && x0 + 4 * gq < L.w) {
-            uint32_t h[10][4];
+            uint2 u[10];
 #pragma unroll
-            for (int r = 0; r < 10; r++) {
-                const uint2 u = *reinterpret_cast<const uint2 *>(hrow + (ry0 + r) * BLUR_TW + 4 * gq);
-                h[r][0] = u.x & 0xffffu; h[r][1] = u.x >> 16; h[r][2] = u.y & 0xffffu; h[r][3] = u.y >> 16;
+            for (int r = 0; r < 10; r++) u[r] = *reinterpret_cast<const uint2 *>(hrow + (ry0 + r) * BLUR_TW + 4 * gq);
+            // pr[k][j]: rows (k, k + 1) of column j as (lower row | upper row << 16), k = 0 .. 8
+            uint32_t pr[9][4];
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                pr[k][0] = __byte_perm(u[k].x, u[k + 1].x, 0x5410);
+                pr[k][1] = __byte_perm(u[k].x, u[k + 1].x, 0x7632);
+                pr[k][2] = __byte_perm(u[k].y, u[k + 1].y, 0x5410);
+                pr[k][3] = __byte_perm(u[k].y, u[k + 1].y, 0x7632);
             }
+            const uint32_t WA = SB_G0 | (SB_G1 << 8), WB = SB_G2 | (SB_G3 << 8), WC = SB_G2 | (SB_G1 << 8), WD = SB_G0, WE = SB_G0 << 8;
             uint8_t *out = a.blur + (long long)img * a.slab + L.off + x0 + 4 * gq;
 #pragma unroll
             for (int ry = 0; ry < 4; ry++) {
@@ -581,8 +590,14 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps ma
                 if (y >= L.h) break;
                 uint32_t o = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    o |= (uint32_t)sb_gauss_col(h[ry][j], h[ry + 1][j], h[ry + 2][j], h[ry + 3][j], h[ry + 4][j], h[ry + 5][j], h[ry + 6][j]) << (8 * j);
+                for (int j = 0; j < 4; j++) {
+                    // rows ry .. ry + 6: pairs (ry, ry+1), (ry+2, ry+3), (ry+4, ry+5) and row ry + 6 alone
+                    uint32_t s = __dp2a_lo(pr[ry][j], WA, 32768u);
+                    s = __dp2a_lo(pr[ry + 2][j], WB, s);
+                    s = __dp2a_lo(pr[ry + 4][j], WC, s);
+                    s = ry < 3 ? __dp2a_lo(pr[ry + 6][j], WD, s) : __dp2a_lo(pr[8][j], WE, s);  // row 9 is the upper half of pair 8
+                    o |= (s >> 16) << (8 * j);
+                }
                 *reinterpret_cast<uint32_t *>(out + (long long)y * L.pitch) = o;
             }
         }
