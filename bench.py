@@ -369,34 +369,41 @@ def main():
     host_np = host_pool.numpy()
     fes = [pkg.StereoFrontend(*ORB_PARAMS, max_w=W, max_h=H, max_pairs=B, device=local_rank) for _ in range(2)]
     outs = [fe.alloc_outputs(B, pinned=True) for fe in fes]
-    hb = {k: torch.from_numpy(v).pin_memory() for k, v in bh.items()}
+    # two back-end handles on ONE stream, used alternately: a batch of windows is submitted without waiting for the
+    # previous one (the stream keeps them in order; nothing idles while the host collects and refills the other buffers)
+    bas = [ba, pkg.LocalBA(max_windows=B, device=local_rank, **BA_CAPS)] if with_ba else []
+    for b_ in bas:
+        b_.set_stream(s2.cuda_stream)
+    hbs = [{k: torch.from_numpy(v).pin_memory() for k, v in bh.items()} for _ in range(2)]
+    hb = hbs[0]
     hb0 = {"poses": hb["poses"].clone(), "points": hb["points"].clone()}
-    h_chi2 = torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.float64).pin_memory()
-    h_outl = torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.uint8).pin_memory()
-    h_info = torch.zeros((B, 4), dtype=torch.int32).pin_memory()
+    h_outs = [(torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.float64).pin_memory(),
+               torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.uint8).pin_memory(),
+               torch.zeros((B, 4), dtype=torch.int32).pin_memory()) for _ in range(2)]
+    h_chi2, h_outl, h_info = h_outs[0]
     Kd = np.ascontiguousarray(KITTI_K, np.float64)
     ext7 = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
 
-    ba_pending = [False]
+    ba_pending = [False, False]
 
-    def ba_wait():
-        if ba_pending[0]:
-            assert lib.sb_ba_wait(ba._h) == 0, pkg.last_error()
-            ba_pending[0] = False
+    def ba_wait(k):
+        if ba_pending[k]:
+            assert lib.sb_ba_wait(bas[k]._h) == 0, pkg.last_error()
+            ba_pending[k] = False
 
-    def ba_submit():
-        ba_wait()                                   # the previous step's batch (its results sit in the pinned buffers)
-        hb["poses"].copy_(hb0["poses"])
-        hb["points"].copy_(hb0["points"])
-        rc = lib.sb_ba_submit(ba._h, B, C.c_void_p(hb["np"].data_ptr()), C.c_void_p(hb["nl"].data_ptr()),
-                              C.c_void_p(hb["ne"].data_ptr()), C.c_void_p(hb["poses"].data_ptr()),
-                              C.c_void_p(hb["points"].data_ptr()), C.c_void_p(hb["fixed"].data_ptr()),
-                              C.c_void_p(hb["op"].data_ptr()), C.c_void_p(hb["ol"].data_ptr()), C.c_void_p(hb["uv"].data_ptr()),
+    def ba_submit(k):
+        ba_wait(k)                                  # this handle's previous batch (two steps ago): its results sit in the pinned buffers
+        hbk, (c2, ol_, inf) = hbs[k], h_outs[k]
+        hbk["poses"].copy_(hb0["poses"])
+        hbk["points"].copy_(hb0["points"])
+        rc = lib.sb_ba_submit(bas[k]._h, B, C.c_void_p(hbk["np"].data_ptr()), C.c_void_p(hbk["nl"].data_ptr()),
+                              C.c_void_p(hbk["ne"].data_ptr()), C.c_void_p(hbk["poses"].data_ptr()),
+                              C.c_void_p(hbk["points"].data_ptr()), C.c_void_p(hbk["fixed"].data_ptr()),
+                              C.c_void_p(hbk["op"].data_ptr()), C.c_void_p(hbk["ol"].data_ptr()), C.c_void_p(hbk["uv"].data_ptr()),
                               C.c_void_p(Kd.ctypes.data), C.c_void_p(ext7.ctypes.data), C.c_double(5.991), C.c_double(5.991),
-                              5, 10, C.c_void_p(h_chi2.data_ptr()), C.c_void_p(h_outl.data_ptr()),
-                              C.c_void_p(h_info.data_ptr()))
+                              5, 10, C.c_void_p(c2.data_ptr()), C.c_void_p(ol_.data_ptr()), C.c_void_p(inf.data_ptr()))
         assert rc == 0, pkg.last_error()
-        ba_pending[0] = True
+        ba_pending[k] = True
 
     def run_host(nsteps):
         # the reference's threading: the front end (extract + match) and the back end (local BA) run side by side;
@@ -410,11 +417,11 @@ def main():
             fes[k].submit(host_np[off:off + B], outs[k])
             pending[k] = True
             if with_ba:
-                ba_submit()
+                ba_submit(k)
         for k in range(2):
             if pending[k]:
                 fes[k].wait()
-        ba_wait()
+            ba_wait(k)
 
     run_host(4)
     barrier()
@@ -540,7 +547,7 @@ def main():
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_ms_max / args.steps,
-                       "api": "sb_stereo_submit/wait on two handles + sb_ba_submit/wait (host pointers, pinned)"},
+                       "api": "sb_stereo_submit/wait and sb_ba_submit/wait, two handles each used alternately (host pointers, pinned)"},
                "gpu_launches": int(sum(stage_launches.values())),
                "roofline": roofline,
                "loop_closing_extras": extras}
