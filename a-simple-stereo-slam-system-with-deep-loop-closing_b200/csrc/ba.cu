@@ -34,6 +34,8 @@ struct sb_ba {
     cudaStream_t stream, own_stream;
     const int32_t *pending_info;  // host `info` of the batch in flight (sb_ba_submit .. sb_ba_wait), else null
     int pending_windows;
+    cudaEvent_t done;             // recorded behind the batch's last copy: sb_ba_wait waits for THIS batch only, not for
+                                  // whatever else shares the stream
     // device copies of the batch (host-pointer entry point) and per-window workspace
     int32_t *d_np, *d_nl, *d_ne, *d_info;
     double *d_poses, *d_points, *d_uv, *d_chi2;
@@ -665,6 +667,7 @@ static void free_ba(sb_ba *h) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->done) cudaEventDestroy(h->done);
     delete h;
 }
 
@@ -708,6 +711,7 @@ extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_
     BA_ALLOC(h->d_ybd, W * MO * 18 * 8);
     BA_ALLOC(h->d_pairs, W * (MP * (MP + 1) / 2) * ML * sizeof(int2));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_bytes(BA_MAX_POSES));
     if (e != cudaSuccess) {
         sb_set_error("sb_ba_create: %s", cudaGetErrorString(e));
@@ -804,6 +808,7 @@ extern "C" int sb_ba_submit(sb_ba_t *h, int n_windows, const int32_t *n_poses, c
     SB_CUDA(cudaMemcpyAsync(chi2, h->d_chi2, W * MO * 8, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaMemcpyAsync(outlier, h->d_outlier, W * MO, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaMemcpyAsync(info, h->d_info, W * 16, cudaMemcpyDeviceToHost, s));
+    SB_CUDA(cudaEventRecord(h->done, s));
     h->pending_info = info;
     h->pending_windows = n_windows;
     return SB_OK;
@@ -817,7 +822,7 @@ extern "C" int sb_ba_wait(sb_ba_t *h) {
     const int32_t *info = h->pending_info;
     const size_t W = (size_t)h->pending_windows;
     h->pending_info = nullptr;
-    SB_CUDA(cudaStreamSynchronize(h->stream));
+    SB_CUDA(cudaEventSynchronize(h->done));
     for (size_t w = 0; w < W; w++)
         if (info[4 * w] < 0) {
             sb_set_error("window %zu: %s", w, info[4 * w + 1] == -2 ? "a keyframe observes the same landmark twice" : "counts or indices out of range");

@@ -361,13 +361,14 @@ def main():
     ba_info = bd["info"].cpu().numpy() if with_ba else np.zeros((B, 4), np.int32)
 
     # ---- e2e: the host-pointer C ABI with pinned host buffers (H2D + D2H inside the timed region):
-    #      two sb_stereo handles used alternately (copies of one batch overlap the kernels of the other)
-    #      and sb_ba_solve on pinned host arrays.
+    #      three sb_stereo handles used in turn (copy in, kernels and copy out of consecutive batches overlap)
+    #      and sb_ba_submit / sb_ba_wait on pinned host arrays.
     del ext, exts, mats
     hp = min(P, 4 * B)
     host_pool = torch.from_numpy(pool_np[:hp]).pin_memory()
     host_np = host_pool.numpy()
-    fes = [pkg.StereoFrontend(*ORB_PARAMS, max_w=W, max_h=H, max_pairs=B, device=local_rank) for _ in range(2)]
+    NE = 3   # front-end handles in flight: copy in, kernels and copy out of consecutive batches overlap
+    fes = [pkg.StereoFrontend(*ORB_PARAMS, max_w=W, max_h=H, max_pairs=B, device=local_rank) for _ in range(NE)]
     outs = [fe.alloc_outputs(B, pinned=True) for fe in fes]
     # two back-end handles on ONE stream, used alternately: a batch of windows is submitted without waiting for the
     # previous one (the stream keeps them in order; nothing idles while the host collects and refills the other buffers)
@@ -408,19 +409,20 @@ def main():
     def run_host(nsteps):
         # the reference's threading: the front end (extract + match) and the back end (local BA) run side by side;
         # here both are asynchronous submissions from one host thread, collected one step later
-        pending = [False, False]
+        pending = [False] * NE
         for i in range(nsteps):
-            k = i % 2
+            k = i % NE
+            if with_ba:
+                ba_submit(i % 2)   # first: its 4 MB of copies must not queue behind the 60 MB of frames on the copy engine
             if pending[k]:
                 fes[k].wait()
             off = (i * B) % hp
             fes[k].submit(host_np[off:off + B], outs[k])
             pending[k] = True
-            if with_ba:
-                ba_submit(k)
-        for k in range(2):
+        for k in range(NE):
             if pending[k]:
                 fes[k].wait()
+        for k in range(2):
             ba_wait(k)
 
     run_host(4)
@@ -547,7 +549,7 @@ def main():
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_ms_max / args.steps,
-                       "api": "sb_stereo_submit/wait and sb_ba_submit/wait, two handles each used alternately (host pointers, pinned)"},
+                       "api": "sb_stereo_submit/wait on three handles and sb_ba_submit/wait on two, used in turn (host pointers, pinned)"},
                "gpu_launches": int(sum(stage_launches.values())),
                "roofline": roofline,
                "loop_closing_extras": extras}
