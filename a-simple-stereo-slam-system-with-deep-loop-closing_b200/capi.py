@@ -321,6 +321,28 @@ class LocalBA:
                         info[k].copy()))
         return out
 
+    def submit(self, windows, K, ext7=(0, 0, 0, 1, 0, 0, 0), huber_delta=5.991, chi2_th=5.991, outer_max=5, inner_iters=10):
+        """sb_ba_submit: enqueue the batch and return; wait() collects it (same result as solve)."""
+        b = self.pack(windows)
+        n = len(windows)
+        st = dict(b=b, n=n, K=np.ascontiguousarray(K, np.float64), ext=np.ascontiguousarray(ext7, np.float64),
+                  chi2=np.zeros((n, self.MO)), outl=np.zeros((n, self.MO), np.uint8), info=np.zeros((n, 4), np.int32))
+        _check(lib().sb_ba_submit(self._h, n, _p(b["np"]), _p(b["nl"]), _p(b["ne"]), _p(b["poses"]), _p(b["points"]),
+                                  _p(b["fixed"]), _p(b["op"]), _p(b["ol"]), _p(b["uv"]), _p(st["K"]), _p(st["ext"]),
+                                  C.c_double(huber_delta), C.c_double(chi2_th), outer_max, inner_iters, _p(st["chi2"]),
+                                  _p(st["outl"]), _p(st["info"])))
+        self._inflight = st   # keeps the host arrays alive until wait()
+
+    def wait(self):
+        st, self._inflight = self._inflight, None
+        _check(lib().sb_ba_wait(self._h))
+        b, out = st["b"], []
+        for k in range(st["n"]):
+            p, l, e = b["np"][k], b["nl"][k], b["ne"][k]
+            out.append((b["poses"][k, :p].copy(), b["points"][k, :l].copy(), st["chi2"][k, :e].copy(), st["outl"][k, :e].copy(),
+                        st["info"][k].copy()))
+        return out
+
     def solve_dev(self, n, d, K, ext7=(0, 0, 0, 1, 0, 0, 0), huber_delta=5.991, chi2_th=5.991, outer_max=5,
                   inner_iters=10):
         """d: dict of device tensors with the keys of pack() plus chi2, outlier, info."""

@@ -290,9 +290,45 @@ public:
         p.outlier.assign(outl.begin(), outl.begin() + ne);
         return true;
     }
+    // The asynchronous halves (the reference's Backend is its own thread, src/backend.cpp:29-45): Submit enqueues the window and
+    // returns, Wait blocks until it is solved and writes the results back into the problem given to Submit, which must stay alive.
+    bool Submit(LocalBAProblem &p, double huber_delta = 5.991, double chi2_th = 5.991, int outer_max = 5, int inner_iters = 10) {
+        const int32_t np = (int32_t)(p.poses.size() / 7), nl = (int32_t)(p.points.size() / 3), ne = (int32_t)p.obs_pose.size();
+        if (np > mp_ || nl > ml_ || ne > mo_ || pending_) { detail::last_status() = pending_ ? SB_ERR_INVALID : SB_ERR_CAPACITY; return false; }
+        np_ = np; nl_ = nl; ne_ = ne;
+        poses_.assign((size_t)mp_ * 7, 0.0); points_.assign((size_t)ml_ * 3, 0.0); uv_.assign((size_t)mo_ * 2, 0.0); chi2_.assign((size_t)mo_, 0.0);
+        fixed_.assign((size_t)ml_, 0); outl_.assign((size_t)mo_, 0); op_.assign((size_t)mo_, 0); ol_.assign((size_t)mo_, 0);
+        std::copy(p.poses.begin(), p.poses.end(), poses_.begin());
+        std::copy(p.points.begin(), p.points.end(), points_.begin());
+        std::copy(p.fixed.begin(), p.fixed.end(), fixed_.begin());
+        std::copy(p.obs_pose.begin(), p.obs_pose.end(), op_.begin());
+        std::copy(p.obs_point.begin(), p.obs_point.end(), ol_.begin());
+        std::copy(p.uv.begin(), p.uv.end(), uv_.begin());
+        detail::last_status() = sb_ba_submit(h_, 1, &np_, &nl_, &ne_, poses_.data(), points_.data(), fixed_.data(), op_.data(), ol_.data(), uv_.data(),
+                                             p.K, p.cam_ext, huber_delta, chi2_th, outer_max, inner_iters, chi2_.data(), outl_.data(), p.info);
+        pending_ = detail::last_status() == SB_OK ? &p : nullptr;
+        return pending_ != nullptr;
+    }
+    bool Wait() {
+        if (!pending_) { detail::last_status() = SB_ERR_INVALID; return false; }
+        LocalBAProblem &p = *pending_;
+        pending_ = nullptr;
+        detail::last_status() = sb_ba_wait(h_);
+        if (detail::last_status() != SB_OK) return false;
+        std::copy(poses_.begin(), poses_.begin() + (size_t)np_ * 7, p.poses.begin());
+        std::copy(points_.begin(), points_.begin() + (size_t)nl_ * 3, p.points.begin());
+        p.chi2.assign(chi2_.begin(), chi2_.begin() + ne_);
+        p.outlier.assign(outl_.begin(), outl_.begin() + ne_);
+        return true;
+    }
 private:
     sb_ba_t *h_ = nullptr;
     int mp_, ml_, mo_;
+    LocalBAProblem *pending_ = nullptr;
+    int32_t np_ = 0, nl_ = 0, ne_ = 0;
+    std::vector<double> poses_, points_, uv_, chi2_;
+    std::vector<uint8_t> fixed_, outl_;
+    std::vector<int32_t> op_, ol_;
 };
 
 // -----------------------------------------------------------------------------------------------------

@@ -88,3 +88,17 @@ def test_bad_input_is_reported(pkg, ba, synth):
     w["uv"] = np.concatenate([w["uv"], w["uv"][:1]])
     with pytest.raises(pkg.SlamB200Error):
         ba.solve([w], synth.KITTI_K)
+
+
+def test_submit_wait_equals_solve(pkg, ba, synth):
+    """sb_ba_submit / sb_ba_wait (the asynchronous back end) give bit-identical results to sb_ba_solve; a second submit
+    before the wait is refused."""
+    windows = [synth.ba_window(s, n_points=120) for s in (50, 51)]
+    want = ba.solve(windows, synth.KITTI_K)
+    ba.submit(windows, synth.KITTI_K)
+    with pytest.raises(pkg.SlamB200Error):
+        ba.submit(windows, synth.KITTI_K)
+    got = ba.wait()
+    for g, w in zip(got, want):
+        for a, b in zip(g, w):
+            assert np.array_equal(a, b)
