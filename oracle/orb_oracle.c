@@ -5,13 +5,16 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library, and only as the checker / the CPU baseline.
  *
- * Parity status: the reference ships no tests or golden vectors for this path and
- * cannot be compiled here (OpenCV/g2o absent) — "parity unpinned by the reference".
- * The pins are (a) the OpenCV primitives restated below are each checked bit-exactly
- * against the in-container cv2 4.13.0 (tests/test_oracle_cv2.py), and (b) the
- * extractor logic follows /root/reference/src/ORBextractor.cpp statement by
- * statement; every function cites the lines it restates (paths relative to
- * /root/reference).
+ * Parity status: PINNED TO THE REFERENCE'S OWN SOURCE for everything the reference itself implements
+ * (ORBextractor: tables, pyramid driver, grid FAST driver + fallback + mask quirk, quadtree, IC_Angle, rBRIEF,
+ * DetectAndCompute / Detect / DetectWithPyramid / ScreenAndComputeKPsParams / CalcDescriptors):
+ * oracle/_ref/libmyslam_orb_ref.so is /root/reference/src/ORBextractor.cpp compiled unmodified (oracle/Makefile
+ * `ref`) and tests/test_ref_pin.py holds this file to it bit for bit — all 200 golden frames, every operator,
+ * and, for the one undefined spot (heap-address tie-break at :731), under the addresses of a real glibc run.
+ * The OpenCV primitives the reference calls (resize, GaussianBlur, FAST, fastAtan2, BFMatcher) are un-vendored
+ * third party; they are restated below from the published algorithms and each is pinned bit-exactly against the
+ * in-container cv2 4.13.0 (tests/test_oracle_cv2.py).  Every function cites the lines it restates (paths
+ * relative to /root/reference).
  *
  * Plain C99, no dependencies.  Scalar float arithmetic is kept un-contracted
  * (build with -ffp-contract=off) because the reference is compiled for baseline
@@ -406,6 +409,7 @@ typedef struct {
     int nkeys;
     int no_more;
     int prev, next; /* list links, -1 = none */
+    uint64_t tie;   /* what stands in for the node's heap address in the (size, pointer) sort at :731 */
 } qnode;
 
 typedef struct {
@@ -413,6 +417,22 @@ typedef struct {
     int npool, cap;
     int head, tail, size;
 } qlist;
+
+/* Test hook: the reference orders equal-size nodes by HEAP ADDRESS (:731).  By default the k-th list node
+ * created gets tie key k ("later-created first").  orc_debug_set_tie_keys(keys, n) replaces that by the
+ * caller's keys — e.g. the addresses a real run of the reference (oracle/_ref, glibc malloc) handed out, in
+ * allocation order — so that tests can show the restatement equals the reference under ANY heap order.
+ * The counter runs on across the per-level calls of one extraction; re-arm before every extraction. */
+static __thread const uint64_t *g_tie_keys = NULL;
+static __thread int g_tie_n = 0;
+static __thread int64_t g_tie_pos = 0;
+void orc_debug_set_tie_keys(const uint64_t *keys, int n) { g_tie_keys = keys; g_tie_n = keys ? n : 0; g_tie_pos = 0; }
+int orc_debug_tie_keys_used(void) { return (int)g_tie_pos; }
+static uint64_t next_tie_key(void) {
+    const int64_t k = g_tie_pos++;
+    if (g_tie_keys) return k < g_tie_n ? g_tie_keys[k] : ~(uint64_t)0;
+    return (uint64_t)k;
+}
 
 static int ql_new(qlist *L) {
     if (L->npool == L->cap) {
@@ -423,12 +443,14 @@ static int ql_new(qlist *L) {
     L->pool[L->npool].prev = L->pool[L->npool].next = -1;
     return L->npool++;
 }
-static void ql_push_back(qlist *L, int id) {
+static void ql_push_back(qlist *L, int id) { /* std::list::push_back: one heap node */
+    L->pool[id].tie = next_tie_key();
     L->pool[id].prev = L->tail; L->pool[id].next = -1;
     if (L->tail >= 0) L->pool[L->tail].next = id; else L->head = id;
     L->tail = id; L->size++;
 }
-static void ql_push_front(qlist *L, int id) {
+static void ql_push_front(qlist *L, int id) { /* std::list::push_front: one heap node */
+    L->pool[id].tie = next_tie_key();
     L->pool[id].next = L->head; L->pool[id].prev = -1;
     if (L->head >= 0) L->pool[L->head].prev = id; else L->tail = id;
     L->head = id; L->size++;
@@ -464,11 +486,11 @@ static void divide_node(qlist *L, int id, const float *kx, const float *ky, int 
         if (L->pool[child[c]].nkeys == 1) L->pool[child[c]].no_more = 1;
 }
 
-typedef struct { int size, id; } size_id;
+typedef struct { int size, id; uint64_t tie; } size_id;
 static int cmp_size_id(const void *a, const void *b) {
     const size_id *x = (const size_id *)a, *y = (const size_id *)b;
     if (x->size != y->size) return x->size < y->size ? -1 : 1;
-    return x->id < y->id ? -1 : (x->id > y->id ? 1 : 0);
+    return x->tie < y->tie ? -1 : (x->tie > y->tie ? 1 : 0);
 }
 
 /* kx, ky, kr: candidate coordinates (border-relative) and responses, n of them.
@@ -477,7 +499,11 @@ static int distribute_octtree(const float *kx, const float *ky, const float *kr,
                               int maxY, int N, int *out_idx) {
     /* :590-592 */
     const int nIni = (int)roundf((float)(maxX - minX) / (maxY - minY));
-    if (nIni < 1 || n == 0) return 0; /* the reference would index an empty vector / divide by 0 */
+    if (nIni < 1) return 0; /* the reference would divide by 0 / index an empty vector */
+    if (n == 0) { /* the reference still allocates its nIni root nodes (:599-610) and erases them (:628-629) */
+        for (int i = 0; i < nIni; i++) (void)next_tie_key();
+        return 0;
+    }
     const float hX = (float)(maxX - minX) / nIni;
     qlist L; memset(&L, 0, sizeof(L)); L.head = L.tail = -1;
     int *ini = (int *)malloc(sizeof(int) * (size_t)nIni);
@@ -519,7 +545,7 @@ static int distribute_octtree(const float *kx, const float *ky, const float *kr,
                     if (L.pool[child[c]].nkeys > 1) {
                         nToExpand++;
                         if (nvsz == capvsz) { capvsz = capvsz ? capvsz * 2 : 256; vsz = (size_id *)realloc(vsz, sizeof(size_id) * (size_t)capvsz); }
-                        vsz[nvsz].size = L.pool[child[c]].nkeys; vsz[nvsz].id = child[c]; nvsz++;
+                        vsz[nvsz].size = L.pool[child[c]].nkeys; vsz[nvsz].id = child[c]; vsz[nvsz].tie = L.pool[child[c]].tie; nvsz++;
                     }
                 }
             }
@@ -543,7 +569,7 @@ static int distribute_octtree(const float *kx, const float *ky, const float *kr,
                             ql_push_front(&L, child[c]);
                             if (L.pool[child[c]].nkeys > 1) {
                                 if (nvsz == capvsz) { capvsz = capvsz ? capvsz * 2 : 256; vsz = (size_id *)realloc(vsz, sizeof(size_id) * (size_t)capvsz); }
-                                vsz[nvsz].size = L.pool[child[c]].nkeys; vsz[nvsz].id = child[c]; nvsz++;
+                                vsz[nvsz].size = L.pool[child[c]].nkeys; vsz[nvsz].id = child[c]; vsz[nvsz].tie = L.pool[child[c]].tie; nvsz++;
                             }
                         }
                     }

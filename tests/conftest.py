@@ -30,3 +30,13 @@ def oracle():
     from oracle import oracle as O
     O.build()
     return O
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """oracle/_ref: the reference's own src/ORBextractor.cpp, compiled unmodified (oracle/Makefile `ref`)."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    R.lib()
+    return R

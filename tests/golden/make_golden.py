@@ -1,11 +1,14 @@
 """Generates tests/golden/config1_digests.npz — the committed correctness anchor of BASELINE config 1 — and
 tests/golden/config3_ba.npz (local BA results of four seeded windows).
 
-Config 1 is "KITTI-00 first 200 frames through the CPU reference path".  KITTI is not available and the reference cannot
-be built here (it needs OpenCV / g2o / Sophus / Caffe), so the anchor is 200 seeded synthetic stereo pairs
-(synth.stereo_pair(seed), seed = frame index) pushed through the CPU restatement in oracle/ (pinned against cv2 4.13.0 by
-tests/test_oracle_cv2.py): per frame the SHA-256 of the keypoint records, of the descriptors and of the left->right match
-result, plus the full arrays of frames 0 and 1.  Run from the repo root:  python tests/golden/make_golden.py
+Config 1 is "KITTI-00 first 200 frames through the CPU reference path".  KITTI is not available, so the anchor is 200 seeded
+synthetic stereo pairs (synth.stereo_pair(seed), seed = frame index).  Keypoints and descriptors come from THE REFERENCE'S
+OWN EXTRACTOR — oracle/_ref, i.e. /root/reference/src/ORBextractor.cpp compiled unmodified (oracle/Makefile `ref`; list nodes
+from the address-monotone arena, see oracle/ref_shim/ref_capi.cpp) — and this script refuses to write unless the restatement
+in oracle/orb_oracle.c gives the same bytes.  The match result comes from the restatement of cv::BFMatcher (OpenCV is
+un-vendored; pinned against cv2 4.13.0 by tests/test_oracle_cv2.py).  Per frame: the SHA-256 of the keypoint records, of the
+descriptors and of the left->right match result, plus the full arrays of frames 0 and 1.  Needs /root/reference (this
+container).  Run from the repo root:  python tests/golden/make_golden.py
 """
 import hashlib
 import importlib
@@ -29,21 +32,26 @@ def digest(*arrays):
     return np.frombuffer(h.digest(), np.uint8)
 
 
-def frame_record(O, synth, seed):
-    ext = O.ORBextractor(*ORB_PARAMS)
+def frame_record(O, R, synth, seed):
+    ext = R.ORBextractor(*ORB_PARAMS)           # the reference source itself
+    chk = O.ORBextractor(*ORB_PARAMS)           # the restatement must agree before anything is written
     left, right = synth.stereo_pair(seed)
     kl, dl = ext.DetectAndCompute(left)
     kr, dr = ext.DetectAndCompute(right)
+    for img, k, d in ((left, kl, dl), (right, kr, dr)):
+        ck, cd = chk.DetectAndCompute(img)
+        assert ck.tobytes() == k.tobytes() and np.array_equal(cd, d), f"frame {seed}: restatement != reference source"
     idx, dist = O.hamming_match(dl, dr)
     return dict(kl=kl, dl=dl, kr=kr, dr=dr, idx=idx, dist=dist)
 
 
 def main():
     synth = importlib.import_module(PKG + ".synth")
-    from oracle import oracle as O
+    from oracle import oracle as O, ref as R
     O.build()
+    R.lib()
     with ThreadPoolExecutor(os.cpu_count() or 1) as pool:
-        recs = list(pool.map(lambda s: frame_record(O, synth, s), range(N_FRAMES)))
+        recs = list(pool.map(lambda s: frame_record(O, R, synth, s), range(N_FRAMES)))
     out = {
         "orb_params": np.array(ORB_PARAMS, np.float64),
         "counts": np.array([[len(r["kl"]), len(r["kr"])] for r in recs], np.int32),
