@@ -26,7 +26,9 @@ struct sb_lcd {
     int max_queries;
     int64_t *h_ids;              // keyframe id of every row, ascending (std::map order of _mvDatabase)
     float *h_scores;             // pinned
+    float *d_stage;              // bulk-load staging, LCD_STAGE_ROWS x 1064 fp32, allocated by the first sb_lcd_add_batch
 };
+#define LCD_STAGE_ROWS 256
 
 // scores[q][r] = <query q, row r>, fp32 accumulate.  grid = (ceil(n / LCD_WARPS), nq)
 template <bool HALF>
@@ -69,7 +71,10 @@ __global__ void __launch_bounds__(LCD_WARPS * 32) k_lcd_score(const void *__rest
     if (lane == 0) scores[(size_t)blockIdx.y * score_stride + r] = acc;
 }
 
-__global__ void k_lcd_store_row(void *db, int row, const float *src, int half) {
+// one CTA per row: database row (row0 + blockIdx.x) <- src[blockIdx.x][1064] (fp32 -> fp16 with zero padding, or fp32 copy)
+__global__ void k_lcd_store_row(void *db, int row0, const float *src_rows, int half) {
+    const int row = row0 + blockIdx.x;
+    const float *src = src_rows + (size_t)blockIdx.x * LCD_DIM;
     for (int i = threadIdx.x; i < LCD_PAD; i += blockDim.x) {
         if (half)
             reinterpret_cast<__half *>(db)[(size_t)row * LCD_PAD + i] = __float2half_rn(i < LCD_DIM ? src[i] : 0.f);
@@ -84,6 +89,7 @@ static void free_lcd(sb_lcd *h) {
     if (h->d_db) cudaFree(h->d_db);
     if (h->d_query) cudaFree(h->d_query);
     if (h->d_scores) cudaFree(h->d_scores);
+    if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_scores) cudaFreeHost(h->h_scores);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     free(h->h_ids);
@@ -154,9 +160,31 @@ extern "C" int sb_lcd_add(sb_lcd_t *h, int64_t kf_id, const float *descr) {
     return SB_OK;
 }
 
-// Bulk load (replay): rows [n][1064] fp32, ids ascending.
+// Bulk load (replay): rows [n][1064] fp32, ids ascending.  fp32 database: the rows are copied straight into place
+// (same layout), no launch.  fp16 database: one host->device copy and one launch per chunk of LCD_STAGE_ROWS rows.
+// Nothing is added when any argument is rejected.
 extern "C" int sb_lcd_add_batch(sb_lcd_t *h, int n, const int64_t *kf_ids, const float *descr) {
-    for (int i = 0; i < n; i++) SB_TRY(sb_lcd_add(h, kf_ids[i], descr + (size_t)i * LCD_DIM));
+    sb_clear_error();
+    SB_REQUIRE(h && (n == 0 || (kf_ids && descr)), "null pointer");
+    SB_REQUIRE(n >= 0 && h->n + n <= h->capacity, "database full");
+    for (int i = 0; i < n; i++)
+        SB_REQUIRE(i ? kf_ids[i] > kf_ids[i - 1] : (h->n == 0 || kf_ids[0] > h->h_ids[h->n - 1]),
+                   "keyframe ids must be added in ascending order");
+    SB_TRY(sb_use_device(h->device));
+    if (h->dtype == SB_LCD_FP32) {
+        if (n) SB_CUDA(cudaMemcpyAsync((float *)h->d_db + (size_t)h->n * LCD_DIM, descr, (size_t)n * LCD_DIM * 4, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        if (!h->d_stage && n) SB_CUDA(cudaMalloc((void **)&h->d_stage, (size_t)LCD_STAGE_ROWS * LCD_DIM * 4));
+        for (int i0 = 0; i0 < n; i0 += LCD_STAGE_ROWS) {
+            const int m = n - i0 < LCD_STAGE_ROWS ? n - i0 : LCD_STAGE_ROWS;
+            SB_CUDA(cudaMemcpyAsync(h->d_stage, descr + (size_t)i0 * LCD_DIM, (size_t)m * LCD_DIM * 4, cudaMemcpyHostToDevice, h->stream));
+            k_lcd_store_row<<<m, 256, 0, h->stream>>>(h->d_db, h->n + i0, h->d_stage, 1);
+            SB_CUDA(cudaGetLastError());
+        }
+    }
+    SB_CUDA(cudaStreamSynchronize(h->stream));  // descr may be reused by the caller
+    for (int i = 0; i < n; i++) h->h_ids[h->n + i] = kf_ids[i];
+    h->n += n;
     return SB_OK;
 }
 

@@ -399,6 +399,32 @@ int sb_pnp_ransac_dev(sb_pnp_t *h, int n_problems, const int32_t *d_n_points, co
                       int max_points, const double *K, int iterations, double reproj_err, uint64_t seed, double *d_pose7,
                       double *d_rvec_tvec, uint8_t *d_inlier, int32_t *d_info);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange step (BASELINE config 5).  The per-frame path shards by frame /
+ * window with no collective; the one exchange is an all-gather of the keyframe poses every rank owns
+ * before LoopClosing::PoseGraphOptimization (src/loopclosing.cpp:537-646), which reads the pose of
+ * EVERY keyframe (:547-566).  The reference is single-process, so there is no reference signature:
+ * these follow SURVEY.md 8b.  One ncclAllGather on the CALLER's communicator and stream; each rank
+ * contributes a fixed-size record ([cap][7] doubles + its count), so no second collective.
+ * NCCL is bound at run time from the caller's process (no link-time dependency; SB_ERR_CUDA with
+ * the loader's text when absent).
+ *   nccl_comm  ncclComm_t of the caller          stream  cudaStream_t (NULL = default stream)
+ *   local      [cap][7] poses (qx,qy,qz,qw,tx,ty,tz), first n_local rows valid
+ *   all        [world][cap][7]; counts [world]   (keyframe k of a round-robin shard = all[k % world][k / world])
+ * sb_allgather_kf_poses: HOST pointers, stages through the communicator's device, synchronises.
+ * sb_allgather_kf_poses_dev: DEVICE pointers, enqueue only; d_scratch = (1 + world) * (cap * 7 + 1) doubles.
+ * ------------------------------------------------------------------------------------------------ */
+int sb_allgather_kf_poses(void *nccl_comm, void *stream, const double *local, int n_local, double *all, int *counts,
+                          int cap);
+int sb_allgather_kf_poses_dev(void *nccl_comm, void *stream, const double *d_local, int n_local, double *d_all,
+                              int32_t *d_counts, int cap, double *d_scratch);
+/* Bootstrap for a host without a communicator: rank 0 makes the 128-byte id and ships it to the others over its
+ * own channel; every rank calls sb_nccl_comm_init (ncclCommInitRank) on its device. */
+int sb_nccl_version(int *version);
+int sb_nccl_unique_id(uint8_t id128[128]);
+int sb_nccl_comm_init(void **nccl_comm, int device, int world, int rank, const uint8_t id128[128]);
+int sb_nccl_comm_destroy(void *nccl_comm);
+
 #ifdef __cplusplus
 }
 #endif
