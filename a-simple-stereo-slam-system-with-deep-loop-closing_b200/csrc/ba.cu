@@ -21,6 +21,9 @@
 #include "se3.cuh"
 
 #define BA_THREADS 256
+#ifndef BA_MIN_BLOCKS
+#define BA_MIN_BLOCKS 1   // CTAs per SM the register budget is held to (launch bounds)
+#endif
 #define BA_MAX_POSES 16
 #ifdef BA_PROFILE
 __device__ long long g_ba_prof[16];
@@ -191,7 +194,7 @@ static __device__ double compute_errors(const EdgeCtx &c, int ne, double *err, d
     return block_sum(chi, red);
 }
 
-__global__ void __launch_bounds__(BA_THREADS) k_ba_solve(const __grid_constant__ BaArgs a) {
+__global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __grid_constant__ BaArgs a) {
     extern __shared__ __align__(16) double sm[];
     const int w = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

@@ -17,13 +17,14 @@ def _blur3(img):
     return k[0] * t[:-2] + k[1] * t[1:-1] + k[2] * t[2:]
 
 
-def stereo_pair(seed, w=KITTI_W, h=KITTI_H, n_rect=1500, noise=4, grid=(3, 8)):
+def stereo_pair(seed, w=KITTI_W, h=KITTI_H, n_rect=1500, noise=4, grid=(3, 8), noise_seed=None):
     """Left/right u8 images of one synthetic stereo frame.
 
     Left: mid-grey canvas + `n_rect` filled random rectangles (w 4-60, h 4-40, grey 0-255) + 3x3
     Gaussian (sigma 0.8).  Depth is piecewise planar: a `grid` of fronto-parallel planes with
     z in [5, 80] m; the right view samples the left one at x + round(bf / z) inside each plane.
-    Independent uniform noise of +-`noise` is then added to both views.
+    Independent uniform noise of +-`noise` is then added to both views.  `noise_seed` (replay: a place seen again)
+    draws that noise from its own generator: same scene, different sensor noise.
     """
     rng = np.random.default_rng(seed)
     canvas = np.full((h, w), 128, np.float32)
@@ -42,6 +43,8 @@ def stereo_pair(seed, w=KITTI_W, h=KITTI_H, n_rect=1500, noise=4, grid=(3, 8)):
     src_x = np.clip(np.arange(w)[None, :] + disp[ys][:, xs], 0, w - 1)
     right_clean = np.take_along_axis(clean, src_x, axis=1)
     out = []
+    if noise_seed is not None:
+        rng = np.random.default_rng(noise_seed)
     for img in (clean, right_clean):
         img = img + rng.integers(-noise, noise + 1, (h, w)).astype(np.float32)
         out.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
@@ -230,6 +233,15 @@ def pose_graph(seed=0, n=742, n_loops=17, n_active=7, odo_noise=(0.0005, 0.02), 
     poses0[fixed == 1] = poses_gt[fixed == 1]
     return {"poses0": poses0, "poses_gt": poses_gt, "fixed": fixed, "v0": np.array(v0, np.int32),
             "v1": np.array(v1, np.int32), "meas": np.array(meas), "loops": loops}
+
+
+def scene_depth(seed, grid=(3, 8)):
+    """The plane depths z [grid] of stereo_pair(seed) (same generator, same draw order)."""
+    rng = np.random.default_rng(seed)
+    n_rect = 1500
+    for _ in range(5):
+        rng.integers(0, 2, n_rect)   # rw, rh, x0, y0, g: five draws of n_rect integers precede the depths
+    return rng.uniform(5.0, 80.0, grid)
 
 
 def _quat_to_R_np(q):
