@@ -333,11 +333,14 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                     g[2] += -wgt * (B[2] * r[0] + B[5] * r[1]);
                     H[0] += wgt * (B[0] * B[0] + B[3] * B[3]); H[1] += wgt * (B[0] * B[1] + B[3] * B[4]); H[2] += wgt * (B[0] * B[2] + B[3] * B[5]);
                     H[3] += wgt * (B[1] * B[1] + B[4] * B[4]); H[4] += wgt * (B[1] * B[2] + B[4] * B[5]); H[5] += wgt * (B[2] * B[2] + B[5] * B[5]);
-                    double *P = hpl + 18 * e;  // Hpl block of this edge: w A^T B (6x3)
+                    double2 *P = reinterpret_cast<double2 *>(hpl + 18 * e);  // Hpl block of this edge: w A^T B (6x3), 9 double2 stores
+                    double hv[18];
 #pragma unroll
                     for (int p = 0; p < 6; p++)
 #pragma unroll
-                        for (int q = 0; q < 3; q++) P[3 * p + q] = wgt * (A[p] * B[q] + A[6 + p] * B[3 + q]);
+                        for (int q = 0; q < 3; q++) hv[3 * p + q] = wgt * (A[p] * B[q] + A[6 + p] * B[3 + q]);
+#pragma unroll
+                    for (int k = 0; k < 9; k++) P[k] = make_double2(hv[2 * k], hv[2 * k + 1]);
                 }
                 double *L = lm + 18 * j;
 #pragma unroll
@@ -382,14 +385,15 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                         if (fixed[j]) continue;
                         const double *L = lm + 18 * j;
                         const double D0 = L[9], D1 = L[10], D2 = L[11], D4 = L[12], D5 = L[13], D8 = L[14];
-                        const double *P = hpl + 18 * e;
-                        double *Y = ybd + 18 * e;
+                        const double2 *P = reinterpret_cast<const double2 *>(hpl + 18 * e);
+                        double2 *Y = reinterpret_cast<double2 *>(ybd + 18 * e);
 #pragma unroll
-                        for (int p = 0; p < 6; p++) {
-                            const double h0 = P[3 * p], h1 = P[3 * p + 1], h2 = P[3 * p + 2];
-                            Y[3 * p] = h0 * D0 + h1 * D1 + h2 * D2;
-                            Y[3 * p + 1] = h0 * D1 + h1 * D4 + h2 * D5;
-                            Y[3 * p + 2] = h0 * D2 + h1 * D5 + h2 * D8;
+                        for (int m = 0; m < 3; m++) {   // two block rows per three double2
+                            const double2 a2 = P[3 * m], b2 = P[3 * m + 1], c2 = P[3 * m + 2];
+                            const double h0 = a2.x, h1 = a2.y, h2 = b2.x, k0 = b2.y, k1 = c2.x, k2 = c2.y;
+                            Y[3 * m] = make_double2(h0 * D0 + h1 * D1 + h2 * D2, h0 * D1 + h1 * D4 + h2 * D5);
+                            Y[3 * m + 1] = make_double2(h0 * D2 + h1 * D5 + h2 * D8, k0 * D0 + k1 * D1 + k2 * D2);
+                            Y[3 * m + 2] = make_double2(k0 * D1 + k1 * D4 + k2 * D5, k0 * D2 + k1 * D5 + k2 * D8);
                         }
                     }
                 __syncthreads();
@@ -410,15 +414,19 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                     for (int k = 0; k < 6; k++) gb[k] = 0;
                     for (int t = lane; t < cnt; t += 32) {
                         const int2 ee = pl[t];
-                        const double *Y = ybd + 18 * ee.x, *P2 = hpl + 18 * ee.y;
+                        // the 18-double blocks are 144 bytes apart: 16-byte aligned, read as 9 double2 each (half the load instructions)
+                        const double2 *Y = reinterpret_cast<const double2 *>(ybd + 18 * ee.x), *P2 = reinterpret_cast<const double2 *>(hpl + 18 * ee.y);
                         double BD[18];
 #pragma unroll
-                        for (int k = 0; k < 18; k++) BD[k] = Y[k];
+                        for (int k = 0; k < 9; k++) { const double2 t = Y[k]; BD[2 * k] = t.x; BD[2 * k + 1] = t.y; }
 #pragma unroll
-                        for (int q = 0; q < 6; q++) {
-                            const double g0 = P2[3 * q], g1 = P2[3 * q + 1], g2 = P2[3 * q + 2];
+                        for (int m = 0; m < 3; m++) {   // block rows 2m and 2m + 1 of Hpl(i2, j)
+                            const double2 ga = P2[3 * m], gb2 = P2[3 * m + 1], gc = P2[3 * m + 2];
 #pragma unroll
-                            for (int p = 0; p < 6; p++) acc[6 * p + q] += BD[3 * p] * g0 + BD[3 * p + 1] * g1 + BD[3 * p + 2] * g2;
+                            for (int p = 0; p < 6; p++) {
+                                acc[6 * p + 2 * m] += BD[3 * p] * ga.x + BD[3 * p + 1] * ga.y + BD[3 * p + 2] * gb2.x;
+                                acc[6 * p + 2 * m + 1] += BD[3 * p] * gb2.y + BD[3 * p + 1] * gc.x + BD[3 * p + 2] * gc.y;
+                            }
                         }
                         if (i1 == i2) {  // b_schur(i1) -= Hpl(i1, j) Dinv_j bl_j
                             const double *L = lm + 18 * ol[ee.x];
@@ -580,11 +588,13 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                         for (int i = 0; i < np; i++) {
                             const int e = edge_of[j * MP + i];
                             if (e < 0) continue;
-                            const double *P = hpl + 18 * e;  // v -= Hpl(i, j)^T xs_i
+                            const double2 *P = reinterpret_cast<const double2 *>(hpl + 18 * e);  // v -= Hpl(i, j)^T xs_i
 #pragma unroll
-                            for (int p = 0; p < 6; p++) {
-                                const double xp = xs[6 * i + p];
-                                v[0] -= P[3 * p] * xp; v[1] -= P[3 * p + 1] * xp; v[2] -= P[3 * p + 2] * xp;
+                            for (int m = 0; m < 3; m++) {
+                                const double2 a2 = P[3 * m], b2 = P[3 * m + 1], c2 = P[3 * m + 2];
+                                const double xa = xs[6 * i + 2 * m], xb = xs[6 * i + 2 * m + 1];
+                                v[0] -= a2.x * xa; v[1] -= a2.y * xa; v[2] -= b2.x * xa;
+                                v[0] -= b2.y * xb; v[1] -= c2.x * xb; v[2] -= c2.y * xb;
                             }
                         }
                         const double x0 = L[9] * v[0] + L[10] * v[1] + L[11] * v[2];
