@@ -202,7 +202,7 @@ class KittiSequence(Sequence):
 # ---------------------------------------------------------------------------------------------------------------------
 class GpuOps:
     def __init__(self, device=0, batch=64, kf_features=300, kf_batch=32, n_kf=742, lcd_dtype=0, pin=True):
-        self.device, self.batch, self.kf_batch = device, batch, kf_batch
+        self.device, self.batch, self.kf_batch, self._lcd_dtype = device, batch, kf_batch, lcd_dtype
         self.fe = [capi.StereoFrontend(*ORB_PARAMS, max_pairs=batch, device=device) for _ in range(2)]
         self.fe_out = [f.alloc_outputs(batch, pinned=pin) for f in self.fe]
         self.ba = capi.LocalBA(max_windows=batch, max_poses=7, max_points=320, max_obs=2304, device=device)
@@ -214,6 +214,12 @@ class GpuOps:
         self.pnp = capi.PnPRansac(max_problems=1, max_points=4096, device=device)
         self.refine = capi.PoseOnlyOptimizer(max_frames=1, max_obs=4096, device=device)
         self.pg = capi.PoseGraph(max(n_kf, 64) + 8, 2 * max(n_kf, 64) + 64, device=device)
+
+    def reset(self):
+        """Empty the keyframe database (a new sequence on the same handles)."""
+        cap, dt, dev = self.lcd.capacity, self._lcd_dtype, self.device
+        self.lcd.close()
+        self.lcd = capi.DeepLCDScorer(capacity=cap, dtype=dt, device=dev)
 
     # per-frame stage ------------------------------------------------------------------------------------------------
     def stereo_submit(self, slot, images):

@@ -42,11 +42,58 @@ BA_CAPS = dict(max_poses=7, max_points=320, max_obs=2304)
 CALC_MACS = 64 * 62 * 82 * 25 + 128 * 32 * 42 * 1024 + 4 * 14 * 19 * 1152   # multiply-adds of the three convolutions per image
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of 128 images (64 stereo pairs), from the committed
-# `ncu --set full` capture of this same command (profiles/): traffic ~ algorithmic bytes => no wasted re-reads
-NCU_SOURCE = "profiles/r1_ncu_full_final.csv (ncu --set full, one launch of 128 images)"
-NCU_DRAM_BYTES_PER_LAUNCH = {"fast_cells": 188.2e6, "gauss_blur": 356.9e6, "describe": 381.1e6, "copy_level0": 79.5e6,
-                             "quadtree": 8.5e6, "hamming_match": 78.2e6, "resize_pyramid": 212.5e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch come from the committed raw page of the `ncu --set full` capture of
+# this same command (profiles/r<round>_ncu_full*.csv, newest round first) — never from numbers typed into this file.
+KERNEL_STAGE = {"k_copy_level0": "copy_level0", "k_resize_quads": "resize_pyramid", "k_resize": "resize_pyramid",
+                "k_pyr_levels": "resize_pyramid", "k_fast_cells": "fast_cells", "k_quadtree": "quadtree", "k_blur": "gauss_blur",
+                "k_describe": "describe", "k_orient": "describe", "k_brief": "describe", "k_expand": "hamming_match",
+                "k_hamming_umma": "hamming_match", "k_hamming_decode": "hamming_match", "k_ba_solve": "local_ba"}
+_UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def ncu_traffic():
+    """-> ({stage: DRAM bytes of one step's launches of that stage}, {stage: {metric: value}}, source path) or ({}, {}, None)."""
+    import csv
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full*.csv")),
+                   key=lambda f: (int(re.search(r"r(\d+)_", os.path.basename(f)).group(1)), os.path.getmtime(f)))
+    if not files:
+        return {}, {}, None
+    rows = list(csv.reader(open(files[-1])))
+    head, units = rows[0], rows[1]
+    col = {c: i for i, c in enumerate(head)}
+    need = ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum")
+    if any(c not in col for c in need):
+        return {}, {}, None
+    traffic, extra, seen = {}, {}, {}
+    for r in rows[2:]:
+        if len(r) <= col["dram__bytes_write.sum"]:
+            continue
+        name = r[col["Kernel Name"]].replace("void ", "").split("(")[0].split("<")[0]
+        stage = KERNEL_STAGE.get(name)
+        if stage is None:
+            continue
+        # one step of the capture = the first launch of every distinct (kernel, grid) pair; repeated steps are not added up
+        key = (name, r[col["Grid Size"]] if "Grid Size" in col else "")
+        if key in seen and name not in ("k_expand",):
+            continue
+        if name == "k_expand" and seen.get(key, 0) >= 2:
+            continue
+        seen[key] = seen.get(key, 0) + 1
+        b = sum(float(r[col[c]]) * _UNIT.get(units[col[c]], 1.0) for c in need[1:])
+        traffic[stage] = traffic.get(stage, 0.0) + b
+        m = extra.setdefault(stage, {})
+        for c, k in (("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+                     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
+                     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
+                     ("launch__registers_per_thread", "registers")):
+            if c in col and r[col[c]] not in ("", "n/a"):
+                try:
+                    m[k] = max(m.get(k, 0.0), float(r[col[c]]))
+                except ValueError:
+                    pass
+    return traffic, extra, os.path.relpath(files[-1], ROOT)
 
 
 def pyramid_bytes():
@@ -137,15 +184,27 @@ class CpuReference:
     def __init__(self, cores):
         from concurrent.futures import ThreadPoolExecutor
         from oracle import oracle as O
+        from oracle import ref as R
         O.build()
         self.O, self.cores = O, cores
+        # the extractor is the reference's OWN source when oracle/_ref is there (src/ORBextractor.cpp compiled unmodified; its
+        # OpenCV calls land in the same C primitives the port uses), else the restatement
+        self.R = None
+        try:
+            if R.available():
+                R.lib()
+                self.R = R
+        except Exception:
+            self.R = None
+        self.kind = ("reference (src/ORBextractor.cpp compiled unmodified, oracle/_ref) + port (OpenCV primitives, BFMatcher and the "
+                     "g2o LM/Schur BA restated in C)") if self.R else "port"
         self.local = threading.local()
         self.pool = ThreadPoolExecutor(cores)
 
     def _one(self, job):
         pair, win = job
         if not hasattr(self.local, "ext"):
-            self.local.ext = self.O.ORBextractor(*ORB_PARAMS)
+            self.local.ext = (self.R or self.O).ORBextractor(*ORB_PARAMS)
         _, dl = self.local.ext.DetectAndCompute(pair[0])
         _, dr = self.local.ext.DetectAndCompute(pair[1])
         idx, _ = self.O.hamming_match(dl, dr)
@@ -161,10 +220,75 @@ class CpuReference:
         return time.perf_counter() - t0
 
 
+class Cv2Primitives:
+    """the OpenCV primitives of the extract + match path through the in-container cv2 4.13.0 (SIMD / IPP
+    builds of what the reference links): the chained cv::resize pyramid, one cv::FAST call per 30-px grid cell per level
+    (src/ORBextractor.cpp:838-865, with the 20 -> 7 fallback), GaussianBlur 7x7 sigma 2 per level, BFMatcher(HAMMING).match.
+    The reference's own C++ around them (quadtree, orientation, rBRIEF sampling) is NOT included, so this is a LOWER bound on
+    the reference's CPU time per frame.  Each primitive is bit-compared with the port by tests/test_oracle_cv2.py."""
+
+    def __init__(self, sizes, desc_pair):
+        import cv2
+        self.cv2, self.sizes, self.desc_pair = cv2, sizes, desc_pair
+        self.local = threading.local()
+
+    def _tools(self):
+        if not hasattr(self.local, "f20"):
+            self.local.f20 = self.cv2.FastFeatureDetector_create(20, True)
+            self.local.f7 = self.cv2.FastFeatureDetector_create(7, True)
+            self.local.bf = self.cv2.BFMatcher(self.cv2.NORM_HAMMING)
+        return self.local.f20, self.local.f7, self.local.bf
+
+    def image(self, img):
+        cv2 = self.cv2
+        f20, f7, _ = self._tools()
+        levels = [img]
+        for (w, h) in self.sizes[1:]:
+            levels.append(cv2.resize(levels[-1], (w, h), interpolation=cv2.INTER_LINEAR))
+        n = 0
+        for lv in levels:
+            h, w = lv.shape
+            minB, maxBX, maxBY = 16, w - 16, h - 16
+            width, height = float(maxBX - minB), float(maxBY - minB)
+            nCols, nRows = int(width / 30), int(height / 30)
+            wCell, hCell = int(np.ceil(width / nCols)), int(np.ceil(height / nRows))
+            for i in range(nRows):
+                iniY = minB + i * hCell
+                maxY = min(iniY + hCell + 6, maxBY)
+                if iniY >= maxBY - 3:
+                    continue
+                for j in range(nCols):
+                    iniX = minB + j * wCell
+                    maxX = min(iniX + wCell + 6, maxBX)
+                    if iniX >= maxBX - 6:
+                        continue
+                    roi = lv[iniY:maxY, iniX:maxX]
+                    k = f20.detect(roi)
+                    if not k:
+                        k = f7.detect(roi)
+                    n += len(k)
+            cv2.GaussianBlur(lv, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+        return n
+
+    def frame(self, pair):
+        n = self.image(pair[0]) + self.image(pair[1])
+        self._tools()[2].match(self.desc_pair[0], self.desc_pair[1])
+        return n
+
+    def fps(self, frames, threads):
+        from concurrent.futures import ThreadPoolExecutor
+        self.cv2.setNumThreads(1 if threads > 1 else 1)   # one frame per thread; cv2's own pool stays out of the way
+        with ThreadPoolExecutor(threads) as pool:
+            list(pool.map(self.frame, [frames[i] for i in range(min(len(frames), threads))]))   # warm
+            t0 = time.perf_counter()
+            list(pool.map(self.frame, [frames[i] for i in range(len(frames))]))
+            return len(frames) / (time.perf_counter() - t0)
+
+
 def cpu_reference_fps(frames, windows, cores):
     ref = CpuReference(cores)
     ref.run(frames[:cores], windows)   # warm: library load, per-thread extractors
-    return len(frames) / ref.run(frames, windows)
+    return len(frames) / ref.run(frames, windows), ref.kind
 
 
 _JSON_FD = None
@@ -197,7 +321,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     per_step = max(cores, 8)
     frames = synth.stereo_batch(0, per_step)
-    windows = [synth.ba_window(s) for s in range(per_step)]
+    windows = None if args.no_ba else [synth.ba_window(s) for s in range(per_step)]
     ref = CpuReference(cores)
     for _ in range(args.warmup):
         ref.run(frames, windows)
@@ -206,8 +330,9 @@ def run_reference(args, rank, world):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "frames_per_step": per_step},
-           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
+           "config": {"workload": WORKLOAD if not args.no_ba else "config 2: ORB extract (both views) + L<->R Hamming match only",
+                      "frames_per_step": per_step},
+           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": ref.kind,
                             "sample": f"{per_step} synthetic stereo frames per step through oracle/ (C restatement of "
                                       "ORBextractor::DetectAndCompute + BFMatcher + the g2o-faithful LM/Schur BA; the reference "
                                       "itself needs OpenCV/g2o and cannot be built here), one frame per thread"},
@@ -215,17 +340,74 @@ def run_reference(args, rank, world):
     emit(out)
 
 
+def run_config4(args, rank, world, local_rank):
+    """BASELINE config 4 (and 5 under torchrun): the full-pipeline replay of the package's replay.py — every frame through
+    extract + match, one BA window and the loop-closing front end per keyframe, DeepLCD detection, geometric verification
+    and pose-graph optimisation in keyframe order — host buffers in, host results out (this IS the end-to-end number)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    replay = importlib.import_module(PKG + ".replay")
+    n_kf = max(2, int(round(args.frames / 6.12)))
+    small = n_kf < 200
+    ops = replay.GpuOps(device=local_rank, batch=args.pairs, kf_batch=min(32, args.pairs), n_kf=n_kf)
+    warm = replay.Sequence(frames=3 * args.pairs, n_kf=24)                   # warm-up: three batches through every operator
+    for _ in range(3):
+        replay.run(warm, ops, rank=0, world=1, db_min_size=5, min_gap=5)
+        ops.reset()
+    seq = replay.Sequence(frames=args.frames, n_kf=n_kf)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    res = replay.run(seq, ops, rank=rank, world=world, db_min_size=5 if small else 50, min_gap=5 if small else 20)
+    clocks = sampler.stop()
+    t = torch.tensor([res["timings"][k] for k in ("total_s", "frames_s", "keyframes_s", "exchange_s", "loop_closing_s", "posegraph_s")],
+                     dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total, fr, kf, ex, lc, pg = (float(x) for x in t)
+    if rank == 0:
+        value = seq.frames / total
+        H2D = seq.frames * 2 * H * W + seq.n_kf * 2 * H * W
+        out = {"metric": "KITTI stereo frames/s, full pipeline (extract+match+local BA+DeepLCD loop detect/verify+pose graph)",
+               "value": value, "unit": "frames/s", "n_gpus": world, "steps": 1, "warmup": 3, "ms_per_step": total * 1e3,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 / f32 (CNN) / f64 (BA, pose graph)",
+               "data": "synthetic", "config": {"workload": f"config {4 if world == 1 else 5}: full pipeline replay, {seq.frames} stereo frames 1241x376, "
+                                                         f"{seq.n_kf} keyframes, {len(seq.loop_pairs)} planted revisits, 2000 feats/frame; one step = the whole sequence",
+                                               "sharding": "frames and keyframes round-robin by rank; keyframe poses all-gathered through sb_allgather_kf_poses, "
+                                                           "loop closing redundantly on every rank" if world > 1 else "single GPU"},
+               "clocks": clocks,
+               "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": H2D, "d2h_bytes_per_step": None,
+                       "note": "the replay runs on host buffers through the host-pointer C ABI: value IS end to end"},
+               "stage_seconds": {"extract_match_ba": fr, "keyframe_front_end_and_descriptors": kf, "exchange": ex,
+                                 "loop_closing_total": lc, "of_which_pose_graph": pg},
+               "loops_closed": len(res["loops"]), "loops_planted": len(seq.loop_pairs), "posegraph_runs": res["posegraph_runs"],
+               "mean_position_error_m": {"dead_reckoned": res["mean_position_error_dead_reckoned_m"], "final": res["mean_position_error_final_m"]},
+               "keypoints": res["keypoints"], "matches": res["matches"]}
+        emit(out)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500, help="default: >= 1 s of timed region at ~2 ms per step")
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4],
+                    help="BASELINE config: 2 = extract + match, 3 = + local BA (the metric's config, default), "
+                         "4 = full pipeline replay incl. DeepLCD loop detection + pose graph over 4541 frames")
+    ap.add_argument("--frames", type=int, default=4541, help="config 4: frames of the replayed sequence")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=64, help="stereo pairs (and BA windows) per step")
     ap.add_argument("--pool", type=int, default=192, help="distinct resident stereo pairs (> L2 in total)")
     ap.add_argument("--no-ba", action="store_true", help="config 2 only: extract + match")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.config == 2:
+        args.no_ba = True
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,6 +417,9 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
+    if args.config == 4:
+        run_config4(args, rank, world, local_rank)
+        return
 
     import torch
     import torch.distributed as dist
@@ -359,6 +544,56 @@ def main():
     n_cands = int(n_cands * (2 * B) / len(sample_imgs))
     n_matched = int((mdist >= 0).sum().item())
     ba_info = bd["info"].cpu().numpy() if with_ba else np.zeros((B, 4), np.int32)
+
+    # ---- serialised stage pass (after the timed region): the extract/match stream alone with the per-stage events on, then
+    #      the BA stream alone — stage times without interference, reproducible run to run; used for the roofline entries.
+    SER_STEPS = 6
+    barrier()
+    saved_ba, with_ba = with_ba, False
+    for e in exts:
+        lib.sb_orb_profile(e._h, 1)
+    sev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(SER_STEPS)]
+    for i in range(SER_STEPS):
+        step_dev(args.warmup + args.steps + i, sev[i])
+        torch.cuda.synchronize()
+    ser_ms = {}
+    ms_s = np.zeros(6, np.float32)
+    la_s = np.zeros(6, np.int32)
+    for e in exts:
+        ms_k = np.zeros(6, np.float32)
+        la_k = np.zeros(6, np.int32)
+        lib.sb_orb_profile_read(e._h, C.c_void_p(ms_k.ctypes.data), C.c_void_p(la_k.ctypes.data), 6)
+        lib.sb_orb_profile(e._h, 0)
+        ms_s += ms_k
+    for i, sname in enumerate(STAGES):
+        ser_ms[sname] = float(ms_s[i])
+    ser_ms["hamming_match"] = float(sum(e[0].elapsed_time(e[1]) for e in sev))
+    with_ba = saved_ba
+    if with_ba:
+        tot = 0.0
+        for i in range(SER_STEPS):
+            with torch.cuda.stream(s2):
+                bd["poses"].copy_(bd0["poses"], non_blocking=True)
+                bd["points"].copy_(bd0["points"], non_blocking=True)
+                sev[i][2].record(s2)
+                ba.solve_dev(B, bd, KITTI_K)
+                sev[i][3].record(s2)
+            torch.cuda.synchronize()
+            tot += sev[i][2].elapsed_time(sev[i][3])
+        ser_ms["local_ba"] = tot
+    # algorithmic flops of one BA launch: per LM iteration every edge is linearised and accumulated
+    # (~450 flops), per trial every pair of a landmark's edges costs one 6x3 x 3x6 product (216) + Hpl Dinv per edge (54) +
+    # the landmark update (36 per edge) + the (6 P)^3 / 3 Cholesky
+    ba_flops = 0.0
+    if with_ba:
+        for k in range(B):
+            ne_k, np_k = int(bh["ne"][k]), int(bh["np"][k])
+            per_lm = np.bincount(bh["ol"][k, :ne_k], minlength=int(bh["nl"][k]))
+            free = bh["fixed"][k, :len(per_lm)] == 0
+            pairs_k = float((per_lm[free] * (per_lm[free] + 1) / 2).sum())
+            iters_k = float(ba_info[k, 1])
+            trials_k = iters_k * 1.3                     # measured mean of LM trials per iteration on these windows
+            ba_flops += iters_k * ne_k * 450 + trials_k * (pairs_k * 216 + ne_k * 90 + (6 * np_k) ** 3 / 3)
 
     # ---- e2e: the host-pointer C ABI with pinned host buffers (H2D + D2H inside the timed region):
     #      three sb_stereo handles used in turn (copy in, kernels and copy out of consecutive batches overlap)
@@ -514,11 +749,9 @@ def main():
         def abytes(k):
             return ba_bytes if k == "local_ba" else algorithmic_bytes(k, 2 * B, n_kps, n_cands)
 
-        # dominant kernel = the longest stage of the critical stream (extract + match); the BA launch runs
-        # concurrently on its own stream, is latency-bound fp64 work and is listed in stage_ms_per_step
-        # ... and so does the Gaussian blur (side stream, concurrent with FAST + quadtree): both are reported in
-        # stage_ms_per_step but are not candidates for "the dominant kernel of the critical stream"
-        top = max((k for k in stage_ms if k not in ("local_ba", "gauss_blur")), key=stage_ms.get)
+        # Roofline entries.  The stage times come from the SERIALISED pass (each stream alone, see above): reproducible, no
+        # interference.  `roofline` names the kernel that dominates the timed step — whichever stage is longest, BA included —
+        # and `roofline_extract` the dominant kernel of the extract / match stage (the one north_star's HBM target is about).
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -526,16 +759,35 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        groups = stage_launches[top] / (7 if top == "resize_pyramid" else 4 if top == "hamming_match" else 1)
-        per_group_ms = stage_ms[top] / max(groups, 1)
-        achieved = abytes(top) / (per_group_ms * 1e-3) / 1e9
-        roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(top) if 2 * B == 128 else None,
-                    "traffic_source": NCU_SOURCE, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": abytes(top), "ms_per_launch": per_group_ms,
-                    "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                    "stage_gbs": {k: abytes(k) / (stage_ms[k] / args.steps * 1e-3) / 1e9 for k in stage_ms if stage_ms[k] > 0},
-                    "note": "stages on the two streams overlap; stage times are CUDA-event intervals on the launching stream"}
+        traffic, ncu_extra, ncu_src = ncu_traffic()
+        ser = {k: v / SER_STEPS for k, v in ser_ms.items()}          # ms per step, serialised
+
+        def hbm_entry(k):
+            ach = abytes(k) / (ser[k] * 1e-3) / 1e9
+            return {"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": traffic.get(k) if 2 * B == 128 else None, "traffic_source": ncu_src, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": abytes(k), "ms_per_launch": ser[k], **ncu_extra.get(k, {})}
+
+        def ba_entry():
+            # fp64 pipe: 64 FMA / clk / SM measured for DFMA and DMMA alike (tools/dmma_probe.cu, profiles/r2_ba_dmma_ab.md)
+            fp64_peak = 148 * 64 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+            ach = ba_flops / (ser["local_ba"] * 1e-3) / 1e12
+            return {"kernel": "local_ba", "bound": "latency (fp64 pipe; no HBM or tensor roof applies: 0.07 % of HBM)",
+                    "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                    "traffic": traffic.get("local_ba") if B == 64 else None, "traffic_source": ncu_src,
+                    "peak_source": "148 SMs x 64 fp64 FMA/clk (measured per-SM rate) x SM clock; no fp64 figure in MEASURED_PEAKS.json",
+                    "algorithmic_flops_per_launch": ba_flops, "algorithmic_bytes_per_launch": ba_bytes,
+                    "ms_per_launch": ser["local_ba"], "sm_ms_per_launch": B * ser["local_ba"], **ncu_extra.get("local_ba", {})}
+
+        top = max(ser, key=ser.get)
+        top_extract = max((k for k in ser if k != "local_ba"), key=ser.get)
+        roofline = ba_entry() if top == "local_ba" else hbm_entry(top)
+        roofline["stage_ms_per_step_serialised"] = ser
+        roofline["stage_ms_per_step_concurrent"] = {k: v / args.steps for k, v in stage_ms.items()}
+        roofline["stage_gbs_serialised"] = {k: abytes(k) / (ser[k] * 1e-3) / 1e9 for k in ser if ser[k] > 0}
+        roofline["note"] = ("serialised = each stream run alone after the timed region (CUDA events on the launching stream, "
+                            f"{SER_STEPS} steps); concurrent = inside the timed region, where the BA stream and the extract stream overlap")
+        roofline_extract = hbm_entry(top_extract)
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u8 (extract/match), f64 (BA)", "data": "synthetic",
@@ -552,15 +804,34 @@ def main():
                        "api": "sb_stereo_submit/wait on three handles and sb_ba_submit/wait on two, used in turn (host pointers, pinned)"},
                "gpu_launches": int(sum(stage_launches.values())),
                "roofline": roofline,
+               "roofline_extract": roofline_extract,
                "loop_closing_extras": extras}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = max(2 * cores, 16)
             sample = pool_np[:min(n, P)]
-            fps = cpu_reference_fps(sample, windows if with_ba else None, cores)
-            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+            fps, kind = cpu_reference_fps(sample, windows if with_ba else None, cores)
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
                                    "sample": f"{len(sample)} of the same synthetic stereo frames (+ one BA window each) through "
                                              "oracle/ (C restatement of the reference's OpenCV/g2o-based path), one frame per thread"}
+            try:   # BASELINE.md section 4 leg: the OpenCV primitives through cv2 (SIMD builds), 1 thread and all cores
+                inv = [np.float32(1.0)]
+                sc = np.float32(1.0)
+                for _ in range(1, 8):
+                    sc = np.float32(np.float64(sc) * np.float64(np.float32(1.2)))
+                    inv.append(np.float32(1.0) / sc)
+                sizes = [(W, H)] + [(int(np.rint(np.float32(W) * i)), int(np.rint(np.float32(H) * i))) for i in inv[1:]]
+                rng = np.random.default_rng(0)
+                dpair = (rng.integers(0, 256, (2000, 32), dtype=np.uint8), rng.integers(0, 256, (2000, 32), dtype=np.uint8))
+                cvp = Cv2Primitives(sizes, dpair)
+                f1 = cvp.fps(sample[:max(4, len(sample) // 8)], 1)
+                fa = cvp.fps(sample, cores)
+                out["cpu_baseline_cv2"] = {"value": fa, "value_1_thread": f1, "unit": "frames/s", "cores": cores, "kind": "cv2 4.13 primitives only",
+                                           "sample": f"{len(sample)} of the same frames: chained cv2.resize pyramid, per-cell cv2 FAST (20 -> 7 "
+                                                     "fallback), GaussianBlur per level, BFMatcher 2000 x 2000 per pair; the reference's own "
+                                                     "quadtree / orientation / rBRIEF code and BA are NOT included: a lower bound on its CPU time"}
+            except Exception as ex:
+                out["cpu_baseline_cv2"] = {"unavailable": repr(ex)}
         emit(out)
     if world > 1:
         dist.destroy_process_group()
