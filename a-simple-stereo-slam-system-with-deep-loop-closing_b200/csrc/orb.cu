@@ -810,11 +810,18 @@ static __device__ __forceinline__ bool is_fast_corner_at(const uint8_t *p, int p
     return hit;
 }
 
+// per_img > 0: a batch of images, keypoint i belongs to image i / per_img and only the first counts[image] slots are live
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_screen(const __grid_constant__ Geom g, const uint8_t *pyr,
-                                                           sb_keypoint *kps, int n, uint8_t *keep, int minTh) {
+                                                           sb_keypoint *kps, int n, uint8_t *keep, int minTh, int per_img,
+                                                           const int32_t *counts) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
     if (i >= n) return;
+    if (per_img > 0) {
+        const int b = i / per_img;
+        if (i - b * per_img >= counts[b]) return;
+        pyr += (long long)b * g.slab;
+    }
     sb_keypoint kp = kps[i];
     const int level = kp.octave;
     bool ok = level >= 0 && level < g.nlevels;
@@ -842,13 +849,18 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_screen(const __grid_constan
 
 // CalcDescriptors (:1180-1226): row i = descriptor of keypoint i on the blurred level `octave`.
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_calc_desc(const __grid_constant__ Geom g, const uint8_t *blur,
-                                                              const sb_keypoint *kps, int n, uint8_t *desc) {
+                                                              const sb_keypoint *kps, int n, uint8_t *desc, int per_img,
+                                                              const uint8_t *keep) {
     __shared__ float4 pat[256];
     load_pattern(pat);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * DESC_WARPS + (threadIdx.x >> 5);
     if (i >= n) return;
+    if (per_img > 0) {   // batch form: only the keypoints the screening kept, on their own image's pyramid
+        if (!keep[i]) return;
+        blur += (long long)(i / per_img) * g.slab;
+    }
     const sb_keypoint kp = kps[i];
     const LevelGeom &L = g.lv[kp.octave];
     const float x = sb_fdiv(kp.x, L.scale), y = sb_fdiv(kp.y, L.scale);
@@ -1602,7 +1614,7 @@ extern "C" int sb_orb_screen_params(sb_orb_t *h, const uint8_t *img, int w, int 
     SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, row, 1, h->nlevels));
     SB_CUDA(cudaMemcpyAsync(h->d_kps_out, in, (size_t)n_in * sizeof(sb_keypoint), cudaMemcpyHostToDevice, h->stream));
     k_screen<<<sb_div_up(n_in, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_pyr, h->d_kps_out, n_in, h->d_keep,
-                                                                           h->minTh);
+                                                                           h->minTh, 0, nullptr);
     SB_CUDA(cudaGetLastError());
     std::vector<uint8_t> keep((size_t)n_in);
     SB_CUDA(cudaMemcpyAsync(in, h->d_kps_out, (size_t)n_in * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
@@ -1638,10 +1650,63 @@ extern "C" int sb_orb_calc_descriptors(sb_orb_t *h, const uint8_t *img, int w, i
     SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, row, 1, h->nlevels));
     SB_TRY(launch_blur(h, 1, h->stream));
     SB_CUDA(cudaMemcpyAsync(h->d_kps_out, kps, (size_t)n * sizeof(sb_keypoint), cudaMemcpyHostToDevice, h->stream));
-    k_calc_desc<<<sb_div_up(n, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_blur, h->d_kps_out, n, h->d_desc_out);
+    k_calc_desc<<<sb_div_up(n, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_blur, h->d_kps_out, n, h->d_desc_out, 0, nullptr);
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaMemcpyAsync(desc, h->d_desc_out, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
     SB_CUDA(cudaStreamSynchronize(h->stream));
+    return SB_OK;
+}
+
+// LoopClosing::ProcessNewKF's two extractor calls (src/loopclosing.cpp:107-112) for a BATCH of keyframe images in one pass:
+// ScreenAndComputeKPsParams (:1083-1129) and then CalcDescriptors (:1180-1226) on its survivors — one staging copy, one pyramid
+// and one blur per image instead of the reference's two pyramids (quirk Q7), one screening and one descriptor launch per batch.
+//   in  [batch][cap_in] (first n_in[b] live; mutated like the reference's vector, quirk Q5)
+//   out [batch][cap_in] survivors in input order, n_out [batch], desc [batch][cap_in][32] (row k <-> out[k])
+extern "C" int sb_orb_screen_describe(sb_orb_t *h, int batch, const uint8_t *const *img, int w, int hgt, int stride, sb_keypoint *in,
+                                      const int32_t *n_in, int cap_in, sb_keypoint *out, int32_t *n_out, uint8_t *desc) {
+    sb_clear_error();
+    SB_REQUIRE(img && in && n_in && out && n_out && desc, "null pointer");
+    SB_TRY(check_shapes(h, batch, w, hgt, stride, cap_in));
+    int total = 0;
+    for (int b = 0; b < batch; b++) {
+        SB_REQUIRE(n_in[b] >= 0 && n_in[b] <= cap_in, "n_in out of range [0, cap_in]");
+        n_out[b] = 0;
+        total += n_in[b];
+    }
+    if (total == 0) return SB_OK;
+    const int row = (int)sb_align_up((size_t)w, 16);
+    const size_t img_bytes = (size_t)row * hgt;
+    SB_TRY(ensure_staging(h, batch, img_bytes, cap_in, false));
+    bool any = false;
+    SB_TRY(stage_images(h, batch, img, nullptr, w, hgt, stride, 0, &any));
+    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, row, batch, h->nlevels));
+    SB_TRY(launch_blur(h, batch, h->stream));
+    const int n = batch * cap_in;
+    SB_CUDA(cudaMemcpyAsync(h->d_kps_out, in, (size_t)n * sizeof(sb_keypoint), cudaMemcpyHostToDevice, h->stream));
+    SB_CUDA(cudaMemcpyAsync(h->d_counts_out, n_in, (size_t)batch * 4, cudaMemcpyHostToDevice, h->stream));
+    SB_CUDA(cudaMemsetAsync(h->d_keep, 0, (size_t)n, h->stream));
+    k_screen<<<sb_div_up(n, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_pyr, h->d_kps_out, n, h->d_keep, h->minTh, cap_in,
+                                                                           h->d_counts_out);
+    SB_CUDA(cudaGetLastError());
+    k_calc_desc<<<sb_div_up(n, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_blur, h->d_kps_out, n, h->d_desc_out, cap_in,
+                                                                              h->d_keep);
+    SB_CUDA(cudaGetLastError());
+    std::vector<uint8_t> keep((size_t)n), dtmp((size_t)n * 32);
+    SB_CUDA(cudaMemcpyAsync(in, h->d_kps_out, (size_t)n * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemcpyAsync(keep.data(), h->d_keep, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemcpyAsync(dtmp.data(), h->d_desc_out, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < batch; b++) {
+        int m = 0;
+        for (int i = 0; i < n_in[b]; i++) {
+            const size_t k = (size_t)b * cap_in + i;
+            if (!keep[k]) continue;
+            out[(size_t)b * cap_in + m] = in[k];   // survivors in input order (:1125)
+            memcpy(desc + ((size_t)b * cap_in + m) * 32, dtmp.data() + k * 32, 32);
+            m++;
+        }
+        n_out[b] = m;
+    }
     return SB_OK;
 }
 

@@ -152,6 +152,27 @@ public:
         store_descriptors(_descriptors, d.data(), (int)k.size());
     }
 
+    // Both calls of LoopClosing::ProcessNewKF (src/loopclosing.cpp:107-112) in one pass over ONE pyramid (the reference builds
+    // it twice, quirk Q7): _keypoints mutated like ScreenAndComputeKPsParams does, survivors + their descriptors out.
+    void ScreenAndDescribe(cv::InputArray _image, std::vector<cv::KeyPoint> &_keypoints, std::vector<cv::KeyPoint> &out_keypoints,
+                           cv::OutputArray _descriptors) {
+        const cv::Mat image = detail::as_mat(_image);
+        if (image.empty() || _keypoints.empty()) return;
+        const int32_t n_in = (int32_t)_keypoints.size();
+        std::vector<sb_keypoint> in((size_t)n_in), out((size_t)n_in);
+        for (size_t i = 0; i < in.size(); i++) in[i] = detail::to_sb(_keypoints[i]);
+        std::vector<uint8_t> d((size_t)n_in * 32);
+        int32_t n = 0;
+        const uint8_t *ip = image.data;
+        detail::last_status() = sb_orb_screen_describe(h_pyramid_, 1, &ip, image.cols, image.rows, (int)image.step, in.data(), &n_in, n_in,
+                                                       out.data(), &n, d.data());
+        out_keypoints.clear();
+        if (detail::last_status() != SB_OK) return;
+        for (size_t i = 0; i < in.size(); i++) _keypoints[i] = detail::from_sb(in[i]);
+        for (int i = 0; i < n; i++) out_keypoints.push_back(detail::from_sb(out[i]));
+        if (n > 0) store_descriptors(_descriptors, d.data(), n);
+    }
+
     int GetLevels() { return nlevels; }
     float GetScaleFactor() { return (float)scaleFactor; }
     std::vector<float> GetScaleFactors() { return mvScaleFactor; }

@@ -247,14 +247,20 @@ class GpuOps:
         return capi.triangulate(ul, ur, synth.KITTI_K, synth.KITTI_K, np.array([0, 0, 0, 1, 0, 0, 0.0]),
                                 np.array([0, 0, 0, 1, -b, 0, 0.0]), T_wc7)
 
+    def triangulate_batch(self, uls, urs):
+        """One sb_triangulate call for the correspondences of a whole batch of keyframes (same two camera poses)."""
+        n = [len(u) for u in uls]
+        p, ok = self.triangulate(np.concatenate(uls), np.concatenate(urs), None)
+        o = np.concatenate([[0], np.cumsum(n)])
+        return [(p[o[i]:o[i + 1]], ok[o[i]:o[i + 1]]) for i in range(len(n))]
+
     def cnn_descr(self, lefts):
         """DeepLCD::calcDescrOriginalImg: returns descriptors; `lefts` come back blurred in place (quirk Q8)."""
         return self.net.calcDescrOriginalImgBatch(lefts, in_place=True)
 
-    def screen_and_describe(self, img, kin):
-        _, kout = self.kf_ext.ScreenAndComputeKPsParams(img, kin)
-        desc = self.kf_ext.CalcDescriptors(img, kout) if len(kout) else np.zeros((0, 32), np.uint8)
-        return kout, desc
+    def screen_and_describe(self, imgs, kins):
+        """ScreenAndComputeKPsParams + CalcDescriptors for a batch of keyframes (sb_orb_screen_describe) -> [(kps, desc)]."""
+        return [(kout, desc) for _, kout, desc in self.kf_ext.ScreenAndDescribeBatch(imgs, kins)]
 
     # loop-closing stage ---------------------------------------------------------------------------------------------
     def lcd_add(self, kf_id, d):
@@ -309,6 +315,12 @@ def expand_octaves(feats, nlevels=8):
     return kin
 
 
+def lap(t, key, t0):
+    now = time.perf_counter()
+    t[key] = t.get(key, 0.0) + now - t0
+    return now
+
+
 def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=False, comm=None, log=None):
     """Runs the whole replay on this rank's share; returns a dict (identical on every rank except timings)."""
     B = ops.batch
@@ -322,10 +334,11 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
     kf_imgs = seq.load(seq.kf_frame[my_kfs])
     windows = [synth.ba_window(int(k)) for k in my_kfs]
     pin = None
-    try:
+    try:   # page-locked host buffers: the H2D copies of every operator run at PCIe speed and asynchronously
         import torch
-        pin = torch.from_numpy(frames_np).pin_memory()
-        frames_np = pin.numpy()
+        if torch.cuda.is_available():
+            pin = (torch.from_numpy(frames_np).pin_memory(), torch.from_numpy(kf_imgs).pin_memory())
+            frames_np, kf_imgs = pin[0].numpy(), pin[1].numpy()
     except Exception:
         pass
     t["load_s"] = time.perf_counter() - t0
@@ -385,15 +398,23 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
         ks = my_kfs[lo:lo + KB]
         lefts = [kf_imgs[lo + i, 0] for i in range(len(ks))]
         rights = [kf_imgs[lo + i, 1] for i in range(len(ks))]
+        tk = time.perf_counter()
         feats = ops.kf_detect(lefts)
         pts = [np.stack([f["x"], f["y"]], 1).astype(np.float32) for f in feats]
+        tk = lap(t, "kf_detect_s", tk)
         tracked = ops.lk_right(lefts, rights, pts)
+        tk = lap(t, "kf_lk_s", tk)
         descr = ops.cnn_descr(lefts)                    # blurs `lefts` in place: the ORB descriptors below see the blurred image
+        tk = lap(t, "kf_cnn_s", tk)
+        described = ops.screen_and_describe(lefts, [expand_octaves(f) for f in feats])
+        tk = lap(t, "kf_screen_describe_s", tk)
+        tri = ops.triangulate_batch(pts, [tr[0] for tr in tracked])
+        tk = lap(t, "kf_triangulate_s", tk)
         for i, k in enumerate(ks):
             ur, status = tracked[i]
-            p_cam, ok = ops.triangulate(pts[i], ur, None)
+            p_cam, ok = tri[i]
             ok = ok & (status != 0)
-            kout, desc = ops.screen_and_describe(lefts[i], expand_octaves(feats[i]))
+            kout, desc = described[i]
             rec[int(k)] = dict(feats=feats[i], p_cam=p_cam.astype(np.float64), has_mp=ok, descr=descr[i].copy(), pyr=kout, orb=desc)
     t["keyframes_s"] = time.perf_counter() - t1
 

@@ -104,6 +104,11 @@ int sb_orb_screen_params(sb_orb_t *h, const uint8_t *img, int w, int hgt, int st
 /* ORBextractor::CalcDescriptors (src/ORBextractor.cpp:1180-1226): desc [n][32], row i <-> kps[i]. */
 int sb_orb_calc_descriptors(sb_orb_t *h, const uint8_t *img, int w, int hgt, int stride, const sb_keypoint *kps,
                             int n, uint8_t *desc);
+/* LoopClosing::ProcessNewKF's two extractor calls (src/loopclosing.cpp:107-112) for a batch of keyframe images in one
+ * pass: ScreenAndComputeKPsParams, then CalcDescriptors on its survivors.  in [batch][cap_in] (first n_in[b] live, mutated
+ * like the reference's vector), out [batch][cap_in] survivors in input order, n_out [batch], desc [batch][cap_in][32]. */
+int sb_orb_screen_describe(sb_orb_t *h, int batch, const uint8_t *const *img, int w, int hgt, int stride, sb_keypoint *in,
+                           const int32_t *n_in, int cap_in, sb_keypoint *out, int32_t *n_out, uint8_t *desc);
 
 /* Debug/inspection: copy pyramid level `level` of image `b` of the LAST call to the host.
  * which: 0 = mvImagePyramid, 1 = Gaussian-blurred working Mat, 2 = mvMaskPyramid.

@@ -56,6 +56,9 @@ class CpuOps:
         b = self.synth.KITTI_BF / self.synth.KITTI_FX
         return O.triangulate(ul, ur, self.synth.KITTI_K, self.synth.KITTI_K, np.array([0, 0, 0, 1, 0, 0, 0.0]), np.array([0, 0, 0, 1, -b, 0, 0.0]), T_wc7)
 
+    def triangulate_batch(self, uls, urs):
+        return [self.triangulate(a, b, None) for a, b in zip(uls, urs)]
+
     def cnn_descr(self, lefts):
         out = []
         for im in lefts:
@@ -64,10 +67,12 @@ class CpuOps:
             out.append(np.asarray(d, np.float32).ravel())
         return np.stack(out)
 
-    def screen_and_describe(self, img, kin):
-        _, kout = self.kf_ext.ScreenAndComputeKPsParams(img, kin)
-        desc = self.kf_ext.CalcDescriptors(img, kout) if len(kout) else np.zeros((0, 32), np.uint8)
-        return kout, desc
+    def screen_and_describe(self, imgs, kins):
+        out = []
+        for img, kin in zip(imgs, kins):
+            _, kout = self.kf_ext.ScreenAndComputeKPsParams(img, kin)
+            out.append((kout, self.kf_ext.CalcDescriptors(img, kout) if len(kout) else np.zeros((0, 32), np.uint8)))
+        return out
 
     def lcd_add(self, kf_id, d):
         self.db_ids.append(kf_id)

@@ -141,6 +141,34 @@ def test_screen_params_and_calc_descriptors(pkg, oracle, synth):
     g.close()
 
 
+def test_batched_screen_and_describe_equals_the_two_single_image_calls(pkg, oracle, synth):
+    """sb_orb_screen_describe (LoopClosing::ProcessNewKF for a batch of keyframes) against the oracle's two calls per image."""
+    g = pkg.ORBextractor(100, 1.2, 8, 20, 7, max_batch=3)
+    c = oracle.ORBextractor(100, 1.2, 8, 20, 7)
+    imgs, kins = [], []
+    for seed, nf in ((17, 300), (18, 120), (19, 0)):
+        left, _ = synth.stereo_pair(seed)
+        feats = oracle.ORBextractor(max(nf, 1), 1.2, 8, 20, 7).Detect(left)[:nf]
+        kin = np.zeros(len(feats) * 8, feats.dtype)
+        for i, f in enumerate(feats):
+            for level in range(8):
+                k = kin[i * 8 + level]
+                k["x"], k["y"], k["size"], k["angle"], k["response"], k["octave"], k["class_id"] = f["x"], f["y"], 7, -1, -1, level, i
+        imgs.append(left)
+        kins.append(kin)
+    got = g.ScreenAndDescribeBatch(imgs, kins)
+    for b in range(3):
+        if len(kins[b]) == 0:
+            assert len(got[b][1]) == 0 and len(got[b][2]) == 0
+            continue
+        c_in, c_out = c.ScreenAndComputeKPsParams(imgs[b], kins[b])
+        assert_kps_equal(got[b][0], c_in, ("mutated input", b))
+        assert_kps_equal(got[b][1], c_out, ("survivors", b))
+        assert np.array_equal(got[b][2], c.CalcDescriptors(imgs[b], c_out)), b
+        assert 0 < len(c_out) < len(kins[b])
+    g.close()
+
+
 # (64, 70): one FAST cell per level-0 grid row; (62, 400): a single grid row of cells; (300, 1000): runs of 5 cells + a rest;
 # (97, 131): cells wider than 40 px (short runs)
 @pytest.mark.parametrize("shape,nlevels", [((480, 640), 8), ((200, 333), 4), ((376, 1241), 1), ((64, 70), 1), ((62, 400), 1),
