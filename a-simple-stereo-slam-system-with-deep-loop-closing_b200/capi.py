@@ -432,9 +432,12 @@ class DeepLCDScorer:
 class PoseGraph:
     """The g2o solve of LoopClosing::PoseGraphOptimization (src/loopclosing.cpp:537-646)."""
 
-    def __init__(self, max_vertices=1024, max_edges=2048, device=0):
+    def __init__(self, max_vertices=1024, max_edges=2048, device=0, max_loops=None):
         self._h = C.c_void_p()
-        _check(lib().sb_posegraph_create(C.byref(self._h), device, max_vertices, max_edges))
+        if max_loops is None:
+            _check(lib().sb_posegraph_create(C.byref(self._h), device, max_vertices, max_edges))
+        else:
+            _check(lib().sb_posegraph_create_loops(C.byref(self._h), device, max_vertices, max_edges, max_loops))
 
     def close(self):
         if self._h:

@@ -10,32 +10,44 @@
 // (17 on KITTI-00), so the LM system is block tridiagonal plus a low-rank term:
 //        H + lambda I = T + J_loop^T J_loop,
 // T from the chain edges and the edges with one fixed end, J_loop (6R x 6n) from the R long-range
-// edges.  It is solved exactly (a direct method, like the reference's sparse Cholesky) by a block
-// Thomas factorisation of T, a multi-right-hand-side substitution for T^-1 [b, J^T] and the
-// Woodbury identity with a dense Cholesky of the 6R x 6R capacitance matrix — O(n) work instead of
-// a general sparse factorisation.  One CTA runs the whole optimisation of one graph in one launch.
+// edges.  It is solved exactly (a direct method, like the reference's sparse Cholesky):
+//   * T^-1 [b, J^T] by BLOCK CYCLIC REDUCTION: at level l every second still-active vertex is eliminated
+//     (6x6 inverse, Schur update of its two neighbours), so the 733-step serial recurrence of a block
+//     Thomas solve becomes ceil(log2 n) = 10 levels of work that is parallel over vertices and over the
+//     1 + 6R right-hand sides;
+//   * the Woodbury identity with a dense Cholesky of the 6R x 6R capacitance matrix in shared memory.
+// One thread-block CLUSTER (8 CTAs on 8 SMs, hardware cluster barrier between the phases) runs the whole
+// optimisation of one graph in one launch: numeric Jacobians, assembly, all LM trials.  Every sum runs in a
+// fixed order: results are bit-reproducible.  R is bounded only by the workspace chosen at create time.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <string.h>
 
 #include "common.cuh"
 #include "se3.cuh"
 
-#define PG_THREADS 256
-#define PG_MAX_LOOPS 64
-#define PG_CHUNK 16
-#define PG_PF 4     // chain steps whose right-hand sides are fetched ahead (PG_CHUNK is a multiple)
+namespace cg = cooperative_groups;
+
+#ifndef PG_THREADS
+#define PG_THREADS 512
+#endif
+#ifndef PG_CLUSTER
+#define PG_CLUSTER 16     // CTAs of the cluster: 16 needs the non-portable cluster size (one GPC of a B200 has the SMs for it)
+#endif
+#define PG_DEFAULT_LOOPS 64
+#define PG_SMEM_LOOPS 26  // capacitance matrices up to (6 x 26)^2 doubles = 190 KB are factored in shared memory
 
 enum { PG_NONE = 0, PG_DIAG = 1, PG_CHAIN = 2, PG_LOOP = 3 };
 
 #ifdef PG_PROFILE  // per-phase clock64 totals (tools/pg_profile.py); the product build has no trace of it
 __device__ long long g_pg_prof[16];
-#define PG_T(i) do { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); g_pg_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
+#define PG_T(i) do { cluster.sync(); if (gtid == 0) { long long t_ = clock64(); g_pg_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
 #else
 #define PG_T(i) ((void)0)
 #endif
 
 struct sb_posegraph {
-    int device, max_vertices, max_edges;
+    int device, max_vertices, max_edges, max_loops;
     cudaStream_t stream, own_stream;
     double *d_poses, *d_meas;
     uint8_t *d_fixed;
@@ -43,19 +55,19 @@ struct sb_posegraph {
     // workspace
     double *d_work;
     int32_t *d_iwork;
-    size_t work_doubles, iwork_ints;
+    size_t work_doubles, iwork_ints, smem_bytes;
 };
 
 struct PgArgs {
-    int n, m, iters;
+    int n, m, iters, max_loops, smem_loops;
     double *poses;
     const uint8_t *fixed;
     const int32_t *v0, *v1;
     const double *meas;
     int32_t *info;  // [4]: LM iterations, trials, free vertices, long-range edges  (info[0] < 0: error)
     double *stats;  // [2]: chi2 at start, chi2 at the end
-    double *Rt, *Rtb, *Zinv, *err, *Ji, *Jj, *A, *B, *bvec, *hdiag, *Sinv, *G, *Q, *M, *yv, *x;
-    int32_t *fidx, *vof, *ecls, *eloop, *inc_start, *inc_edge, *loop_edge;
+    double *Rt, *Rtb, *Zinv, *err, *Ji, *Jj, *A, *B, *bvec, *D, *L0, *L1, *G, *U, *Q, *M, *yv, *x, *part;
+    int32_t *fidx, *vof, *ecls, *eloop, *inc_start, *inc_edge, *loop_edge, *flags;
 };
 
 static __device__ double pg_block_sum(double v, double *red) {
@@ -78,6 +90,35 @@ static __device__ double pg_block_max(double v, double *red) {
     for (int k = 1; k < PG_THREADS / 32; k++) s = fmax(s, red[k]);
     return s;
 }
+// cluster-wide reductions: per-CTA partials through global memory, double-buffered by `phase` so that one cluster
+// barrier per reduction is enough; every CTA adds the partials in the same order -> identical values everywhere
+static __device__ double pg_cluster_sum(cg::cluster_group &cluster, double v, double *red, double *part, int &phase) {
+    const double s = pg_block_sum(v, red);
+    double *buf = part + (phase & 1) * 2 * PG_CLUSTER;
+    phase++;
+    if (threadIdx.x == 0) { __stcg(buf + blockIdx.x, s); }
+    __threadfence();
+    cluster.sync();
+    double t = 0;
+    for (int b = 0; b < (int)gridDim.x; b++) t += __ldcg(buf + b);
+    return t;
+}
+static __device__ double pg_cluster_max(cg::cluster_group &cluster, double v, double *red, double *part, int &phase) {
+    const double s = pg_block_max(v, red);
+    double *buf = part + (phase & 1) * 2 * PG_CLUSTER;
+    phase++;
+    if (threadIdx.x == 0) { __stcg(buf + blockIdx.x, s); }
+    __threadfence();
+    cluster.sync();
+    double t = __ldcg(buf);
+    for (int b = 1; b < (int)gridDim.x; b++) t = fmax(t, __ldcg(buf + b));
+    return t;
+}
+// barrier between two phases that exchange data through global memory
+static __device__ __forceinline__ void pg_sync(cg::cluster_group &cluster) {
+    __threadfence();
+    cluster.sync();
+}
 
 // EdgePoseGraph::computeError with explicit vertex poses
 static __device__ __forceinline__ void pg_edge_error(const double *Zinv, const double *T0, const double *T1, double *e) {
@@ -88,28 +129,66 @@ static __device__ __forceinline__ void pg_edge_error(const double *Zinv, const d
     se3_log(P, e);
 }
 
-static __device__ double pg_errors(const PgArgs &a, double *red) {
-    double chi = 0;
-    for (int e = threadIdx.x; e < a.m; e += PG_THREADS) {
-        double r[6];
-        pg_edge_error(a.Zinv + 12 * e, a.Rt + 12 * a.v0[e], a.Rt + 12 * a.v1[e], r);
+// inverse of a symmetric positive definite 6x6 block by Cholesky (lower triangle of D is read); returns false when a
+// pivot is not positive
+static __device__ bool pg_inv6(const double *D, double *G) {
+    double Lc[21], Li[21];  // packed lower triangles, (r, c) at r (r + 1) / 2 + c
+    bool ok = true;
 #pragma unroll
-        for (int k = 0; k < 6; k++) { a.err[6 * e + k] = r[k]; chi += r[k] * r[k]; }
+    for (int c = 0; c < 6; c++) {
+        double d = D[6 * c + c];
+#pragma unroll
+        for (int k = 0; k < c; k++) d -= Lc[c * (c + 1) / 2 + k] * Lc[c * (c + 1) / 2 + k];
+        if (!(d > 0)) ok = false;
+        const double inv = rsqrt(d);
+        Lc[c * (c + 1) / 2 + c] = inv;  // the diagonal holds the reciprocal
+#pragma unroll
+        for (int r = c + 1; r < 6; r++) {
+            double v = 0.5 * (D[6 * r + c] + D[6 * c + r]);  // symmetrise against round-off
+#pragma unroll
+            for (int k = 0; k < c; k++) v -= Lc[r * (r + 1) / 2 + k] * Lc[c * (c + 1) / 2 + k];
+            Lc[r * (r + 1) / 2 + c] = v * inv;
+        }
     }
-    return pg_block_sum(chi, red);
+    // Li = Lc^-1 (lower triangular)
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+        Li[c * (c + 1) / 2 + c] = Lc[c * (c + 1) / 2 + c];
+#pragma unroll
+        for (int r = c + 1; r < 6; r++) {
+            double v = 0;
+#pragma unroll
+            for (int k = c; k < r; k++) v -= Lc[r * (r + 1) / 2 + k] * Li[k * (k + 1) / 2 + c];
+            Li[r * (r + 1) / 2 + c] = v * Lc[r * (r + 1) / 2 + r];
+        }
+    }
+    // G = Li^T Li
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+            double v = 0;
+#pragma unroll
+            for (int k = i; k < 6; k++) v += Li[k * (k + 1) / 2 + i] * Li[k * (k + 1) / 2 + j];
+            G[6 * i + j] = v;
+            G[6 * j + i] = v;
+        }
+    return ok;
 }
 
-__global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant__ PgArgs a) {
+__global__ void __launch_bounds__(PG_THREADS) k_posegraph(const PgArgs a) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double smM[];  // CTA 0: the capacitance matrix during its factorisation
     __shared__ double red[16];
-    __shared__ double w_B[36], w_G[36], w_M[36], w_I[36];  // 6x6 work blocks of the factorisation warp
-    __shared__ __align__(16) double w_stage[2 * PG_CHUNK * 36];           // G / (S^-1, B) of a chunk of chain steps
-    __shared__ int s_nf, s_R, s_bad;
-    __shared__ double s_diag[6 * PG_MAX_LOOPS];  // diagonal of the capacitance matrix' Cholesky factor
+    __shared__ double s_diag[6 * PG_SMEM_LOOPS];
+    __shared__ int s_bad;
     const int tid = threadIdx.x;
+    const int gtid = blockIdx.x * PG_THREADS + tid, gsz = gridDim.x * PG_THREADS;
     const int n = a.n, m = a.m;
+    int phase = 0;
 
     // ---- set-up: free-vertex numbering, edge classes, vertex -> edge incidence (serial, once)
-    if (tid == 0) {
+    if (gtid == 0) {
         int nf = 0, bad = 0;
         for (int v = 0; v < n; v++) {
             if (a.fixed[v]) a.fidx[v] = -1;
@@ -129,7 +208,7 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
             a.ecls[e] = cls;
             a.eloop[e] = -1;
             if (cls == PG_LOOP) {
-                if (R >= PG_MAX_LOOPS) { bad = 2; break; }
+                if (R >= a.max_loops) { bad = 2; break; }
                 a.eloop[e] = R;
                 a.loop_edge[R] = e;
                 R++;
@@ -137,36 +216,35 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
             a.inc_start[u0 + 1]++;
             a.inc_start[u1 + 1]++;
         }
-        if (!bad)
+        if (!bad) {
             for (int v = 0; v < n; v++) a.inc_start[v + 1] += a.inc_start[v];
-        s_nf = nf; s_R = R; s_bad = bad;
+            int *cursor = a.eloop + m;  // scratch of n ints behind eloop
+            for (int v = 0; v < n; v++) cursor[v] = a.inc_start[v];
+            for (int e = 0; e < m; e++) {  // ascending edge index per vertex: deterministic
+                a.inc_edge[cursor[a.v0[e]]++] = e;
+                a.inc_edge[cursor[a.v1[e]]++] = e;
+            }
+        }
+        a.flags[0] = nf; a.flags[1] = R; a.flags[2] = bad;
     }
-    __syncthreads();
-    if (s_bad) {
-        if (tid == 0) { a.info[0] = -1; a.info[1] = -s_bad; a.info[2] = a.info[3] = 0; }
+    pg_sync(cluster);
+    const int nf = __ldcg(a.flags), R = __ldcg(a.flags + 1), bad0 = __ldcg(a.flags + 2);
+    if (bad0) {
+        if (gtid == 0) { a.info[0] = -1; a.info[1] = -bad0; a.info[2] = a.info[3] = 0; }
         return;
     }
-    const int nf = s_nf, R = s_R, NC = 1 + 6 * R;
-    // incidence lists: vertex v's edges in ascending edge index (serial fill keeps the order deterministic)
-    if (tid == 0) {
-        int *cursor = a.eloop + m;  // scratch of n ints behind eloop
-        for (int v = 0; v < n; v++) cursor[v] = a.inc_start[v];
-        for (int e = 0; e < m; e++) {
-            a.inc_edge[cursor[a.v0[e]]++] = e;
-            a.inc_edge[cursor[a.v1[e]]++] = e;
-        }
-    }
-    for (int v = tid; v < n; v += PG_THREADS) {
+    const int NC = 1 + 6 * R, n6r = 6 * R;
+    for (int v = gtid; v < n; v += gsz) {
         quat_to_R(a.poses + 7 * v, a.Rt + 12 * v);
         a.Rt[12 * v + 9] = a.poses[7 * v + 4]; a.Rt[12 * v + 10] = a.poses[7 * v + 5]; a.Rt[12 * v + 11] = a.poses[7 * v + 6];
     }
-    for (int e = tid; e < m; e += PG_THREADS) {
+    for (int e = gtid; e < m; e += gsz) {
         double Z[12];
         quat_to_R(a.meas + 7 * e, Z);
         Z[9] = a.meas[7 * e + 4]; Z[10] = a.meas[7 * e + 5]; Z[11] = a.meas[7 * e + 6];
         se3_inv(Z, a.Zinv + 12 * e);
     }
-    __syncthreads();
+    pg_sync(cluster);
 
     double lambda = 0, ni = 2, chi_start = 0, chi_end = 0;
     int lm_iters = 0, trials = 0;
@@ -174,15 +252,27 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
 #ifdef PG_PROFILE
     long long t_prev = clock64();
 #endif
+
+    // computeActiveErrors + chi2, edges over the whole cluster
+    auto errors = [&]() -> double {
+        double chi = 0;
+        for (int e = gtid; e < m; e += gsz) {
+            double r[6];
+            pg_edge_error(a.Zinv + 12 * e, a.Rt + 12 * a.v0[e], a.Rt + 12 * a.v1[e], r);
+#pragma unroll
+            for (int k = 0; k < 6; k++) { a.err[6 * e + k] = r[k]; chi += r[k] * r[k]; }
+        }
+        return pg_cluster_sum(cluster, chi, red, a.part, phase);
+    };
+
     for (int it = 0; it < a.iters && !terminated; it++) {
-        PG_T(7);
-        double currentChi = pg_errors(a, red);
+        double currentChi = errors();
         PG_T(0);
         if (it == 0) chi_start = currentChi;
         chi_end = currentChi;
         if (nf == 0) break;
         // ---- numeric Jacobians (g2o BaseBinaryEdge::linearizeOplus): one work item per (edge, vertex, column)
-        for (int item = tid; item < m * 12; item += PG_THREADS) {
+        for (int item = gtid; item < m * 12; item += gsz) {
             const int e = item / 12, side = (item % 12) / 6, d = item % 6;
             const int u0 = a.v0[e], u1 = a.v1[e];
             if (a.fixed[side ? u1 : u0]) continue;
@@ -203,141 +293,82 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
 #pragma unroll
             for (int r = 0; r < 6; r++) J[6 * r + d] = scalar * (ep[r] - em[r]);
         }
-        __syncthreads();
+        pg_sync(cluster);
         PG_T(1);
-        // ---- assembly, one thread per free vertex (gather over its incident edges, ascending edge index)
+        // ---- assembly, one thread per (free vertex, block row): gather over the incident edges in ascending edge index
         double mx = 0;
-        for (int p = tid; p < nf; p += PG_THREADS) {
+        for (int item = gtid; item < nf * 6; item += gsz) {
+            const int p = item / 6, i = item - 6 * p;
             const int v = a.vof[p];
-            double Ap[36], Bp[36], g[6], hd[6];
-            for (int k = 0; k < 36; k++) { Ap[k] = 0; Bp[k] = 0; }
-            for (int k = 0; k < 6; k++) { g[k] = 0; hd[k] = 0; }
+            double Ap[6] = {0, 0, 0, 0, 0, 0}, Bp[6] = {0, 0, 0, 0, 0, 0}, g = 0, hd = 0;
             for (int q = a.inc_start[v]; q < a.inc_start[v + 1]; q++) {
                 const int e = a.inc_edge[q];
                 const int cls = a.ecls[e];
                 const bool first = a.v0[e] == v;
                 const double *Jv = (first ? a.Ji : a.Jj) + 36 * e;
                 const double *er = a.err + 6 * e;
-                for (int i = 0; i < 6; i++) {
-                    double s = 0;
-                    for (int r = 0; r < 6; r++) s += Jv[6 * r + i] * er[r];
-                    g[i] -= s;
-                    double dd = 0;
-                    for (int r = 0; r < 6; r++) dd += Jv[6 * r + i] * Jv[6 * r + i];
-                    hd[i] += dd;
-                }
+                double ji[6];
+#pragma unroll
+                for (int r = 0; r < 6; r++) ji[r] = Jv[6 * r + i];
+                double s = 0, dd = 0;
+#pragma unroll
+                for (int r = 0; r < 6; r++) { s += ji[r] * er[r]; dd += ji[r] * ji[r]; }
+                g -= s;
+                hd += dd;
                 if (cls == PG_DIAG || cls == PG_CHAIN) {
-                    for (int i = 0; i < 6; i++)
-                        for (int j = 0; j < 6; j++) {
-                            double s = 0;
-                            for (int r = 0; r < 6; r++) s += Jv[6 * r + i] * Jv[6 * r + j];
-                            Ap[6 * i + j] += s;
-                        }
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        double t = 0;
+#pragma unroll
+                        for (int r = 0; r < 6; r++) t += ji[r] * Jv[6 * r + j];
+                        Ap[j] += t;
+                    }
                 }
                 if (cls == PG_CHAIN) {
                     const int other = first ? a.v1[e] : a.v0[e];
                     if (a.fidx[other] == p - 1) {  // block (p, p-1) = J_p^T J_{p-1}
                         const double *Jo = (first ? a.Jj : a.Ji) + 36 * e;
-                        for (int i = 0; i < 6; i++)
-                            for (int j = 0; j < 6; j++) {
-                                double s = 0;
-                                for (int r = 0; r < 6; r++) s += Jv[6 * r + i] * Jo[6 * r + j];
-                                Bp[6 * i + j] += s;
-                            }
+#pragma unroll
+                        for (int j = 0; j < 6; j++) {
+                            double t = 0;
+#pragma unroll
+                            for (int r = 0; r < 6; r++) t += ji[r] * Jo[6 * r + j];
+                            Bp[j] += t;
+                        }
                     }
                 }
             }
-            for (int k = 0; k < 36; k++) { a.A[36 * p + k] = Ap[k]; a.B[36 * p + k] = Bp[k]; }
-            for (int k = 0; k < 6; k++) { a.bvec[6 * p + k] = g[k]; mx = fmax(mx, fabs(hd[k])); }
+#pragma unroll
+            for (int j = 0; j < 6; j++) { a.A[36 * p + 6 * i + j] = Ap[j]; a.B[36 * p + 6 * i + j] = Bp[j]; }
+            a.bvec[6 * p + i] = g;
+            mx = fmax(mx, fabs(hd));
         }
         if (it == 0) {  // computeLambdaInit
-            lambda = 1e-5 * pg_block_max(mx, red);
+            lambda = 1e-5 * pg_cluster_max(cluster, mx, red, a.part, phase);
             ni = 2;
+        } else {
+            pg_sync(cluster);
         }
-        __syncthreads();
 
         double rho = 0;
         int qmax = 0;
         PG_T(2);
         do {
-            PG_T(7);
-            for (int k = tid; k < 12 * n; k += PG_THREADS) a.Rtb[k] = a.Rt[k];  // push()
-            // ---- block Thomas factorisation of T = tridiag(B, A + lambda I, B^T): S_p = A_p - G_p B_p^T with
-            //      G_p = B_p S_{p-1}^-1.  The recurrence is serial in p; inside a step one warp works on the 6x6
-            //      blocks (18 lanes x 2 elements: rows r and r + 3 of column c), products and the Gauss-Jordan
-            //      inverse go through shared memory with warp-level synchronisation only.
-            if (tid < 32) {
-                const int l = tid, r = l / 6, cc = l % 6;  // lanes 0..17 own (r, cc) and (r + 3, cc)
-                const bool act = l < 18;
-                int bad = 0;
-                // the blocks of step p + 1 are loaded during step p: the recurrence is a chain of dependent 6 x 6 operations,
-                // and a global load at the head of every step would sit on its critical path
-                double nA0 = 0, nA1 = 0, nB0 = 0, nB1 = 0;
-                if (act && nf > 0) { nA0 = a.A[6 * r + cc]; nA1 = a.A[6 * (r + 3) + cc]; }
-                for (int p = 0; p < nf; p++) {
-                    double e0 = 0, e1 = 0;
-                    if (act) {
-                        e0 = nA0 + (r == cc ? lambda : 0.0);
-                        e1 = nA1 + (r + 3 == cc ? lambda : 0.0);
-                        if (p > 0) { w_B[6 * r + cc] = nB0; w_B[6 * (r + 3) + cc] = nB1; }
-                        if (p + 1 < nf) {
-                            nA0 = a.A[36 * (p + 1) + 6 * r + cc]; nA1 = a.A[36 * (p + 1) + 6 * (r + 3) + cc];
-                            nB0 = a.B[36 * (p + 1) + 6 * r + cc]; nB1 = a.B[36 * (p + 1) + 6 * (r + 3) + cc];
-                        }
-                    }
-                    __syncwarp();
-                    if (p > 0) {
-                        if (act) {  // G = B S_{p-1}^-1
-                            double g0 = 0, g1 = 0;
-#pragma unroll
-                            for (int k = 0; k < 6; k++) { g0 += w_B[6 * r + k] * w_I[6 * k + cc]; g1 += w_B[6 * (r + 3) + k] * w_I[6 * k + cc]; }
-                            w_G[6 * r + cc] = g0; w_G[6 * (r + 3) + cc] = g1;
-                            a.G[36 * p + 6 * r + cc] = g0; a.G[36 * p + 6 * (r + 3) + cc] = g1;
-                        }
-                        __syncwarp();
-                        if (act) {  // S = A - G B^T
-#pragma unroll
-                            for (int k = 0; k < 6; k++) { e0 -= w_G[6 * r + k] * w_B[6 * cc + k]; e1 -= w_G[6 * (r + 3) + k] * w_B[6 * cc + k]; }
-                        }
-                    }
-                    if (act) { w_M[6 * r + cc] = e0; w_M[6 * (r + 3) + cc] = e1; }
-                    __syncwarp();
-                    if (act) {  // symmetrise against round-off, start Gauss-Jordan on [M | I]
-                        e0 = 0.5 * (w_M[6 * r + cc] + w_M[6 * cc + r]);
-                        e1 = 0.5 * (w_M[6 * (r + 3) + cc] + w_M[6 * cc + r + 3]);
-                    }
-                    double i0 = r == cc ? 1.0 : 0.0, i1 = r + 3 == cc ? 1.0 : 0.0;
-                    // Gauss-Jordan on [M | I] in registers: the pivot row and the pivot column travel by warp shuffles
-                    // (element (r, cc) lives in lane 6 r + cc, rows 3..5 in the second register of lanes 0..17)
-                    const int col_src = act ? 6 * r : 0;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        const double rowm = k < 3 ? e0 : e1, rowi = k < 3 ? i0 : i1;
-                        const double piv = __shfl_sync(0xffffffffu, rowm, 6 * (k % 3) + k);
-                        double mk = __shfl_sync(0xffffffffu, rowm, 6 * (k % 3) + cc);
-                        double ik = __shfl_sync(0xffffffffu, rowi, 6 * (k % 3) + cc);
-                        const double f0 = __shfl_sync(0xffffffffu, e0, col_src + k), f1 = __shfl_sync(0xffffffffu, e1, col_src + k);
-                        if (!(piv > 0)) bad = 1;  // positive definite blocks have positive pivots without pivoting
-                        const double ip = 1.0 / piv;
-                        mk *= ip;
-                        ik *= ip;
-                        e0 = r == k ? mk : e0 - f0 * mk;      i0 = r == k ? ik : i0 - f0 * ik;
-                        e1 = r + 3 == k ? mk : e1 - f1 * mk;  i1 = r + 3 == k ? ik : i1 - f1 * ik;
-                    }
-                    __syncwarp();
-                    if (act) { w_I[6 * r + cc] = i0; w_I[6 * (r + 3) + cc] = i1; }
-                    __syncwarp();
-                    if (act) { a.Sinv[36 * p + 6 * r + cc] = i0; a.Sinv[36 * p + 6 * (r + 3) + cc] = i1; }
-                    if (__any_sync(0xffffffffu, bad)) break;
-                }
-                if (tid == 0) s_bad = bad;
+            // ---- push(), the damped block-tridiagonal system and the right-hand sides
+            //      Q[p][c][6]: column 0 = b, column 1 + 6 r + k = row k of J_loop,r (as a column of J^T)
+            for (int k = gtid; k < 12 * n; k += gsz) a.Rtb[k] = a.Rt[k];
+            for (int k = gtid; k < 36 * nf; k += gsz) {
+                const int rc = k % 36;
+                a.D[k] = a.A[k] + ((rc / 6 == rc % 6) ? lambda : 0.0);
+                a.L0[k] = a.B[k];
             }
-            PG_T(3);
-            // ---- right-hand sides Q[p][c][6]: column 0 = b, column 1 + 6r + k = row k of J_loop,r (as a column of J^T)
-            for (int idx = tid; idx < nf * NC * 6; idx += PG_THREADS) a.Q[idx] = 0;
-            __syncthreads();
-            for (int idx = tid; idx < nf * 6; idx += PG_THREADS) a.Q[(size_t)(idx / 6) * NC * 6 + idx % 6] = a.bvec[idx];
-            for (int idx = tid; idx < R * 6 * 2; idx += PG_THREADS) {
+            for (size_t idx = gtid; idx < (size_t)nf * NC * 6; idx += gsz) {
+                const int p = (int)(idx / ((size_t)NC * 6)), rem = (int)(idx - (size_t)p * NC * 6);
+                a.Q[idx] = rem < 6 ? a.bvec[6 * p + rem] : 0.0;
+            }
+            if (gtid == 0) a.flags[3] = 0;
+            pg_sync(cluster);
+            for (int idx = gtid; idx < R * 6 * 2; idx += gsz) {
                 const int r = idx / 12, k = (idx % 12) / 2, side = idx % 2;
                 const int e = a.loop_edge[r];
                 const int p = a.fidx[side ? a.v1[e] : a.v0[e]];
@@ -346,215 +377,312 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 6; i++) q[i] = J[6 * k + i];
             }
-            __syncthreads();
-            int ok = !s_bad;
-            __syncthreads();
-            PG_T(4);
-            if (ok) {
-                // ---- T^-1 [b, J^T]: one thread per column, sequential over the chain; the 6x6 blocks every column
-                //      needs (G_p forward, S_p^-1 and B_{p+1} backward) are staged through shared memory in chunks.
-                {
-                    const int ncol_iters = (NC + PG_THREADS - 1) / PG_THREADS;
-                    for (int ci = 0; ci < ncol_iters; ci++) {
-                        const int c = ci * PG_THREADS + tid;
-                        const bool on = c < NC;
-                        // The recurrences only carry y (forward) and x (backward); the right-hand sides live in L2 (3.6 MB for
-                        // KITTI-00), ~700 cycles away.  They are therefore fetched a block of PG_PF steps ahead of their use —
-                        // without this every step waits for its own loads behind the previous step's stores.
-                        double y[6] = {0, 0, 0, 0, 0, 0};
-                        double cur[PG_PF][6], nxt[PG_PF][6];
+            PG_T(3);
+            // ---- block cyclic reduction, forward.  Level l (stride s = 2^l): active vertices are p with (p + 1) % s == 0;
+            //      those with (p + 1) % 2s == s are ELIMINATED, the others survive.  Row p reads
+            //      Lp x_{p-s} + D_p x_p + L_{p+s}^T x_{p+s} = r_p   (L_p couples p to its left active neighbour).
+            //      Phase a:  [right-hand sides of the previous level's survivors] + [G_e = D_e^-1, U_e = L_{e+s} saved]
+            //      Phase b:  [y_e = G_e r_e for every column] + [D, L of the survivors]
+            int levels = 0;
+            for (int s = 1; s - 1 < nf; s <<= 1) levels++;
+            for (int l = 0, s = 1; l < levels; l++, s <<= 1) {
+                const double *Lc = (l & 1) ? a.L1 : a.L0;
+                double *Ln = (l & 1) ? a.L0 : a.L1;
+                // phase a (1): right-hand sides of the survivors of level l - 1 (stride s / 2), every column
+                if (l > 0) {
+                    const int sp = s >> 1;   // previous stride; survivors v = 2 sp - 1 + 2 sp k = s - 1 + s k
+                    const double *Lp = ((l - 1) & 1) ? a.L1 : a.L0;
+                    const int nsv = (nf - (s - 1) + s - 1) / s;   // vertices v = s - 1 + s k < nf
+                    for (size_t item = gtid; item < (size_t)nsv * NC; item += gsz) {
+                        const int k = (int)(item / NC), c = (int)(item - (size_t)k * NC);
+                        const int v = s - 1 + s * k;
+                        double *rv = a.Q + ((size_t)v * NC + c) * 6;
+                        double acc[6];
 #pragma unroll
-                        for (int s4 = 0; s4 < PG_PF; s4++)
+                        for (int i = 0; i < 6; i++) acc[i] = rv[i];
+                        {   // left eliminated neighbour v - sp (always exists)
+                            const double *y = a.Q + ((size_t)(v - sp) * NC + c) * 6, *Lv = Lp + 36 * v;
 #pragma unroll
-                            for (int i = 0; i < 6; i++) cur[s4][i] = (on && s4 < nf) ? a.Q[((size_t)s4 * NC + c) * 6 + i] : 0.0;
-                        for (int p0 = 0; p0 < nf; p0 += PG_CHUNK) {
-                            const int pn = min(PG_CHUNK, nf - p0);
-                            __syncthreads();
-                            for (int k = tid; k < pn * 36; k += PG_THREADS) w_stage[k] = a.G[36 * p0 + k];
-                            __syncthreads();
-                            if (on)
-                                for (int pb = 0; pb < pn; pb += PG_PF) {
+                            for (int i = 0; i < 6; i++)
 #pragma unroll
-                                    for (int s4 = 0; s4 < PG_PF; s4++) {  // the block after this one
-                                        const int pnx = p0 + pb + PG_PF + s4;
-#pragma unroll
-                                        for (int i = 0; i < 6; i++) nxt[s4][i] = pnx < nf ? a.Q[((size_t)pnx * NC + c) * 6 + i] : 0.0;
-                                    }
-#pragma unroll
-                                    for (int s4 = 0; s4 < PG_PF; s4++) {
-                                        const int pp = pb + s4, p = p0 + pp;
-                                        if (pp < pn) {
-                                            double v[6];
-#pragma unroll
-                                            for (int i = 0; i < 6; i++) v[i] = cur[s4][i];
-                                            if (p > 0) {
-                                                const double *Gp = w_stage + 36 * pp;
-#pragma unroll
-                                                for (int i = 0; i < 6; i++) {
-                                                    double sacc = v[i];
-#pragma unroll
-                                                    for (int k = 0; k < 6; k++) sacc -= Gp[6 * i + k] * y[k];
-                                                    v[i] = sacc;
-                                                }
-                                                double *q = a.Q + ((size_t)p * NC + c) * 6;
-#pragma unroll
-                                                for (int i = 0; i < 6; i++) q[i] = v[i];
-                                            }
-#pragma unroll
-                                            for (int i = 0; i < 6; i++) y[i] = v[i];
-                                        }
-                                    }
-#pragma unroll
-                                    for (int s4 = 0; s4 < PG_PF; s4++)
-#pragma unroll
-                                        for (int i = 0; i < 6; i++) cur[s4][i] = nxt[s4][i];
-                                }
+                                for (int j = 0; j < 6; j++) acc[i] -= Lv[6 * i + j] * y[j];
                         }
-                        double xn[6] = {0, 0, 0, 0, 0, 0};
-                        // backward: block s4 = 0 is the highest step; the forward pass' stores are visible to this thread
+                        if (v + sp < nf) {   // right eliminated neighbour: its L couples it to v
+                            const double *y = a.Q + ((size_t)(v + sp) * NC + c) * 6, *Le = Lp + 36 * (v + sp);
 #pragma unroll
-                        for (int s4 = 0; s4 < PG_PF; s4++)
+                            for (int i = 0; i < 6; i++)
 #pragma unroll
-                            for (int i = 0; i < 6; i++) cur[s4][i] = (on && nf - 1 - s4 >= 0) ? a.Q[((size_t)(nf - 1 - s4) * NC + c) * 6 + i] : 0.0;
-                        for (int pend = nf; pend > 0; pend -= PG_CHUNK) {
-                            const int p0 = max(0, pend - PG_CHUNK), pn = pend - p0;
-                            __syncthreads();
-                            for (int k = tid; k < pn * 36; k += PG_THREADS) {
-                                w_stage[k] = a.Sinv[36 * p0 + k];
-                                w_stage[PG_CHUNK * 36 + k] = p0 + k / 36 + 1 < nf ? a.B[36 * (p0 + 1) + k] : 0.0;  // B_{p+1}
+                                for (int j = 0; j < 6; j++) acc[i] -= Le[6 * j + i] * y[j];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 6; i++) rv[i] = acc[i];
+                    }
+                }
+                // phase a (2): inverse of the eliminated vertices' diagonal blocks, copy of their right neighbour's coupling
+                const int nel = (nf - (s - 1) + 2 * s - 1) / (2 * s);   // vertices e = s - 1 + 2 s k < nf
+                for (int k = gtid; k < nel; k += gsz) {
+                    const int e = s - 1 + 2 * s * k;
+                    if (!pg_inv6(a.D + 36 * e, a.G + 36 * e)) a.flags[3] = 1;
+                    if (e + s < nf) {   // all 18 loads first, then the stores (the compiler must assume the two arrays alias)
+                        const double2 *src = reinterpret_cast<const double2 *>(Lc + 36 * (e + s));
+                        double2 *dst = reinterpret_cast<double2 *>(a.U + 36 * e);
+                        double2 tmp[18];
+#pragma unroll
+                        for (int q = 0; q < 18; q++) tmp[q] = src[q];
+#pragma unroll
+                        for (int q = 0; q < 18; q++) dst[q] = tmp[q];
+                    }
+                }
+                pg_sync(cluster);
+                PG_T(8);
+                // phase b (1): y_e = G_e r_e in place, every column
+                for (size_t item = gtid; item < (size_t)nel * NC; item += gsz) {
+                    const int k = (int)(item / NC), c = (int)(item - (size_t)k * NC);
+                    const int e = s - 1 + 2 * s * k;
+                    double *re = a.Q + ((size_t)e * NC + c) * 6;
+                    const double *G = a.G + 36 * e;
+                    double r[6], y[6];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) r[i] = re[i];
+#pragma unroll
+                    for (int i = 0; i < 6; i++) {
+                        double v = 0;
+#pragma unroll
+                        for (int j = 0; j < 6; j++) v += G[6 * i + j] * r[j];
+                        y[i] = v;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; i++) re[i] = y[i];
+                }
+                // phase b (2): Schur update of the survivors v = 2 s - 1 + 2 s k, one thread per (vertex, block row)
+                const int nsv2 = (nf - (2 * s - 1) + 2 * s - 1) / (2 * s);
+                for (int item = gtid; item < 6 * nsv2 && 2 * s - 1 < nf; item += gsz) {
+                    const int k = item / 6, i = item - 6 * k;
+                    const int v = 2 * s - 1 + 2 * s * k;
+                    double drow[6], lrow[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+                    for (int j = 0; j < 6; j++) drow[j] = a.D[36 * v + 6 * i + j];
+                    {   // left eliminated neighbour e1 = v - s:  T = L_v G_e1;  D -= T L_v^T;  L' = -T L_e1
+                        const int e1 = v - s;
+                        const double *Lv = Lc + 36 * v, *G = a.G + 36 * e1, *Le = Lc + 36 * e1;
+                        double t[6];
+#pragma unroll
+                        for (int j = 0; j < 6; j++) {
+                            double x = 0;
+#pragma unroll
+                            for (int q = 0; q < 6; q++) x += Lv[6 * i + q] * G[6 * q + j];
+                            t[j] = x;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 6; j++) {
+                            double x = 0;
+#pragma unroll
+                            for (int q = 0; q < 6; q++) x += t[q] * Lv[6 * j + q];
+                            drow[j] -= x;
+                        }
+                        if (e1 - s >= 0) {
+#pragma unroll
+                            for (int j = 0; j < 6; j++) {
+                                double x = 0;
+#pragma unroll
+                                for (int q = 0; q < 6; q++) x += t[q] * Le[6 * q + j];
+                                lrow[j] = -x;
                             }
-                            __syncthreads();
-                            if (on)
-                                for (int pb = pn - 1; pb >= 0; pb -= PG_PF) {
+                        }
+                    }
+                    if (v + s < nf) {   // right eliminated neighbour e2 = v + s:  T = L_e2^T G_e2;  D -= T L_e2
+                        const int e2 = v + s;
+                        const double *Le = Lc + 36 * e2, *G = a.G + 36 * e2;
+                        double t[6];
 #pragma unroll
-                                    for (int s4 = 0; s4 < PG_PF; s4++) {  // the block below this one
-                                        const int pnx = p0 + pb - PG_PF - s4;
+                        for (int j = 0; j < 6; j++) {
+                            double x = 0;
 #pragma unroll
-                                        for (int i = 0; i < 6; i++) nxt[s4][i] = pnx >= 0 ? a.Q[((size_t)pnx * NC + c) * 6 + i] : 0.0;
-                                    }
+                            for (int q = 0; q < 6; q++) x += Le[6 * q + i] * G[6 * q + j];
+                            t[j] = x;
+                        }
 #pragma unroll
-                                    for (int s4 = 0; s4 < PG_PF; s4++) {
-                                        const int pp = pb - s4, p = p0 + pp;
-                                        if (pp >= 0) {
-                                            double r6[6];
+                        for (int j = 0; j < 6; j++) {
+                            double x = 0;
 #pragma unroll
-                                            for (int i = 0; i < 6; i++) r6[i] = cur[s4][i];
-                                            if (p + 1 < nf) {
-                                                const double *Bn = w_stage + PG_CHUNK * 36 + 36 * pp;  // (B_{p+1})^T x_{p+1}
+                            for (int q = 0; q < 6; q++) x += t[q] * Le[6 * q + j];
+                            drow[j] -= x;
+                        }
+                    }
 #pragma unroll
-                                                for (int i = 0; i < 6; i++) {
-                                                    double sacc = 0;
+                    for (int j = 0; j < 6; j++) { a.D[36 * v + 6 * i + j] = drow[j]; Ln[36 * v + 6 * i + j] = lrow[j]; }
+                }
+                pg_sync(cluster);
+                PG_T(9);
+            }
+            int ok = !__ldcg(a.flags + 3);
+            PG_T(4);
+            // ---- backward: x_e = y_e - G_e (L_e x_{e-s} + U_e^T x_{e+s}), from the last level down; Q ends as T^-1 [b, J^T]
+            for (int l = levels - 1, s = 1 << (levels - 1); l >= 0 && ok; l--, s >>= 1) {
+                const double *Lc = (l & 1) ? a.L1 : a.L0;
+                const int nel = (nf - (s - 1) + 2 * s - 1) / (2 * s);
+                for (size_t item = gtid; item < (size_t)nel * NC; item += gsz) {
+                    const int k = (int)(item / NC), c = (int)(item - (size_t)k * NC);
+                    const int e = s - 1 + 2 * s * k;
+                    double w[6] = {0, 0, 0, 0, 0, 0};
+                    bool any = false;
+                    if (e - s >= 0) {
+                        const double *xa = a.Q + ((size_t)(e - s) * NC + c) * 6, *Le = Lc + 36 * e;
 #pragma unroll
-                                                    for (int k = 0; k < 6; k++) sacc += Bn[6 * k + i] * xn[k];
-                                                    r6[i] -= sacc;
-                                                }
-                                            }
-                                            const double *Si = w_stage + 36 * pp;
+                        for (int i = 0; i < 6; i++)
 #pragma unroll
-                                            for (int i = 0; i < 6; i++) {
-                                                double sacc = 0;
+                            for (int j = 0; j < 6; j++) w[i] += Le[6 * i + j] * xa[j];
+                        any = true;
+                    }
+                    if (e + s < nf) {
+                        const double *xc = a.Q + ((size_t)(e + s) * NC + c) * 6, *Ue = a.U + 36 * e;
 #pragma unroll
-                                                for (int k = 0; k < 6; k++) sacc += Si[6 * i + k] * r6[k];
-                                                xn[i] = sacc;
-                                            }
-                                            double *q = a.Q + ((size_t)p * NC + c) * 6;
+                        for (int i = 0; i < 6; i++)
 #pragma unroll
-                                            for (int i = 0; i < 6; i++) q[i] = xn[i];
-                                        }
-                                    }
+                            for (int j = 0; j < 6; j++) w[i] += Ue[6 * j + i] * xc[j];
+                        any = true;
+                    }
+                    if (any) {
+                        double *xe = a.Q + ((size_t)e * NC + c) * 6;
+                        const double *G = a.G + 36 * e;
 #pragma unroll
-                                    for (int s4 = 0; s4 < PG_PF; s4++)
+                        for (int i = 0; i < 6; i++) {
+                            double v = 0;
 #pragma unroll
-                                        for (int i = 0; i < 6; i++) cur[s4][i] = nxt[s4][i];
-                                }
+                            for (int j = 0; j < 6; j++) v += G[6 * i + j] * w[j];
+                            xe[i] -= v;
                         }
                     }
                 }
-                __syncthreads();
-                PG_T(5);
-                const int n6r = 6 * R;
-                if (R > 0) {
-                    // ---- capacitance matrix M = I + J Z and right-hand side v = J x0
-                    for (int idx = tid; idx < n6r * (n6r + 1); idx += PG_THREADS) {
-                        const int row = idx / (n6r + 1), col = idx % (n6r + 1);  // col n6r = the vector v
-                        const int r = row / 6, k = row % 6;
-                        const int e = a.loop_edge[r];
-                        const int pa = a.fidx[a.v0[e]], pb = a.fidx[a.v1[e]];
-                        const int c = col == n6r ? 0 : 1 + col;
-                        const double *za = a.Q + ((size_t)pa * NC + c) * 6, *zb = a.Q + ((size_t)pb * NC + c) * 6;
-                        const double *Ja = a.Ji + 36 * e + 6 * k, *Jb = a.Jj + 36 * e + 6 * k;
-                        double s = 0;
+                pg_sync(cluster);
+            }
+            PG_T(5);
+            if (ok && R > 0) {
+                // ---- capacitance matrix M = I + J Z and right-hand side v = J x0
+                for (int idx = gtid; idx < n6r * (n6r + 1); idx += gsz) {
+                    const int row = idx / (n6r + 1), col = idx % (n6r + 1);  // col n6r = the vector v
+                    const int r = row / 6, k = row % 6;
+                    const int e = a.loop_edge[r];
+                    const int pa = a.fidx[a.v0[e]], pb = a.fidx[a.v1[e]];
+                    const int c = col == n6r ? 0 : 1 + col;
+                    const double *za = a.Q + ((size_t)pa * NC + c) * 6, *zb = a.Q + ((size_t)pb * NC + c) * 6;
+                    const double *Ja = a.Ji + 36 * e + 6 * k, *Jb = a.Jj + 36 * e + 6 * k;
+                    double s = 0;
 #pragma unroll
-                        for (int i = 0; i < 6; i++) s += Ja[i] * za[i] + Jb[i] * zb[i];
-                        if (col == n6r) a.yv[row] = s;
-                        else a.M[(size_t)row * n6r + col] = s + (row == col ? 1.0 : 0.0);
-                    }
+                    for (int i = 0; i < 6; i++) s += Ja[i] * za[i] + Jb[i] * zb[i];
+                    if (col == n6r) a.yv[row] = s;
+                    else a.M[(size_t)row * n6r + col] = s + (row == col ? 1.0 : 0.0);
+                }
+                pg_sync(cluster);
+                PG_T(10);
+                // ---- dense Cholesky of M + the two substitutions by CTA 0 (in shared memory when it fits)
+                if (blockIdx.x == 0) {
+                    const bool in_smem = R <= a.smem_loops;
+                    double *Mw = in_smem ? smM : a.M;
+                    const int ld = in_smem ? n6r + 1 : n6r;   // odd leading dimension in shared memory: 6R is a multiple of 32 banks' worth for R = 16
+                    if (in_smem)
+                        for (int k = tid; k < n6r * n6r; k += PG_THREADS) smM[(k / n6r) * ld + k % n6r] = a.M[k];
+                    if (tid == 0) s_bad = 0;
                     __syncthreads();
-                    // ---- dense Cholesky of M, right-looking with one barrier per column: every thread reads the pivot and
-                    //      forms the scaled column entries it needs itself; column j of L goes to ROW j of the upper triangle
-                    //      (M[j][i], i > j), the trailing update works on the lower triangle, the diagonal of L is kept apart.
-                    {
-                        const int r0 = tid >> 3, c0 = tid & 7;
-                        for (int j = 0; j < n6r; j++) {
-                            const double d = a.M[(size_t)j * n6r + j];
-                            if (!(d > 0)) { if (tid == 0) s_bad = 1; break; }  // uniform: every thread reads the same entry
-                            const double dj = sqrt(d), inv = 1.0 / dj;
-                            if (tid == 0) s_diag[j] = dj;
-                            for (int i = j + 1 + r0; i < n6r; i += PG_THREADS / 8) {
-                                const double lij = a.M[(size_t)i * n6r + j] * inv;
-                                if (c0 == 0) a.M[(size_t)j * n6r + i] = lij;
-                                for (int k = j + 1 + c0; k <= i; k += 8) a.M[(size_t)i * n6r + k] -= lij * (a.M[(size_t)k * n6r + j] * inv);
-                            }
-                            __syncthreads();
+                    // right-looking, one barrier per column: every thread reads the pivot and forms the scaled column entries
+                    // it needs itself; column j of L goes to ROW j of the upper triangle (M[j][i], i > j), the trailing update
+                    // works on the lower triangle, the diagonal of L is kept apart.
+                    double *diag = in_smem ? s_diag : a.yv + n6r;
+                    const int r0 = tid >> 3, c0 = tid & 7;
+                    for (int j = 0; j < n6r; j++) {
+                        const double d = Mw[(size_t)j * ld + j];
+                        if (!(d > 0)) { if (tid == 0) s_bad = 1; break; }  // uniform: every thread reads the same entry
+                        const double inv = rsqrt(d);
+                        if (tid == 0) diag[j] = inv;   // reciprocal pivots: no division in the substitutions
+                        for (int i = j + 1 + r0; i < n6r; i += PG_THREADS / 8) {
+                            const double lij = Mw[(size_t)i * ld + j] * inv;
+                            if (c0 == 0) Mw[(size_t)j * ld + i] = lij;
+                            for (int k = j + 1 + c0; k <= i; k += 8) Mw[(size_t)i * ld + k] -= lij * (Mw[(size_t)k * ld + j] * inv);
                         }
+                        __syncthreads();
                     }
                     __syncthreads();
-                    ok = !s_bad;
-                    __syncthreads();
-                    if (ok && tid < 32) {  // M y = v by one warp: L(i, k) = M[k][i]
+                    if (!s_bad && tid < 32 && in_smem) {
+                        // M y = v by one warp, the unknowns in registers (lane l owns rows l, l + 32, ...): per step one broadcast of
+                        // the solved unknown and one multiply-add per owned row; L(i, j) = M[j][i] (row j of the upper triangle).
+                        const int lane = tid;
+                        constexpr int NR = (6 * PG_SMEM_LOOPS + 31) / 32;
+                        double xr[NR];
+#pragma unroll
+                        for (int q = 0; q < NR; q++) xr[q] = lane + 32 * q < n6r ? __ldcg(a.yv + lane + 32 * q) : 0.0;
+                        for (int j = 0; j < n6r; j++) {   // forward, column oriented
+                            double src = 0;
+#pragma unroll
+                            for (int q = 0; q < NR; q++) src = (j >> 5) == q ? xr[q] : src;
+                            const double yj = __shfl_sync(0xffffffffu, src, j & 31) * diag[j];
+                            const double *row = Mw + (size_t)j * ld;
+#pragma unroll
+                            for (int q = 0; q < NR; q++) {
+                                const int i = lane + 32 * q;
+                                if (i == j) xr[q] = yj;
+                                else if (i > j && i < n6r) xr[q] -= row[i] * yj;
+                            }
+                        }
+                        for (int j = n6r - 1; j >= 0; j--) {   // backward with L^T: L^T(i, j) = L(j, i) = M[i][j], i < j
+                            double src = 0;
+#pragma unroll
+                            for (int q = 0; q < NR; q++) src = (j >> 5) == q ? xr[q] : src;
+                            const double xj = __shfl_sync(0xffffffffu, src, j & 31) * diag[j];
+#pragma unroll
+                            for (int q = 0; q < NR; q++) {
+                                const int i = lane + 32 * q;
+                                if (i == j) xr[q] = xj;
+                                else if (i < j) xr[q] -= Mw[(size_t)i * ld + j] * xj;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < NR; q++)
+                            if (lane + 32 * q < n6r) a.yv[lane + 32 * q] = xr[q];
+                    } else if (!s_bad && tid < 32) {  // workspace in global memory (more loop edges than fit shared memory)
                         const int lane = tid;
                         for (int i = 0; i < n6r; i++) {
                             double v = 0;
-                            for (int k = lane; k < i; k += 32) v += a.M[(size_t)k * n6r + i] * a.yv[k];
+                            for (int k = lane; k < i; k += 32) v += Mw[(size_t)k * ld + i] * a.yv[k];
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                            if (lane == 0) a.yv[i] = (a.yv[i] - v) / s_diag[i];
+                            if (lane == 0) a.yv[i] = (a.yv[i] - v) * diag[i];
                             __syncwarp();
                         }
                         for (int i = n6r - 1; i >= 0; i--) {
                             double v = 0;
-                            for (int k = i + 1 + lane; k < n6r; k += 32) v += a.M[(size_t)i * n6r + k] * a.yv[k];
+                            for (int k = i + 1 + lane; k < n6r; k += 32) v += Mw[(size_t)i * ld + k] * a.yv[k];
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                            if (lane == 0) a.yv[i] = (a.yv[i] - v) / s_diag[i];
+                            if (lane == 0) a.yv[i] = (a.yv[i] - v) * diag[i];
                             __syncwarp();
                         }
                     }
                     __syncthreads();
+                    if (tid == 0 && s_bad) a.flags[3] = 1;
                 }
-                if (ok) {
-                    // ---- x = x0 - Z y
-                    for (int idx = tid; idx < nf * 6; idx += PG_THREADS) {
-                        const int p = idx / 6, i = idx % 6;
-                        const double *q = a.Q + (size_t)p * NC * 6;
-                        double s = q[i];
-                        for (int c = 0; c < n6r; c++) s -= q[(1 + c) * 6 + i] * a.yv[c];
-                        a.x[idx] = s;
-                    }
-                    __syncthreads();
+                pg_sync(cluster);
+                PG_T(11);
+                ok = !__ldcg(a.flags + 3);
+            }
+            if (ok) {
+                // ---- x = x0 - Z y
+                for (int idx = gtid; idx < nf * 6; idx += gsz) {
+                    const int p = idx / 6, i = idx % 6;
+                    const double *q = a.Q + (size_t)p * NC * 6;
+                    double s = q[i];
+                    for (int c = 0; c < n6r; c++) s -= q[(1 + c) * 6 + i] * __ldcg(a.yv + c);
+                    a.x[idx] = s;
                 }
             }
-            __syncthreads();
+            pg_sync(cluster);
             PG_T(6);
-            if (tid == 0) s_bad = 0;
             double scale = 0;
             if (ok) {
-                for (int idx = tid; idx < nf * 6; idx += PG_THREADS) scale += a.x[idx] * (lambda * a.x[idx] + a.bvec[idx]);
-                scale = pg_block_sum(scale, red);
-                for (int p = tid; p < nf; p += PG_THREADS) pose_oplus(a.Rt + 12 * a.vof[p], a.x + 6 * p);
-                __syncthreads();
+                for (int idx = gtid; idx < nf * 6; idx += gsz) scale += a.x[idx] * (lambda * a.x[idx] + a.bvec[idx]);
+                for (int p = gtid; p < nf; p += gsz) pose_oplus(a.Rt + 12 * a.vof[p], a.x + 6 * p);
             }
-            double tempChi = pg_errors(a, red);
+            scale = pg_cluster_sum(cluster, scale, red, a.part, phase);
+            double tempChi = errors();
             if (!ok) tempChi = 1.7976931348623157e308;
             rho = (currentChi - tempChi) / (scale + 1e-3);
             trials++;
@@ -568,22 +696,22 @@ __global__ void __launch_bounds__(PG_THREADS) k_posegraph(const __grid_constant_
             } else {
                 lambda *= ni;
                 ni *= 2;
-                __syncthreads();
-                for (int k = tid; k < 12 * n; k += PG_THREADS) a.Rt[k] = a.Rtb[k];  // pop()
-                __syncthreads();
+                for (int k = gtid; k < 12 * n; k += gsz) a.Rt[k] = a.Rtb[k];  // pop()
+                pg_sync(cluster);
             }
             qmax++;
+            PG_T(7);
         } while (rho < 0 && qmax < 10);
         lm_iters++;
         if (qmax == 10 || rho == 0) terminated = true;
     }
-    __syncthreads();
-    for (int v = tid; v < n; v += PG_THREADS) {
+    pg_sync(cluster);
+    for (int v = gtid; v < n; v += gsz) {
         if (a.fixed[v]) continue;  // fixed vertices keep their input bits
         R_to_quat(a.Rt + 12 * v, a.poses + 7 * v);
         a.poses[7 * v + 4] = a.Rt[12 * v + 9]; a.poses[7 * v + 5] = a.Rt[12 * v + 10]; a.poses[7 * v + 6] = a.Rt[12 * v + 11];
     }
-    if (tid == 0) {
+    if (gtid == 0) {
         a.info[0] = lm_iters; a.info[1] = trials; a.info[2] = nf; a.info[3] = R;
         a.stats[0] = chi_start; a.stats[1] = chi_end;
     }
@@ -602,21 +730,26 @@ static void free_pg(sb_posegraph *h) {
     delete h;
 }
 
-extern "C" int sb_posegraph_create(sb_posegraph_t **out, int device, int max_vertices, int max_edges) {
+static int pg_create(sb_posegraph_t **out, int device, int max_vertices, int max_edges, int max_loops) {
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
     SB_REQUIRE(max_vertices >= 2 && max_vertices <= (1 << 20), "max_vertices out of range");
     SB_REQUIRE(max_edges >= 1 && max_edges <= (1 << 22), "max_edges out of range");
+    SB_REQUIRE(max_loops >= 1 && max_loops <= 4096, "max_loops out of range [1, 4096]");
+    const size_t n = max_vertices, m = max_edges, NC = 1 + 6 * (size_t)max_loops, R6 = 6 * (size_t)max_loops;
+    SB_REQUIRE(n * NC * 6 * 8 <= ((size_t)48 << 30), "max_vertices x max_loops needs more than 48 GB of workspace");
     SB_TRY(sb_use_device(device));
     sb_posegraph *h = new sb_posegraph();
     memset(h, 0, sizeof(*h));
     h->device = device;
     h->max_vertices = max_vertices;
     h->max_edges = max_edges;
-    const size_t n = max_vertices, m = max_edges, NC = 1 + 6 * PG_MAX_LOOPS, R6 = 6 * PG_MAX_LOOPS;
-    h->work_doubles = 24 * n + 12 * m + 6 * m + 72 * m + 36 * n * 4 + 6 * n * 3 + n * NC * 6 + R6 * R6 + R6 + 8;
-    h->iwork_ints = 2 * n + 3 * m + n + (n + 1) + 2 * m + PG_MAX_LOOPS + 16;
+    h->max_loops = max_loops;
+    h->work_doubles = 24 * n + 12 * m + 6 * m + 72 * m + 36 * n * 7 + 6 * n * 2 + n * NC * 6 + R6 * R6 + 2 * R6 + 4 * PG_CLUSTER + 8;
+    h->iwork_ints = 2 * n + 3 * m + n + (n + 1) + 2 * m + max_loops + 16;
+    const int sl = max_loops < PG_SMEM_LOOPS ? max_loops : PG_SMEM_LOOPS;
+    h->smem_bytes = (size_t)6 * sl * (6 * sl + 1) * 8;
     cudaError_t e = cudaMalloc((void **)&h->d_poses, n * 56);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_meas, m * 56);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_fixed, n);
@@ -626,6 +759,8 @@ extern "C" int sb_posegraph_create(sb_posegraph_t **out, int device, int max_ver
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_work, h->work_doubles * 8);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_iwork, h->iwork_ints * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_posegraph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)6 * PG_SMEM_LOOPS * (6 * PG_SMEM_LOOPS + 1) * 8));
+    if (e == cudaSuccess && PG_CLUSTER > 8) e = cudaFuncSetAttribute(k_posegraph, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) {
         sb_set_error("sb_posegraph_create: %s", cudaGetErrorString(e));
         free_pg(h);
@@ -634,6 +769,16 @@ extern "C" int sb_posegraph_create(sb_posegraph_t **out, int device, int max_ver
     h->stream = h->own_stream;
     *out = h;
     return SB_OK;
+}
+
+extern "C" int sb_posegraph_create(sb_posegraph_t **out, int device, int max_vertices, int max_edges) {
+    return pg_create(out, device, max_vertices, max_edges, PG_DEFAULT_LOOPS);
+}
+// max_loops: the largest number of long-range (non-chain) edges between free vertices a solve may contain.  The reference
+// re-adds every historical loop edge on each PoseGraphOptimization (src/loopclosing.cpp:585-599), so a long run needs a
+// generous bound; the workspace grows with max_vertices x max_loops x 288 bytes.
+extern "C" int sb_posegraph_create_loops(sb_posegraph_t **out, int device, int max_vertices, int max_edges, int max_loops) {
+    return pg_create(out, device, max_vertices, max_edges, max_loops);
 }
 
 extern "C" int sb_posegraph_destroy(sb_posegraph_t *h) {
@@ -660,9 +805,10 @@ extern "C" int sb_posegraph_solve_dev(sb_posegraph_t *h, int n_vertices, double 
     SB_REQUIRE(n_edges >= 0 && n_edges <= h->max_edges, "n_edges out of range [0, max_edges]");
     SB_REQUIRE(iters >= 1, "iters must be positive");
     SB_TRY(sb_use_device(h->device));
-    const size_t n = h->max_vertices, m = h->max_edges, NC = 1 + 6 * PG_MAX_LOOPS, R6 = 6 * PG_MAX_LOOPS;
+    const size_t n = h->max_vertices, m = h->max_edges, NC = 1 + 6 * (size_t)h->max_loops, R6 = 6 * (size_t)h->max_loops;
     PgArgs a;
-    a.n = n_vertices; a.m = n_edges; a.iters = iters;
+    a.n = n_vertices; a.m = n_edges; a.iters = iters; a.max_loops = h->max_loops;
+    a.smem_loops = h->max_loops < PG_SMEM_LOOPS ? h->max_loops : PG_SMEM_LOOPS;
     a.poses = d_poses; a.fixed = d_fixed; a.v0 = d_v0; a.v1 = d_v1; a.meas = d_meas; a.info = d_info; a.stats = d_stats;
     double *w = h->d_work;
     a.Rt = w; w += 12 * n;
@@ -673,14 +819,17 @@ extern "C" int sb_posegraph_solve_dev(sb_posegraph_t *h, int n_vertices, double 
     a.Jj = w; w += 36 * m;
     a.A = w; w += 36 * n;
     a.B = w; w += 36 * n;
-    a.Sinv = w; w += 36 * n;
+    a.D = w; w += 36 * n;
+    a.L0 = w; w += 36 * n;
+    a.L1 = w; w += 36 * n;
     a.G = w; w += 36 * n;
+    a.U = w; w += 36 * n;
     a.bvec = w; w += 6 * n;
-    a.hdiag = w; w += 6 * n;
     a.x = w; w += 6 * n;
     a.Q = w; w += n * NC * 6;
     a.M = w; w += R6 * R6;
-    a.yv = w; w += R6;
+    a.yv = w; w += 2 * R6;
+    a.part = w; w += 4 * PG_CLUSTER;
     int32_t *iw = h->d_iwork;
     a.fidx = iw; iw += n;
     a.vof = iw; iw += n;
@@ -688,9 +837,21 @@ extern "C" int sb_posegraph_solve_dev(sb_posegraph_t *h, int n_vertices, double 
     a.eloop = iw; iw += m + n;  // + n ints of cursor scratch
     a.inc_start = iw; iw += n + 1;
     a.inc_edge = iw; iw += 2 * m;
-    a.loop_edge = iw; iw += PG_MAX_LOOPS;
-    k_posegraph<<<1, PG_THREADS, 0, h->stream>>>(a);
-    SB_CUDA(cudaGetLastError());
+    a.loop_edge = iw; iw += h->max_loops;
+    a.flags = iw; iw += 8;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(PG_CLUSTER);
+    cfg.blockDim = dim3(PG_THREADS);
+    cfg.dynamicSmemBytes = h->smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = PG_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SB_CUDA(cudaLaunchKernelEx(&cfg, k_posegraph, a));
     return SB_OK;
 }
 
@@ -719,7 +880,7 @@ extern "C" int sb_posegraph_solve(sb_posegraph_t *h, int n_vertices, double *pos
     SB_CUDA(cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaStreamSynchronize(s));
     if (info[0] < 0) {
-        sb_set_error(info[1] == -2 ? "more than 64 long-range (non-chain) edges between free vertices" : "edge endpoints out of range");
+        sb_set_error(info[1] == -2 ? "more long-range (non-chain) edges between free vertices than the handle's max_loops (sb_posegraph_create_loops)" : "edge endpoints out of range");
         return info[1] == -2 ? SB_ERR_CAPACITY : SB_ERR_INVALID;
     }
     return SB_OK;

@@ -432,8 +432,10 @@ private:
 // The solver of LoopClosing::PoseGraphOptimization (src/loopclosing.cpp:537-646): vertices in ascending keyframe id.
 class PoseGraphSolver {
 public:
-    PoseGraphSolver(int max_vertices = 8192, int max_edges = 16384, int device = 0) {
-        if (sb_posegraph_create(&h_, device, max_vertices, max_edges) != SB_OK) throw std::runtime_error(std::string("sb_posegraph_create: ") + sb_last_error());
+    // max_loops bounds the loop edges of one optimisation; the reference re-adds every historical loop edge on each call
+    // (src/loopclosing.cpp:585-599), so it must cover the whole run (KITTI-00 ends with 17)
+    PoseGraphSolver(int max_vertices = 8192, int max_edges = 16384, int device = 0, int max_loops = 256) {
+        if (sb_posegraph_create_loops(&h_, device, max_vertices, max_edges, max_loops) != SB_OK) throw std::runtime_error(std::string("sb_posegraph_create: ") + sb_last_error());
     }
     ~PoseGraphSolver() { sb_posegraph_destroy(h_); }
     bool Optimize(std::vector<double> &poses7, const std::vector<uint8_t> &fixed, const std::vector<int32_t> &v0, const std::vector<int32_t> &v1,

@@ -257,11 +257,15 @@ int sb_lcd_detect_loop(sb_lcd_t *h, int64_t cur_kf_id, const float *query, float
  *   fixed [n]: the reference fixes the active keyframes, the loop keyframe and keyframe 0 (:559-562);
  *   edge k: vertex v0[k] -> vertex v1[k] with measurement meas[k] = T_v0 * T_v1^-1
  *           (mRelativePoseToLastKF / mRelativePoseToLoopKF, :571-599).
- * The graph must be a chain plus at most 64 long-range edges between free vertices (KITTI-00: 17).
+ * The graph must be a chain plus long-range edges between free vertices (loop edges; KITTI-00: 17): at most 64 with
+ * sb_posegraph_create, at most `max_loops` (<= 4096) with sb_posegraph_create_loops — the reference re-adds every
+ * historical loop edge on each call (:585-599), so size max_loops for the whole run; the workspace is
+ * max_vertices x max_loops x 288 bytes.  More long-range edges than that: SB_ERR_CAPACITY, nothing is modified.
  *   info [4] = LM iterations, LM trials, free vertices, long-range edges;  stats [2] = chi2 before, after.
  * --------------------------------------------------------------------------------------------- */
 typedef struct sb_posegraph sb_posegraph_t;
 int sb_posegraph_create(sb_posegraph_t **h, int device, int max_vertices, int max_edges);
+int sb_posegraph_create_loops(sb_posegraph_t **h, int device, int max_vertices, int max_edges, int max_loops);
 int sb_posegraph_destroy(sb_posegraph_t *h);
 int sb_posegraph_set_stream(sb_posegraph_t *h, void *stream);
 int sb_posegraph_solve(sb_posegraph_t *h, int n_vertices, double *poses, const uint8_t *fixed, int n_edges,

@@ -77,3 +77,36 @@ def test_all_fixed_and_capacity_errors(pkg, pg, synth):
     with pytest.raises(pkg.SlamB200Error) as e:
         pg.solve(g["poses0"], g["fixed"], v0, v1, meas)
     assert e.value.code == -3
+
+
+def test_more_than_64_loop_edges_with_a_larger_workspace(pkg, synth):
+    """The reference re-adds every historical loop edge on each PoseGraphOptimization (src/loopclosing.cpp:585-599), with
+    no limit: a handle created with sb_posegraph_create_loops solves graphs beyond the default 64 (here 80; the
+    capacitance matrix no longer fits shared memory and is factored in global memory)."""
+    g = synth.pose_graph(8, n=160, n_loops=2, n_active=3)
+    rng = np.random.default_rng(1)
+    gt = g["poses_gt"]
+    v0, v1, meas = list(g["v0"]), list(g["v1"]), list(g["meas"])
+    n_extra = 0
+    for i in range(30, 150):
+        for j in (i - 25, i - 27):
+            if n_extra >= 78 or j < 1:
+                break
+            Ri, ti = PG.se3_from7(gt[i])
+            Rj, tj = PG.se3_from7(gt[j])
+            Rji, tji = PG.se3_inv((Rj, tj))
+            R, t = PG.se3_mul((Ri, ti), (Rji, tji))
+            v0.append(i); v1.append(j); meas.append(PG.se3_to7(R, t + rng.normal(0, 0.01, 3)))
+            n_extra += 1
+    v0, v1, meas = np.array(v0, np.int32), np.array(v1, np.int32), np.array(meas)
+    big = pkg.PoseGraph(max_vertices=256, max_edges=1024, max_loops=96)
+    got, ginfo = big.solve(g["poses0"], g["fixed"], v0, v1, meas)
+    want, winfo = PG.solve(g["poses0"], g["fixed"], v0, v1, meas)
+    assert ginfo["loops"] >= 65 and ginfo["lm_iters"] == winfo["lm_iters"]
+    assert rel_close(got, want), np.abs(got - want).max()
+    small = pkg.PoseGraph(max_vertices=256, max_edges=1024)                  # default capacity: refused, poses untouched
+    with pytest.raises(pkg.SlamB200Error) as e:
+        small.solve(g["poses0"], g["fixed"], v0, v1, meas)
+    assert e.value.code == -3
+    big.close()
+    small.close()

@@ -14,9 +14,10 @@ pkg.lib().sb_posegraph_debug_profile(prof)
 _, info = pg.solve(g["poses0"], g["fixed"], g["v0"], g["v1"], g["meas"])
 pkg.lib().sb_posegraph_debug_profile(prof)
 print("info", info)
-names = ["errors", "numeric Jacobians", "assembly", "block Thomas factorisation", "right-hand sides", "chain substitutions",
-         "capacitance + Cholesky + x", "push / update / trial errors"]
-tot = sum(prof[:8])
-for n, v in zip(names, prof[:8]):
+names = ["errors", "numeric Jacobians", "assembly", "push + system + right-hand sides", "cyclic reduction, forward", "cyclic reduction, backward",
+         "capacitance + Cholesky + x", "update / trial errors"]
+names += ["  CR forward: phase a (rhs of survivors, 6x6 inverses)", "  CR forward: phase b (y = G r, Schur update)", "  capacitance: build", "  capacitance: Cholesky + substitutions"]
+tot = sum(prof[:12])
+for n, v in zip(names, prof[:12]):
     print(f"{n:30s} {v:12d} cyc  {100 * v / tot:5.1f}%")
 print("total cycles", tot, "=", tot / 1.965e6, "ms at 1965 MHz")
