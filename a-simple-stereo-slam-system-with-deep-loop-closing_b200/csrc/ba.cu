@@ -787,6 +787,11 @@ extern "C" int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_pos
     return SB_OK;
 }
 
+static int ba_enqueue(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t *n_points, const int32_t *n_obs, double *poses,
+                      double *points, const uint8_t *fixed, const int32_t *obs_pose, const int32_t *obs_point, const double *uv,
+                      const double *K, const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
+                      double *chi2, uint8_t *outlier, int32_t *info);
+
 // Asynchronous host-pointer form: the reference's Backend runs in its own thread beside the front end
 // (src/backend.cpp:29-45), so the caller enqueues a batch of windows and collects it later.  Host arrays
 // must stay valid (and should be pinned) until sb_ba_wait returns.
@@ -801,7 +806,28 @@ extern "C" int sb_ba_submit(sb_ba_t *h, int n_windows, const int32_t *n_poses, c
     SB_REQUIRE(n_windows >= 1 && n_windows <= h->max_windows, "n_windows out of range [1, max_windows]");
     SB_REQUIRE(n_poses && n_points && n_obs && poses && points && fixed && obs_pose && obs_point && uv && chi2 && outlier && info,
                "null pointer");
+    // everything sb_ba_solve_dev checks is checked BEFORE the first asynchronous copy touches the caller's buffers: an
+    // argument error must not leave copies in flight behind a call that reported "nothing pending"
+    SB_REQUIRE(K && cam_ext7, "null pointer");
+    SB_REQUIRE(huber_delta > 0 && outer_max >= 1 && inner_iters >= 1, "bad solver parameters");
     SB_TRY(sb_use_device(h->device));
+    const size_t W = n_windows, MP = h->max_poses, ML = h->max_points, MO = h->max_obs;
+    cudaStream_t s = h->stream;
+    const int rc = ba_enqueue(h, n_windows, n_poses, n_points, n_obs, poses, points, fixed, obs_pose, obs_point, uv, K, cam_ext7,
+                              huber_delta, chi2_th, outer_max, inner_iters, chi2, outlier, info);
+    if (rc != SB_OK) {   // a CUDA error in the middle of the sequence: drain the stream so that no copy still reads or
+        cudaStreamSynchronize(s);   // writes the caller's buffers after the error return
+        return rc;
+    }
+    h->pending_info = info;
+    h->pending_windows = n_windows;
+    return SB_OK;
+}
+
+static int ba_enqueue(sb_ba_t *h, int n_windows, const int32_t *n_poses, const int32_t *n_points, const int32_t *n_obs, double *poses,
+                      double *points, const uint8_t *fixed, const int32_t *obs_pose, const int32_t *obs_point, const double *uv,
+                      const double *K, const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
+                      double *chi2, uint8_t *outlier, int32_t *info) {
     const size_t W = n_windows, MP = h->max_poses, ML = h->max_points, MO = h->max_obs;
     cudaStream_t s = h->stream;
     SB_CUDA(cudaMemcpyAsync(h->d_np, n_poses, W * 4, cudaMemcpyHostToDevice, s));
@@ -822,8 +848,6 @@ extern "C" int sb_ba_submit(sb_ba_t *h, int n_windows, const int32_t *n_poses, c
     SB_CUDA(cudaMemcpyAsync(outlier, h->d_outlier, W * MO, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaMemcpyAsync(info, h->d_info, W * 16, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaEventRecord(h->done, s));
-    h->pending_info = info;
-    h->pending_windows = n_windows;
     return SB_OK;
 }
 

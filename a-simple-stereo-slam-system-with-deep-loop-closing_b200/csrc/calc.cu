@@ -383,6 +383,12 @@ extern "C" int sb_calc_set_stream(sb_calc_t *h, void *stream) {
 }
 
 extern "C" int sb_calc_descr_dim(const sb_calc_t *h) { return h ? h->dim : SB_ERR_INVALID; }
+extern "C" int sb_calc_input_size(const sb_calc_t *h, int *in_h, int *in_w) {
+    if (!h || !in_h || !in_w) return SB_ERR_INVALID;
+    *in_h = h->in_h;
+    *in_w = h->in_w;
+    return SB_OK;
+}
 
 // Net::Forward over d_act[0] (the input blobs) + normalisation into d_descr.
 static int run_net(sb_calc *h, int batch, float *d_descr) {

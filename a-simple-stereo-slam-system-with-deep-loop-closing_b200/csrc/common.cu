@@ -80,3 +80,23 @@ int sb_make_tensor_map_u8_sw128(CUtensorMap *map, const void *base, int rank, co
                                 const uint32_t *box) {
     return make_tensor_map_u8(map, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
+
+// Page-locked host memory for the asynchronous host-pointer entry points (sb_stereo_submit, sb_ba_submit): copies from / to
+// pageable memory make cudaMemcpyAsync synchronous, which silently serialises "submit ... wait" pairs.
+extern "C" int sb_host_alloc(void **ptr, size_t bytes) {
+    sb_clear_error();
+    SB_REQUIRE(ptr && bytes > 0, "null pointer or zero size");
+    *ptr = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        sb_set_error("no CUDA device available; libslamb200 has no CPU fallback");
+        return SB_ERR_CUDA;
+    }
+    SB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    return SB_OK;
+}
+extern "C" int sb_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+    return SB_OK;
+}

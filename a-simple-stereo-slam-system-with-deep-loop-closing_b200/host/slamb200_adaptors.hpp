@@ -73,6 +73,28 @@ inline cv::KeyPoint from_sb(const sb_keypoint &k) {
 }
 // The reference logs with glog and carries on; the adaptors keep the last C-ABI status readable instead.
 inline int &last_status() { static thread_local int s = SB_OK; return s; }
+// Page-locked staging array (sb_host_alloc): what the asynchronous entry points need for their copies to be asynchronous.
+template <typename T> class Pinned {
+public:
+    Pinned() = default;
+    explicit Pinned(size_t n) { reset(n); }
+    ~Pinned() { sb_host_free(p_); }
+    Pinned(const Pinned &) = delete;
+    Pinned &operator=(const Pinned &) = delete;
+    void reset(size_t n) {
+        sb_host_free(p_);
+        p_ = nullptr; n_ = 0;
+        void *q = nullptr;
+        if (sb_host_alloc(&q, n * sizeof(T)) != SB_OK) throw std::runtime_error(std::string("sb_host_alloc: ") + sb_last_error());
+        p_ = static_cast<T *>(q); n_ = n;
+    }
+    T *data() { return p_; }
+    size_t size() const { return n_; }
+    void fill(const T &v) { for (size_t i = 0; i < n_; i++) p_[i] = v; }
+private:
+    T *p_ = nullptr;
+    size_t n_ = 0;
+};
 }  // namespace detail
 
 // -----------------------------------------------------------------------------------------------------
@@ -247,6 +269,8 @@ public:
         matches.clear();
         if (q.empty() || t.empty()) return;
         const int cap = q.rows > t.rows ? q.rows : t.rows;
+        if (cap > max_rows_) { detail::last_status() = SB_ERR_CAPACITY; return; }   // more descriptors than the handle was created for
+        if (q.cols != 32 || t.cols != 32) { detail::last_status() = SB_ERR_INVALID; return; }
         std::vector<uint8_t> qb((size_t)cap * 32), tb((size_t)cap * 32);
         for (int i = 0; i < q.rows; i++) std::memcpy(&qb[(size_t)i * 32], q.ptr(i), 32);
         for (int i = 0; i < t.rows; i++) std::memcpy(&tb[(size_t)i * 32], t.ptr(i), 32);
@@ -287,46 +311,39 @@ public:
     LocalBASolver(int max_poses = 7, int max_points = 4096, int max_obs = 32768, int device = 0)
         : mp_(max_poses), ml_(max_points), mo_(max_obs) {
         if (sb_ba_create(&h_, device, 1, max_poses, max_points, max_obs) != SB_OK) throw std::runtime_error(std::string("sb_ba_create: ") + sb_last_error());
+        // page-locked staging, allocated once: Submit's copies are then truly asynchronous (with pageable vectors
+        // cudaMemcpyAsync blocks and Submit would only return when the window is solved)
+        poses_.reset((size_t)mp_ * 7); points_.reset((size_t)ml_ * 3); uv_.reset((size_t)mo_ * 2); chi2_.reset((size_t)mo_);
+        fixed_.reset((size_t)ml_); outl_.reset((size_t)mo_); op_.reset((size_t)mo_); ol_.reset((size_t)mo_);
+        cnt_.reset(3); info_.reset(4);
     }
     ~LocalBASolver() { sb_ba_destroy(h_); }
     // chi2_th 5.991, Huber delta 5.991, up to 5 rounds of optimize(10): src/backend.cpp:155,198-200,212-232
     bool Optimize(LocalBAProblem &p, double huber_delta = 5.991, double chi2_th = 5.991, int outer_max = 5, int inner_iters = 10) {
-        const int32_t np = (int32_t)(p.poses.size() / 7), nl = (int32_t)(p.points.size() / 3), ne = (int32_t)p.obs_pose.size();
-        if (np > mp_ || nl > ml_ || ne > mo_) { detail::last_status() = SB_ERR_CAPACITY; return false; }
-        std::vector<double> poses((size_t)mp_ * 7, 0.0), points((size_t)ml_ * 3, 0.0), uv((size_t)mo_ * 2, 0.0), chi2((size_t)mo_);
-        std::vector<uint8_t> fixed((size_t)ml_, 0), outl((size_t)mo_);
-        std::vector<int32_t> op((size_t)mo_, 0), ol((size_t)mo_, 0);
-        std::copy(p.poses.begin(), p.poses.end(), poses.begin());
-        std::copy(p.points.begin(), p.points.end(), points.begin());
-        std::copy(p.fixed.begin(), p.fixed.end(), fixed.begin());
-        std::copy(p.obs_pose.begin(), p.obs_pose.end(), op.begin());
-        std::copy(p.obs_point.begin(), p.obs_point.end(), ol.begin());
-        std::copy(p.uv.begin(), p.uv.end(), uv.begin());
-        detail::last_status() = sb_ba_solve(h_, 1, &np, &nl, &ne, poses.data(), points.data(), fixed.data(), op.data(), ol.data(), uv.data(),
-                                            p.K, p.cam_ext, huber_delta, chi2_th, outer_max, inner_iters, chi2.data(), outl.data(), p.info);
-        if (detail::last_status() != SB_OK) return false;
-        std::copy(poses.begin(), poses.begin() + (size_t)np * 7, p.poses.begin());
-        std::copy(points.begin(), points.begin() + (size_t)nl * 3, p.points.begin());
-        p.chi2.assign(chi2.begin(), chi2.begin() + ne);
-        p.outlier.assign(outl.begin(), outl.begin() + ne);
-        return true;
+        return Submit(p, huber_delta, chi2_th, outer_max, inner_iters) && Wait();
     }
     // The asynchronous halves (the reference's Backend is its own thread, src/backend.cpp:29-45): Submit enqueues the window and
     // returns, Wait blocks until it is solved and writes the results back into the problem given to Submit, which must stay alive.
     bool Submit(LocalBAProblem &p, double huber_delta = 5.991, double chi2_th = 5.991, int outer_max = 5, int inner_iters = 10) {
-        const int32_t np = (int32_t)(p.poses.size() / 7), nl = (int32_t)(p.points.size() / 3), ne = (int32_t)p.obs_pose.size();
-        if (np > mp_ || nl > ml_ || ne > mo_ || pending_) { detail::last_status() = pending_ ? SB_ERR_INVALID : SB_ERR_CAPACITY; return false; }
-        np_ = np; nl_ = nl; ne_ = ne;
-        poses_.assign((size_t)mp_ * 7, 0.0); points_.assign((size_t)ml_ * 3, 0.0); uv_.assign((size_t)mo_ * 2, 0.0); chi2_.assign((size_t)mo_, 0.0);
-        fixed_.assign((size_t)ml_, 0); outl_.assign((size_t)mo_, 0); op_.assign((size_t)mo_, 0); ol_.assign((size_t)mo_, 0);
-        std::copy(p.poses.begin(), p.poses.end(), poses_.begin());
-        std::copy(p.points.begin(), p.points.end(), points_.begin());
-        std::copy(p.fixed.begin(), p.fixed.end(), fixed_.begin());
-        std::copy(p.obs_pose.begin(), p.obs_pose.end(), op_.begin());
-        std::copy(p.obs_point.begin(), p.obs_point.end(), ol_.begin());
-        std::copy(p.uv.begin(), p.uv.end(), uv_.begin());
-        detail::last_status() = sb_ba_submit(h_, 1, &np_, &nl_, &ne_, poses_.data(), points_.data(), fixed_.data(), op_.data(), ol_.data(), uv_.data(),
-                                             p.K, p.cam_ext, huber_delta, chi2_th, outer_max, inner_iters, chi2_.data(), outl_.data(), p.info);
+        const size_t np = p.poses.size() / 7, nl = p.points.size() / 3, ne = p.obs_pose.size();
+        if (pending_) { detail::last_status() = SB_ERR_INVALID; return false; }
+        if (np > (size_t)mp_ || nl > (size_t)ml_ || ne > (size_t)mo_) { detail::last_status() = SB_ERR_CAPACITY; return false; }
+        // the flat arrays must agree with each other: an oversized vector would overrun the staging, a short one feed zeros
+        if (p.poses.size() != np * 7 || p.points.size() != nl * 3 || p.fixed.size() != nl || p.obs_point.size() != ne || p.uv.size() != 2 * ne) {
+            detail::last_status() = SB_ERR_INVALID;
+            return false;
+        }
+        poses_.fill(0.0); points_.fill(0.0); uv_.fill(0.0); fixed_.fill(0); op_.fill(0); ol_.fill(0);
+        std::copy(p.poses.begin(), p.poses.end(), poses_.data());
+        std::copy(p.points.begin(), p.points.end(), points_.data());
+        std::copy(p.fixed.begin(), p.fixed.end(), fixed_.data());
+        std::copy(p.obs_pose.begin(), p.obs_pose.end(), op_.data());
+        std::copy(p.obs_point.begin(), p.obs_point.end(), ol_.data());
+        std::copy(p.uv.begin(), p.uv.end(), uv_.data());
+        cnt_.data()[0] = (int32_t)np; cnt_.data()[1] = (int32_t)nl; cnt_.data()[2] = (int32_t)ne;
+        detail::last_status() = sb_ba_submit(h_, 1, cnt_.data(), cnt_.data() + 1, cnt_.data() + 2, poses_.data(), points_.data(), fixed_.data(),
+                                             op_.data(), ol_.data(), uv_.data(), p.K, p.cam_ext, huber_delta, chi2_th, outer_max, inner_iters,
+                                             chi2_.data(), outl_.data(), info_.data());
         pending_ = detail::last_status() == SB_OK ? &p : nullptr;
         return pending_ != nullptr;
     }
@@ -336,20 +353,21 @@ public:
         pending_ = nullptr;
         detail::last_status() = sb_ba_wait(h_);
         if (detail::last_status() != SB_OK) return false;
-        std::copy(poses_.begin(), poses_.begin() + (size_t)np_ * 7, p.poses.begin());
-        std::copy(points_.begin(), points_.begin() + (size_t)nl_ * 3, p.points.begin());
-        p.chi2.assign(chi2_.begin(), chi2_.begin() + ne_);
-        p.outlier.assign(outl_.begin(), outl_.begin() + ne_);
+        const size_t np = (size_t)cnt_.data()[0], nl = (size_t)cnt_.data()[1], ne = (size_t)cnt_.data()[2];
+        std::copy(poses_.data(), poses_.data() + np * 7, p.poses.begin());
+        std::copy(points_.data(), points_.data() + nl * 3, p.points.begin());
+        p.chi2.assign(chi2_.data(), chi2_.data() + ne);
+        p.outlier.assign(outl_.data(), outl_.data() + ne);
+        for (int k = 0; k < 4; k++) p.info[k] = info_.data()[k];
         return true;
     }
 private:
     sb_ba_t *h_ = nullptr;
     int mp_, ml_, mo_;
     LocalBAProblem *pending_ = nullptr;
-    int32_t np_ = 0, nl_ = 0, ne_ = 0;
-    std::vector<double> poses_, points_, uv_, chi2_;
-    std::vector<uint8_t> fixed_, outl_;
-    std::vector<int32_t> op_, ol_;
+    detail::Pinned<double> poses_, points_, uv_, chi2_;
+    detail::Pinned<uint8_t> fixed_, outl_;
+    detail::Pinned<int32_t> op_, ol_, cnt_, info_;
 };
 
 // -----------------------------------------------------------------------------------------------------
@@ -420,6 +438,9 @@ public:
     DescrVector calcDescr(const cv::Mat &im) {
         DescrVector d((size_t)descrDim(), 0.f);
         if (im.empty()) { detail::last_status() = SB_ERR_INVALID; return d; }
+        int in_h = 0, in_w = 0;
+        sb_calc_input_size(h_, &in_h, &in_w);
+        if (im.rows != in_h || im.cols != in_w) { detail::last_status() = SB_ERR_INVALID; return d; }   // the reference resizes before calcDescr
         const uint8_t *in = im.data;
         detail::last_status() = sb_calc_descr(h_, 1, &in, (int)im.step, d.data());
         return d;

@@ -37,6 +37,11 @@ const char *sb_last_error(void);
 /* Library version string and compiled SM architecture. */
 const char *sb_version(void);
 
+/* Page-locked host memory for the buffers handed to the asynchronous host-pointer entry points (sb_stereo_submit,
+ * sb_ba_submit): with pageable memory the copies — and therefore the submit call — block until they are done. */
+int sb_host_alloc(void **ptr, size_t bytes);
+int sb_host_free(void *ptr);
+
 /* field-for-field cv::KeyPoint (28 bytes) */
 typedef struct sb_keypoint {
     float x, y;      /* pt, level-0 pixel coordinates */
@@ -361,6 +366,8 @@ int sb_calc_destroy(sb_calc_t *h);
 int sb_calc_set_stream(sb_calc_t *h, void *stream);
 /* autoencoder_output->channels() (src/deeplcd.cpp:72): 1064 for the reference's network. */
 int sb_calc_descr_dim(const sb_calc_t *h);
+/* the network's input size (rows, cols): what sb_calc_descr expects */
+int sb_calc_input_size(const sb_calc_t *h, int *in_h, int *in_w);
 /* calcDescrOriginalImg: img = `batch` pointers to w x hgt u8 images; descr [batch][dim];
  * blurred_out = null, or `batch` pointers (entries may be null) that receive the blurred image —
  * pass the input pointers to reproduce the reference's in-place blur of KeyFrame::mImageLeft. */

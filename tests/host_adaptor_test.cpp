@@ -103,5 +103,52 @@ int main(int argc, char **argv) {
         if (!v.accepted || v.inliers < 200 || !v.needCorrect) return 7;
         if (std::fabs(v.correctedPose[4] - 0.5) > 0.02 || std::fabs(v.correctedPose[6] - 2.0) > 0.02) return 8;
     }
+    {   // Backend::OptimizeActiveMap through the adaptor: Submit / Wait on page-locked staging, argument checks, and the
+        // one-pass ProcessNewKF call
+        const double K[4] = {718.856, 718.856, 607.1928, 185.2157};
+        myslam::LocalBAProblem p;
+        for (int i = 0; i < 4; i++) { const double z = 1.5 * i; const double q[7] = {0, 0, 0, 1, 0, 0, -z}; p.poses.insert(p.poses.end(), q, q + 7); }
+        for (int j = 0; j < 60; j++) {
+            s = s * 1664525u + 1013904223u; const double x = ((s >> 8) % 2000) / 100.0 - 10.0;
+            s = s * 1664525u + 1013904223u; const double y = ((s >> 8) % 600) / 100.0 - 3.0;
+            s = s * 1664525u + 1013904223u; const double z = ((s >> 8) % 3000) / 100.0 + 12.0;
+            p.points.push_back(x + 0.05); p.points.push_back(y - 0.05); p.points.push_back(z + 0.1);   // perturbed start
+            p.fixed.push_back(j % 3 == 0);
+            for (int i = 0; i < 4; i++) {
+                const double zc = z - 1.5 * i;
+                p.obs_pose.push_back(i); p.obs_point.push_back(j);
+                p.uv.push_back(K[0] * x / zc + K[2]); p.uv.push_back(K[1] * y / zc + K[3]);
+            }
+        }
+        for (int k = 0; k < 4; k++) p.K[k] = K[k];
+        myslam::LocalBASolver ba(7, 256, 2048);
+        myslam::LocalBAProblem bad = p;
+        bad.fixed.pop_back();                                            // arrays that disagree are refused, not padded with zeros
+        if (ba.Submit(bad) || myslam::detail::last_status() != SB_ERR_INVALID) return 9;
+        bad = p;
+        bad.uv.push_back(0.0);
+        if (ba.Optimize(bad) || myslam::detail::last_status() != SB_ERR_INVALID) return 10;
+        if (!ba.Submit(p)) return 11;
+        if (ba.Submit(p)) return 12;                                     // one window in flight per solver
+        if (!ba.Wait()) return 13;
+        std::printf("LocalBA: rounds %d, LM iterations %d, inliers %d, outliers %d\n", p.info[0], p.info[1], p.info[2], p.info[3]);
+        if (p.info[1] < 1 || p.info[2] < 200 || p.chi2.size() != 240) return 14;
+        std::vector<cv::KeyPoint> pyr2, kept;
+        for (size_t i = 0; i < kps.size(); i++)
+            for (int l = 0; l < 8; l++) { cv::KeyPoint k = kps[i]; k.octave = l; k.class_id = (int)i; pyr2.push_back(k); }
+        cv::Mat d3, d4;
+        std::vector<cv::KeyPoint> pyr3 = pyr2, kept2;                    // img was blurred in place by calcDescrOriginalImg above:
+        ext.ScreenAndComputeKPsParams(img, pyr3, kept2);                 // the two-call sequence again, on the image as it is now
+        ext.CalcDescriptors(img, kept2, d4);
+        ext.ScreenAndDescribe(img, pyr2, kept, d3);                      // both ProcessNewKF calls over one pyramid
+        if (kept.empty() || kept.size() != kept2.size() || d3.rows != d4.rows || std::memcmp(d3.data, d4.data, (size_t)d4.rows * 32) != 0) return 15;
+        for (size_t i = 0; i < kept.size(); i++)
+            if (kept[i].pt.x != kept2[i].pt.x || kept[i].angle != kept2[i].angle || kept[i].class_id != kept2[i].class_id) return 17;
+        std::printf("ScreenAndDescribe: %zu survivors, descriptors identical to the two-call sequence\n", kept.size());
+        myslam::HammingMatcher tiny(8);
+        std::vector<cv::DMatch> mm;
+        tiny.match(desc, desc, mm);                                      // more rows than the handle holds: reported, not silently empty
+        if (!mm.empty() || myslam::detail::last_status() != SB_ERR_CAPACITY) return 16;
+    }
     return 0;
 }
