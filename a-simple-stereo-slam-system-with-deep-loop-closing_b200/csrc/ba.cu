@@ -25,6 +25,7 @@
 #define BA_MIN_BLOCKS 1   // CTAs per SM the register budget is held to (launch bounds)
 #endif
 #define BA_MAX_POSES 16
+#define LM_STRIDE 20   // doubles per landmark record: 160 bytes, so that bl and Dinv start on 16-byte boundaries (double2 loads)
 #ifdef BA_PROFILE
 __device__ long long g_ba_prof[16];
 #define BA_T(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) { long long t_ = clock64(); g_ba_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
@@ -49,8 +50,8 @@ struct sb_ba {
     double *d_ptbak;     // [W][ML][3]
     double *d_err;       // [W][2][MO][2]
     double *d_hpl;       // [W][MO][18]: w A^T B of every edge to a free landmark (the Hpl block), rebuilt each iteration
-    double *d_ybd;       // [W][MO][18]: Hpl Dinv of the same edges (rebuilt for every lambda)
-    int2 *d_pairs;       // [W][MP (MP + 1) / 2][ML]: per pose-block pair (i1 <= i2) the (edge to i1, edge to i2) of every free
+    double *d_ybd;       // [W][MO][10]: per edge the landmark's share w B^T B (6), -w B^T r (3) of the linearised system
+    int4 *d_pairs;       // [W][MP (MP + 1) / 2][ML]: per pose-block pair (i1 <= i2) the (edge to i1, edge to i2, landmark) of every free
                          //                           landmark both observe — the structure of the Schur complement, built once
 };
 
@@ -66,7 +67,7 @@ struct BaArgs {
     int32_t *info;           // [W][4] out: outer rounds, LM iterations, inliers, outliers (or -1: bad input)
     int32_t *edge_of;
     double *lm, *ptbak, *err, *hpl, *ybd;
-    int2 *pairs;
+    int4 *pairs;
     int MP, ML, MO;
     double fx, fy, cx, cy;
     double extR[9], extT[3];
@@ -216,11 +217,11 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
     const uint8_t *fixed = a.fixed + (size_t)w * a.ML;
     const int32_t *op = a.op + (size_t)w * a.MO, *ol = a.ol + (size_t)w * a.MO;
     int32_t *edge_of = a.edge_of + (size_t)w * a.ML * MP;
-    double *lm = a.lm + (size_t)w * a.ML * 18;
+    double *lm = a.lm + (size_t)w * a.ML * LM_STRIDE;   // per landmark: Hll(0..5) bl(6..8) - Dinv(10..15) xl(16..18) -
     double *ptb = a.ptbak + (size_t)w * a.ML * 3;
     double *hpl = a.hpl + (size_t)w * a.MO * 18;
-    double *ybd = a.ybd + (size_t)w * a.MO * 18;
-    int2 *pairs = a.pairs + (size_t)w * (MP * (MP + 1) / 2) * a.ML;
+    double *lmc = a.ybd + (size_t)w * a.MO * 10;   // per edge: the landmark's share of Hll and bl (10 doubles)
+    int4 *pairs = a.pairs + (size_t)w * (MP * (MP + 1) / 2) * a.ML;
     double *err = a.err + (size_t)w * a.MO * 4;   // errors of the last evaluation
     double *elin = err + (size_t)a.MO * 2;         // errors at the linearisation state
     int32_t *info = a.info + 4 * w;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
         int i1 = 0, rem = blk;
         while (rem >= np - i1) { rem -= np - i1; i1++; }
         const int i2 = i1 + rem;
-        int2 *pl = pairs + (size_t)blk * a.ML;
+        int4 *pl = pairs + (size_t)blk * a.ML;
         int cnt = 0;
         for (int j0 = 0; j0 < nl; j0 += 32) {
             const int j = j0 + lane;
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
             if (j < nl && !fixed[j]) { e1 = edge_of[j * MP + i1]; e2 = edge_of[j * MP + i2]; }
             const bool ok = e1 >= 0 && e2 >= 0;
             const unsigned bal = __ballot_sync(0xffffffffu, ok);
-            if (ok) pl[cnt + __popc(bal & ((1u << lane) - 1u))] = make_int2(e1, e2);
+            if (ok) pl[cnt + __popc(bal & ((1u << lane) - 1u))] = make_int4(e1, e2, j, 0);
             cnt += __popc(bal);
         }
         if (lane == 0) pcnt[blk] = cnt;
@@ -283,7 +284,9 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
             BA_T(0);
             double currentChi = compute_errors(c, ne, err, elin, red);
             BA_T(1);
-            // ---- buildSystem.  Pose blocks: one warp per pose, lanes over the landmarks it observes.
+            // ---- buildSystem.  Every edge is linearised ONCE, in the pose pass (one warp per pose, lanes over the landmarks it
+            //      observes): pose block and gradient by warp reduction, and per edge to a free landmark the Hpl block w A^T B and
+            //      the landmark's share (w B^T B, -w B^T r) for the landmark pass below.
             for (int i = wid; i < np; i += BA_THREADS / 32) {
                 double h[21], g[6];
 #pragma unroll
@@ -302,6 +305,22 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
 #pragma unroll
                         for (int q = p; q < 6; q++) h[k++] += wgt * (A[p] * A[q] + A[6 + p] * A[6 + q]);
                     }
+                    if (!fixed[j]) {
+                        double2 *P = reinterpret_cast<double2 *>(hpl + 18 * e);  // Hpl block of this edge: w A^T B (6x3), 9 double2 stores
+                        double hv[18];
+#pragma unroll
+                        for (int p = 0; p < 6; p++)
+#pragma unroll
+                            for (int q = 0; q < 3; q++) hv[3 * p + q] = wgt * (A[p] * B[q] + A[6 + p] * B[3 + q]);
+#pragma unroll
+                        for (int k2 = 0; k2 < 9; k2++) P[k2] = make_double2(hv[2 * k2], hv[2 * k2 + 1]);
+                        double2 *Cn = reinterpret_cast<double2 *>(lmc + 10 * e);   // Hll share (00 01 02 11 12 22), bl share (3), pad
+                        Cn[0] = make_double2(wgt * (B[0] * B[0] + B[3] * B[3]), wgt * (B[0] * B[1] + B[3] * B[4]));
+                        Cn[1] = make_double2(wgt * (B[0] * B[2] + B[3] * B[5]), wgt * (B[1] * B[1] + B[4] * B[4]));
+                        Cn[2] = make_double2(wgt * (B[1] * B[2] + B[4] * B[5]), wgt * (B[2] * B[2] + B[5] * B[5]));
+                        Cn[3] = make_double2(-wgt * (B[0] * r[0] + B[3] * r[1]), -wgt * (B[1] * r[0] + B[4] * r[1]));
+                        Cn[4] = make_double2(-wgt * (B[2] * r[0] + B[5] * r[1]), 0.0);
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < 21; k++)
@@ -319,30 +338,25 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                     }
                 }
             }
-            // Landmark blocks: one thread per free landmark.  lm[j] = Hll(6: 00 01 02 11 12 22) bl(3) Dinv(6) xl(3)
+            __syncthreads();
+            // Landmark blocks: one thread per free landmark sums the shares of its edges in ascending pose order (all edge
+            // indices are fetched before the shares: two load levels per landmark instead of two per edge).
+            // lm[j] = Hll(6: 00 01 02 11 12 22) bl(3) - Dinv(6) xl(3) -
             for (int j = tid; j < nl; j += BA_THREADS) {
                 if (fixed[j]) continue;
+                int es[BA_MAX_POSES];
+#pragma unroll
+                for (int i = 0; i < BA_MAX_POSES; i++) es[i] = i < np ? edge_of[j * MP + i] : -1;
                 double H[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
-                for (int i = 0; i < np; i++) {
-                    const int e = edge_of[j * MP + i];
-                    if (e < 0) continue;
-                    double A[12], B[6], r[2], wgt;
-                    edge_lin(c, e, elin, A, B, r, wgt);
-                    g[0] += -wgt * (B[0] * r[0] + B[3] * r[1]);
-                    g[1] += -wgt * (B[1] * r[0] + B[4] * r[1]);
-                    g[2] += -wgt * (B[2] * r[0] + B[5] * r[1]);
-                    H[0] += wgt * (B[0] * B[0] + B[3] * B[3]); H[1] += wgt * (B[0] * B[1] + B[3] * B[4]); H[2] += wgt * (B[0] * B[2] + B[3] * B[5]);
-                    H[3] += wgt * (B[1] * B[1] + B[4] * B[4]); H[4] += wgt * (B[1] * B[2] + B[4] * B[5]); H[5] += wgt * (B[2] * B[2] + B[5] * B[5]);
-                    double2 *P = reinterpret_cast<double2 *>(hpl + 18 * e);  // Hpl block of this edge: w A^T B (6x3), 9 double2 stores
-                    double hv[18];
 #pragma unroll
-                    for (int p = 0; p < 6; p++)
-#pragma unroll
-                        for (int q = 0; q < 3; q++) hv[3 * p + q] = wgt * (A[p] * B[q] + A[6 + p] * B[3 + q]);
-#pragma unroll
-                    for (int k = 0; k < 9; k++) P[k] = make_double2(hv[2 * k], hv[2 * k + 1]);
+                for (int i = 0; i < BA_MAX_POSES; i++) {
+                    if (es[i] < 0) continue;
+                    const double2 *Cn = reinterpret_cast<const double2 *>(lmc + 10 * es[i]);
+                    const double2 c0 = Cn[0], c1 = Cn[1], c2 = Cn[2], c3 = Cn[3], c4 = Cn[4];
+                    H[0] += c0.x; H[1] += c0.y; H[2] += c1.x; H[3] += c1.y; H[4] += c2.x; H[5] += c2.y;
+                    g[0] += c3.x; g[1] += c3.y; g[2] += c4.x;
                 }
-                double *L = lm + 18 * j;
+                double *L = lm + LM_STRIDE * j;
 #pragma unroll
                 for (int k = 0; k < 6; k++) L[k] = H[k];
                 L[6] = g[0]; L[7] = g[1]; L[8] = g[2];
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                 double mx = 0;
                 for (int k = tid; k < n6; k += BA_THREADS) mx = fmax(mx, fabs(Hpp[36 * (k / 6) + 7 * (k % 6)]));
                 for (int j = tid; j < nl; j += BA_THREADS)
-                    if (!fixed[j]) mx = fmax(mx, fmax(fabs(lm[18 * j]), fmax(fabs(lm[18 * j + 3]), fabs(lm[18 * j + 5]))));
+                    if (!fixed[j]) mx = fmax(mx, fmax(fabs(lm[LM_STRIDE * j]), fmax(fabs(lm[LM_STRIDE * j + 3]), fabs(lm[LM_STRIDE * j + 5]))));
                 lambda = 1e-5 * block_max(mx, red);
                 ni = 2;
             }
@@ -367,35 +381,17 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                 int bad = 0;
                 for (int j = tid; j < nl; j += BA_THREADS) {
                     if (fixed[j]) continue;
-                    double *L = lm + 18 * j;
+                    double *L = lm + LM_STRIDE * j;
                     const double A0 = L[0] + lambda, b = L[1], cc = L[2], d = L[3] + lambda, e = L[4], f = L[5] + lambda;
                     const double c00 = d * f - e * e, c01 = cc * e - b * f, c02 = b * e - cc * d;
                     const double det = A0 * c00 + b * c01 + cc * c02;
                     if (det == 0 || det != det) bad = 1;
                     const double id = 1.0 / det;
-                    L[9] = c00 * id; L[10] = c01 * id; L[11] = c02 * id;
-                    L[12] = (A0 * f - cc * cc) * id; L[13] = (b * cc - A0 * e) * id; L[14] = (A0 * d - b * b) * id;
+                    L[10] = c00 * id; L[11] = c01 * id; L[12] = c02 * id;
+                    L[13] = (A0 * f - cc * cc) * id; L[14] = (b * cc - A0 * e) * id; L[15] = (A0 * d - b * b) * id;
                 }
                 int ok = !__syncthreads_or(bad);
-                // ---- Y_e = Hpl_e Dinv_j for every edge to a free landmark (one thread per edge)
                 if (tid == 0) s_next = BA_THREADS / 32;
-                if (ok)
-                    for (int e = tid; e < ne; e += BA_THREADS) {
-                        const int j = ol[e];
-                        if (fixed[j]) continue;
-                        const double *L = lm + 18 * j;
-                        const double D0 = L[9], D1 = L[10], D2 = L[11], D4 = L[12], D5 = L[13], D8 = L[14];
-                        const double2 *P = reinterpret_cast<const double2 *>(hpl + 18 * e);
-                        double2 *Y = reinterpret_cast<double2 *>(ybd + 18 * e);
-#pragma unroll
-                        for (int m = 0; m < 3; m++) {   // two block rows per three double2
-                            const double2 a2 = P[3 * m], b2 = P[3 * m + 1], c2 = P[3 * m + 2];
-                            const double h0 = a2.x, h1 = a2.y, h2 = b2.x, k0 = b2.y, k1 = c2.x, k2 = c2.y;
-                            Y[3 * m] = make_double2(h0 * D0 + h1 * D1 + h2 * D2, h0 * D1 + h1 * D4 + h2 * D5);
-                            Y[3 * m + 1] = make_double2(h0 * D2 + h1 * D5 + h2 * D8, k0 * D0 + k1 * D1 + k2 * D2);
-                            Y[3 * m + 2] = make_double2(k0 * D1 + k1 * D4 + k2 * D5, k0 * D2 + k1 * D5 + k2 * D8);
-                        }
-                    }
                 __syncthreads();
                 BA_T(3);
                 // ---- Schur complement: S(i1,i2) = Hpp'(i1,i2) - sum_j Y(i1,j) Hpl(i2,j)^T over the pair's list, one warp per
@@ -405,35 +401,65 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                     int i1 = 0, rem = blk;
                     while (rem >= np - i1) { rem -= np - i1; i1++; }
                     const int i2 = i1 + rem;
-                    const int2 *pl = pairs + (size_t)blk * a.ML;
+                    const int4 *pl = pairs + (size_t)blk * a.ML;
                     const int cnt = pcnt[blk];
+                    // Y = Hpl(i1, j) Dinv_j is formed on the fly from the Hpl block and the landmark's Dinv (16-byte vector loads), so
+                    // no Y array is written or read; a diagonal block (i1 == i2: the longest lists) is symmetric and needs only its
+                    // 21 upper entries.  The branch is uniform over the block.
                     double acc[36], gb[6];
 #pragma unroll
                     for (int k = 0; k < 36; k++) acc[k] = 0;
 #pragma unroll
                     for (int k = 0; k < 6; k++) gb[k] = 0;
+                    const bool diag = i1 == i2;
+                    // the list entry of the NEXT round is fetched before this round's blocks are used: the entry -> blocks chain is
+                    // two dependent global loads long, and the entry carries the landmark so that no third level (ol[e]) is needed
+                    int4 nxt = lane < cnt ? pl[lane] : make_int4(0, 0, 0, 0);
                     for (int t = lane; t < cnt; t += 32) {
-                        const int2 ee = pl[t];
-                        // the 18-double blocks are 144 bytes apart: 16-byte aligned, read as 9 double2 each (half the load instructions)
-                        const double2 *Y = reinterpret_cast<const double2 *>(ybd + 18 * ee.x), *P2 = reinterpret_cast<const double2 *>(hpl + 18 * ee.y);
-                        double BD[18];
+                        const int4 ee = nxt;
+                        if (t + 32 < cnt) nxt = pl[t + 32];
+                        const double *L = lm + LM_STRIDE * ee.z;
+                        const double2 *P1 = reinterpret_cast<const double2 *>(hpl + 18 * ee.x);
+                        const double2 d01 = *reinterpret_cast<const double2 *>(L + 10), d23 = *reinterpret_cast<const double2 *>(L + 12),
+                                      d45 = *reinterpret_cast<const double2 *>(L + 14);
+                        const double D0 = d01.x, D1 = d01.y, D2 = d23.x, D4 = d23.y, D5 = d45.x, D8 = d45.y;
+                        double Pa[18], Y[18];
 #pragma unroll
-                        for (int k = 0; k < 9; k++) { const double2 t = Y[k]; BD[2 * k] = t.x; BD[2 * k + 1] = t.y; }
+                        for (int k = 0; k < 9; k++) { const double2 v2 = P1[k]; Pa[2 * k] = v2.x; Pa[2 * k + 1] = v2.y; }
 #pragma unroll
-                        for (int m = 0; m < 3; m++) {   // block rows 2m and 2m + 1 of Hpl(i2, j)
-                            const double2 ga = P2[3 * m], gb2 = P2[3 * m + 1], gc = P2[3 * m + 2];
+                        for (int p = 0; p < 6; p++) {
+                            const double h0 = Pa[3 * p], h1 = Pa[3 * p + 1], h2 = Pa[3 * p + 2];
+                            Y[3 * p] = h0 * D0 + h1 * D1 + h2 * D2;
+                            Y[3 * p + 1] = h0 * D1 + h1 * D4 + h2 * D5;
+                            Y[3 * p + 2] = h0 * D2 + h1 * D5 + h2 * D8;
+                        }
+                        if (diag) {   // Y Hpl^T with the same block: upper triangle only; and b_schur(i1) -= Y bl_j
+                            const double2 b01 = *reinterpret_cast<const double2 *>(L + 6);
+                            const double b0 = b01.x, b1 = b01.y, b2 = L[8];
 #pragma unroll
                             for (int p = 0; p < 6; p++) {
-                                acc[6 * p + 2 * m] += BD[3 * p] * ga.x + BD[3 * p + 1] * ga.y + BD[3 * p + 2] * gb2.x;
-                                acc[6 * p + 2 * m + 1] += BD[3 * p] * gb2.y + BD[3 * p + 1] * gc.x + BD[3 * p + 2] * gc.y;
+                                gb[p] += Y[3 * p] * b0 + Y[3 * p + 1] * b1 + Y[3 * p + 2] * b2;
+#pragma unroll
+                                for (int q = p; q < 6; q++) acc[6 * p + q] += Y[3 * p] * Pa[3 * q] + Y[3 * p + 1] * Pa[3 * q + 1] + Y[3 * p + 2] * Pa[3 * q + 2];
+                            }
+                        } else {
+                            const double2 *P2 = reinterpret_cast<const double2 *>(hpl + 18 * ee.y);
+#pragma unroll
+                            for (int m = 0; m < 3; m++) {   // block rows 2m and 2m + 1 of Hpl(i2, j)
+                                const double2 ga = P2[3 * m], gb2 = P2[3 * m + 1], gc = P2[3 * m + 2];
+#pragma unroll
+                                for (int p = 0; p < 6; p++) {
+                                    acc[6 * p + 2 * m] += Y[3 * p] * ga.x + Y[3 * p + 1] * ga.y + Y[3 * p + 2] * gb2.x;
+                                    acc[6 * p + 2 * m + 1] += Y[3 * p] * gb2.y + Y[3 * p + 1] * gc.x + Y[3 * p + 2] * gc.y;
+                                }
                             }
                         }
-                        if (i1 == i2) {  // b_schur(i1) -= Hpl(i1, j) Dinv_j bl_j
-                            const double *L = lm + 18 * ol[ee.x];
-                            const double b0 = L[6], b1 = L[7], b2 = L[8];
+                    }
+                    if (diag) {   // mirror the upper triangle (before the reduction: every lane holds its own partial block)
 #pragma unroll
-                            for (int p = 0; p < 6; p++) gb[p] += BD[3 * p] * b0 + BD[3 * p + 1] * b1 + BD[3 * p + 2] * b2;
-                        }
+                        for (int p = 1; p < 6; p++)
+#pragma unroll
+                            for (int q = 0; q < p; q++) acc[6 * p + q] = acc[6 * q + p];
                     }
                     // entries 0..31 by the butterfly (lane l ends with entry l), 32..35 and b by plain trees
                     double head[32];
@@ -583,10 +609,14 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                     // ---- landmark increments: xl = Dinv (bl - sum_i Hpl(i,j)^T xs_i), then the state update
                     for (int j = tid; j < nl; j += BA_THREADS) {
                         if (fixed[j]) continue;
-                        double *L = lm + 18 * j;
+                        double *L = lm + LM_STRIDE * j;
                         double v[3] = {L[6], L[7], L[8]};
-                        for (int i = 0; i < np; i++) {
-                            const int e = edge_of[j * MP + i];
+                        int es[BA_MAX_POSES];
+#pragma unroll
+                        for (int i = 0; i < BA_MAX_POSES; i++) es[i] = i < np ? edge_of[j * MP + i] : -1;
+#pragma unroll
+                        for (int i = 0; i < BA_MAX_POSES; i++) {
+                            const int e = es[i];
                             if (e < 0) continue;
                             const double2 *P = reinterpret_cast<const double2 *>(hpl + 18 * e);  // v -= Hpl(i, j)^T xs_i
 #pragma unroll
@@ -597,10 +627,10 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                                 v[0] -= b2.y * xb; v[1] -= c2.x * xb; v[2] -= c2.y * xb;
                             }
                         }
-                        const double x0 = L[9] * v[0] + L[10] * v[1] + L[11] * v[2];
-                        const double x1 = L[10] * v[0] + L[12] * v[1] + L[13] * v[2];
-                        const double x2 = L[11] * v[0] + L[13] * v[1] + L[14] * v[2];
-                        L[15] = x0; L[16] = x1; L[17] = x2;
+                        const double x0 = L[10] * v[0] + L[11] * v[1] + L[12] * v[2];
+                        const double x1 = L[11] * v[0] + L[13] * v[1] + L[14] * v[2];
+                        const double x2 = L[12] * v[0] + L[14] * v[1] + L[15] * v[2];
+                        L[16] = x0; L[17] = x1; L[18] = x2;
                         scale += x0 * (lambda * x0 + L[6]) + x1 * (lambda * x1 + L[7]) + x2 * (lambda * x2 + L[8]);
                     }
                     for (int k = tid; k < n6; k += BA_THREADS) scale += xs[k] * (lambda * xs[k] + bp[k]);
@@ -608,7 +638,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                     // every Jacobian above used the un-updated state: only now move it
                     for (int j = tid; j < nl; j += BA_THREADS) {
                         if (fixed[j]) continue;
-                        pts[3 * j] += lm[18 * j + 15]; pts[3 * j + 1] += lm[18 * j + 16]; pts[3 * j + 2] += lm[18 * j + 17];
+                        pts[3 * j] += lm[LM_STRIDE * j + 16]; pts[3 * j + 1] += lm[LM_STRIDE * j + 17]; pts[3 * j + 2] += lm[LM_STRIDE * j + 18];
                     }
                     for (int i = tid; i < np; i += BA_THREADS) pose_oplus(Rt + 12 * i, xs + 6 * i);
                     __syncthreads();
@@ -717,12 +747,12 @@ extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_
     BA_ALLOC(h->d_op, W * MO * 4);
     BA_ALLOC(h->d_ol, W * MO * 4);
     BA_ALLOC(h->d_edge_of, W * ML * MP * 4);
-    BA_ALLOC(h->d_lm, W * ML * 18 * 8);
+    BA_ALLOC(h->d_lm, W * ML * LM_STRIDE * 8);
     BA_ALLOC(h->d_ptbak, W * ML * 3 * 8);
     BA_ALLOC(h->d_err, W * MO * 4 * 8);
     BA_ALLOC(h->d_hpl, W * MO * 18 * 8);
-    BA_ALLOC(h->d_ybd, W * MO * 18 * 8);
-    BA_ALLOC(h->d_pairs, W * (MP * (MP + 1) / 2) * ML * sizeof(int2));
+    BA_ALLOC(h->d_ybd, W * MO * 10 * 8);
+    BA_ALLOC(h->d_pairs, W * (MP * (MP + 1) / 2) * ML * sizeof(int4));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_bytes(BA_MAX_POSES));
