@@ -20,7 +20,9 @@
 #include "common.cuh"
 #include "se3.cuh"
 
+#ifndef BA_THREADS
 #define BA_THREADS 256
+#endif
 #ifndef BA_MIN_BLOCKS
 #define BA_MIN_BLOCKS 1   // CTAs per SM the register budget is held to (launch bounds)
 #endif

@@ -39,6 +39,7 @@ def nccl_comm(device_index):
     import torch
     import torch.distributed as dist
     from . import capi
+    torch.cuda.set_device(device_index)
     try:
         backend = dist.group.WORLD._get_backend(torch.device("cuda", device_index))
         # NCCL communicators are created lazily: one tiny collective makes sure this one exists
@@ -95,7 +96,7 @@ def allgather_kf_poses(local_poses, n_total, rank=None, world=None, device=None)
         return local.copy()
     if dist.get_backend() == "nccl":
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        gathered, counts = allgather_kf_poses_capi(local, cap, nccl_comm(dev.index or 0))
+        gathered, counts = allgather_kf_poses_capi(local, cap, nccl_comm(dev.index if dev.index is not None else torch.cuda.current_device()))
         assert counts.tolist() == [len(shard_indices(n_total, r, world)) for r in range(world)], counts
         return uninterleave(gathered, n_total)
     buf = torch.zeros((cap, 7), dtype=torch.float64)

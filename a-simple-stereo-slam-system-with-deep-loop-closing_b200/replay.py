@@ -245,7 +245,7 @@ class GpuOps:
     def triangulate(self, ul, ur, T_wc7):
         b = synth.KITTI_BF / synth.KITTI_FX
         return capi.triangulate(ul, ur, synth.KITTI_K, synth.KITTI_K, np.array([0, 0, 0, 1, 0, 0, 0.0]),
-                                np.array([0, 0, 0, 1, -b, 0, 0.0]), T_wc7)
+                                np.array([0, 0, 0, 1, -b, 0, 0.0]), T_wc7, device=self.device)
 
     def triangulate_batch(self, uls, urs):
         """One sb_triangulate call for the correspondences of a whole batch of keyframes (same two camera poses)."""
@@ -424,8 +424,10 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
     for i in range(len(my_kfs)):
         poses_ba[i] = ba_results[i][0][-1]              # the newest pose of keyframe k's window after BA (replayed windows)
     if world > 1:
+        import torch
         import torch.distributed as dist
-        poses_all = par.allgather_kf_poses(poses_ba, seq.n_kf, rank, world)
+        torch.cuda.set_device(ops.device)               # the C ABI selects its handle's device per call; make torch's explicit too
+        poses_all = par.allgather_kf_poses(poses_ba, seq.n_kf, rank, world, device=torch.device("cuda", ops.device))
         gathered = [None] * world
         dist.all_gather_object(gathered, rec)
         rec = {}
