@@ -10,7 +10,8 @@
 // 2x6 / 2x3 Jacobians are ~60 flops and are recomputed wherever they are needed, so the working set
 // per window is the 6x6 pose blocks and the reduced (6P)^2 system in shared memory plus 18 doubles
 // per landmark in L2.  Every sum runs in a fixed order (no floating-point atomics): results are
-// bit-reproducible run to run.  The only index structure is edge_of[landmark][pose].
+// bit-reproducible run to run.  The only index structure is edge_of[landmark][pose] (+ a chain through next_dup for the rare
+// window in which one keyframe observes a landmark more than once, as LoopLocalFusion can produce: src/loopclosing.cpp:478-505).
 //
 // All arithmetic is fp64 like g2o's: the window has no fixed pose, its gauge is held only by the LM
 // damping and the fixed landmarks, and fp32 normal equations do not keep the 1e-4 parity bound there.
@@ -47,7 +48,8 @@ struct sb_ba {
     double *d_poses, *d_points, *d_uv, *d_chi2;
     uint8_t *d_fixed, *d_outlier;
     int32_t *d_op, *d_ol;
-    int32_t *d_edge_of;  // [W][ML][MP]
+    int32_t *d_edge_of;  // [W][ML][MP]: first edge (lowest index) of (landmark, pose), -1 if none
+    int32_t *d_next;     // [W][MO]: next edge with the same (landmark, pose), ascending, -1 at the end
     double *d_lm;        // [W][ML][18]: Hll(6) bl(3) Dinv(6) xl(3)
     double *d_ptbak;     // [W][ML][3]
     double *d_err;       // [W][2][MO][2]
@@ -67,7 +69,7 @@ struct BaArgs {
     double *chi2;            // [W][MO] out
     uint8_t *outlier;        // [W][MO] out
     int32_t *info;           // [W][4] out: outer rounds, LM iterations, inliers, outliers (or -1: bad input)
-    int32_t *edge_of;
+    int32_t *edge_of, *next_dup;
     double *lm, *ptbak, *err, *hpl, *ybd;
     int4 *pairs;
     int MP, ML, MO;
@@ -213,12 +215,13 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
     double *red = S + 36 * MP * MP;     // [16]
     double *dinv = red + 16;            // [6 MP] reciprocal pivots of the Cholesky factor
     int *pcnt = reinterpret_cast<int *>(dinv + 6 * MP);  // [MP (MP + 1) / 2] entries of each pair list
-    __shared__ int s_bad, s_next;
+    __shared__ int s_bad, s_next, s_dup;
     double *poses = a.poses + (size_t)w * MP * 7;
     double *pts = a.points + (size_t)w * a.ML * 3;
     const uint8_t *fixed = a.fixed + (size_t)w * a.ML;
     const int32_t *op = a.op + (size_t)w * a.MO, *ol = a.ol + (size_t)w * a.MO;
     int32_t *edge_of = a.edge_of + (size_t)w * a.ML * MP;
+    int32_t *next_dup = a.next_dup + (size_t)w * a.MO;
     double *lm = a.lm + (size_t)w * a.ML * LM_STRIDE;   // per landmark: Hll(0..5) bl(6..8) - Dinv(10..15) xl(16..18) -
     double *ptb = a.ptbak + (size_t)w * a.ML * 3;
     double *hpl = a.hpl + (size_t)w * a.MO * 18;
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
     int32_t *info = a.info + 4 * w;
 
     // ---- input checks and the edge_of[landmark][pose] table
-    if (tid == 0) s_bad = (np < 1 || np > MP || nl < 0 || nl > a.ML || ne < 0 || ne > a.MO) ? 1 : 0;
+    if (tid == 0) { s_bad = (np < 1 || np > MP || nl < 0 || nl > a.ML || ne < 0 || ne > a.MO) ? 1 : 0; s_dup = 0; }
     __syncthreads();
     if (!s_bad) {
         for (int k = tid; k < nl * MP; k += BA_THREADS) edge_of[k] = -1;
@@ -237,10 +240,28 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
         for (int e = tid; e < ne; e += BA_THREADS) {
             const int i = op[e], j = ol[e];
             if (i < 0 || i >= np || j < 0 || j >= nl) s_bad = 1;
-            else if (atomicCAS(&edge_of[j * MP + i], -1, e) != -1) s_bad = 2;  // one keyframe observes a landmark twice
+            else if (atomicCAS(&edge_of[j * MP + i], -1, e) != -1) s_dup = 1;  // one keyframe observes a landmark more than once
         }
     }
     __syncthreads();
+    if (!s_bad && s_dup) {
+        // Rare (a window right after a loop fusion): g2o simply has several edges between the same two vertices.  Their
+        // blocks add up, so the (landmark, pose) slot keeps its FIRST edge and the others hang off it in ascending edge
+        // order — rebuilt serially so that the chains do not depend on which thread won the race above.
+        for (int k = tid; k < nl * MP; k += BA_THREADS) edge_of[k] = -1;
+        for (int e = tid; e < ne; e += BA_THREADS) next_dup[e] = -1;
+        __syncthreads();
+        if (tid == 0)
+            for (int e = 0; e < ne; e++) {
+                int *slot = &edge_of[ol[e] * MP + op[e]];
+                if (*slot < 0) { *slot = e; continue; }
+                int t = *slot;
+                while (next_dup[t] >= 0) t = next_dup[t];
+                next_dup[t] = e;
+            }
+        __syncthreads();
+    }
+    const bool has_dup = s_dup != 0;
     if (s_bad) {
         if (tid == 0) { info[0] = -1; info[1] = -s_bad; info[2] = info[3] = 0; }
         return;
@@ -298,30 +319,41 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                 for (int j = lane; j < nl; j += 32) {
                     const int e = edge_of[j * MP + i];
                     if (e < 0) continue;
-                    double A[12], B[6], r[2], wgt;
-                    edge_lin(c, e, elin, A, B, r, wgt);
-                    int k = 0;
+                    const bool fr = !fixed[j];
+                    double hv[18], cn[9];   // Hpl block w A^T B (6x3) and the landmark's share (w B^T B: 00 01 02 11 12 22, -w B^T r)
 #pragma unroll
-                    for (int p = 0; p < 6; p++) {
-                        g[p] += -wgt * (A[p] * r[0] + A[6 + p] * r[1]);
+                    for (int k2 = 0; k2 < 18; k2++) hv[k2] = 0;
 #pragma unroll
-                        for (int q = p; q < 6; q++) h[k++] += wgt * (A[p] * A[q] + A[6 + p] * A[6 + q]);
+                    for (int k2 = 0; k2 < 9; k2++) cn[k2] = 0;
+                    for (int ee = e; ee >= 0; ee = has_dup ? next_dup[ee] : -1) {   // one edge, unless the keyframe sees the landmark twice
+                        double A[12], B[6], r[2], wgt;
+                        edge_lin(c, ee, elin, A, B, r, wgt);
+                        int k = 0;
+#pragma unroll
+                        for (int p = 0; p < 6; p++) {
+                            g[p] += -wgt * (A[p] * r[0] + A[6 + p] * r[1]);
+#pragma unroll
+                            for (int q = p; q < 6; q++) h[k++] += wgt * (A[p] * A[q] + A[6 + p] * A[6 + q]);
+                        }
+                        if (fr) {
+#pragma unroll
+                            for (int p = 0; p < 6; p++)
+#pragma unroll
+                                for (int q = 0; q < 3; q++) hv[3 * p + q] += wgt * (A[p] * B[q] + A[6 + p] * B[3 + q]);
+                            cn[0] += wgt * (B[0] * B[0] + B[3] * B[3]); cn[1] += wgt * (B[0] * B[1] + B[3] * B[4]);
+                            cn[2] += wgt * (B[0] * B[2] + B[3] * B[5]); cn[3] += wgt * (B[1] * B[1] + B[4] * B[4]);
+                            cn[4] += wgt * (B[1] * B[2] + B[4] * B[5]); cn[5] += wgt * (B[2] * B[2] + B[5] * B[5]);
+                            cn[6] += -wgt * (B[0] * r[0] + B[3] * r[1]); cn[7] += -wgt * (B[1] * r[0] + B[4] * r[1]);
+                            cn[8] += -wgt * (B[2] * r[0] + B[5] * r[1]);
+                        }
                     }
-                    if (!fixed[j]) {
-                        double2 *P = reinterpret_cast<double2 *>(hpl + 18 * e);  // Hpl block of this edge: w A^T B (6x3), 9 double2 stores
-                        double hv[18];
-#pragma unroll
-                        for (int p = 0; p < 6; p++)
-#pragma unroll
-                            for (int q = 0; q < 3; q++) hv[3 * p + q] = wgt * (A[p] * B[q] + A[6 + p] * B[3 + q]);
+                    if (fr) {   // stored in the slot of the first edge: 9 + 5 double2 stores
+                        double2 *P = reinterpret_cast<double2 *>(hpl + 18 * e);
 #pragma unroll
                         for (int k2 = 0; k2 < 9; k2++) P[k2] = make_double2(hv[2 * k2], hv[2 * k2 + 1]);
-                        double2 *Cn = reinterpret_cast<double2 *>(lmc + 10 * e);   // Hll share (00 01 02 11 12 22), bl share (3), pad
-                        Cn[0] = make_double2(wgt * (B[0] * B[0] + B[3] * B[3]), wgt * (B[0] * B[1] + B[3] * B[4]));
-                        Cn[1] = make_double2(wgt * (B[0] * B[2] + B[3] * B[5]), wgt * (B[1] * B[1] + B[4] * B[4]));
-                        Cn[2] = make_double2(wgt * (B[1] * B[2] + B[4] * B[5]), wgt * (B[2] * B[2] + B[5] * B[5]));
-                        Cn[3] = make_double2(-wgt * (B[0] * r[0] + B[3] * r[1]), -wgt * (B[1] * r[0] + B[4] * r[1]));
-                        Cn[4] = make_double2(-wgt * (B[2] * r[0] + B[5] * r[1]), 0.0);
+                        double2 *Cn = reinterpret_cast<double2 *>(lmc + 10 * e);
+                        Cn[0] = make_double2(cn[0], cn[1]); Cn[1] = make_double2(cn[2], cn[3]); Cn[2] = make_double2(cn[4], cn[5]);
+                        Cn[3] = make_double2(cn[6], cn[7]); Cn[4] = make_double2(cn[8], 0.0);
                     }
                 }
 #pragma unroll
@@ -708,7 +740,7 @@ static void free_ba(sb_ba *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_np, h->d_nl, h->d_ne, h->d_info, h->d_poses, h->d_points, h->d_uv, h->d_chi2, h->d_fixed,
-                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_lm, h->d_ptbak, h->d_err, h->d_hpl, h->d_ybd, h->d_pairs};
+                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_next, h->d_lm, h->d_ptbak, h->d_err, h->d_hpl, h->d_ybd, h->d_pairs};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -749,6 +781,7 @@ extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_
     BA_ALLOC(h->d_op, W * MO * 4);
     BA_ALLOC(h->d_ol, W * MO * 4);
     BA_ALLOC(h->d_edge_of, W * ML * MP * 4);
+    BA_ALLOC(h->d_next, W * MO * 4);
     BA_ALLOC(h->d_lm, W * ML * LM_STRIDE * 8);
     BA_ALLOC(h->d_ptbak, W * ML * 3 * 8);
     BA_ALLOC(h->d_err, W * MO * 4 * 8);
@@ -809,7 +842,7 @@ extern "C" int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_pos
     a.np = d_n_poses; a.nl = d_n_points; a.ne = d_n_obs;
     a.poses = d_poses; a.points = d_points; a.fixed = d_fixed; a.op = d_obs_pose; a.ol = d_obs_point; a.uv = d_uv;
     a.chi2 = d_chi2; a.outlier = d_outlier; a.info = d_info;
-    a.edge_of = h->d_edge_of; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err; a.hpl = h->d_hpl; a.ybd = h->d_ybd; a.pairs = h->d_pairs;
+    a.edge_of = h->d_edge_of; a.next_dup = h->d_next; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err; a.hpl = h->d_hpl; a.ybd = h->d_ybd; a.pairs = h->d_pairs;
     a.MP = h->max_poses; a.ML = h->max_points; a.MO = h->max_obs;
     a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
     quat7_to_ext(cam_ext7, a.extR, a.extT);
@@ -894,7 +927,7 @@ extern "C" int sb_ba_wait(sb_ba_t *h) {
     SB_CUDA(cudaEventSynchronize(h->done));
     for (size_t w = 0; w < W; w++)
         if (info[4 * w] < 0) {
-            sb_set_error("window %zu: %s", w, info[4 * w + 1] == -2 ? "a keyframe observes the same landmark twice" : "counts or indices out of range");
+            sb_set_error("window %zu: %s", w, "counts or indices out of range");
             return SB_ERR_INVALID;
         }
     return SB_OK;

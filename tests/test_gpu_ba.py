@@ -82,12 +82,26 @@ def test_bad_input_is_reported(pkg, ba, synth):
     w["obs_point"][3] = 999
     with pytest.raises(pkg.SlamB200Error):
         ba.solve([w], synth.KITTI_K)
-    w = synth.ba_window(41, n_points=30)
-    w["obs_pose"] = np.concatenate([w["obs_pose"], w["obs_pose"][:1]])   # the same (keyframe, landmark) twice
-    w["obs_point"] = np.concatenate([w["obs_point"], w["obs_point"][:1]])
-    w["uv"] = np.concatenate([w["uv"], w["uv"][:1]])
-    with pytest.raises(pkg.SlamB200Error):
-        ba.solve([w], synth.KITTI_K)
+
+
+def test_a_keyframe_may_observe_a_landmark_more_than_once(ba, oracle, synth):
+    """After LoopLocalFusion (src/loopclosing.cpp:478-505) two features of the current keyframe can end up on the same map
+    point: g2o then simply has two edges between the same vertices.  Same result as the oracle, which treats every
+    observation as its own edge; the window next to it in the batch (no duplicates) is unaffected."""
+    rng = np.random.default_rng(5)
+    w = synth.ba_window(41, n_points=120)
+    pick = rng.choice(len(w["obs_pose"]), 25, replace=False)
+    pick = np.concatenate([pick, pick[:5]])                                  # five (keyframe, landmark) pairs even three times
+    w["obs_pose"] = np.concatenate([w["obs_pose"], w["obs_pose"][pick]])
+    w["obs_point"] = np.concatenate([w["obs_point"], w["obs_point"][pick]])
+    w["uv"] = np.concatenate([w["uv"], w["uv"][pick] + rng.normal(0, 0.7, (len(pick), 2))])
+    perm = rng.permutation(len(w["obs_pose"]))                               # duplicates anywhere in the edge list
+    for k in ("obs_pose", "obs_point", "uv"):
+        w[k] = w[k][perm]
+    plain = synth.ba_window(42, n_points=120)
+    res = ba.solve([w, plain], synth.KITTI_K)
+    check_window(oracle, synth, w, res[0])
+    check_window(oracle, synth, plain, res[1])
 
 
 def test_submit_wait_equals_solve(pkg, ba, synth):
