@@ -196,8 +196,10 @@ class CpuReference:
                 self.R = R
         except Exception:
             self.R = None
-        self.kind = ("reference (src/ORBextractor.cpp compiled unmodified, oracle/_ref) + port (OpenCV primitives, BFMatcher and the "
-                     "g2o LM/Schur BA restated in C)") if self.R else "port"
+        self.kind = "reference" if self.R else "port"
+        self.kind_detail = ("extractor: the reference's own src/ORBextractor.cpp compiled unmodified (oracle/_ref); the OpenCV primitives it "
+                            "calls, BFMatcher and the g2o LM / Schur BA: restated in C (oracle/)") if self.R else \
+            "oracle/: C restatement of the reference's OpenCV / g2o based path"
         self.local = threading.local()
         self.pool = ThreadPoolExecutor(cores)
 
@@ -288,7 +290,7 @@ class Cv2Primitives:
 def cpu_reference_fps(frames, windows, cores):
     ref = CpuReference(cores)
     ref.run(frames[:cores], windows)   # warm: library load, per-thread extractors
-    return len(frames) / ref.run(frames, windows), ref.kind
+    return len(frames) / ref.run(frames, windows), ref.kind, ref.kind_detail
 
 
 _JSON_FD = None
@@ -332,7 +334,7 @@ def run_reference(args, rank, world):
            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": {"workload": WORKLOAD if not args.no_ba else "config 2: ORB extract (both views) + L<->R Hamming match only",
                       "frames_per_step": per_step},
-           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": ref.kind,
+           "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": ref.kind, "kind_detail": ref.kind_detail,
                             "sample": f"{per_step} synthetic stereo frames per step through oracle/ (C restatement of "
                                       "ORBextractor::DetectAndCompute + BFMatcher + the g2o-faithful LM/Schur BA; the reference "
                                       "itself needs OpenCV/g2o and cannot be built here), one frame per thread"},
@@ -810,8 +812,8 @@ def main():
             cores = os.cpu_count() or 1
             n = max(2 * cores, 16)
             sample = pool_np[:min(n, P)]
-            fps, kind = cpu_reference_fps(sample, windows if with_ba else None, cores)
-            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+            fps, kind, kind_detail = cpu_reference_fps(sample, windows if with_ba else None, cores)
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "kind_detail": kind_detail,
                                    "sample": f"{len(sample)} of the same synthetic stereo frames (+ one BA window each) through "
                                              "oracle/ (C restatement of the reference's OpenCV/g2o-based path), one frame per thread"}
             try:   # BASELINE.md section 4 leg: the OpenCV primitives through cv2 (SIMD builds), 1 thread and all cores
