@@ -18,8 +18,12 @@ if which in ("all", "orb"):
     _, ks = ext.ScreenAndComputeKPsParams(frames[0, 0], kin)
     d = ext.CalcDescriptors(frames[0, 0], ks)
     print("detect/screen/calc", len(k), len(ks), d.shape)
+    got = ext.ScreenAndDescribeBatch([frames[0, 0]], [kin])   # sb_orb_screen_describe
+    print("screen_describe", len(got[0][1]), got[0][2].shape)
 if which in ("all", "ba"):
     w = [synth.ba_window(s, n_points=60) for s in range(2)]
+    for k_ in ("obs_pose", "obs_point", "uv"):   # a duplicated observation: the chain path of the kernel
+        w[1][k_] = np.concatenate([w[1][k_], w[1][k_][:3]])
     r = pkg.LocalBA(max_windows=2, max_poses=7, max_points=64, max_obs=512).solve(w, synth.KITTI_K)
     print("ba", r[0][4].tolist())
 if which in ("all", "lcd"):
@@ -31,6 +35,10 @@ if which in ("all", "pg"):
     g = synth.pose_graph(1, n=50, n_loops=2)
     p, info = pkg.PoseGraph(64, 128).solve(g["poses0"], g["fixed"], g["v0"], g["v1"], g["meas"], iters=5)
     print("pg", info)
+    big = pkg.PoseGraph(64, 256, max_loops=40)   # capacitance matrix in global memory (more loop edges than fit shared memory)
+    v0 = np.concatenate([g["v0"], np.arange(20, 48, dtype=np.int32)]); v1 = np.concatenate([g["v1"], np.arange(2, 30, dtype=np.int32)])
+    meas = np.concatenate([g["meas"], np.tile(np.array([[0, 0, 0, 1, 0, 0, 0.0]]), (28, 1))])
+    print("pg loops", big.solve(g["poses0"], g["fixed"], v0, v1, meas, iters=2)[1])
 if which in ("all", "pnp"):
     pr = [synth.pnp_problem(s, n_points=200) for s in range(2)]
     r = pkg.PnPRansac(max_problems=2, max_points=256).solve([(p["obj"], p["img"]) for p in pr], synth.KITTI_K)
