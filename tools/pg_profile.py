@@ -3,7 +3,7 @@ import ctypes as C, importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 PKG = "a-simple-stereo-slam-system-with-deep-loop-closing_b200"
 capi = importlib.import_module(PKG + ".capi")
-capi.lib_path = lambda: os.path.join(os.path.dirname(os.path.abspath(__file__)), "libslamb200_prof.so")
+capi.lib_path = lambda: os.path.join(os.path.dirname(os.path.abspath(__file__)), os.environ.get("SB_PROF_LIB", "libslamb200_prof.so"))
 pkg = importlib.import_module(PKG)
 synth = importlib.import_module(PKG + ".synth")
 g = synth.pose_graph(0, n=742)
