@@ -10,6 +10,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "se3.cuh"
 
@@ -148,19 +150,34 @@ extern "C" int sb_triangulate(int device, int n, const float *uv_left, const flo
     if (n == 0) return SB_OK;
     SB_REQUIRE(uv_left && uv_right && points && ok, "null pointer");
     SB_TRY(sb_use_device(device));
-    float *d_uv = nullptr;
-    double *d_p = nullptr;
-    uint8_t *d_ok = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_uv, (size_t)n * 16);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_p, (size_t)n * 24);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&d_ok, (size_t)n);
+    // Device scratch of the host-pointer entry point: one grow-only buffer per device, kept between calls (a cudaMalloc /
+    // cudaFree pair per call costs milliseconds: cudaFree synchronises the device), handed out under a lock.
+    enum { SB_MAX_DEVICES = 64 };
+    static std::mutex mu;
+    static void *scratch[SB_MAX_DEVICES] = {nullptr};
+    static size_t scratch_bytes[SB_MAX_DEVICES] = {0};
+    SB_REQUIRE(device >= 0 && device < SB_MAX_DEVICES, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    const size_t off_p = sb_align_up((size_t)n * 16, 256), off_ok = off_p + sb_align_up((size_t)n * 24, 256);
+    const size_t need = off_ok + sb_align_up((size_t)n, 256);
+    cudaError_t e = cudaSuccess;
+    if (scratch_bytes[device] < need) {
+        if (scratch[device]) cudaFree(scratch[device]);
+        scratch[device] = nullptr;
+        scratch_bytes[device] = 0;
+        const size_t want = need < ((size_t)1 << 20) ? ((size_t)1 << 20) : 2 * need;
+        e = cudaMalloc(&scratch[device], want);
+        if (e == cudaSuccess) scratch_bytes[device] = want;
+    }
+    float *d_uv = reinterpret_cast<float *>(scratch[device]);
+    double *d_p = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(scratch[device]) + off_p);
+    uint8_t *d_ok = reinterpret_cast<uint8_t *>(scratch[device]) + off_ok;
     int rc = SB_OK;
     if (e == cudaSuccess) e = cudaMemcpy(d_uv, uv_left, (size_t)n * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_uv + 2 * (size_t)n, uv_right, (size_t)n * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) rc = sb_triangulate_dev(device, nullptr, n, d_uv, d_uv + 2 * (size_t)n, K_left, K_right, pose_left7, pose_right7, T_wc7, ratio_th, d_p, d_ok);
     if (e == cudaSuccess && rc == SB_OK) e = cudaMemcpy(points, d_p, (size_t)n * 24, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && rc == SB_OK) e = cudaMemcpy(ok, d_ok, (size_t)n, cudaMemcpyDeviceToHost);
-    cudaFree(d_uv); cudaFree(d_p); cudaFree(d_ok);
     if (e != cudaSuccess) { sb_set_error("sb_triangulate: %s", cudaGetErrorString(e)); return SB_ERR_CUDA; }
     return rc;
 }

@@ -30,6 +30,7 @@ from . import capi, synth
 from . import parallel as par
 
 ORB_PARAMS = (2000, 1.2, 8, 20, 7)
+_SYNC_TIMERS = bool(int(__import__("os").environ.get("REPLAY_SYNC_TIMERS", "0")))
 KF_SCENE0 = 100000
 
 
@@ -316,6 +317,9 @@ def expand_octaves(feats, nlevels=8):
 
 
 def lap(t, key, t0):
+    if _SYNC_TIMERS:   # diagnosis only: attribute asynchronous device work to the stage that enqueued it
+        import torch
+        torch.cuda.synchronize()
     now = time.perf_counter()
     t[key] = t.get(key, 0.0) + now - t0
     return now
@@ -539,9 +543,12 @@ def correct_and_optimise(ops, seq, est, k, loop_kf, T_corr, loop_edge, n_active=
     fixed[loop_kf] = 1
     fixed[0] = 1
     v0, v1, meas = [], [], []
+    odo7 = getattr(seq, "_odo7", None)                             # the odometry measurements as pose7, converted once
+    if odo7 is None:
+        odo7 = seq._odo7 = [T_to7(T) if i > 0 else None for i, T in enumerate(seq.odo)]
     for i in range(n):                                             # allKFs in id order: sequential edge, then loop edge
         if i > 0:
-            v0.append(i); v1.append(i - 1); meas.append(T_to7(seq.odo[i]))
+            v0.append(i); v1.append(i - 1); meas.append(odo7[i])
         if i in loop_edge:
             v0.append(i); v1.append(loop_edge[i][0]); meas.append(T_to7(loop_edge[i][1]))
     poses = np.stack([T_to7(T) for T in est[:n]])

@@ -384,6 +384,7 @@ def run_config4(args, rank, world, local_rank):
                        "note": "the replay runs on host buffers through the host-pointer C ABI: value IS end to end"},
                "stage_seconds": {"extract_match_ba": fr, "keyframe_front_end_and_descriptors": kf, "exchange": ex,
                                  "loop_closing_total": lc, "of_which_pose_graph": pg},
+               "keyframe_stage_seconds_rank0": {k[3:-2]: round(v, 4) for k, v in res["timings"].items() if k.startswith("kf_")},
                "loops_closed": len(res["loops"]), "loops_planted": len(seq.loop_pairs), "posegraph_runs": res["posegraph_runs"],
                "mean_position_error_m": {"dead_reckoned": res["mean_position_error_dead_reckoned_m"], "final": res["mean_position_error_final_m"]},
                "keypoints": res["keypoints"], "matches": res["matches"]}
@@ -456,6 +457,7 @@ def main():
     exts = [pkg.ORBextractor(*ORB_PARAMS, max_w=W, max_h=H, max_batch=2 * B, device=local_rank) for _ in range(NH)]
     mats = [pkg.HammingMatcher(max_batch=B, max_rows=exts[0].cap, device=local_rank) for _ in range(NH)]
     ba = pkg.LocalBA(max_windows=B, device=local_rank, **BA_CAPS)
+    NBA = int(os.environ.get("BENCH_BA_STREAMS", "1"))   # back-end batches in flight (each on its own stream and buffers)
     for k in range(NH):
         exts[k].set_stream(sx[k].cuda_stream)
         mats[k].set_stream(sx[k].cuda_stream)
@@ -473,20 +475,27 @@ def main():
     bd["chi2"] = torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.float64, device="cuda")
     bd["outlier"] = torch.zeros((B, BA_CAPS["max_obs"]), dtype=torch.uint8, device="cuda")
     bd["info"] = torch.zeros((B, 4), dtype=torch.int32, device="cuda")
+    ba_set = [(ba, bd, s2)]
+    for _ in range(1, NBA if with_ba else 1):
+        b_ = pkg.LocalBA(max_windows=B, device=local_rank, **BA_CAPS)
+        s_ = torch.cuda.Stream()
+        b_.set_stream(s_.cuda_stream)
+        ba_set.append((b_, {k: v.clone() for k, v in bd.items()}, s_))
     ba_bytes = int(bh["ne"].sum()) * (8 + 16 + 8 + 1) + int(bh["nl"].sum()) * (48 + 1) + int(bh["np"].sum()) * 112
 
     def step_dev(i, ev=None):
         off = (i * B) % P
         k = i % NH
         if with_ba:
-            with torch.cuda.stream(s2):
-                bd["poses"].copy_(bd0["poses"], non_blocking=True)      # every step starts from the same windows
-                bd["points"].copy_(bd0["points"], non_blocking=True)
+            ba_, bd_, s_ = ba_set[i % len(ba_set)]
+            with torch.cuda.stream(s_):
+                bd_["poses"].copy_(bd0["poses"], non_blocking=True)      # every step starts from the same windows
+                bd_["points"].copy_(bd0["points"], non_blocking=True)
                 if ev:
-                    ev[2].record(s2)
-                ba.solve_dev(B, bd, KITTI_K)
+                    ev[2].record(s_)
+                ba_.solve_dev(B, bd_, KITTI_K)
                 if ev:
-                    ev[3].record(s2)
+                    ev[3].record(s_)
         exts[k].detect_and_compute_dev(2 * B, pool[off], H * W, W, H, W, kps[k], desc[k], counts[k], cap)
         if ev:
             ev[0].record(sx[k])
@@ -515,11 +524,11 @@ def main():
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     main = torch.cuda.current_stream()
     e0.record(main)
-    for st in sx + [s2]:
+    for st in sx + [b[2] for b in ba_set]:
         st.wait_stream(main)
     for i in range(args.steps):
         step_dev(args.warmup + i, evs[i])
-    for st in sx + [s2]:
+    for st in sx + [b[2] for b in ba_set]:
         main.wait_stream(st)
     e1.record(main)
     barrier()
