@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "umma.cuh"
 
 #define LCD_DIM 1064
 #define LCD_PAD 1088
@@ -26,6 +27,8 @@ struct sb_lcd {
     int max_queries;
     int64_t *h_ids;              // keyframe id of every row, ascending (std::map order of _mvDatabase)
     float *h_scores;             // pinned
+    __half *d_qh;                // fp16 database only: the queries of a batch as fp16 [max_queries rounded up to 128][1088]
+    CUtensorMap map_q, map_db;   // ... and both operands as [rows][2176 bytes], 128-byte swizzle (tensor-core batch path)
     float *d_stage;              // bulk-load staging, LCD_STAGE_ROWS x 1064 fp32, allocated by the first sb_lcd_add_batch
 };
 #define LCD_STAGE_ROWS 256
@@ -71,6 +74,116 @@ __global__ void __launch_bounds__(LCD_WARPS * 32) k_lcd_score(const void *__rest
     if (lane == 0) scores[(size_t)blockIdx.y * score_stride + r] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Batch scoring on the 5th-generation tensor cores (fp16 database, >= LCD_UMMA_MIN_Q queries): scores = Q . DB^T is a
+// GEMM, [nq x 1088] x [1088 x n], fp16 operands, fp32 accumulate — tcgen05.mma kind::f16.  Both operands are K-major
+// rows of 2176 bytes, so a K chunk of 64 halves is one 128-byte swizzle span: TMA (SWIZZLE_128B) drops a 128-query and a
+// 256-row panel per chunk into a 4-deep shared-memory ring, one elected thread issues 4 UMMAs (M 128, N 256, K 16) per
+// chunk into a 128 x 256 fp32 accumulator in tensor memory, and four epilogue warps read it back with tcgen05.ld and
+// store the scores.  CTA = one 128 x 256 output tile; warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2-5 = epilogue (TMEM lane quadrant = warp % 4).  The queries are rounded to fp16 first (k_lcd_q2h): against the
+// GEMV path (fp32 queries) a score moves by a few 1e-4, inside the fp16 database's own tolerance (tests/test_gpu_lcd.py).
+// ---------------------------------------------------------------------------------------------------------------------
+#define LCD_UMMA_MIN_Q 64
+#define LG_M 128
+#define LG_N 256
+#define LG_KC (LCD_PAD / 64)          // 17 chunks of 64 halves
+#define LG_ST 4                       // ring depth
+#define LG_A_BYTES (LG_M * 128)
+#define LG_B_BYTES (LG_N * 128)
+#define LG_STAGE (LG_A_BYTES + LG_B_BYTES)
+#define LG_SMEM (LG_ST * LG_STAGE + 1024)
+#define LG_THREADS 192
+
+// queries fp32 [nq][1064] -> fp16 [gridDim.x][1088], rows >= nq and the padding columns are zero
+__global__ void k_lcd_q2h(const float *__restrict__ q, int nq, __half *__restrict__ out) {
+    const int r = blockIdx.x;
+    for (int i = threadIdx.x; i < LCD_PAD; i += blockDim.x)
+        out[(size_t)r * LCD_PAD + i] = __float2half_rn(r < nq && i < LCD_DIM ? q[(size_t)r * LCD_DIM + i] : 0.f);
+}
+
+// grid = (ceil(nq / 128), ceil(n / 256))
+__global__ void __launch_bounds__(LG_THREADS, 1) k_lcd_score_umma(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
+                                                                 int nq, int n, float *__restrict__ scores, int stride) {
+    extern __shared__ uint8_t lg_raw[];
+    __shared__ __align__(8) uint64_t full[LG_ST], empty[LG_ST], acc_full;
+    __shared__ uint32_t tmem_slot;
+    const int q0 = blockIdx.x * LG_M, r0 = blockIdx.y * LG_N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *smem = lg_raw + ((1024u - (sb_smem_u32(lg_raw) & 1023u)) & 1023u);  // swizzle panels need 1024-byte alignment
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < LG_ST; i++) {
+            sb_mbar_init(&full[i], 1);
+            sb_mbar_init(&empty[i], 1);
+        }
+        sb_mbar_init(&acc_full, 1);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb_smem_u32(&tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer
+            for (int kc = 0; kc < LG_KC; kc++) {
+                const int s = kc % LG_ST, u = kc / LG_ST;
+                if (u >= 1) sb_mbar_wait(&empty[s], (u - 1) & 1);
+                sb_mbar_expect_tx(&full[s], LG_STAGE);
+                um_tma_load_2d(smem + s * LG_STAGE, &map_q, kc * 128, q0, &full[s]);
+                um_tma_load_2d(smem + s * LG_STAGE + LG_A_BYTES, &map_db, kc * 128, r0, &full[s]);  // rows past the capacity: zero-filled
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer
+            // instruction descriptor: D = f32 (1 << 4), A = B = f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(LG_N >> 3) << 17) | ((uint32_t)(LG_M >> 4) << 24);
+            for (int kc = 0; kc < LG_KC; kc++) {
+                const int s = kc % LG_ST;
+                sb_mbar_wait(&full[s], (kc / LG_ST) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t ad = um_smem_desc(smem + s * LG_STAGE + k * 32);
+                    const uint64_t bd = um_smem_desc(smem + s * LG_STAGE + LG_A_BYTES + k * 32);
+                    um_mma_f16(tmem, ad, bd, idesc, (kc | k) != 0);
+                }
+                um_commit(&empty[s]);
+            }
+            um_commit(&acc_full);
+        }
+    } else {  // ===== epilogue: one thread per query row
+        const int quad = warp & 3;
+        const int row = q0 + quad * 32 + lane;
+        sb_mbar_wait(&acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float *out = scores + (size_t)row * stride + r0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < LG_N; c0 += 64) {
+            uint32_t va[32], vb[32];
+            const uint32_t tbase = tmem + (((uint32_t)quad * 32u) << 16) + (uint32_t)c0;
+            um_tmem_ld32_issue(tbase, va);
+            um_tmem_ld32_issue(tbase + 32, vb);
+            um_tmem_ld_wait(va);
+            um_tmem_ld_wait(vb);
+            if (row < nq) {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (r0 + c0 + j < n) out[c0 + j] = __uint_as_float(va[j]);
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (r0 + c0 + 32 + j < n) out[c0 + 32 + j] = __uint_as_float(vb[j]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
 // one CTA per row: database row (row0 + blockIdx.x) <- src[blockIdx.x][1064] (fp32 -> fp16 with zero padding, or fp32 copy)
 __global__ void k_lcd_store_row(void *db, int row0, const float *src_rows, int half) {
     const int row = row0 + blockIdx.x;
@@ -90,6 +203,7 @@ static void free_lcd(sb_lcd *h) {
     if (h->d_query) cudaFree(h->d_query);
     if (h->d_scores) cudaFree(h->d_scores);
     if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_qh) cudaFree(h->d_qh);
     if (h->h_scores) cudaFreeHost(h->h_scores);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     free(h->h_ids);
@@ -117,10 +231,26 @@ extern "C" int sb_lcd_create(sb_lcd_t **out, int device, int capacity, int dtype
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_scores, (size_t)max_queries * capacity * 4);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_scores, (size_t)capacity * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    const size_t q_rows = sb_align_up((size_t)max_queries, LG_M);
+    if (e == cudaSuccess && dtype == SB_LCD_FP16 && max_queries >= LCD_UMMA_MIN_Q) {   // tensor-core batch path
+        e = cudaMalloc((void **)&h->d_qh, q_rows * LCD_PAD * 2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lcd_score_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, LG_SMEM);
+    }
     if (e != cudaSuccess) {
         sb_set_error("sb_lcd_create: %s", cudaGetErrorString(e));
         free_lcd(h);
         return SB_ERR_CUDA;
+    }
+    if (h->d_qh) {
+        const uint64_t strides[1] = {LCD_PAD * 2};
+        const uint64_t dq[2] = {LCD_PAD * 2, (uint64_t)q_rows}, dd[2] = {LCD_PAD * 2, (uint64_t)capacity};
+        const uint32_t bq[2] = {128, LG_M}, bd[2] = {128, LG_N};
+        int rc = sb_make_tensor_map_u8_sw128(&h->map_q, h->d_qh, 2, dq, strides, bq);
+        if (rc == SB_OK) rc = sb_make_tensor_map_u8_sw128(&h->map_db, h->d_db, 2, dd, strides, bd);
+        if (rc != SB_OK) {
+            free_lcd(h);
+            return rc;
+        }
     }
     h->stream = h->own_stream;
     *out = h;
@@ -210,6 +340,13 @@ extern "C" int sb_lcd_remove(sb_lcd_t *h, int64_t kf_id) {
 
 static int launch_scores(sb_lcd *h, int nq, const float *d_queries, float *d_scores, int stride) {
     if (h->n == 0) return SB_OK;
+    if (h->d_qh && nq >= LCD_UMMA_MIN_Q && nq <= h->max_queries) {   // a batch of queries against the fp16 database: tensor cores
+        const int q_rows = (int)sb_align_up((size_t)nq, LG_M);
+        k_lcd_q2h<<<q_rows, 256, 0, h->stream>>>(d_queries, nq, h->d_qh);
+        k_lcd_score_umma<<<dim3(q_rows / LG_M, sb_div_up(h->n, LG_N)), LG_THREADS, LG_SMEM, h->stream>>>(h->map_q, h->map_db, nq, h->n, d_scores, stride);
+        SB_CUDA(cudaGetLastError());
+        return SB_OK;
+    }
     dim3 grid(sb_div_up(h->n, LCD_WARPS), nq);
     if (h->dtype == SB_LCD_FP16)
         k_lcd_score<true><<<grid, LCD_WARPS * 32, 0, h->stream>>>(h->d_db, h->n, d_queries, d_scores, stride);

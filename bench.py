@@ -721,6 +721,28 @@ def main():
         lms = a0.elapsed_time(a1) / 10
         extras["lcd_score_queries_per_s"] = n_kf / (lms * 1e-3)
         extras["lcd_score_gbs"] = n_kf * n_kf * 1088 * 2 / (lms * 1e-3) / 1e9
+        extras["lcd_score_path"] = "tcgen05 kind::f16 GEMM (>= 64 queries per call; a single query runs the fp16 GEMV)"
+        # the same kernel at a size that fills the GPU: 4096 queries against a 16384-row database
+        nq_big, n_big = 4096, 16384
+        rng = np.random.default_rng(0)
+        big = rng.standard_normal((n_big, 1064), dtype=np.float32)
+        big /= np.linalg.norm(big, axis=1, keepdims=True)
+        lcd_big = pkg.DeepLCDScorer(capacity=n_big, dtype=1, max_queries=nq_big, device=local_rank)
+        lcd_big.add_batch(np.arange(n_big), big)
+        lcd_big.set_stream(sl.cuda_stream)
+        dq_big = torch.from_numpy(big[:nq_big]).cuda()
+        ds_big = torch.zeros((nq_big, n_big), dtype=torch.float32, device="cuda")
+        lcd_big.score_dev(nq_big, dq_big, ds_big, n_big)
+        a0.record(sl)
+        for _ in range(5):
+            lcd_big.score_dev(nq_big, dq_big, ds_big, n_big)
+        a1.record(sl)
+        torch.cuda.synchronize()
+        gms = a0.elapsed_time(a1) / 5
+        extras["lcd_gemm_4096x16384"] = {"ms": gms, "tflops_fp16": 2.0 * nq_big * n_big * 1088 / (gms * 1e-3) / 1e12,
+                                         "score_write_gbs": nq_big * n_big * 4 / (gms * 1e-3) / 1e9}
+        lcd_big.close()
+        del dq_big, ds_big
         # DeepLCD CNN forward ("next" row 2): whole-image descriptors of 64 keyframes per call (seeded random weights of the
         # CALC architecture; the trained model is a configure-time download of the reference)
         nb = 64

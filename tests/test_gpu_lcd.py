@@ -51,3 +51,24 @@ def test_remove_and_recency_break(pkg, oracle, synth):
     s = lcd.score(db[100:101])
     assert s.shape == (1, 99)
     lcd.close()
+
+
+@pytest.mark.parametrize("n_db,nq", [(742, 742), (300, 64), (1025, 130), (7, 64)])
+def test_batch_scores_tensor_core_path(pkg, oracle, synth, n_db, nq):
+    """A batch of >= 64 queries against the fp16 database runs as an fp16 GEMM on tcgen05 (k_lcd_score_umma): every score
+    within the fp16 tolerance (1e-3, the bound of the GEMV path) of the fp32 DeepLCD::score, within 5e-4 of the GEMV
+    path, and the same loop decisions; ragged tile edges (rows, queries not multiples of 256 / 128)."""
+    db = synth.lcd_database(3, n=max(n_db, nq))
+    rows, queries = db[:n_db], db[:nq][::-1].copy()
+    lcd = pkg.DeepLCDScorer(capacity=n_db + 3, dtype=1, max_queries=nq)
+    lcd.add_batch(np.arange(n_db), rows)
+    got = lcd.score(queries)                                   # tensor-core path (nq >= 64)
+    assert got.shape == (nq, n_db)
+    want = (queries.astype(np.float32) @ rows.astype(np.float32).T)
+    assert np.abs(got - want).max() <= 1e-3
+    gemv = np.stack([lcd.score(queries[i:i + 1])[0] for i in range(0, nq, max(1, nq // 16))])   # GEMV path (one query)
+    assert np.abs(got[::max(1, nq // 16)] - gemv).max() <= 5e-4
+    if n_db >= 2:   # the best-scoring row (the loop candidate) is the same wherever the top two are further apart than the tolerance
+        srt = np.sort(want, 1)
+        clear = (srt[:, -1] - srt[:, -2]) > 2e-3
+        assert np.array_equal(got.argmax(1)[clear], want.argmax(1)[clear])
