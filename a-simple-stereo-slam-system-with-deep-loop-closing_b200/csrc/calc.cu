@@ -13,15 +13,20 @@
 // The network is DATA: the layer list (what deploy.prototxt says) and one flat fp32 weight buffer in Caffe's blob order
 // (what calc.caffemodel holds) are given at create time.  Caffe's layer rules are restated in oracle/calc_oracle.py.
 // Activations live in HBM as fp32 [batch][C][H][W], two ping-pong buffers sized for the largest blob.
-// Convolutions run as implicit GEMM in fp32 on the CUDA cores (64 pixels x 64 output channels per CTA, K in chunks of
-// 16 through shared memory): the reference computes in fp32 and its two score thresholds are 0.02 apart.
+// Convolutions: the GEMM-shaped layers (conv2, conv3) run on the tensor cores — tcgen05.mma kind::tf32 with the
+// three-product split that keeps fp32 accuracy, operands by 4-D TMA from a channels-last copy (k_calc_conv_umma below);
+// the others (conv1: one input channel) as implicit GEMM in fp32 on the CUDA cores (64 pixels x 64 output channels per
+// CTA, K in chunks of 16 through shared memory).  The reference computes in fp32 and its two score thresholds are 0.02 apart.
 #include <math.h>
 #include <string.h>
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "orb_core.inl"
+#include "umma.cuh"
 
 #define CALC_MAX_LAYERS 32
 #define CONV_TP 64   // output pixels per CTA
@@ -40,8 +45,12 @@ struct CalcLayer {
     size_t w_off, b_off; // into d_wt: transposed weights [K][ocp], bias [ocp]
     int ocp, K;          // oc rounded up to CONV_TC, ic * kernel^2
     size_t kt_off;       // into d_ktab
+    int tc;              // convolution runs on the tensor cores (k_calc_conv_umma)
+    int tc_rows, tc_stages, tc_smem, tc_cols, tc_nacc;   // output rows per tile, ring depth, dynamic shared memory, TMEM columns
+    size_t ws_off;       // into d_wsplit: W_hi [oc][K'] then W_lo [oc][K'], K' ordered (ky, kx, ci)
 };
 
+struct ConvTcArgs;
 struct sb_calc {
     int device, in_h, in_w, max_batch, max_img_w, max_img_h, dim;
     cudaStream_t stream, own_stream;
@@ -55,6 +64,9 @@ struct sb_calc {
     int2 *d_xtab, *d_ytab;     // resize tables for (cur_w, cur_h) -> (in_w, in_h)
     int cur_w, cur_h;
     float *h_descr;            // pinned
+    // tensor-core convolutions: channels-last hi / lo copies of the layer input, split weights, per-layer TMA maps
+    float *d_nhwc_hi, *d_nhwc_lo, *d_wsplit;
+    std::vector<ConvTcArgs> *tc_args;   // parallel to *plan (unused entries for the other layers)
 };
 
 // ================================================================================================
@@ -196,6 +208,167 @@ __global__ void __launch_bounds__(256) k_calc_conv(const __grid_constant__ ConvA
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Convolution on the 5th-generation tensor cores (tcgen05.mma kind::tf32) for the layers that are GEMM-shaped enough:
+// stride 1, input channels a multiple of 32, at most 256 output channels (padded with zero weights to a multiple of 16),
+// output rows of 8..128 pixels — the CALC net's conv2 (64 -> 128 channels, 4 x 4, 92 % of the network's multiply-adds) and conv3
+// (128 -> 4, 3 x 3); conv1 (one input channel, stride 2) stays on the CUDA cores.
+//   * Implicit GEMM without an im2col buffer: the input is kept channels-last ([b][y][x][c], k_calc_nhwc_split), so for
+//     one kernel tap (ky, kx) and one block of 32 input channels the operand rows of R = 128 / ow output rows x ow output
+//     pixels are ONE 4-D TMA box (128 bytes of channels, ow pixels, R rows, 1 image) at coordinates
+//     (channel block, kx - pad, oy0 + ky - pad, b) — the zero padding is TMA's out-of-bounds fill.  The K loop walks
+//     taps x channel blocks; the weights are stored [oc][tap][c], one 2-D box per step.
+//   * fp32 parity (the oracle bound is 1e-5 on unit-norm descriptors, and DetectLoop's thresholds sit 0.02 apart) with
+//     tf32 inputs by the three-product split: x = hi + lo with hi = x rounded down to tf32 (low 13 mantissa bits cleared),
+//     lo = x - hi (exact in fp32); acc += a_lo w_hi + a_hi w_lo + a_hi w_hi in the fp32 accumulator in tensor memory.
+//     What is dropped (a_lo w_lo, and tf32(lo) - lo) is ~2^-21 of a product.
+//   * CTA = one tile of R x ow output pixels x all output channels; warp 0 = TMA producer (ring of LC_ST stages of four
+//     operand panels), warp 1 = TMEM owner + single-lane MMA issuer (12 UMMAs per stage), warps 2-5 = epilogue
+//     (tcgen05.ld, + bias, ReLU, NCHW store: for a fixed channel the tile's pixels are contiguous).
+// ---------------------------------------------------------------------------------------------------------------------
+#define LC_THREADS 192
+#ifndef CALC_TC_NACC
+#define CALC_TC_NACC 8   // partial accumulators per output tile (as many as fit the 512 TMEM columns: 4 for conv2, 8 for conv3)
+#endif
+#define LC_A_BYTES (128 * 128)   // one A panel: 128 pixel rows x 128 bytes (32 floats) of channels
+
+struct ConvTcArgs {
+    CUtensorMap a_hi, a_lo, w_hi, w_lo;
+    const float *bias;
+    float *out;
+    long long out_img;
+    int oc, ocp, oh, ow, rows, kernel, pad, cblocks, nstages, tmem_cols, nacc, acc_cols;   // ocp: oc rounded up to the UMMA's N granule (16)   // nacc accumulators of acc_cols columns each
+};
+
+// NCHW fp32 -> channels-last hi / lo planes.  grid = (ceil(hw / 32), c / 32, batch), block = (32, 8).
+__global__ void __launch_bounds__(256) k_calc_nhwc_split(const float *__restrict__ in, long long in_img, int c, int hw, float *__restrict__ hi,
+                                                         float *__restrict__ lo) {
+    __shared__ float t[32][33];
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float *I = in + (long long)blockIdx.z * in_img;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int p = p0 + threadIdx.x;
+        t[r][threadIdx.x] = p < hw ? I[(size_t)(c0 + r) * hw + p] : 0.f;
+    }
+    __syncthreads();
+    const size_t obase = (size_t)blockIdx.z * hw * c;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int p = p0 + r;
+        if (p >= hw) continue;
+        const float v = t[threadIdx.x][r];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        hi[obase + (size_t)p * c + c0 + threadIdx.x] = h;
+        lo[obase + (size_t)p * c + c0 + threadIdx.x] = v - h;   // exact
+    }
+}
+
+template <bool RELU>
+__global__ void __launch_bounds__(LC_THREADS, 1) k_calc_conv_umma(const __grid_constant__ ConvTcArgs a) {
+    extern __shared__ uint8_t lc_raw[];
+    __shared__ __align__(8) uint64_t full[4], empty[4], acc_full;
+    __shared__ uint32_t tmem_slot;
+    const int oy0 = blockIdx.x * a.rows, img = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *smem = lc_raw + ((1024u - (sb_smem_u32(lc_raw) & 1023u)) & 1023u);  // swizzle panels need 1024-byte alignment
+    const int w_bytes = a.ocp * 128;                   // one weight panel
+    const int stage = 2 * LC_A_BYTES + 2 * w_bytes;   // [a_hi | a_lo | w_hi | w_lo]
+    const int nsteps = a.kernel * a.kernel * a.cblocks;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.nstages; i++) {
+            sb_mbar_init(&full[i], 1);
+            sb_mbar_init(&empty[i], 1);
+        }
+        sb_mbar_init(&acc_full, 1);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb_smem_u32(&tmem_slot)), "r"((uint32_t)a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer
+            const uint32_t tx = (uint32_t)(2 * a.rows * a.ow * 128 + 2 * w_bytes);
+            for (int q = 0; q < nsteps; q++) {
+                const int s = q % a.nstages, u = q / a.nstages;
+                const int tap = q / a.cblocks, cb = q - tap * a.cblocks;
+                const int ky = tap / a.kernel, kx = tap - ky * a.kernel;
+                if (u >= 1) sb_mbar_wait(&empty[s], (u - 1) & 1);
+                sb_mbar_expect_tx(&full[s], tx);
+                uint8_t *st = smem + (size_t)s * stage;
+                um_tma_load_4d(st, &a.a_hi, cb * 128, kx - a.pad, oy0 + ky - a.pad, img, &full[s]);
+                um_tma_load_4d(st + LC_A_BYTES, &a.a_lo, cb * 128, kx - a.pad, oy0 + ky - a.pad, img, &full[s]);
+                um_tma_load_2d(st + 2 * LC_A_BYTES, &a.w_hi, q * 128, 0, &full[s]);
+                um_tma_load_2d(st + 2 * LC_A_BYTES + w_bytes, &a.w_lo, q * 128, 0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer
+            // instruction descriptor: D = f32 (1 << 4), A = B = tf32 (2 at bits 7 and 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.ocp >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int q = 0; q < nsteps; q++) {
+                const int s = q % a.nstages;
+                sb_mbar_wait(&full[s], (q / a.nstages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint8_t *st = smem + (size_t)s * stage;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint64_t ah = um_smem_desc(st + k * 32), al = um_smem_desc(st + LC_A_BYTES + k * 32);
+                    const uint64_t wh = um_smem_desc(st + 2 * LC_A_BYTES + k * 32), wl = um_smem_desc(st + 2 * LC_A_BYTES + w_bytes + k * 32);
+                    // step q adds into accumulator q % nacc: the tensor core's fp32 accumulation truncates, and the error grows
+                    // with the length of one accumulation chain (measured: 1.0e-5 on a unit-norm descriptor with one
+                    // accumulator for all 384 additions); the epilogue adds the partial sums with round-to-nearest
+                    const uint32_t acc = tmem + (uint32_t)((q % a.nacc) * a.acc_cols);
+                    um_mma_tf32(acc, al, wh, idesc, (q >= a.nacc) || k != 0);   // the small terms first
+                    um_mma_tf32(acc, ah, wl, idesc, 1);
+                    um_mma_tf32(acc, ah, wh, idesc, 1);
+                }
+                um_commit(&empty[s]);
+            }
+            um_commit(&acc_full);
+        }
+    } else {  // ===== epilogue: one thread per output pixel of the tile
+        const int quad = warp & 3;
+        const int t = quad * 32 + lane;                 // tile row = pixel index
+        const int oy = oy0 + t / a.ow, ox = t - (t / a.ow) * a.ow;
+        const bool valid = t < a.rows * a.ow && oy < a.oh;
+        sb_mbar_wait(&acc_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float *out = a.out + (long long)img * a.out_img + (size_t)oy * a.ow + ox;
+        const size_t cstride = (size_t)a.oh * a.ow;
+        for (int c0 = 0; c0 < a.oc; c0 += 32) {   // the last chunk may be partly used (TMEM columns are allocated in powers of two >= 32)
+            uint32_t v[32];
+            float sum[32];
+            um_tmem_ld32_issue(tmem + (((uint32_t)quad * 32u) << 16) + (uint32_t)c0, v);
+            um_tmem_ld_wait(v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) sum[j] = __uint_as_float(v[j]);
+            for (int g = 1; g < a.nacc; g++) {
+                um_tmem_ld32_issue(tmem + (((uint32_t)quad * 32u) << 16) + (uint32_t)(g * a.acc_cols + c0), v);
+                um_tmem_ld_wait(v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) sum[j] += __uint_as_float(v[j]);
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if (c0 + j < a.oc) {
+                        float r = sum[j] + __ldg(a.bias + c0 + j);
+                        if (RELU) r = fmaxf(r, 0.f);
+                        out[(size_t)(c0 + j) * cstride] = r;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)a.tmem_cols) : "memory");
+}
+
 // Caffe Pooling MAX: windows clipped to the image.  One thread per output element.
 __global__ void k_calc_pool(const float *__restrict__ in, float *__restrict__ out, long long in_img, long long out_img, int c, int ih, int iw,
                             int oh, int ow, int kernel, int stride, int pad) {
@@ -250,12 +423,14 @@ __global__ void __launch_bounds__(256) k_calc_normalize(const float *__restrict_
 static void free_calc(sb_calc *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    void *ptrs[] = {h->d_wt, h->d_ktab, h->d_act[0], h->d_act[1], h->d_img, h->d_blur, h->d_descr, h->d_xtab, h->d_ytab};
+    void *ptrs[] = {h->d_wt, h->d_ktab, h->d_act[0], h->d_act[1], h->d_img, h->d_blur, h->d_descr, h->d_xtab, h->d_ytab,
+                    h->d_nhwc_hi, h->d_nhwc_lo, h->d_wsplit};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->h_descr) cudaFreeHost(h->h_descr);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h->plan;
+    delete h->tc_args;
     delete h;
 }
 
@@ -275,6 +450,10 @@ extern "C" int sb_calc_create(sb_calc_t **out, int device, int in_h, int in_w, c
     std::vector<CalcLayer> plan;
     std::vector<float> wt;
     std::vector<int2> ktab;
+    std::vector<float> wsplit;
+    size_t nhwc_elems = 0;
+    const char *no_tc = getenv("SLAMB200_CALC_NO_TC");   // development switch: every convolution on the CUDA cores (A/B runs)
+    const bool allow_tc = !(no_tc && no_tc[0] == '1');
     int c = 1, hh = in_h, ww = in_w;
     size_t consumed = 0, max_elems = (size_t)in_h * in_w;
     for (int i = 0; i < n_layers; i++) {
@@ -308,6 +487,43 @@ extern "C" int sb_calc_create(sb_calc_t **out, int device, int in_h, int in_w, c
                 for (int ky = 0; ky < S.kernel; ky++)
                     for (int kx = 0; kx < S.kernel; kx++) ktab.push_back(make_int2(ci * hh * ww + ky * ww + kx, ky | (kx << 8)));
             L.relu = (i + 1 < n_layers && layers[i + 1].type == SB_CALC_RELU) ? 1 : 0;
+            if (allow_tc && S.stride == 1 && c % 32 == 0 && L.oc <= 256 && L.ow <= 128 && L.ow >= 8) {
+                const int ocp16 = (int)sb_align_up((size_t)L.oc, 16);   // output channels padded with zero weights to the UMMA's N granule
+                L.tc = 1;
+                L.tc_rows = 128 / L.ow;
+                if (L.tc_rows > L.oh) L.tc_rows = L.oh;
+                const int stage = 2 * LC_A_BYTES + 2 * ocp16 * 128;
+                L.tc_stages = (226 * 1024) / stage;
+                if (L.tc_stages > 4) L.tc_stages = 4;
+                L.tc_smem = L.tc_stages * stage + 1024;
+                L.tc_cols = 32;
+                while (L.tc_cols < ocp16) L.tc_cols *= 2;
+                L.tc_nacc = 512 / L.tc_cols > CALC_TC_NACC ? CALC_TC_NACC : 512 / L.tc_cols;   // partial accumulators (all of TMEM at most)
+                const int steps = S.kernel * S.kernel * (c / 32);
+                if (L.tc_nacc > steps) L.tc_nacc = steps;
+                while (L.tc_nacc & (L.tc_nacc - 1)) L.tc_nacc--;   // TMEM is allocated in powers of two
+                if (L.tc_stages < 2) L.tc = 0;
+            }
+            if (L.tc) {   // weights as W[oc][(ky, kx, ci)], split into a tf32 part and the exact remainder
+                L.ws_off = wsplit.size();
+                const size_t ocp16 = sb_align_up((size_t)L.oc, 16);
+                wsplit.resize(wsplit.size() + 2 * ocp16 * L.K, 0.f);
+                const float *W = weights + (consumed - L.oc - nw);
+                const int kk = S.kernel * S.kernel;
+                for (int o = 0; o < L.oc; o++)
+                    for (int ci = 0; ci < c; ci++)
+                        for (int t = 0; t < kk; t++) {
+                            const float v = W[(size_t)o * L.K + (size_t)ci * kk + t];
+                            uint32_t bits;
+                            memcpy(&bits, &v, 4);
+                            bits &= 0xffffe000u;
+                            float hi;
+                            memcpy(&hi, &bits, 4);
+                            wsplit[L.ws_off + (size_t)o * L.K + (size_t)t * c + ci] = hi;
+                            wsplit[L.ws_off + ocp16 * L.K + (size_t)o * L.K + (size_t)t * c + ci] = v - hi;
+                        }
+                if ((size_t)c * hh * ww > nhwc_elems) nhwc_elems = (size_t)c * hh * ww;
+            }
         } else if (S.type == SB_CALC_RELU) {
             SB_REQUIRE(i > 0 && layers[i - 1].type == SB_CALC_CONV, "a ReLU layer must follow a Convolution layer");
             continue;  // fused into the convolution before it
@@ -355,12 +571,48 @@ extern "C" int sb_calc_create(sb_calc_t **out, int device, int in_h, int in_w, c
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_ytab, (size_t)in_h * sizeof(int2));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_descr, B * h->dim * sizeof(float));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess && nhwc_elems) {
+        e = cudaMalloc((void **)&h->d_nhwc_hi, B * nhwc_elems * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_nhwc_lo, B * nhwc_elems * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_wsplit, wsplit.size() * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_wsplit, wsplit.data(), wsplit.size() * sizeof(float), cudaMemcpyHostToDevice);
+        int tc_smem = 0;
+        for (const CalcLayer &L : plan)
+            if (L.type == SB_CALC_CONV && L.tc && L.tc_smem > tc_smem) tc_smem = L.tc_smem;
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_calc_conv_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_calc_conv_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem);
+    }
     if (e == cudaSuccess && !wt.empty()) e = cudaMemcpy(h->d_wt, wt.data(), wt.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && !ktab.empty()) e = cudaMemcpy(h->d_ktab, ktab.data(), ktab.size() * sizeof(int2), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         sb_set_error("sb_calc_create: %s", cudaGetErrorString(e));
         free_calc(h);
         return SB_ERR_CUDA;
+    }
+    h->tc_args = new std::vector<ConvTcArgs>(h->plan->size());
+    for (size_t li = 0; li < h->plan->size(); li++) {
+        const CalcLayer &L = (*h->plan)[li];
+        if (L.type != SB_CALC_CONV || !L.tc) continue;
+        ConvTcArgs &t = (*h->tc_args)[li];
+        memset(&t, 0, sizeof(t));
+        const uint64_t cb = (uint64_t)L.ic * 4;
+        const uint64_t adims[4] = {cb, (uint64_t)L.iw, (uint64_t)L.ih, (uint64_t)B};
+        const uint64_t astr[3] = {cb, cb * L.iw, cb * L.iw * L.ih};
+        const uint32_t abox[4] = {128, (uint32_t)L.ow, (uint32_t)L.tc_rows, 1};
+        const uint64_t ocp16 = sb_align_up((size_t)L.oc, 16);
+        const uint64_t wdims[2] = {(uint64_t)L.K * 4, ocp16}, wstr[1] = {(uint64_t)L.K * 4};
+        const uint32_t wbox[2] = {128, (uint32_t)ocp16};
+        int rc = sb_make_tensor_map_u8_sw128(&t.a_hi, h->d_nhwc_hi, 4, adims, astr, abox);
+        if (rc == SB_OK) rc = sb_make_tensor_map_u8_sw128(&t.a_lo, h->d_nhwc_lo, 4, adims, astr, abox);
+        if (rc == SB_OK) rc = sb_make_tensor_map_u8_sw128(&t.w_hi, h->d_wsplit + L.ws_off, 2, wdims, wstr, wbox);
+        if (rc == SB_OK) rc = sb_make_tensor_map_u8_sw128(&t.w_lo, h->d_wsplit + L.ws_off + (size_t)ocp16 * L.K, 2, wdims, wstr, wbox);
+        if (rc != SB_OK) {
+            free_calc(h);
+            return rc;
+        }
+        t.bias = h->d_wt + L.b_off;
+        t.oc = L.oc; t.ocp = (int)ocp16; t.oh = L.oh; t.ow = L.ow; t.rows = L.tc_rows; t.kernel = L.kernel; t.pad = L.pad; t.cblocks = L.ic / 32;
+        t.nstages = L.tc_stages; t.acc_cols = L.tc_cols; t.nacc = L.tc_nacc; t.tmem_cols = L.tc_cols * L.tc_nacc;
     }
     h->stream = h->own_stream;
     *out = h;
@@ -395,10 +647,20 @@ static int run_net(sb_calc *h, int batch, float *d_descr) {
     cudaStream_t s = h->stream;
     int cur = 0;
     const long long img = (long long)h->act_elems;
-    for (const CalcLayer &L : *h->plan) {
+    for (size_t li = 0; li < h->plan->size(); li++) {
+        const CalcLayer &L = (*h->plan)[li];
         const float *in = h->d_act[cur];
         float *out = h->d_act[cur ^ 1];
-        if (L.type == SB_CALC_CONV) {
+        if (L.type == SB_CALC_CONV && L.tc) {
+            ConvTcArgs t = (*h->tc_args)[li];
+            t.out = out;
+            t.out_img = img;
+            k_calc_nhwc_split<<<dim3(sb_div_up(L.ih * L.iw, 32), L.ic / 32, batch), dim3(32, 8), 0, s>>>(in, img, L.ic, L.ih * L.iw, h->d_nhwc_hi,
+                                                                                                 h->d_nhwc_lo);
+            const dim3 grid(sb_div_up(L.oh, L.tc_rows), batch);
+            if (L.relu) k_calc_conv_umma<true><<<grid, LC_THREADS, L.tc_smem, s>>>(t);
+            else k_calc_conv_umma<false><<<grid, LC_THREADS, L.tc_smem, s>>>(t);
+        } else if (L.type == SB_CALC_CONV) {
             ConvArgs a;
             a.in = in; a.out = out; a.wt = h->d_wt + L.w_off; a.bias = h->d_wt + L.b_off; a.ktab = h->d_ktab + L.kt_off;
             a.in_img = img; a.out_img = img;

@@ -757,7 +757,8 @@ def main():
         torch.cuda.synchronize()
         cms = a0.elapsed_time(a1) / 10
         extras["calc_descr_keyframes_per_s"] = nb / (cms * 1e-3)
-        extras["calc_descr_tflops_fp32"] = nb * 2 * CALC_MACS / (cms * 1e-3) / 1e12
+        extras["calc_descr_tflops_fp32"] = nb * 2 * CALC_MACS / (cms * 1e-3) / 1e12   # fp32-equivalent (the tensor-core layers do 3 tf32 products per multiply-add)
+        extras["calc_conv_path"] = "conv2 / conv3: tcgen05 kind::tf32, 3-product split, 4-D TMA implicit GEMM; conv1: fp32 CUDA cores"
     except Exception as ex:   # the extras never invalidate the headline measurement
         extras["error"] = repr(ex)
 
