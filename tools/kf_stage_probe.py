@@ -18,7 +18,8 @@ def timed(name, f, n=6):
 feats = timed("kf_detect", lambda: ops.kf_detect(lefts0))
 pts = [np.stack([f["x"], f["y"]], 1).astype(np.float32) for f in feats]
 tracked = timed("lk_right", lambda: ops.lk_right(lefts0, rights, pts))
-lefts = [l.copy() for l in lefts0]
+pinned = torch.from_numpy(np.stack(lefts0)).pin_memory().numpy()      # the replay keeps its keyframe images page-locked
+lefts = [pinned[i] for i in range(32)]
 timed("cnn_descr", lambda: ops.cnn_descr(lefts))
 kins = timed("expand_octaves (host)", lambda: [replay.expand_octaves(f) for f in feats])
 timed("screen_and_describe", lambda: ops.screen_and_describe(lefts, kins))
