@@ -745,14 +745,22 @@ extern "C" int sb_calc_descr_original(sb_calc_t *h, int batch, const uint8_t *co
     SB_TRY(sb_use_device(h->device));
     cudaStream_t s = h->stream;
     const size_t row = calc_row(h), plane = row * h->max_img_h;
-    for (int b = 0; b < batch; b++)
-        SB_CUDA(cudaMemcpy2DAsync(h->d_img + b * plane, row, img[b], (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, s));
-    SB_TRY(sb_calc_descr_original_dev(h, batch, h->d_img, (int64_t)plane, w, hgt, (int)row, h->d_descr, h->d_blur));
+    // a tightly packed image travels as one contiguous copy and keeps its row length on the device (and so does the blurred
+    // image on the way back); other strides are re-pitched to align16(w) by a 2-D copy
+    const bool flat = stride == w;
+    const int dstride = flat ? w : (int)row;
+    for (int b = 0; b < batch; b++) {
+        if (flat) SB_CUDA(cudaMemcpyAsync(h->d_img + b * plane, img[b], (size_t)w * hgt, cudaMemcpyHostToDevice, s));
+        else SB_CUDA(cudaMemcpy2DAsync(h->d_img + b * plane, row, img[b], (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, s));
+    }
+    SB_TRY(sb_calc_descr_original_dev(h, batch, h->d_img, (int64_t)plane, w, hgt, dstride, h->d_descr, h->d_blur));
     SB_CUDA(cudaMemcpyAsync(h->h_descr, h->d_descr, (size_t)batch * h->dim * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (blurred_out)
         for (int b = 0; b < batch; b++)
-            if (blurred_out[b])
-                SB_CUDA(cudaMemcpy2DAsync(blurred_out[b], (size_t)stride, h->d_blur + b * plane, row, (size_t)w, (size_t)hgt, cudaMemcpyDeviceToHost, s));
+            if (blurred_out[b]) {
+                if (flat) SB_CUDA(cudaMemcpyAsync(blurred_out[b], h->d_blur + b * plane, (size_t)w * hgt, cudaMemcpyDeviceToHost, s));
+                else SB_CUDA(cudaMemcpy2DAsync(blurred_out[b], (size_t)stride, h->d_blur + b * plane, row, (size_t)w, (size_t)hgt, cudaMemcpyDeviceToHost, s));
+            }
     SB_CUDA(cudaStreamSynchronize(s));
     memcpy(descr, h->h_descr, (size_t)batch * h->dim * sizeof(float));
     return SB_OK;

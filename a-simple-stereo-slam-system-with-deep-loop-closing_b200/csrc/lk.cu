@@ -349,14 +349,23 @@ extern "C" int sb_lk_track(sb_lk_t *h, int batch, const uint8_t *const *prev, co
     SB_TRY(sb_use_device(h->device));
     cudaStream_t s = h->stream;
     const size_t row = sb_align_up((size_t)w, 16), plane = row * hgt, P = (size_t)batch * h->max_pts;
+    // a tightly packed image goes up as one contiguous copy and keeps its row length on the device (a 2-D copy of odd-length
+    // rows runs at a fraction of the link rate); other strides are re-pitched to align16(w) by the copy
+    const bool flat = stride == w;
+    const int dstride = flat ? w : (int)row;
     for (int b = 0; b < batch; b++) {
-        SB_CUDA(cudaMemcpy2DAsync(h->d_in + b * plane, row, prev[b], (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, s));
-        SB_CUDA(cudaMemcpy2DAsync(h->d_in + ((size_t)batch + b) * plane, row, next[b], (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, s));
+        if (flat) {
+            SB_CUDA(cudaMemcpyAsync(h->d_in + b * plane, prev[b], (size_t)w * hgt, cudaMemcpyHostToDevice, s));
+            SB_CUDA(cudaMemcpyAsync(h->d_in + ((size_t)batch + b) * plane, next[b], (size_t)w * hgt, cudaMemcpyHostToDevice, s));
+        } else {
+            SB_CUDA(cudaMemcpy2DAsync(h->d_in + b * plane, row, prev[b], (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, s));
+            SB_CUDA(cudaMemcpy2DAsync(h->d_in + ((size_t)batch + b) * plane, row, next[b], (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, s));
+        }
     }
     SB_CUDA(cudaMemcpyAsync(h->d_n, n_pts, (size_t)batch * 4, cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(h->d_prev, prev_pts, P * 8, cudaMemcpyHostToDevice, s));
     SB_CUDA(cudaMemcpyAsync(h->d_next, next_pts, P * 8, cudaMemcpyHostToDevice, s));
-    SB_TRY(sb_lk_track_dev(h, batch, h->d_in, h->d_in + (size_t)batch * plane, (int64_t)plane, w, hgt, (int)row, h->d_n, h->d_prev, h->d_next,
+    SB_TRY(sb_lk_track_dev(h, batch, h->d_in, h->d_in + (size_t)batch * plane, (int64_t)plane, w, hgt, dstride, h->d_n, h->d_prev, h->d_next,
                            h->d_status, win, max_count, eps, use_initial_flow, min_eig_th));
     SB_CUDA(cudaMemcpyAsync(next_pts, h->d_next, P * 8, cudaMemcpyDeviceToHost, s));
     SB_CUDA(cudaMemcpyAsync(status, h->d_status, P, cudaMemcpyDeviceToHost, s));

@@ -907,6 +907,8 @@ struct sb_orb {
     size_t in_cap;
     int stage_cap, stage_batch;
     int *h_flags;  // pinned
+    uint8_t *h_stage;     // pinned staging of sb_orb_screen_describe's results (grow-only)
+    size_t h_stage_cap;
     uint8_t *dbg_buf;  // inspection only (sb_orb_debug_fast_cell)
     int dbg_cell;
     // per-stage CUDA-event timing (sb_orb_profile): event pairs recorded on the launching stream
@@ -941,6 +943,7 @@ static void free_orb(sb_orb *h) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1529,8 +1532,12 @@ static int ensure_staging(sb_orb *h, int batch, size_t img_bytes, int cap, bool 
     return SB_OK;
 }
 
+// Host images -> h->d_in (one slot of align16(w) * hgt bytes per image).  A tightly packed image (stride == w) goes up as ONE
+// contiguous copy and keeps its row length on the device — k_copy_level0 re-pitches unaligned rows anyway — because a 2-D
+// copy of 1241-byte rows runs at a fraction of the link rate; other strides take the 2-D copy into rows of align16(w).
+// *dstride / *dmstride: the row length the device-side entry points have to be given.
 static int stage_images(sb_orb *h, int batch, const uint8_t *const *img, const uint8_t *const *mask, int w, int hgt,
-                        int stride, int mstride, bool *any_mask) {
+                        int stride, int mstride, bool *any_mask, int *dstride, int *dmstride = nullptr) {
     const size_t img_bytes = (size_t)sb_align_up((size_t)w, 16) * hgt;
     *any_mask = false;
     if (mask)
@@ -1538,11 +1545,19 @@ static int stage_images(sb_orb *h, int batch, const uint8_t *const *img, const u
             if (mask[b]) *any_mask = true;
     for (int b = 0; b < batch; b++) SB_REQUIRE(img[b], "null image pointer");
     const size_t row = sb_align_up((size_t)w, 16);
+    const bool flat = stride == w, mflat = mstride == w;
+    *dstride = flat ? w : (int)row;
+    if (dmstride) *dmstride = mflat ? w : (int)row;
     for (int b = 0; b < batch; b++) {
-        SB_CUDA(cudaMemcpy2DAsync(h->d_in + b * img_bytes, row, img[b], (size_t)stride, (size_t)w, (size_t)hgt,
-                                  cudaMemcpyHostToDevice, h->stream));
+        if (flat)
+            SB_CUDA(cudaMemcpyAsync(h->d_in + b * img_bytes, img[b], (size_t)w * hgt, cudaMemcpyHostToDevice, h->stream));
+        else
+            SB_CUDA(cudaMemcpy2DAsync(h->d_in + b * img_bytes, row, img[b], (size_t)stride, (size_t)w, (size_t)hgt,
+                                      cudaMemcpyHostToDevice, h->stream));
         if (*any_mask) {
-            if (mask[b])
+            if (mask[b] && mflat)
+                SB_CUDA(cudaMemcpyAsync(h->d_in_mask + b * img_bytes, mask[b], (size_t)w * hgt, cudaMemcpyHostToDevice, h->stream));
+            else if (mask[b])
                 SB_CUDA(cudaMemcpy2DAsync(h->d_in_mask + b * img_bytes, row, mask[b], (size_t)mstride, (size_t)w,
                                           (size_t)hgt, cudaMemcpyHostToDevice, h->stream));
             else
@@ -1566,9 +1581,10 @@ extern "C" int sb_orb_detect_and_compute(sb_orb_t *h, int batch, const uint8_t *
             if (mask[b]) any_mask = true;
     SB_REQUIRE(!any_mask || mstride >= w, "bad mask stride");
     SB_TRY(ensure_staging(h, batch, img_bytes, cap, any_mask));
-    SB_TRY(stage_images(h, batch, img, mask, w, hgt, stride, mstride, &any_mask));
+    int ds = row, dms = row;
+    SB_TRY(stage_images(h, batch, img, mask, w, hgt, stride, mstride, &any_mask, &ds, &dms));
     SB_TRY(sb_orb_detect_and_compute_dev(h, batch, h->d_in, (int64_t)img_bytes, any_mask ? h->d_in_mask : nullptr,
-                                         (int64_t)img_bytes, w, hgt, row, row, h->d_kps_out, desc ? h->d_desc_out : nullptr,
+                                         (int64_t)img_bytes, w, hgt, ds, dms, h->d_kps_out, desc ? h->d_desc_out : nullptr,
                                          h->d_counts_out, cap));
     SB_CUDA(cudaMemcpyAsync(kps, h->d_kps_out, (size_t)batch * cap * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
     if (desc) SB_CUDA(cudaMemcpyAsync(desc, h->d_desc_out, (size_t)batch * cap * 32, cudaMemcpyDeviceToHost, h->stream));
@@ -1589,9 +1605,10 @@ extern "C" int sb_orb_detect(sb_orb_t *h, int batch, const uint8_t *const *img, 
             if (mask[b]) any_mask = true;
     SB_REQUIRE(!any_mask || mstride >= w, "bad mask stride");
     SB_TRY(ensure_staging(h, batch, img_bytes, cap, any_mask));
-    SB_TRY(stage_images(h, batch, img, mask, w, hgt, stride, mstride, &any_mask));
+    int ds = row, dms = row;
+    SB_TRY(stage_images(h, batch, img, mask, w, hgt, stride, mstride, &any_mask, &ds, &dms));
     SB_TRY(sb_orb_detect_dev(h, batch, h->d_in, (int64_t)img_bytes, any_mask ? h->d_in_mask : nullptr, (int64_t)img_bytes, w,
-                             hgt, row, row, h->d_kps_out, h->d_counts_out, cap));
+                             hgt, ds, dms, h->d_kps_out, h->d_counts_out, cap));
     SB_CUDA(cudaMemcpyAsync(kps, h->d_kps_out, (size_t)batch * cap * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
     SB_CUDA(cudaMemcpyAsync(counts, h->d_counts_out, (size_t)batch * 4, cudaMemcpyDeviceToHost, h->stream));
     return finish_and_check(h);
@@ -1610,8 +1627,9 @@ extern "C" int sb_orb_screen_params(sb_orb_t *h, const uint8_t *img, int w, int 
     SB_TRY(ensure_staging(h, 1, img_bytes, n_in, false));
     const uint8_t *imgs[1] = {img};
     bool any = false;
-    SB_TRY(stage_images(h, 1, imgs, nullptr, w, hgt, stride, 0, &any));
-    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, row, 1, h->nlevels));
+    int ds = row;
+    SB_TRY(stage_images(h, 1, imgs, nullptr, w, hgt, stride, 0, &any, &ds));
+    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, ds, 1, h->nlevels));
     SB_CUDA(cudaMemcpyAsync(h->d_kps_out, in, (size_t)n_in * sizeof(sb_keypoint), cudaMemcpyHostToDevice, h->stream));
     k_screen<<<sb_div_up(n_in, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_pyr, h->d_kps_out, n_in, h->d_keep,
                                                                            h->minTh, 0, nullptr);
@@ -1646,8 +1664,9 @@ extern "C" int sb_orb_calc_descriptors(sb_orb_t *h, const uint8_t *img, int w, i
     SB_TRY(ensure_staging(h, 1, img_bytes, n, false));
     const uint8_t *imgs[1] = {img};
     bool any = false;
-    SB_TRY(stage_images(h, 1, imgs, nullptr, w, hgt, stride, 0, &any));
-    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, row, 1, h->nlevels));
+    int ds = row;
+    SB_TRY(stage_images(h, 1, imgs, nullptr, w, hgt, stride, 0, &any, &ds));
+    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, ds, 1, h->nlevels));
     SB_TRY(launch_blur(h, 1, h->stream));
     SB_CUDA(cudaMemcpyAsync(h->d_kps_out, kps, (size_t)n * sizeof(sb_keypoint), cudaMemcpyHostToDevice, h->stream));
     k_calc_desc<<<sb_div_up(n, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_blur, h->d_kps_out, n, h->d_desc_out, 0, nullptr);
@@ -1678,8 +1697,9 @@ extern "C" int sb_orb_screen_describe(sb_orb_t *h, int batch, const uint8_t *con
     const size_t img_bytes = (size_t)row * hgt;
     SB_TRY(ensure_staging(h, batch, img_bytes, cap_in, false));
     bool any = false;
-    SB_TRY(stage_images(h, batch, img, nullptr, w, hgt, stride, 0, &any));
-    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, row, batch, h->nlevels));
+    int ds = row;
+    SB_TRY(stage_images(h, batch, img, nullptr, w, hgt, stride, 0, &any, &ds));
+    SB_TRY(launch_pyramid(h, h->d_pyr, h->d_in, (long long)img_bytes, ds, batch, h->nlevels));
     SB_TRY(launch_blur(h, batch, h->stream));
     const int n = batch * cap_in;
     SB_CUDA(cudaMemcpyAsync(h->d_kps_out, in, (size_t)n * sizeof(sb_keypoint), cudaMemcpyHostToDevice, h->stream));
@@ -1691,18 +1711,31 @@ extern "C" int sb_orb_screen_describe(sb_orb_t *h, int batch, const uint8_t *con
     k_calc_desc<<<sb_div_up(n, DESC_WARPS), DESC_WARPS * 32, 0, h->stream>>>(h->geom, h->d_blur, h->d_kps_out, n, h->d_desc_out, cap_in,
                                                                               h->d_keep);
     SB_CUDA(cudaGetLastError());
-    std::vector<uint8_t> keep((size_t)n), dtmp((size_t)n * 32);
-    SB_CUDA(cudaMemcpyAsync(in, h->d_kps_out, (size_t)n * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
-    SB_CUDA(cudaMemcpyAsync(keep.data(), h->d_keep, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-    SB_CUDA(cudaMemcpyAsync(dtmp.data(), h->d_desc_out, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
+    // results come back through page-locked staging (a copy into pageable memory runs at a fraction of the link rate and
+    // blocks): [keypoints n x 28][keep flags n][descriptors n x 32]
+    const size_t off_keep = sb_align_up((size_t)n * sizeof(sb_keypoint), 256), off_desc = off_keep + sb_align_up((size_t)n, 256);
+    const size_t need = off_desc + (size_t)n * 32;
+    if (need > h->h_stage_cap) {
+        SB_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        h->h_stage = nullptr;
+        h->h_stage_cap = 0;
+        SB_CUDA(cudaHostAlloc((void **)&h->h_stage, need, cudaHostAllocPortable));
+        h->h_stage_cap = need;
+    }
+    const uint8_t *keep = h->h_stage + off_keep, *dtmp = h->h_stage + off_desc;
+    SB_CUDA(cudaMemcpyAsync(h->h_stage, h->d_kps_out, (size_t)n * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemcpyAsync(h->h_stage + off_keep, h->d_keep, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemcpyAsync(h->h_stage + off_desc, h->d_desc_out, (size_t)n * 32, cudaMemcpyDeviceToHost, h->stream));
     SB_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(in, h->h_stage, (size_t)n * sizeof(sb_keypoint));   // the reference mutates its input keypoints (:1100-1121)
     for (int b = 0; b < batch; b++) {
         int m = 0;
         for (int i = 0; i < n_in[b]; i++) {
             const size_t k = (size_t)b * cap_in + i;
             if (!keep[k]) continue;
             out[(size_t)b * cap_in + m] = in[k];   // survivors in input order (:1125)
-            memcpy(desc + ((size_t)b * cap_in + m) * 32, dtmp.data() + k * 32, 32);
+            memcpy(desc + ((size_t)b * cap_in + m) * 32, dtmp + k * 32, 32);
             m++;
         }
         n_out[b] = m;
