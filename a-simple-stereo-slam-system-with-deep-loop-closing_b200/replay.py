@@ -48,6 +48,36 @@ def T_to7(T):
     return synth.pose7(T[:3, :3], T[:3, 3])
 
 
+def T_to7_batch(Ts):
+    """T_to7 for a stack of poses [n, 4, 4] -> [n, 7]: the trace > 0 rows are vectorised, the rest take the scalar path."""
+    Ts = np.asarray(Ts)
+    R, out = Ts[:, :3, :3], np.empty((len(Ts), 7))
+    tr = R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]
+    pos = tr > 0
+    s_ = np.sqrt(np.where(pos, tr, 0.0) + 1.0) * 2
+    q = np.stack([(R[:, 2, 1] - R[:, 1, 2]) / s_, (R[:, 0, 2] - R[:, 2, 0]) / s_, (R[:, 1, 0] - R[:, 0, 1]) / s_, 0.25 * s_], 1)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)       # q[3] = s / 4 > 0: no sign flip
+    out[:, :4] = q
+    out[:, 4:] = Ts[:, :3, 3]
+    for i in np.nonzero(~pos)[0]:
+        out[i] = T_to7(Ts[i])
+    return out
+
+
+def T_from7_batch(p):
+    """T_from7 for [n, 7] -> [n, 4, 4]."""
+    p = np.asarray(p, np.float64)
+    q = p[:, :4] / np.linalg.norm(p[:, :4], axis=1, keepdims=True)
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    T = np.zeros((len(p), 4, 4))
+    T[:, 0, 0] = 1 - 2 * (y * y + z * z); T[:, 0, 1] = 2 * (x * y - z * w); T[:, 0, 2] = 2 * (x * z + y * w)
+    T[:, 1, 0] = 2 * (x * y + z * w); T[:, 1, 1] = 1 - 2 * (x * x + z * z); T[:, 1, 2] = 2 * (y * z - x * w)
+    T[:, 2, 0] = 2 * (x * z - y * w); T[:, 2, 1] = 2 * (y * z + x * w); T[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    T[:, :3, 3] = p[:, 4:7]
+    T[:, 3, 3] = 1.0
+    return T
+
+
 def T_inv(T):
     R, t = T[:3, :3], T[:3, 3]
     out = np.eye(4)
@@ -551,7 +581,8 @@ def correct_and_optimise(ops, seq, est, k, loop_kf, T_corr, loop_edge, n_active=
             v0.append(i); v1.append(i - 1); meas.append(odo7[i])
         if i in loop_edge:
             v0.append(i); v1.append(loop_edge[i][0]); meas.append(T_to7(loop_edge[i][1]))
-    poses = np.stack([T_to7(T) for T in est[:n]])
+    poses = T_to7_batch(np.stack(est[:n]))
     new, _ = ops.posegraph(poses, fixed, np.array(v0, np.int32), np.array(v1, np.int32), np.array(meas))
+    Tn = T_from7_batch(new)
     for i in range(n):
-        est[i] = T_from7(new[i])
+        est[i] = Tn[i]
