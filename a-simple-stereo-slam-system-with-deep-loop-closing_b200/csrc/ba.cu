@@ -55,6 +55,7 @@ struct sb_ba {
     double *d_err;       // [W][2][MO][2]
     double *d_hpl;       // [W][MO][18]: w A^T B of every edge to a free landmark (the Hpl block), rebuilt each iteration
     double *d_ybd;       // [W][MO][10]: per edge the landmark's share w B^T B (6), -w B^T r (3) of the linearised system
+    int2 *d_plist;       // [W][MP][ML]: per pose the compact list of (first edge, landmark) it observes — the lanes of the build pass
     int4 *d_pairs;       // [W][MP (MP + 1) / 2][ML]: per pose-block pair (i1 <= i2) the (edge to i1, edge to i2, landmark) of every free
                          //                           landmark both observe — the structure of the Schur complement, built once
 };
@@ -72,6 +73,7 @@ struct BaArgs {
     int32_t *edge_of, *next_dup;
     double *lm, *ptbak, *err, *hpl, *ybd;
     int4 *pairs;
+    int2 *plist;             // [W][MP][ML]: per pose the (edge, landmark) of every landmark it observes, ascending landmark
     int MP, ML, MO;
     double fx, fy, cx, cy;
     double extR[9], extT[3];
@@ -124,10 +126,20 @@ static __device__ __forceinline__ void edge_error(const EdgeCtx &c, int e, doubl
 }
 
 // EdgeProjection::linearizeOplus (:124-144) + Huber weight of the stored error
-static __device__ __forceinline__ void edge_lin(const EdgeCtx &c, int e, const double *err, double *A, double *B, double *r,
-                                                double &w) {
-    double pe[3], RR[9];
-    edge_cam(c, c.op[e], c.ol[e], pe, RR);
+// (i, j) = the edge's pose and landmark (the caller knows them: no op[e] / ol[e] load level); RR = extR * R_i, the same for every
+// edge of pose i (the caller forms it once per pose with pose_RR)
+static __device__ __forceinline__ void pose_RR(const EdgeCtx &c, int i, double *RR) {
+    const double *T = c.Rt + 12 * i;
+    const BaArgs &a = *c.a;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) RR[3 * r + k] = a.extR[3 * r] * T[k] + a.extR[3 * r + 1] * T[3 + k] + a.extR[3 * r + 2] * T[6 + k];
+}
+static __device__ __forceinline__ void edge_lin(const EdgeCtx &c, int e, int i, int j, const double *RR, const double *err, double *A, double *B,
+                                                double *r, double &w) {
+    double pe[3];
+    edge_cam(c, i, j, pe, nullptr);
     const BaArgs &a = *c.a;
     const double X = pe[0], Y = pe[1], Z = pe[2];
     const double Zinv = 1.0 / (Z + 1e-18), Zinv2 = Zinv * Zinv;
@@ -217,6 +229,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
     double *linv = dinv + 6 * MP;       // [MP][36] inverses of the factor's 6 x 6 diagonal blocks (lower triangular), for the substitutions
     int *pcnt = reinterpret_cast<int *>(linv + 36 * MP);  // [MP (MP + 1) / 2] entries of each pair list
     __shared__ int s_bad, s_next, s_dup;
+    __shared__ int plcnt[BA_MAX_POSES];   // entries of each pose list
     double *poses = a.poses + (size_t)w * MP * 7;
     double *pts = a.points + (size_t)w * a.ML * 3;
     const uint8_t *fixed = a.fixed + (size_t)w * a.ML;
@@ -228,6 +241,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
     double *hpl = a.hpl + (size_t)w * a.MO * 18;
     double *lmc = a.ybd + (size_t)w * a.MO * 10;   // per edge: the landmark's share of Hll and bl (10 doubles)
     int4 *pairs = a.pairs + (size_t)w * (MP * (MP + 1) / 2) * a.ML;
+    int2 *plist = a.plist + (size_t)w * MP * a.ML;
     double *err = a.err + (size_t)w * a.MO * 4;   // errors of the last evaluation
     double *elin = err + (size_t)a.MO * 2;         // errors at the linearisation state
     int32_t *info = a.info + 4 * w;
@@ -291,6 +305,20 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
         }
         if (lane == 0) pcnt[blk] = cnt;
     }
+    // ... and per pose the landmarks it observes (fixed ones too), compacted the same way: the build pass walks these lists, so
+    // every lane of a round holds an edge (by landmark index only 2 of 3 lanes would: a pose sees ~200 of the 300 landmarks)
+    for (int i = wid; i < np; i += BA_THREADS / 32) {
+        int2 *pl = plist + (size_t)i * a.ML;
+        int cnt = 0;
+        for (int j0 = 0; j0 < nl; j0 += 32) {
+            const int j = j0 + lane;
+            const int e = j < nl ? edge_of[j * MP + i] : -1;
+            const unsigned bal = __ballot_sync(0xffffffffu, e >= 0);
+            if (e >= 0) pl[cnt + __popc(bal & ((1u << lane) - 1u))] = make_int2(e, j);
+            cnt += __popc(bal);
+        }
+        if (lane == 0) plcnt[i] = cnt;
+    }
     __syncthreads();
 
     EdgeCtx c;
@@ -317,9 +345,15 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                 for (int k = 0; k < 21; k++) h[k] = 0;
 #pragma unroll
                 for (int k = 0; k < 6; k++) g[k] = 0;
-                for (int j = lane; j < nl; j += 32) {
-                    const int e = edge_of[j * MP + i];
-                    if (e < 0) continue;
+                const int2 *pl = plist + (size_t)i * a.ML;
+                const int pn = plcnt[i];
+                double RR[9];
+                pose_RR(c, i, RR);
+                int2 nxt = lane < pn ? pl[lane] : make_int2(0, 0);   // the list entry of the next round is fetched a round ahead
+                for (int t = lane; t < pn; t += 32) {
+                    const int2 ej = nxt;
+                    if (t + 32 < pn) nxt = pl[t + 32];
+                    const int e = ej.x, j = ej.y;
                     const bool fr = !fixed[j];
                     double hv[18], cn[9];   // Hpl block w A^T B (6x3) and the landmark's share (w B^T B: 00 01 02 11 12 22, -w B^T r)
 #pragma unroll
@@ -328,7 +362,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                     for (int k2 = 0; k2 < 9; k2++) cn[k2] = 0;
                     for (int ee = e; ee >= 0; ee = has_dup ? next_dup[ee] : -1) {   // one edge, unless the keyframe sees the landmark twice
                         double A[12], B[6], r[2], wgt;
-                        edge_lin(c, ee, elin, A, B, r, wgt);
+                        edge_lin(c, ee, i, j, RR, elin, A, B, r, wgt);
                         int k = 0;
 #pragma unroll
                         for (int p = 0; p < 6; p++) {
@@ -374,6 +408,7 @@ __global__ void __launch_bounds__(BA_THREADS, BA_MIN_BLOCKS) k_ba_solve(const __
                 }
             }
             __syncthreads();
+            BA_T(11);
             // Landmark blocks: one thread per free landmark sums the shares of its edges in ascending pose order (all edge
             // indices are fetched before the shares: two load levels per landmark instead of two per edge).
             // lm[j] = Hll(6: 00 01 02 11 12 22) bl(3) - Dinv(6) xl(3) -
@@ -812,7 +847,7 @@ static void free_ba(sb_ba *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_np, h->d_nl, h->d_ne, h->d_info, h->d_poses, h->d_points, h->d_uv, h->d_chi2, h->d_fixed,
-                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_next, h->d_lm, h->d_ptbak, h->d_err, h->d_hpl, h->d_ybd, h->d_pairs};
+                    h->d_outlier, h->d_op, h->d_ol, h->d_edge_of, h->d_next, h->d_lm, h->d_ptbak, h->d_err, h->d_hpl, h->d_ybd, h->d_pairs, h->d_plist};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -860,6 +895,7 @@ extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_
     BA_ALLOC(h->d_hpl, W * MO * 18 * 8);
     BA_ALLOC(h->d_ybd, W * MO * 10 * 8);
     BA_ALLOC(h->d_pairs, W * (MP * (MP + 1) / 2) * ML * sizeof(int4));
+    BA_ALLOC(h->d_plist, W * MP * ML * sizeof(int2));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ba_smem_bytes(BA_MAX_POSES));
@@ -914,7 +950,7 @@ extern "C" int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_pos
     a.np = d_n_poses; a.nl = d_n_points; a.ne = d_n_obs;
     a.poses = d_poses; a.points = d_points; a.fixed = d_fixed; a.op = d_obs_pose; a.ol = d_obs_point; a.uv = d_uv;
     a.chi2 = d_chi2; a.outlier = d_outlier; a.info = d_info;
-    a.edge_of = h->d_edge_of; a.next_dup = h->d_next; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err; a.hpl = h->d_hpl; a.ybd = h->d_ybd; a.pairs = h->d_pairs;
+    a.edge_of = h->d_edge_of; a.next_dup = h->d_next; a.lm = h->d_lm; a.ptbak = h->d_ptbak; a.err = h->d_err; a.hpl = h->d_hpl; a.ybd = h->d_ybd; a.pairs = h->d_pairs; a.plist = h->d_plist;
     a.MP = h->max_poses; a.ML = h->max_points; a.MO = h->max_obs;
     a.fx = K[0]; a.fy = K[1]; a.cx = K[2]; a.cy = K[3];
     quat7_to_ext(cam_ext7, a.extR, a.extT);

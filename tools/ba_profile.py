@@ -12,9 +12,9 @@ prof = (C.c_longlong * 16)()
 pkg.lib().sb_ba_debug_profile(prof)
 res = ba.solve(ws[:1], synth.KITTI_K); print("info", res[0][4])
 pkg.lib().sb_ba_debug_profile(prof)
-names = ["loop/accept", "errors", "build", "lambda+push+Dinv", "schur", "cholesky+solve (rest)", "xl+update", "errors(trial)",
-         "  cholesky: diagonal block + panel", "  cholesky: trailing update", "  substitutions"]
-tot = sum(prof[:11])
-for n, v in zip(names, prof[:11]):
+names = ["loop/accept", "errors", "build (landmark pass)", "lambda+push+Dinv", "schur", "cholesky+solve (rest)", "xl+update", "errors(trial)",
+         "  cholesky: diagonal block + panel", "  cholesky: trailing update", "  substitutions", "  build: pose pass"]
+tot = sum(prof[:12])
+for n, v in zip(names, prof[:12]):
     print(f"{n:18s} {v:10d} cyc  {100*v/tot:5.1f}%")
 print("total cycles", tot, "=", tot / 1.965e3, "us at 1965 MHz")
