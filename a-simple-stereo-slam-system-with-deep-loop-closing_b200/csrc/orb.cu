@@ -297,135 +297,170 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_consta
     __syncthreads();
     sb_mbar_wait(&bar, 0);
 
-    // Phase 1: pixels that pass the cheap necessary test (sb_fast_maybe's rule on the four compass ring pixels: one
-    // of each opposite pair darker than v - t, or one of each pair brighter than v + t) are compacted into a list, so that the response
-    // (about 80 instructions) is later computed by full warps instead of a few lanes of every warp.
-    // A work item is 4 horizontally adjacent pixels: five aligned 32-bit loads, two funnel shifts, then the
-    // order statistics for two pixels at a time in packed 2 x int16 arithmetic.  Every warp appends to its own
-    // segment of the list with a warp-uniform running count: no atomics.  Pixels of the first / last item of a
-    // row that fall outside the tested columns [3, rw - 3) are listed too and dropped in phase 2.
-    const int t0 = min(a.iniTh, a.minTh);
-    uint16_t *mine = plist + warp * a.seg;
-    int cnt = 0;
-    {
-        const unsigned lt = (1u << lane) - 1u;
-        // only the 4-pixel groups that overlap the tested ROI columns [3, rw - 3)
-        const int g0 = (xo + 3) >> 2, G = c.G, rows = c.rh - 6;
-        const int items = (rows > 0 && c.rw > 6) ? rows * G : 0;
-        // per 16-bit half: s2 + t + 512 - v in [257, 1022], "< 512" <=> bit 9 clear; no borrow crosses the halves,
-        // so one 32-bit IADD3 does both pixels (there is no packed 16-bit integer add on sm_100a: __vadd2 is 5 ops)
-        const uint32_t Tb = (uint32_t)(t0 + 512) * 0x00010001u;
-        constexpr int bw4 = BW >> 2;
-        for (int it0 = warp * 32; it0 < items; it0 += FAST_THREADS) {
-            const int it = it0 + lane;
-            uint32_t hit = 0;  // bit j: pixel j of the item passes
-            int e0 = 0;
-            if (it < items) {
-                const int yy = (int)(((uint32_t)it * (uint32_t)c.rcpG) >> 20);  // it / G
-                const int y = 3 + yy;
-                const int col = (g0 + it - yy * G) << 2;  // tile column of pixel 0
-                e0 = (y << 8) + col - xo;
-                const uint32_t *pw = reinterpret_cast<const uint32_t *>(tile + y * BW + col);
-                const uint32_t C = pw[0], U = pw[-3 * bw4], D = pw[3 * bw4];
-                const uint32_t Lw = __funnelshift_r(pw[-1], C, 8), R = __funnelshift_r(C, pw[1], 24);
-#pragma unroll
-                for (int hpair = 0; hpair < 2; hpair++) {
-                    const uint32_t sel = hpair ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> two 16-bit halves
-                    const uint32_t v = __byte_perm(C, 0u, sel), r0 = __byte_perm(D, 0u, sel), r8 = __byte_perm(U, 0u, sel);
-                    const uint32_t r4 = __byte_perm(R, 0u, sel), r12 = __byte_perm(Lw, 0u, sel);
-                    // a 9-arc holds at least one pixel of each opposite pair (0, 8) and (4, 12): the brighter of the two
-                    // pair minima must be darker than v - t, or the darker of the two pair maxima brighter than v + t
-                    const uint32_t s2 = __vmaxs2(__vmins2(r0, r8), __vmins2(r4, r12));
-                    const uint32_t s3 = __vmins2(__vmaxs2(r0, r8), __vmaxs2(r4, r12));
-                    // darker: s2 < v - t  <=>  s2 + t - v < 0 ;  brighter: s3 > v + t  <=>  v + t - s3 < 0
-                    const uint32_t dk = s2 + Tb - v, br = v + Tb - s3;
-                    const uint32_t neg = ~(dk & br) & 0x02000200u;  // bit 9 of a half clear in either
-                    hit |= (((neg >> 9) & 1u) | ((neg >> 24) & 2u)) << (2 * hpair);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const bool m = (hit >> j) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, m);
-                if (m) mine[cnt + __popc(bal & lt)] = (uint16_t)(e0 + j);  // (y << 8) | ROI column
-                cnt += __popc(bal);
-            }
-        }
-    }
-    __syncwarp();
-    // Phase 2: responses of the listed pixels; every warp walks its own segment.  Only ROI columns [3, rw - 3)
-    // are tested by cv::FAST: the response plane stays 0 elsewhere.
-    for (int i = lane; i < cnt; i += 32) {
-        const int e = mine[i];
-        const int y = e >> 8, x = e & 255;
-        if (x < 3 || x >= c.rw - 3) continue;
-        const int s = sb_fast_score(tile + y * BW + xo + x, BW);
-        if (s >= t0) sc[y * BW + xo + x] = (uint8_t)s;
-    }
-    __syncthreads();
-    if (a.dbg && img == 0 && (int)blockIdx.x == a.dbg_cell) {
-        for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) a.dbg[i] = tile[i];
-        __syncthreads();
-    }
-    // Phase 3: 3x3 non-maximum suppression (only listed pixels can be maxima).  Tested columns only; a neighbour
-    // in the adjacent cell counts as 0, exactly as if each cell had been given to cv::FAST on its own.
+    // Two tiers, as the reference's two cv::FAST calls: tier 0 works at iniTh over the whole group (a pixel below iniTh
+    // can neither be reported nor suppress a pixel at or above it, so neither its response nor its place in the list is
+    // needed); tier 1 repeats the passes at minTh for the cells in which no maximum reached iniTh (rare on textured
+    // images, cheap on flat ones) after the tier-0 maxima have been flushed and the tile re-fetched.
+    const int t_hi = a.iniTh, t_lo = min(a.iniTh, a.minTh);
     const int wC = c.wCell;
-    for (int i = lane; i < cnt; i += 32) {
-        const int e = mine[i];
-        const int y = e >> 8, x = e & 255;
-        const uint8_t *q = sc + y * BW + xo + x;
-        const int s = q[0];
-        if (s == 0) continue;  // listed by the pre-test but not a corner (the majority)
-        const int jl = (int)(((uint32_t)(x - 3) * (uint32_t)c.rcpW) >> 20);  // cell of the group
-        const int xr = x - 3 - jl * wC;
-        int nb = max((int)q[-BW], (int)q[BW]);
-        if (xr != 0) nb = max(nb, max(max((int)q[-1], (int)q[-BW - 1]), (int)q[BW - 1]));
-        if (xr != wC - 1) nb = max(nb, max(max((int)q[1], (int)q[-BW + 1]), (int)q[BW + 1]));
-        if (s > nb) {  // s > 0 follows: neighbours are >= 0
-            const int k = atomicAdd(&s_n, 1);
-            if (k < a.list_cap) list[k] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
-            if (s >= a.iniTh) s_any[jl] = 1;
-        }
-    }
-    __syncthreads();
-    if (a.dbg && img == 0 && (int)blockIdx.x == a.dbg_cell) {
-        for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) a.dbg[a.tile_bytes + i] = sc[i];
-        if (tid == 0) {
-            int *info = reinterpret_cast<int *>(a.dbg + 2 * a.tile_bytes);
-            info[0] = BW; info[1] = BH; info[2] = xo; info[3] = c.x0; info[4] = c.y0; info[5] = c.rw; info[6] = c.rh;
-            info[7] = s_n; info[8] = s_any[0]; info[9] = c.level; info[10] = c.ncells; info[11] = c.wCell;
-        }
-    }
-    const int n = min(s_n, a.list_cap);
     const int slot = img * a.nlevels + c.level;
     const unsigned lt = (1u << lane) - 1u;
-    for (int base = 0; base < n; base += FAST_THREADS) {  // one global atomic per warp
-        const int i = base + tid;
-        bool ok = false;
-        uint32_t out = 0;
-        if (i < n) {
-            const uint32_t w = list[i];
-            const int s = (int)(w >> 24), xl = (int)(w & 0xfff);
-            const int jl = (int)(((uint32_t)(xl - 3) * (uint32_t)c.rcpW) >> 20);
-            // the reference's second cv::FAST call (minTh) only if the first (iniTh) found nothing in this cell
-            ok = s >= (s_any[jl] ? a.iniTh : a.minTh);
-            const int x = xl + c.offx, y = (int)((w >> 12) & 0xfff) + c.offy;  // border-relative
-            // quirk Q1 (:871-877): the mask is read at the border-relative coordinates
-            if (ok && a.mask_pyr && a.mask_pyr[(long long)img * a.slab + L.off + (long long)y * L.pitch + x] == 0) ok = false;
-            out = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (bal) {
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(&a.cand_cnt[slot], __popc(bal));
-            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & lt);
-            if (ok) {
-                if (pos < SB_CAND_CAP)
-                    a.cand[(long long)slot * SB_CAND_CAP + pos] = out;
-                else
-                    a.flags[0] = 1;
+    uint16_t *mine = plist + warp * a.seg;
+    unsigned empty = 0;  // tier 1: bit j set = cell j of the group found nothing at iniTh
+    for (int tier = 0;; tier++) {
+        const int t0 = tier ? t_lo : t_hi;
+        // Phase 1: pixels that pass the cheap necessary test (sb_fast_maybe's rule on the four compass ring pixels: one
+        // of each opposite pair darker than v - t, or one of each pair brighter than v + t) are compacted into a list, so that the response
+        // (about 80 instructions) is later computed by full warps instead of a few lanes of every warp.
+        // A work item is 4 horizontally adjacent pixels: five aligned 32-bit loads, two funnel shifts, then the
+        // order statistics for two pixels at a time in packed 2 x int16 arithmetic.  Every warp appends to its own
+        // segment of the list with a warp-uniform running count: no atomics.  Pixels of the first / last item of a
+        // row that fall outside the tested columns [3, rw - 3) are listed too and dropped in phase 2.
+        int cnt = 0;
+        {
+            // only the 4-pixel groups that overlap the tested ROI columns [3, rw - 3)
+            const int g0 = (xo + 3) >> 2, G = c.G, rows = c.rh - 6;
+            const int items = (rows > 0 && c.rw > 6) ? rows * G : 0;
+            // per 16-bit half: s2 + t + 512 - v in [257, 1022], "< 512" <=> bit 9 clear; no borrow crosses the halves,
+            // so one 32-bit IADD3 does both pixels (there is no packed 16-bit integer add on sm_100a: __vadd2 is 5 ops)
+            const uint32_t Tb = (uint32_t)(t0 + 512) * 0x00010001u;
+            constexpr int bw4 = BW >> 2;
+            for (int it0 = warp * 32; it0 < items; it0 += FAST_THREADS) {
+                const int it = it0 + lane;
+                uint32_t hit = 0;  // bit j: pixel j of the item passes
+                int e0 = 0;
+                bool live = it < items;
+                int y = 0, col = 0;
+                if (live) {
+                    const int yy = (int)(((uint32_t)it * (uint32_t)c.rcpG) >> 20);  // it / G
+                    y = 3 + yy;
+                    col = (g0 + it - yy * G) << 2;  // tile column of pixel 0
+                    e0 = (y << 8) + col - xo;
+                    if (tier) {  // only items that touch a cell without a tier-0 maximum (an item spans at most two cells)
+                        const int xa = min(max(col - xo, 3), c.rw - 4), xb = min(max(col - xo + 3, 3), c.rw - 4);
+                        const int ja = (int)(((uint32_t)(xa - 3) * (uint32_t)c.rcpW) >> 20);
+                        const int jb = (int)(((uint32_t)(xb - 3) * (uint32_t)c.rcpW) >> 20);
+                        live = ((empty >> ja) | (empty >> jb)) & 1u;
+                    }
+                }
+                if (live) {
+                    const uint32_t *pw = reinterpret_cast<const uint32_t *>(tile + y * BW + col);
+                    const uint32_t C = pw[0], U = pw[-3 * bw4], D = pw[3 * bw4];
+                    const uint32_t Lw = __funnelshift_r(pw[-1], C, 8), R = __funnelshift_r(C, pw[1], 24);
+#pragma unroll
+                    for (int hpair = 0; hpair < 2; hpair++) {
+                        const uint32_t sel = hpair ? 0x4342u : 0x4140u;  // bytes (2,3) or (0,1) -> two 16-bit halves
+                        const uint32_t v = __byte_perm(C, 0u, sel), r0 = __byte_perm(D, 0u, sel), r8 = __byte_perm(U, 0u, sel);
+                        const uint32_t r4 = __byte_perm(R, 0u, sel), r12 = __byte_perm(Lw, 0u, sel);
+                        // a 9-arc holds at least one pixel of each opposite pair (0, 8) and (4, 12): the brighter of the two
+                        // pair minima must be darker than v - t, or the darker of the two pair maxima brighter than v + t
+                        const uint32_t s2 = __vmaxs2(__vmins2(r0, r8), __vmins2(r4, r12));
+                        const uint32_t s3 = __vmins2(__vmaxs2(r0, r8), __vmaxs2(r4, r12));
+                        // darker: s2 < v - t  <=>  s2 + t - v < 0 ;  brighter: s3 > v + t  <=>  v + t - s3 < 0
+                        const uint32_t dk = s2 + Tb - v, br = v + Tb - s3;
+                        const uint32_t neg = ~(dk & br) & 0x02000200u;  // bit 9 of a half clear in either
+                        hit |= (((neg >> 9) & 1u) | ((neg >> 24) & 2u)) << (2 * hpair);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool m = (hit >> j) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, m);
+                    if (m) mine[cnt + __popc(bal & lt)] = (uint16_t)(e0 + j);  // (y << 8) | ROI column
+                    cnt += __popc(bal);
+                }
             }
         }
+        __syncwarp();
+        // Phase 2: responses of the listed pixels; every warp walks its own segment.  Only ROI columns [3, rw - 3)
+        // are tested by cv::FAST: the response plane stays 0 elsewhere.  (Tier 1 recomputes a few tier-0 responses of
+        // the cells it revisits: same values.)
+        for (int i = lane; i < cnt; i += 32) {
+            const int e = mine[i];
+            const int y = e >> 8, x = e & 255;
+            if (x < 3 || x >= c.rw - 3) continue;
+            if (tier && !((empty >> (int)(((uint32_t)(x - 3) * (uint32_t)c.rcpW) >> 20)) & 1u)) continue;
+            const int s = sb_fast_score(tile + y * BW + xo + x, BW);
+            if (s >= t0) sc[y * BW + xo + x] = (uint8_t)s;
+        }
+        __syncthreads();
+        if (a.dbg && img == 0 && (int)blockIdx.x == a.dbg_cell && tier == 0) {
+            for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) a.dbg[i] = tile[i];
+            __syncthreads();
+        }
+        // Phase 3: 3x3 non-maximum suppression (only listed pixels can be maxima).  Tested columns only; a neighbour
+        // in the adjacent cell counts as 0, exactly as if each cell had been given to cv::FAST on its own.
+        for (int i = lane; i < cnt; i += 32) {
+            const int e = mine[i];
+            const int y = e >> 8, x = e & 255;
+            const uint8_t *q = sc + y * BW + xo + x;
+            const int s = q[0];
+            if (s == 0) continue;  // listed by the pre-test but not a corner
+            const int jl = (int)(((uint32_t)(x - 3) * (uint32_t)c.rcpW) >> 20);  // cell of the group
+            if (tier && !((empty >> jl) & 1u)) continue;  // that cell was served by tier 0
+            const int xr = x - 3 - jl * wC;
+            int nb = max((int)q[-BW], (int)q[BW]);
+            if (xr != 0) nb = max(nb, max(max((int)q[-1], (int)q[-BW - 1]), (int)q[BW - 1]));
+            if (xr != wC - 1) nb = max(nb, max(max((int)q[1], (int)q[-BW + 1]), (int)q[BW + 1]));
+            if (s > nb) {  // s > 0 follows: neighbours are >= 0
+                const int k = atomicAdd(&s_n, 1);
+                if (k < a.list_cap) list[k] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+                if (s >= a.iniTh) s_any[jl] = 1;  // tier 0: every maximum; tier 1: none (its cells have no maximum >= iniTh)
+            }
+        }
+        __syncthreads();
+        if (a.dbg && img == 0 && (int)blockIdx.x == a.dbg_cell && tier == 0) {
+            for (int i = tid; i < a.tile_bytes; i += FAST_THREADS) a.dbg[a.tile_bytes + i] = sc[i];
+            if (tid == 0) {
+                int *info = reinterpret_cast<int *>(a.dbg + 2 * a.tile_bytes);
+                info[0] = BW; info[1] = BH; info[2] = xo; info[3] = c.x0; info[4] = c.y0; info[5] = c.rw; info[6] = c.rh;
+                info[7] = s_n; info[8] = s_any[0]; info[9] = c.level; info[10] = c.ncells; info[11] = c.wCell;
+            }
+        }
+        // the maxima of this tier go to the level's candidate list: one global atomic per warp
+        const int n = min(s_n, a.list_cap);
+        for (int base = 0; base < n; base += FAST_THREADS) {
+            const int i = base + tid;
+            bool ok = false;
+            uint32_t out = 0;
+            if (i < n) {
+                const uint32_t w = list[i];
+                const int s = (int)(w >> 24), xl = (int)(w & 0xfff);
+                const int jl = (int)(((uint32_t)(xl - 3) * (uint32_t)c.rcpW) >> 20);
+                // the reference's second cv::FAST call (minTh) only if the first (iniTh) found nothing in this cell
+                ok = s >= (s_any[jl] ? a.iniTh : a.minTh);
+                const int x = xl + c.offx, y = (int)((w >> 12) & 0xfff) + c.offy;  // border-relative
+                // quirk Q1 (:871-877): the mask is read at the border-relative coordinates
+                if (ok && a.mask_pyr && a.mask_pyr[(long long)img * a.slab + L.off + (long long)y * L.pitch + x] == 0) ok = false;
+                out = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            if (bal) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&a.cand_cnt[slot], __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & lt);
+                if (ok) {
+                    if (pos < SB_CAND_CAP)
+                        a.cand[(long long)slot * SB_CAND_CAP + pos] = out;
+                    else
+                        a.flags[0] = 1;
+                }
+            }
+        }
+        if (tier || a.minTh >= a.iniTh) break;  // a stricter second threshold finds a subset of nothing
+        for (int j = 0; j < c.ncells; j++)
+            if (!s_any[j]) empty |= 1u << j;
+        if (!empty) break;
+        // the maxima list lives in the tile: fetch the tile again for the second tier
+        __syncthreads();
+        if (tid == 0) {
+            s_n = 0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            sb_mbar_expect_tx(&bar, (uint32_t)(BW * BH));
+            sb_tma_load_3d(tile, &maps.m[c.level], c.x0 - xo, c.y0, img, &bar);
+        }
+        __syncthreads();
+        sb_mbar_wait(&bar, 1);
     }
 }
 
