@@ -856,6 +856,7 @@ static void free_ba(sb_ba *h) {
 }
 
 extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_poses, int max_points, int max_obs) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -910,6 +911,7 @@ extern "C" int sb_ba_create(sb_ba_t **out, int device, int max_windows, int max_
 }
 
 extern "C" int sb_ba_destroy(sb_ba_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -919,6 +921,7 @@ extern "C" int sb_ba_destroy(sb_ba_t *h) {
 }
 
 extern "C" int sb_ba_set_stream(sb_ba_t *h, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
     return SB_OK;
@@ -938,6 +941,7 @@ extern "C" int sb_ba_solve_dev(sb_ba_t *h, int n_windows, const int32_t *d_n_pos
                                const int32_t *d_obs_pose, const int32_t *d_obs_point, const double *d_uv, const double *K,
                                const double *cam_ext7, double huber_delta, double chi2_th, int outer_max,
                                int inner_iters, double *d_chi2, uint8_t *d_outlier, int32_t *d_info) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_REQUIRE(n_windows >= 1 && n_windows <= h->max_windows, "n_windows out of range [1, max_windows]");
@@ -973,6 +977,7 @@ extern "C" int sb_ba_submit(sb_ba_t *h, int n_windows, const int32_t *n_poses, c
                             const int32_t *obs_pose, const int32_t *obs_point, const double *uv, const double *K,
                             const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
                             double *chi2, uint8_t *outlier, int32_t *info) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_REQUIRE(!h->pending_info, "a batch is already in flight: call sb_ba_wait first");
@@ -1025,6 +1030,7 @@ static int ba_enqueue(sb_ba_t *h, int n_windows, const int32_t *n_poses, const i
 }
 
 extern "C" int sb_ba_wait(sb_ba_t *h) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_REQUIRE(h->pending_info, "no batch in flight");
@@ -1046,6 +1052,7 @@ extern "C" int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, co
                            const int32_t *obs_pose, const int32_t *obs_point, const double *uv, const double *K,
                            const double *cam_ext7, double huber_delta, double chi2_th, int outer_max, int inner_iters,
                            double *chi2, uint8_t *outlier, int32_t *info) {
+    SB_NVTX_FN();
     SB_TRY(sb_ba_submit(h, n_windows, n_poses, n_points, n_obs, poses, points, fixed, obs_pose, obs_point, uv, K, cam_ext7,
                         huber_delta, chi2_th, outer_max, inner_iters, chi2, outlier, info));
     return sb_ba_wait(h);
@@ -1053,6 +1060,7 @@ extern "C" int sb_ba_solve(sb_ba_t *h, int n_windows, const int32_t *n_poses, co
 
 #ifdef BA_PROFILE
 extern "C" int sb_ba_debug_profile(long long *out) {
+    SB_NVTX_FN();
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out, g_ba_prof, sizeof(long long) * 16);
     long long z[16] = {0};

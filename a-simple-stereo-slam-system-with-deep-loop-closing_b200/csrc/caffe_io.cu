@@ -385,6 +385,7 @@ int load(const char *prototxt, const char *caffemodel, ParsedNet &net, std::vect
 // sizes; shape [2] = net input (height, width).
 extern "C" int sb_calc_parse_caffe(const char *prototxt_path, const char *caffemodel_path, sb_calc_layer *layers, int cap_layers, int *n_layers,
                                    float *weights, int64_t cap_weights, int64_t *n_weights, int *shape) {
+    SB_NVTX_FN();
     sb_clear_error();
     ParsedNet net;
     std::vector<float> w;
@@ -406,6 +407,7 @@ extern "C" int sb_calc_parse_caffe(const char *prototxt_path, const char *caffem
 // DeepLCD::DeepLCD(network_definition_file, pre_trained_model_file, gpu_id) (src/deeplcd.cpp:10-31).
 extern "C" int sb_calc_create_from_caffe(sb_calc_t **h, int device, const char *prototxt_path, const char *caffemodel_path, int max_batch,
                                          int max_img_w, int max_img_h) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle pointer");
     *h = nullptr;

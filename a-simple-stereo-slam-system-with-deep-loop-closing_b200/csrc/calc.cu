@@ -438,6 +438,7 @@ static size_t calc_row(const sb_calc *h) { return sb_align_up((size_t)h->max_img
 
 extern "C" int sb_calc_create(sb_calc_t **out, int device, int in_h, int in_w, const sb_calc_layer *layers, int n_layers,
                               const float *weights, int64_t n_weights, int max_batch, int max_img_w, int max_img_h) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -620,6 +621,7 @@ extern "C" int sb_calc_create(sb_calc_t **out, int device, int in_h, int in_w, c
 }
 
 extern "C" int sb_calc_destroy(sb_calc_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -629,6 +631,7 @@ extern "C" int sb_calc_destroy(sb_calc_t *h) {
 }
 
 extern "C" int sb_calc_set_stream(sb_calc_t *h, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
     return SB_OK;
@@ -636,6 +639,7 @@ extern "C" int sb_calc_set_stream(sb_calc_t *h, void *stream) {
 
 extern "C" int sb_calc_descr_dim(const sb_calc_t *h) { return h ? h->dim : SB_ERR_INVALID; }
 extern "C" int sb_calc_input_size(const sb_calc_t *h, int *in_h, int *in_w) {
+    SB_NVTX_FN();
     if (!h || !in_h || !in_w) return SB_ERR_INVALID;
     *in_h = h->in_h;
     *in_w = h->in_w;
@@ -705,6 +709,7 @@ static int ensure_tables(sb_calc *h, int w, int hgt) {
 // d_blurred (nullable, same layout) receives the blurred images — what the reference leaves in the caller's cv::Mat.
 extern "C" int sb_calc_descr_original_dev(sb_calc_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes, int w, int hgt, int stride,
                                           float *d_descr, uint8_t *d_blurred) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && d_img && d_descr, "null pointer");
     SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
@@ -723,6 +728,7 @@ extern "C" int sb_calc_descr_original_dev(sb_calc_t *h, int batch, const uint8_t
 
 // DeepLCD::calcDescr on device images that already have the net's input size.
 extern "C" int sb_calc_descr_dev(sb_calc_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes, int stride, float *d_descr) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && d_img && d_descr, "null pointer");
     SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
@@ -737,6 +743,7 @@ extern "C" int sb_calc_descr_dev(sb_calc_t *h, int batch, const uint8_t *d_img, 
 // the input's geometry that receive the blurred input (pass the input pointers to reproduce the reference's in-place blur).
 extern "C" int sb_calc_descr_original(sb_calc_t *h, int batch, const uint8_t *const *img, int w, int hgt, int stride, float *descr,
                                       uint8_t *const *blurred_out) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && img && descr, "null pointer");
     SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
@@ -767,6 +774,7 @@ extern "C" int sb_calc_descr_original(sb_calc_t *h, int batch, const uint8_t *co
 }
 
 extern "C" int sb_calc_descr(sb_calc_t *h, int batch, const uint8_t *const *img, int stride, float *descr) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && img && descr, "null pointer");
     SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");

@@ -92,6 +92,7 @@ __global__ void k_pack_record(const double *__restrict__ local, int n_local, int
 }  // namespace
 
 extern "C" int sb_nccl_version(int *version) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(version, "null pointer");
     SB_TRY(load_nccl());
@@ -103,6 +104,7 @@ extern "C" int sb_nccl_version(int *version) {
 // Rank 0 calls sb_nccl_unique_id and ships the 128 bytes to the other ranks over its own channel; every rank then
 // calls sb_nccl_comm_init on its device.
 extern "C" int sb_nccl_unique_id(uint8_t id128[128]) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(id128, "null pointer");
     SB_TRY(load_nccl());
@@ -113,6 +115,7 @@ extern "C" int sb_nccl_unique_id(uint8_t id128[128]) {
     return SB_OK;
 }
 extern "C" int sb_nccl_comm_init(void **comm, int device, int world, int rank, const uint8_t id128[128]) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(comm && id128, "null pointer");
     SB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "rank / world out of range");
@@ -127,6 +130,7 @@ extern "C" int sb_nccl_comm_init(void **comm, int device, int world, int rank, c
     return SB_OK;
 }
 extern "C" int sb_nccl_comm_destroy(void *comm) {
+    SB_NVTX_FN();
     sb_clear_error();
     if (!comm) return SB_OK;
     SB_TRY(load_nccl());
@@ -139,6 +143,7 @@ extern "C" int sb_nccl_comm_destroy(void *comm) {
 //   d_counts  [world] int32                                 d_scratch (1 + world) * (cap * 7 + 1) doubles
 extern "C" int sb_allgather_kf_poses_dev(void *nccl_comm, void *stream, const double *d_local, int n_local, double *d_all,
                                          int32_t *d_counts, int cap, double *d_scratch) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(nccl_comm && d_local && d_all && d_counts && d_scratch, "null pointer");
     SB_REQUIRE(cap >= 1 && cap <= (1 << 24) && n_local >= 0 && n_local <= cap, "n_local out of range [0, cap]");
@@ -164,6 +169,7 @@ extern "C" int sb_allgather_kf_poses_dev(void *nccl_comm, void *stream, const do
 // on the communicator's device, runs on `stream` (NULL = the default stream) and synchronises it before returning.
 extern "C" int sb_allgather_kf_poses(void *nccl_comm, void *stream, const double *local, int n_local, double *all, int *counts,
                                      int cap) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(nccl_comm && local && all && counts, "null pointer");
     SB_REQUIRE(cap >= 1 && cap <= (1 << 24) && n_local >= 0 && n_local <= cap, "n_local out of range [0, cap]");

@@ -84,6 +84,7 @@ int sb_make_tensor_map_u8_sw128(CUtensorMap *map, const void *base, int rank, co
 // Page-locked host memory for the asynchronous host-pointer entry points (sb_stereo_submit, sb_ba_submit): copies from / to
 // pageable memory make cudaMemcpyAsync synchronous, which silently serialises "submit ... wait" pairs.
 extern "C" int sb_host_alloc(void **ptr, size_t bytes) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(ptr && bytes > 0, "null pointer or zero size");
     *ptr = nullptr;
@@ -97,6 +98,7 @@ extern "C" int sb_host_alloc(void **ptr, size_t bytes) {
     return SB_OK;
 }
 extern "C" int sb_host_free(void *ptr) {
+    SB_NVTX_FN();
     if (ptr) cudaFreeHost(ptr);
     return SB_OK;
 }

@@ -5,7 +5,21 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/slamb200.h"
+
+// NVTX ranges (tracing): every C-ABI entry point is one range named after the function, every
+// kernel stage of the extractor one nested range.  NVTX 3 is header-only and a no-op unless a tool (Nsight
+// Systems / Compute) is attached to the process.
+struct SbNvtxRange {
+    explicit SbNvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~SbNvtxRange() { nvtxRangePop(); }
+    SbNvtxRange(const SbNvtxRange &) = delete;
+    SbNvtxRange &operator=(const SbNvtxRange &) = delete;
+};
+#define SB_NVTX_FN() SbNvtxRange sb_nvtx_range__(__func__)
+#define SB_NVTX_RANGE(name) SbNvtxRange sb_nvtx_range2__(name)
 
 #define SB_STR2(x) #x
 #define SB_STR(x) SB_STR2(x)

@@ -211,6 +211,7 @@ static void free_lcd(sb_lcd *h) {
 }
 
 extern "C" int sb_lcd_create(sb_lcd_t **out, int device, int capacity, int dtype, int max_queries) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -258,6 +259,7 @@ extern "C" int sb_lcd_create(sb_lcd_t **out, int device, int capacity, int dtype
 }
 
 extern "C" int sb_lcd_destroy(sb_lcd_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -267,6 +269,7 @@ extern "C" int sb_lcd_destroy(sb_lcd_t *h) {
 }
 
 extern "C" int sb_lcd_set_stream(sb_lcd_t *h, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
     return SB_OK;
@@ -277,6 +280,7 @@ extern "C" int sb_lcd_size(const sb_lcd_t *h) { return h ? h->n : SB_ERR_INVALID
 // LoopClosing::AddToDatabase (src/loopclosing.cpp:651-659): _mvDatabase is a std::map keyed by KF id;
 // ids must arrive in ascending order (they do: keyframes are processed in creation order).
 extern "C" int sb_lcd_add(sb_lcd_t *h, int64_t kf_id, const float *descr) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && descr, "null pointer");
     SB_REQUIRE(h->n < h->capacity, "database full");
@@ -294,6 +298,7 @@ extern "C" int sb_lcd_add(sb_lcd_t *h, int64_t kf_id, const float *descr) {
 // (same layout), no launch.  fp16 database: one host->device copy and one launch per chunk of LCD_STAGE_ROWS rows.
 // Nothing is added when any argument is rejected.
 extern "C" int sb_lcd_add_batch(sb_lcd_t *h, int n, const int64_t *kf_ids, const float *descr) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && (n == 0 || (kf_ids && descr)), "null pointer");
     SB_REQUIRE(n >= 0 && h->n + n <= h->capacity, "database full");
@@ -320,6 +325,7 @@ extern "C" int sb_lcd_add_batch(sb_lcd_t *h, int n, const int64_t *kf_ids, const
 
 // _mvDatabase.erase(id) (src/loopclosing.cpp:73-75): the row is dropped, later rows move up.
 extern "C" int sb_lcd_remove(sb_lcd_t *h, int64_t kf_id) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_TRY(sb_use_device(h->device));
@@ -358,6 +364,7 @@ static int launch_scores(sb_lcd *h, int nq, const float *d_queries, float *d_sco
 
 // scores[q][r] for nq queries against all rows; device pointers, asynchronous.  score_stride >= size.
 extern "C" int sb_lcd_score_dev(sb_lcd_t *h, int nq, const float *d_queries, float *d_scores, int score_stride) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && d_queries && d_scores, "null pointer");
     SB_REQUIRE(nq >= 1 && nq <= 65535 && score_stride >= h->n, "bad nq / score_stride");
@@ -367,6 +374,7 @@ extern "C" int sb_lcd_score_dev(sb_lcd_t *h, int nq, const float *d_queries, flo
 
 // DeepLCD::score of `nq` query descriptors against every database row: scores [nq][size] (host).
 extern "C" int sb_lcd_score(sb_lcd_t *h, int nq, const float *queries, float *scores) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && queries && scores, "null pointer");
     SB_REQUIRE(nq >= 1 && nq <= h->max_queries, "nq out of range [1, max_queries]");
@@ -386,6 +394,7 @@ extern "C" int sb_lcd_score(sb_lcd_t *h, int nq, const float *queries, float *sc
 extern "C" int sb_lcd_detect_loop(sb_lcd_t *h, int64_t cur_kf_id, const float *query, float thres_high, float thres_low,
                                   int min_gap, int max_suspected, int *found, int64_t *best_id, float *max_score,
                                   int *n_suspected) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && query && found && best_id && max_score && n_suspected, "null pointer");
     SB_TRY(sb_use_device(h->device));

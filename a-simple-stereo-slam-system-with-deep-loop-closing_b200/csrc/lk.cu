@@ -247,6 +247,7 @@ static void lk_geometry(int w, int hgt, int max_level, int win, LkGeom *g) {
 }
 
 extern "C" int sb_lk_create(sb_lk_t **out, int device, int max_w, int max_h, int max_batch, int max_pts, int max_level) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -282,6 +283,7 @@ extern "C" int sb_lk_create(sb_lk_t **out, int device, int max_w, int max_h, int
 }
 
 extern "C" int sb_lk_destroy(sb_lk_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -291,6 +293,7 @@ extern "C" int sb_lk_destroy(sb_lk_t *h) {
 }
 
 extern "C" int sb_lk_set_stream(sb_lk_t *h, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
     return SB_OK;
@@ -300,6 +303,7 @@ extern "C" int sb_lk_set_stream(sb_lk_t *h, void *stream) {
 extern "C" int sb_lk_track_dev(sb_lk_t *h, int batch, const uint8_t *d_prev_img, const uint8_t *d_next_img, int64_t img_pitch_bytes,
                                int w, int hgt, int stride, const int32_t *d_n_pts, const float *d_prev_pts, float *d_next_pts,
                                uint8_t *d_status, int win, int max_count, double eps, int use_initial_flow, float min_eig_th) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && d_prev_img && d_next_img && d_n_pts && d_prev_pts && d_next_pts && d_status, "null pointer");
     SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");
@@ -341,6 +345,7 @@ extern "C" int sb_lk_track_dev(sb_lk_t *h, int batch, const uint8_t *d_prev_img,
 extern "C" int sb_lk_track(sb_lk_t *h, int batch, const uint8_t *const *prev, const uint8_t *const *next, int w, int hgt, int stride,
                            const int32_t *n_pts, const float *prev_pts, float *next_pts, uint8_t *status, int win, int max_count,
                            double eps, int use_initial_flow, float min_eig_th) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && prev && next && n_pts && prev_pts && next_pts && status, "null pointer");
     SB_REQUIRE(batch >= 1 && batch <= h->max_batch, "batch out of range [1, max_batch]");

@@ -242,6 +242,7 @@ static void free_matcher(sb_matcher *m) {
 }
 
 extern "C" int sb_matcher_create(sb_matcher_t **out, int device, int max_batch, int max_rows) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -289,6 +290,7 @@ extern "C" int sb_matcher_create(sb_matcher_t **out, int device, int max_batch, 
 }
 
 extern "C" int sb_matcher_destroy(sb_matcher_t *m) {
+    SB_NVTX_FN();
     if (m) {
         cudaSetDevice(m->device);
         cudaDeviceSynchronize();
@@ -298,6 +300,7 @@ extern "C" int sb_matcher_destroy(sb_matcher_t *m) {
 }
 
 extern "C" int sb_matcher_set_stream(sb_matcher_t *m, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(m, "null handle");
     m->stream = stream ? (cudaStream_t)stream : m->own_stream;
     return SB_OK;
@@ -307,6 +310,7 @@ extern "C" int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d
                                     const int32_t *d_nq, int nq_stride, const uint8_t *d_t, int64_t t_set_stride,
                                     const int32_t *d_nt, int nt_stride, int max_rows, int32_t *d_train_idx,
                                     int32_t *d_dist, int64_t out_stride) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(m, "null handle");
     SB_REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
@@ -336,6 +340,7 @@ extern "C" int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d
 
 extern "C" int sb_hamming_match(sb_matcher_t *m, int batch, const uint8_t *q, const int32_t *nq, const uint8_t *t,
                                 const int32_t *nt, int cap, int32_t *train_idx, int32_t *dist) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(m, "null handle");
     SB_REQUIRE(batch >= 1 && batch <= m->max_batch, "batch out of range [1, max_batch]");

@@ -952,7 +952,9 @@ struct sb_orb {
     int prof_stage[SB_PROF_MAX], prof_launches[SB_PROF_MAX];
 };
 
+static const char *const kStageName[SB_STAGE_COUNT] = {"copy_level0", "resize_pyramid", "fast_cells", "quadtree", "gauss_blur", "describe"};
 static void prof_begin(sb_orb *h, int stage, int launches, cudaStream_t s) {
+    nvtxRangePushA(kStageName[stage]);  // closed by prof_end: the stage's launches sit inside the range
     if (!h->prof_on || h->prof_n >= SB_PROF_MAX) return;
     const int i = h->prof_n;
     if (!h->prof_ev[i][0]) {
@@ -964,6 +966,7 @@ static void prof_begin(sb_orb *h, int stage, int launches, cudaStream_t s) {
     cudaEventRecord(h->prof_ev[i][0], s);
 }
 static void prof_end(sb_orb *h, cudaStream_t s) {
+    nvtxRangePop();
     if (!h->prof_on || h->prof_n >= SB_PROF_MAX) return;
     cudaEventRecord(h->prof_ev[h->prof_n][1], s);
     h->prof_n++;
@@ -1223,6 +1226,7 @@ static int configure(sb_orb *h, int w, int hgt) {
 
 extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
                              int minThFAST, int max_w, int max_h, int max_batch) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -1322,6 +1326,7 @@ extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float sc
 static int finish_and_check(sb_orb *h);
 
 extern "C" int sb_orb_destroy(sb_orb_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -1331,12 +1336,14 @@ extern "C" int sb_orb_destroy(sb_orb_t *h) {
 }
 
 extern "C" int sb_orb_set_stream(sb_orb_t *h, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
     return SB_OK;
 }
 
 extern "C" int sb_orb_sync_status(sb_orb_t *h) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_TRY(sb_use_device(h->device));
@@ -1347,6 +1354,7 @@ extern "C" int sb_orb_capacity(const sb_orb_t *h) { return h ? h->kp_cap : SB_ER
 
 extern "C" int sb_orb_get_tables(const sb_orb_t *h, int *nlevels, float *scale, float *inv_scale, float *sigma2,
                                  float *inv_sigma2, int *features_per_level) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     if (nlevels) *nlevels = h->nlevels;
     for (int i = 0; i < h->nlevels; i++) {
@@ -1483,6 +1491,7 @@ extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8
                                              const uint8_t *d_mask, int64_t mask_pitch_bytes, int w, int hgt,
                                              int stride, int mstride, sb_keypoint *d_kps, uint8_t *d_desc,
                                              int32_t *d_counts, int cap) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
     SB_REQUIRE(d_img && d_kps && d_counts, "null device pointer");
@@ -1518,6 +1527,7 @@ extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8
 extern "C" int sb_orb_detect_dev(sb_orb_t *h, int batch, const uint8_t *d_img, int64_t img_pitch_bytes,
                                  const uint8_t *d_mask, int64_t mask_pitch_bytes, int w, int hgt, int stride,
                                  int mstride, sb_keypoint *d_kps, int32_t *d_counts, int cap) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
     SB_REQUIRE(d_img && d_kps && d_counts, "null device pointer");
@@ -1605,6 +1615,7 @@ static int stage_images(sb_orb *h, int batch, const uint8_t *const *img, const u
 extern "C" int sb_orb_detect_and_compute(sb_orb_t *h, int batch, const uint8_t *const *img, const uint8_t *const *mask,
                                          int w, int hgt, int stride, int mstride, sb_keypoint *kps, uint8_t *desc,
                                          int32_t *counts, int cap) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
     SB_REQUIRE(img && kps && counts, "null pointer");
@@ -1629,6 +1640,7 @@ extern "C" int sb_orb_detect_and_compute(sb_orb_t *h, int batch, const uint8_t *
 
 extern "C" int sb_orb_detect(sb_orb_t *h, int batch, const uint8_t *const *img, const uint8_t *const *mask, int w,
                              int hgt, int stride, int mstride, sb_keypoint *kps, int32_t *counts, int cap) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
     SB_REQUIRE(img && kps && counts, "null pointer");
@@ -1651,6 +1663,7 @@ extern "C" int sb_orb_detect(sb_orb_t *h, int batch, const uint8_t *const *img, 
 
 extern "C" int sb_orb_screen_params(sb_orb_t *h, const uint8_t *img, int w, int hgt, int stride, sb_keypoint *in,
                                     int n_in, sb_keypoint *out, int32_t *n_out) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(n_out, "null n_out");
     *n_out = 0;
@@ -1682,6 +1695,7 @@ extern "C" int sb_orb_screen_params(sb_orb_t *h, const uint8_t *img, int w, int 
 
 extern "C" int sb_orb_calc_descriptors(sb_orb_t *h, const uint8_t *img, int w, int hgt, int stride,
                                        const sb_keypoint *kps, int n, uint8_t *desc) {
+    SB_NVTX_FN();
     sb_clear_error();
     if (n <= 0) return SB_OK;
     SB_TRY(check_shapes(h, 1, w, hgt, stride, n));
@@ -1718,6 +1732,7 @@ extern "C" int sb_orb_calc_descriptors(sb_orb_t *h, const uint8_t *img, int w, i
 //   out [batch][cap_in] survivors in input order, n_out [batch], desc [batch][cap_in][32] (row k <-> out[k])
 extern "C" int sb_orb_screen_describe(sb_orb_t *h, int batch, const uint8_t *const *img, int w, int hgt, int stride, sb_keypoint *in,
                                       const int32_t *n_in, int cap_in, sb_keypoint *out, int32_t *n_out, uint8_t *desc) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(img && in && n_in && out && n_out && desc, "null pointer");
     SB_TRY(check_shapes(h, batch, w, hgt, stride, cap_in));
@@ -1781,6 +1796,7 @@ extern "C" int sb_orb_screen_describe(sb_orb_t *h, int batch, const uint8_t *con
 // ---- inspection --------------------------------------------------------------------------------------
 extern "C" int sb_orb_debug_level(sb_orb_t *h, int b, int level, int which, uint8_t *out, int out_bytes, int *lw,
                                   int *lh) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && h->cur_w > 0, "no call has been made on this handle yet");
     SB_REQUIRE(b >= 0 && b < h->max_batch && level >= 0 && level < h->nlevels && which >= 0 && which <= 2, "bad index");
@@ -1799,6 +1815,7 @@ extern "C" int sb_orb_debug_level(sb_orb_t *h, int b, int level, int which, uint
 }
 
 extern "C" int sb_orb_debug_candidates(sb_orb_t *h, int b, int level, uint32_t *out, int cap, int32_t *n) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && out && n, "null pointer");
     SB_REQUIRE(b >= 0 && b < h->max_batch && level >= 0 && level < h->nlevels, "bad index");
@@ -1818,6 +1835,7 @@ extern "C" int sb_orb_debug_candidates(sb_orb_t *h, int b, int level, uint32_t *
 // Inspection: arm (buf != null) or disarm the capture of one FAST cell of image 0; after the next call
 // `out` (2 * tile_bytes + 64 bytes) holds the TMA tile, the response plane and 10 ints of geometry.
 extern "C" int sb_orb_debug_fast_cell(sb_orb_t *h, int cell, uint8_t *out, int out_bytes, int *tile_bytes) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_TRY(sb_use_device(h->device));
@@ -1839,6 +1857,7 @@ extern "C" int sb_orb_debug_fast_cell(sb_orb_t *h, int cell, uint8_t *out, int o
 
 // Per-stage timing with CUDA events on the launching streams.  enable != 0 starts a fresh recording.
 extern "C" int sb_orb_profile(sb_orb_t *h, int enable) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_TRY(sb_use_device(h->device));
@@ -1851,6 +1870,7 @@ extern "C" int sb_orb_profile(sb_orb_t *h, int enable) {
 
 // Sums the recorded intervals per stage (SB_ORB_STAGE_*): ms[nstages], launches[nstages].
 extern "C" int sb_orb_profile_read(sb_orb_t *h, float *ms, int32_t *launches, int nstages) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && ms && launches && nstages >= SB_STAGE_COUNT, "bad arguments");
     SB_TRY(sb_use_device(h->device));

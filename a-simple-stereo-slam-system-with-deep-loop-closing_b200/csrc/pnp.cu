@@ -322,6 +322,7 @@ static void free_pnp(sb_pnp *h) {
 }
 
 extern "C" int sb_pnp_create(sb_pnp_t **out, int device, int max_problems, int max_points) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -354,6 +355,7 @@ extern "C" int sb_pnp_create(sb_pnp_t **out, int device, int max_problems, int m
 }
 
 extern "C" int sb_pnp_destroy(sb_pnp_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -363,6 +365,7 @@ extern "C" int sb_pnp_destroy(sb_pnp_t *h) {
 }
 
 extern "C" int sb_pnp_set_stream(sb_pnp_t *h, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
     return SB_OK;
@@ -371,6 +374,7 @@ extern "C" int sb_pnp_set_stream(sb_pnp_t *h, void *stream) {
 extern "C" int sb_pnp_ransac_dev(sb_pnp_t *h, int n_problems, const int32_t *d_n_points, const float *d_obj, const float *d_img,
                                  int max_points, const double *K, int iterations, double reproj_err, uint64_t seed,
                                  double *d_pose7, double *d_rvec_tvec, uint8_t *d_inlier, int32_t *d_info) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_REQUIRE(n_problems >= 1 && n_problems <= 65535, "n_problems out of range");
@@ -393,6 +397,7 @@ extern "C" int sb_pnp_ransac_dev(sb_pnp_t *h, int n_problems, const int32_t *d_n
 extern "C" int sb_pnp_ransac(sb_pnp_t *h, int n_problems, const int32_t *n_points, const float *obj, const float *img,
                              const double *K, int iterations, double reproj_err, uint64_t seed, double *pose7,
                              double *rvec_tvec, uint8_t *inlier, int32_t *info) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     SB_REQUIRE(n_problems >= 1 && n_problems <= h->max_problems, "n_problems out of range [1, max_problems]");

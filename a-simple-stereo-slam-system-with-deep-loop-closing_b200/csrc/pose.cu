@@ -257,6 +257,7 @@ static void free_pose(sb_pose *h) {
 }
 
 extern "C" int sb_pose_create(sb_pose_t **out, int device, int max_frames, int max_obs) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -289,6 +290,7 @@ extern "C" int sb_pose_create(sb_pose_t **out, int device, int max_frames, int m
 }
 
 extern "C" int sb_pose_destroy(sb_pose_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -298,6 +300,7 @@ extern "C" int sb_pose_destroy(sb_pose_t *h) {
 }
 
 extern "C" int sb_pose_set_stream(sb_pose_t *h, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
     return SB_OK;
@@ -306,6 +309,7 @@ extern "C" int sb_pose_set_stream(sb_pose_t *h, void *stream) {
 extern "C" int sb_pose_solve_dev(sb_pose_t *h, int n_frames, const int32_t *d_n_obs, double *d_poses, const double *d_points,
                                  const double *d_uv, const double *K, double huber_delta, double chi2_th, int pre_rounds,
                                  int rounds, int inner_iters, uint8_t *d_outlier, int32_t *d_info) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && d_n_obs && d_poses && d_points && d_uv && K && d_outlier && d_info, "null pointer");
     SB_REQUIRE(n_frames >= 1 && n_frames <= h->max_frames, "n_frames out of range [1, max_frames]");
@@ -324,6 +328,7 @@ extern "C" int sb_pose_solve_dev(sb_pose_t *h, int n_frames, const int32_t *d_n_
 extern "C" int sb_pose_solve(sb_pose_t *h, int n_frames, const int32_t *n_obs, double *poses, const double *points,
                              const double *uv, const double *K, double huber_delta, double chi2_th, int pre_rounds, int rounds,
                              int inner_iters, uint8_t *outlier, int32_t *info) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && n_obs && poses && points && uv && outlier && info, "null pointer");
     SB_REQUIRE(n_frames >= 1 && n_frames <= h->max_frames, "n_frames out of range [1, max_frames]");

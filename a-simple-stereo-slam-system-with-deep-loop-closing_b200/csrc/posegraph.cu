@@ -772,16 +772,19 @@ static int pg_create(sb_posegraph_t **out, int device, int max_vertices, int max
 }
 
 extern "C" int sb_posegraph_create(sb_posegraph_t **out, int device, int max_vertices, int max_edges) {
+    SB_NVTX_FN();
     return pg_create(out, device, max_vertices, max_edges, PG_DEFAULT_LOOPS);
 }
 // max_loops: the largest number of long-range (non-chain) edges between free vertices a solve may contain.  The reference
 // re-adds every historical loop edge on each PoseGraphOptimization (src/loopclosing.cpp:585-599), so a long run needs a
 // generous bound; the workspace grows with max_vertices x max_loops x 288 bytes.
 extern "C" int sb_posegraph_create_loops(sb_posegraph_t **out, int device, int max_vertices, int max_edges, int max_loops) {
+    SB_NVTX_FN();
     return pg_create(out, device, max_vertices, max_edges, max_loops);
 }
 
 extern "C" int sb_posegraph_destroy(sb_posegraph_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -791,6 +794,7 @@ extern "C" int sb_posegraph_destroy(sb_posegraph_t *h) {
 }
 
 extern "C" int sb_posegraph_set_stream(sb_posegraph_t *h, void *stream) {
+    SB_NVTX_FN();
     SB_REQUIRE(h, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
     return SB_OK;
@@ -799,6 +803,7 @@ extern "C" int sb_posegraph_set_stream(sb_posegraph_t *h, void *stream) {
 extern "C" int sb_posegraph_solve_dev(sb_posegraph_t *h, int n_vertices, double *d_poses, const uint8_t *d_fixed,
                                       int n_edges, const int32_t *d_v0, const int32_t *d_v1, const double *d_meas,
                                       int iters, int32_t *d_info, double *d_stats) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && d_poses && d_fixed && d_v0 && d_v1 && d_meas && d_info && d_stats, "null pointer");
     SB_REQUIRE(n_vertices >= 1 && n_vertices <= h->max_vertices, "n_vertices out of range [1, max_vertices]");
@@ -858,6 +863,7 @@ extern "C" int sb_posegraph_solve_dev(sb_posegraph_t *h, int n_vertices, double 
 extern "C" int sb_posegraph_solve(sb_posegraph_t *h, int n_vertices, double *poses, const uint8_t *fixed, int n_edges,
                                   const int32_t *v0, const int32_t *v1, const double *meas, int iters, int32_t *info,
                                   double *stats) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && poses && fixed && info && stats, "null pointer");
     SB_REQUIRE(n_edges == 0 || (v0 && v1 && meas), "null edge arrays");
@@ -888,6 +894,7 @@ extern "C" int sb_posegraph_solve(sb_posegraph_t *h, int n_vertices, double *pos
 
 #ifdef PG_PROFILE
 extern "C" int sb_posegraph_debug_profile(long long *out) {
+    SB_NVTX_FN();
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out, g_pg_prof, sizeof(long long) * 16);
     long long z[16] = {0};

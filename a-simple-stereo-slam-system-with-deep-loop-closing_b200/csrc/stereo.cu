@@ -38,6 +38,7 @@ static void free_stereo(sb_stereo *h) {
 
 extern "C" int sb_stereo_create(sb_stereo_t **out, int device, int nfeatures, float scaleFactor, int nlevels, int iniThFAST,
                                 int minThFAST, int max_w, int max_h, int max_pairs) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(out, "null handle pointer");
     *out = nullptr;
@@ -74,6 +75,7 @@ extern "C" int sb_stereo_create(sb_stereo_t **out, int device, int nfeatures, fl
 }
 
 extern "C" int sb_stereo_destroy(sb_stereo_t *h) {
+    SB_NVTX_FN();
     if (h) {
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
@@ -91,6 +93,7 @@ extern "C" int sb_stereo_capacity(const sb_stereo_t *h) { return h ? h->cap : SB
 extern "C" int sb_stereo_submit(sb_stereo_t *h, int pairs, const uint8_t *images, int64_t frame_pitch, int64_t view_pitch,
                                 int w, int hgt, int stride, sb_keypoint *kps, uint8_t *desc, int32_t *counts,
                                 int32_t *match_idx, int32_t *match_dist) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h && images && kps && desc && counts && match_idx && match_dist, "null pointer");
     SB_REQUIRE(pairs >= 1 && pairs <= h->max_pairs, "pairs out of range [1, max_pairs]");
@@ -130,6 +133,7 @@ extern "C" int sb_stereo_submit(sb_stereo_t *h, int pairs, const uint8_t *images
 
 // Wait for the submitted batch; SB_ERR_OVERFLOW / SB_ERR_CAPACITY as flagged on the device.
 extern "C" int sb_stereo_wait(sb_stereo_t *h) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(h, "null handle");
     if (!h->pending) return SB_OK;
@@ -140,6 +144,7 @@ extern "C" int sb_stereo_wait(sb_stereo_t *h) {
 extern "C" int sb_stereo_extract_match(sb_stereo_t *h, int pairs, const uint8_t *images, int64_t frame_pitch,
                                        int64_t view_pitch, int w, int hgt, int stride, sb_keypoint *kps, uint8_t *desc,
                                        int32_t *counts, int32_t *match_idx, int32_t *match_dist) {
+    SB_NVTX_FN();
     SB_TRY(sb_stereo_submit(h, pairs, images, frame_pitch, view_pitch, w, hgt, stride, kps, desc, counts, match_idx, match_dist));
     return sb_stereo_wait(h);
 }

@@ -119,6 +119,7 @@ static void pose7_to_m34(const double *p, double *M) {  // rows of [R | t]
 extern "C" int sb_triangulate_dev(int device, void *stream, int n, const float *d_uv_left, const float *d_uv_right,
                                   const double *K_left, const double *K_right, const double *pose_left7, const double *pose_right7,
                                   const double *T_wc7, double ratio_th, double *d_points, uint8_t *d_ok) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(n >= 0, "negative count");
     if (n == 0) return SB_OK;
@@ -145,6 +146,7 @@ extern "C" int sb_triangulate_dev(int device, void *stream, int n, const float *
 extern "C" int sb_triangulate(int device, int n, const float *uv_left, const float *uv_right, const double *K_left,
                               const double *K_right, const double *pose_left7, const double *pose_right7, const double *T_wc7,
                               double ratio_th, double *points, uint8_t *ok) {
+    SB_NVTX_FN();
     sb_clear_error();
     SB_REQUIRE(n >= 0, "negative count");
     if (n == 0) return SB_OK;

@@ -50,3 +50,13 @@ def test_argument_validation_needs_no_device(pkg):
     assert "nfeatures" in pkg.last_error()
     assert pkg.lib().sb_ba_create(C.byref(h), 0, 1, 99, 10, 10) == -1                                 # too many poses
     assert pkg.lib().sb_lcd_create(C.byref(h), 0, 10, 7, 1) == -1                                     # bad dtype
+
+
+def test_nvtx_ranges_are_compiled_in(pkg):
+    """the C-ABI entry points and the extractor's kernel stages open NVTX ranges; NVTX 3 is
+    header-only (no libnvToolsExt dependency) and idle unless a profiler injects itself through NVTX_INJECTION64_PATH."""
+    import os
+    blob = open(os.path.join(os.path.dirname(pkg.__file__), "libslamb200.so"), "rb").read()
+    assert b"NVTX_INJECTION64_PATH" in blob
+    for stage in (b"copy_level0", b"resize_pyramid", b"fast_cells", b"quadtree", b"gauss_blur", b"describe"):
+        assert stage in blob
