@@ -78,7 +78,10 @@ SB_HD bool sb_fast_maybe(const uint8_t *p, int pitch, int t) {
 // (ptxas 12.9 mis-folds max(a, -max3(...)) into VIMNMX3 on sm_100a — measured, tools/fast_probe.cu).
 SB_HD int sb_fast_score(const uint8_t *p, int pitch) {
     const uint32_t v = p[0];
-    const uint32_t cv = (0u - (v << 16)) + v + 256u;  // ((-v) << 16) + (v + 256)
+    uint32_t cv = (0u - (v << 16)) + v + 256u;  // ((-v) << 16) + (v + 256)
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+r"(cv));  // opaque: otherwise nvcc rewrites r * 65535 + cv as (r - v) * 65535 + 256, two instructions per ring pixel
+#endif
     uint32_t d[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
