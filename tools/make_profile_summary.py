@@ -5,7 +5,7 @@ import collections
 import csv
 import sys
 
-OUTSIDE = ("k_posegraph", "k_lcd_store_row", "k_lcd_score", "k_calc_conv", "k_calc_resize", "k_calc_blur", "k_calc_pool", "k_calc_lrn",
+OUTSIDE = ("k_posegraph", "k_lcd_store_row", "k_lcd_score", "k_lcd_score_umma", "k_lcd_q2h", "k_calc_conv", "k_calc_conv_umma", "k_calc_nhwc_split", "k_calc_resize", "k_calc_blur", "k_calc_pool", "k_calc_lrn",
            "k_calc_norm", "k_calc_normalize", "k_pack_record", "k_unpack_records")
 TITLE = sys.argv[3] if len(sys.argv) > 3 else "Round 1, final kernels (session 4)"
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
@@ -27,6 +27,9 @@ for k, v in sorted(ours.items(), key=lambda kv: -kv[1][1]):
     print(f"| {k} | {v[0]} | {v[1] / v[0] / 1e3:.1f} | {100 * v[1] / tot:.1f}% | {inside} |")
 r = list(csv.reader(open(sys.argv[2])))
 h = r[0]
+units = r[1]
+TO_MS = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}
+TO_MB = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
 cols = [("gpu__time_duration.sum", "ms"), ("dram__bytes_read.sum", "MB rd"), ("dram__bytes_write.sum", "MB wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
@@ -40,7 +43,9 @@ for row in r[2:]:
     for c, _ in cols:
         v = row[h.index(c)] if c in h else ""
         try:
-            v = f"{float(v):.4g}"
+            u = units[h.index(c)] if c in h else ""
+            scale = TO_MS.get(u, 1.0) if c.startswith("gpu__time") else TO_MB.get(u, 1.0) if c.startswith("dram__bytes") else 1.0
+            v = f"{float(v) * scale:.4g}"
         except ValueError:
             pass
         vals.append(v)
