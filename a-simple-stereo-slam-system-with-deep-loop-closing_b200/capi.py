@@ -491,6 +491,10 @@ class StereoFrontend:
         except Exception:
             pass
 
+    def set_compute_stream(self, stream):
+        """Kernels on `stream` (an int cudaStream_t shared by several handles), copies on the handle's own stream."""
+        _check(lib().sb_stereo_set_compute_stream(self._h, C.c_void_p(stream)))
+
     def alloc_outputs(self, pairs, pinned=False):
         """Output buffers for submit(): dict of numpy arrays (backed by pinned torch tensors if pinned)."""
         shapes = {"kps": ((pairs, 2, self.cap), KP_DTYPE), "desc": ((pairs, 2, self.cap, 32), np.uint8),

@@ -1369,6 +1369,29 @@ extern "C" int sb_orb_sync_status(sb_orb_t *h) {
     return finish_and_check(h);
 }
 
+extern "C" int sb_orb_status_async(sb_orb_t *h, int32_t *host_flags) {
+    SB_NVTX_FN();
+    sb_clear_error();
+    SB_REQUIRE(h && host_flags, "null pointer");
+    SB_TRY(sb_use_device(h->device));
+    SB_CUDA(cudaMemcpyAsync(host_flags, h->d_flags, 16, cudaMemcpyDeviceToHost, h->stream));
+    SB_CUDA(cudaMemsetAsync(h->d_flags, 0, 16, h->stream));
+    return SB_OK;
+}
+
+extern "C" int sb_orb_status_decode(const int32_t *host_flags) {
+    SB_REQUIRE(host_flags, "null pointer");
+    if (host_flags[0]) {
+        sb_set_error("more than %d FAST candidates on one pyramid level", SB_CAND_CAP);
+        return SB_ERR_OVERFLOW;
+    }
+    if (host_flags[1]) {
+        sb_set_error("keypoint capacity `cap` too small; use sb_orb_capacity()");
+        return SB_ERR_CAPACITY;
+    }
+    return SB_OK;
+}
+
 extern "C" int sb_orb_capacity(const sb_orb_t *h) { return h ? h->kp_cap : SB_ERR_INVALID; }
 
 extern "C" int sb_orb_get_tables(const sb_orb_t *h, int *nlevels, float *scale, float *inv_scale, float *sigma2,

@@ -22,6 +22,10 @@ struct sb_stereo {
     int32_t *d_counts;   // [max_pairs][2]
     int32_t *d_midx, *d_mdist;  // [max_pairs][cap]
     int pending;
+    int pending_probe;  // probe builds only
+    cudaStream_t compute;        // sb_stereo_set_compute_stream: kernels here, copies on `stream`; null = everything on `stream`
+    cudaEvent_t ev_in, ev_done;  // copy in finished / kernels finished
+    int32_t *h_flags;            // page-locked copy of the extractor's device flags (compute-stream mode)
 };
 
 static void free_stereo(sb_stereo *h) {
@@ -33,6 +37,9 @@ static void free_stereo(sb_stereo *h) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
     delete h;
 }
 
@@ -63,6 +70,9 @@ extern "C" int sb_stereo_create(sb_stereo_t **out, int device, int nfeatures, fl
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_counts, P * 2 * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_midx, P * h->cap * 4);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->d_mdist, P * h->cap * 4);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&h->h_flags, 16);
     if (e != cudaSuccess) {
         sb_set_error("sb_stereo_create: %s", cudaGetErrorString(e));
         free_stereo(h);
@@ -85,6 +95,18 @@ extern "C" int sb_stereo_destroy(sb_stereo_t *h) {
 }
 
 extern "C" int sb_stereo_capacity(const sb_stereo_t *h) { return h ? h->cap : SB_ERR_INVALID; }
+
+extern "C" int sb_stereo_set_compute_stream(sb_stereo_t *h, void *stream) {
+    SB_NVTX_FN();
+    sb_clear_error();
+    SB_REQUIRE(h, "null handle");
+    SB_REQUIRE(!h->pending, "a batch is in flight");
+    h->compute = (cudaStream_t)stream;
+    cudaStream_t k = h->compute ? h->compute : h->stream;
+    sb_orb_set_stream(h->orb, k);
+    sb_matcher_set_stream(h->mat, k);
+    return SB_OK;
+}
 
 // Enqueue one batch.  images: `pairs` frames, frame p = left plane then right plane, each `hgt` rows of
 // `stride` bytes, consecutive frames `frame_pitch` bytes apart (host memory; pinned memory makes the
@@ -110,7 +132,13 @@ extern "C" int sb_stereo_submit(sb_stereo_t *h, int pairs, const uint8_t *images
         (size_t)stride * hgt <= plane_cap) {
         plane = (size_t)stride * hgt;
         dev_stride = stride;
+#ifdef SB_PROBE_SKIP_H2D  // tools/ probe builds only (csrc/Makefile EXTRA=...): where the end-to-end time goes — only the first batch is copied
+        if (!h->pending_probe)
+#endif
         SB_CUDA(cudaMemcpyAsync(h->d_img, images, (size_t)pairs * 2 * plane, cudaMemcpyHostToDevice, h->stream));
+#ifdef SB_PROBE_SKIP_H2D
+        h->pending_probe = 1;
+#endif
     } else {
         for (int p = 0; p < pairs; p++)
             for (int v = 0; v < 2; v++)
@@ -118,12 +146,23 @@ extern "C" int sb_stereo_submit(sb_stereo_t *h, int pairs, const uint8_t *images
                                           (size_t)stride, (size_t)w, (size_t)hgt, cudaMemcpyHostToDevice, h->stream));
     }
     const int cap = h->cap;
+    if (h->compute) {  // the kernels wait for this batch's images, not for the other handles' copies
+        SB_CUDA(cudaEventRecord(h->ev_in, h->stream));
+        SB_CUDA(cudaStreamWaitEvent(h->compute, h->ev_in, 0));
+    }
     SB_TRY(sb_orb_detect_and_compute_dev(h->orb, 2 * pairs, h->d_img, (int64_t)plane, nullptr, 0, w, hgt, dev_stride, 0, h->d_kps,
                                          h->d_desc, h->d_counts, cap));
     SB_TRY(sb_hamming_match_dev(h->mat, pairs, h->d_desc, (int64_t)2 * cap * 32, h->d_counts, 2, h->d_desc + (size_t)cap * 32,
                                 (int64_t)2 * cap * 32, h->d_counts + 1, 2, cap, h->d_midx, h->d_mdist, cap));
+    if (h->compute) {  // the copies out wait for this batch's kernels; the status flags travel with them
+        SB_TRY(sb_orb_status_async(h->orb, h->h_flags));
+        SB_CUDA(cudaEventRecord(h->ev_done, h->compute));
+        SB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_done, 0));
+    }
+#ifndef SB_PROBE_SKIP_D2H
     SB_CUDA(cudaMemcpyAsync(kps, h->d_kps, (size_t)pairs * 2 * cap * sizeof(sb_keypoint), cudaMemcpyDeviceToHost, h->stream));
     SB_CUDA(cudaMemcpyAsync(desc, h->d_desc, (size_t)pairs * 2 * cap * 32, cudaMemcpyDeviceToHost, h->stream));
+#endif
     SB_CUDA(cudaMemcpyAsync(counts, h->d_counts, (size_t)pairs * 2 * 4, cudaMemcpyDeviceToHost, h->stream));
     SB_CUDA(cudaMemcpyAsync(match_idx, h->d_midx, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, h->stream));
     SB_CUDA(cudaMemcpyAsync(match_dist, h->d_mdist, (size_t)pairs * cap * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -138,6 +177,11 @@ extern "C" int sb_stereo_wait(sb_stereo_t *h) {
     SB_REQUIRE(h, "null handle");
     if (!h->pending) return SB_OK;
     h->pending = 0;
+    if (h->compute) {
+        SB_TRY(sb_use_device(h->device));
+        SB_CUDA(cudaStreamSynchronize(h->stream));  // the copies out, hence this batch's kernels; later batches keep running
+        return sb_orb_status_decode(h->h_flags);
+    }
     return sb_orb_sync_status(h->orb);
 }
 

@@ -453,7 +453,9 @@ def main():
     # measured gain 3 % — the kernels are issue-bound — at the price of smeared per-stage event times, so 1.)
     NH = 1
     sx = [torch.cuda.Stream() for _ in range(NH)]
-    s2 = torch.cuda.Stream()
+    # (BENCH_BA_PRIORITY=-1 gives the BA stream the higher priority: measured 39.0 k -> 36.0 k frames/s — a window's CTA needs a
+    #  whole SM, and holding back the extractor's CTAs until 64 SMs have drained costs more SM-time than it saves)
+    s2 = torch.cuda.Stream(priority=int(os.environ.get("BENCH_BA_PRIORITY", "0")))
     exts = [pkg.ORBextractor(*ORB_PARAMS, max_w=W, max_h=H, max_batch=2 * B, device=local_rank) for _ in range(NH)]
     mats = [pkg.HammingMatcher(max_batch=B, max_rows=exts[0].cap, device=local_rank) for _ in range(NH)]
     ba = pkg.LocalBA(max_windows=B, device=local_rank, **BA_CAPS)
@@ -607,20 +609,34 @@ def main():
             ba_flops += iters_k * ne_k * 450 + trials_k * (pairs_k * 216 + ne_k * 90 + (6 * np_k) ** 3 / 3)
 
     # ---- e2e: the host-pointer C ABI with pinned host buffers (H2D + D2H inside the timed region):
-    #      three sb_stereo handles used in turn (copy in, kernels and copy out of consecutive batches overlap)
+    #      sb_stereo handles used in turn (copy in, kernels and copy out of consecutive batches overlap)
     #      and sb_ba_submit / sb_ba_wait on pinned host arrays.
     del ext, exts, mats
     hp = min(P, 4 * B)
     host_pool = torch.from_numpy(pool_np[:hp]).pin_memory()
     host_np = host_pool.numpy()
-    NE = 3   # front-end handles in flight: copy in, kernels and copy out of consecutive batches overlap
+    # front-end handles in flight: copy in, kernels and copy out of consecutive batches overlap.  Beside BA two are enough and better
+    # than three (a third batch's 60 MB copy in sits in the copy engine's queue ahead of the next BA batch's 4 MB)
+    NE = int(os.environ.get("BENCH_FE_HANDLES", "2" if with_ba else "3"))
     fes = [pkg.StereoFrontend(*ORB_PARAMS, max_w=W, max_h=H, max_pairs=B, device=local_rank) for _ in range(NE)]
     outs = [fe.alloc_outputs(B, pinned=True) for fe in fes]
-    # two back-end handles on ONE stream, used alternately: a batch of windows is submitted without waiting for the
-    # previous one (the stream keeps them in order; nothing idles while the host collects and refills the other buffers)
+    # with the back end beside it, the front-end handles put their kernels on ONE stream (copies stay on their own): batches follow one
+    # another like a single-stream loop and BA's whole-SM CTAs find free SMs at every kernel boundary (measured e2e 35.7 k -> 37.6 k
+    # frames/s); without BA the kernels of neighbouring batches may as well overlap (48.3 k vs 46.7 k)
+    fe_shared = os.environ.get("BENCH_FE_SHARED_STREAM", "1" if with_ba else "0") == "1"
+    if fe_shared:
+        s_fe = torch.cuda.Stream()
+        for fe in fes:
+            fe.set_compute_stream(s_fe.cuda_stream)
+    # two back-end handles used alternately: a batch of windows is submitted without waiting for the previous one
     bas = [ba, pkg.LocalBA(max_windows=B, device=local_rank, **BA_CAPS)] if with_ba else []
-    for b_ in bas:
-        b_.set_stream(s2.cuda_stream)
+    # the two back-end handles on their own streams (the copies of one batch overlap the kernel of the other), with the higher
+    # priority (end to end the BA batch is what the host waits for; measured 36.0 k -> 38.4 k frames/s with the shared front-end stream)
+    e2e_prio = int(os.environ.get("BENCH_BA_E2E_PRIORITY", "-1"))
+    s2e = torch.cuda.Stream(priority=e2e_prio)
+    e2e_ba_streams = [s2e, torch.cuda.Stream(priority=e2e_prio)] if os.environ.get("BENCH_BA_E2E_STREAMS", "2") == "2" else [s2e, s2e]
+    for b_, st_ in zip(bas, e2e_ba_streams):
+        b_.set_stream(st_.cuda_stream)
     hbs = [{k: torch.from_numpy(v).pin_memory() for k, v in bh.items()} for _ in range(2)]
     hb = hbs[0]
     hb0 = {"poses": hb["poses"].clone(), "points": hb["points"].clone()}
@@ -652,19 +668,28 @@ def main():
         assert rc == 0, pkg.last_error()
         ba_pending[k] = True
 
+    host_t = {"ba_submit": 0.0, "fe_wait": 0.0, "fe_submit": 0.0}   # where the host thread spends the end-to-end loop
+
     def run_host(nsteps):
         # the reference's threading: the front end (extract + match) and the back end (local BA) run side by side;
         # here both are asynchronous submissions from one host thread, collected one step later
         pending = [False] * NE
         for i in range(nsteps):
             k = i % NE
+            ta = time.perf_counter()
             if with_ba:
                 ba_submit(i % 2)   # first: its 4 MB of copies must not queue behind the 60 MB of frames on the copy engine
+            tb = time.perf_counter()
             if pending[k]:
                 fes[k].wait()
+            tc = time.perf_counter()
             off = (i * B) % hp
             fes[k].submit(host_np[off:off + B], outs[k])
             pending[k] = True
+            td = time.perf_counter()
+            host_t["ba_submit"] += tb - ta
+            host_t["fe_wait"] += tc - tb
+            host_t["fe_submit"] += td - tc
         for k in range(NE):
             if pending[k]:
                 fes[k].wait()
@@ -673,6 +698,8 @@ def main():
 
     run_host(4)
     barrier()
+    for k_ in host_t:
+        host_t[k_] = 0.0
     t0 = time.perf_counter()
     run_host(args.steps)
     barrier()
@@ -835,7 +862,8 @@ def main():
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_ms_max / args.steps,
-                       "api": "sb_stereo_submit/wait on three handles and sb_ba_submit/wait on two, used in turn (host pointers, pinned)"},
+                       "host_thread_ms_per_step": {k_: 1e3 * v_ / args.steps for k_, v_ in host_t.items()},
+                       "api": f"sb_stereo_submit/wait on {NE} handles" + (" (kernels on one shared stream, sb_stereo_set_compute_stream)" if fe_shared else "") + " and sb_ba_submit/wait on two, used in turn (host pointers, pinned)"},
                "gpu_launches": int(sum(stage_launches.values())),
                "roofline": roofline,
                "roofline_extract": roofline_extract,

@@ -68,6 +68,11 @@ int sb_orb_set_stream(sb_orb_t *h, void *stream);
 /* Waits for the handle's stream and reports what the asynchronous "_dev" calls since the last
  * check flagged on the device: SB_OK, SB_ERR_OVERFLOW or SB_ERR_CAPACITY. */
 int sb_orb_sync_status(sb_orb_t *h);
+/* The same check without a stream synchronisation: enqueues, on the handle's stream, a copy of the device flags into
+ * host_flags (4 ints, page-locked) and their reset; after the caller has synchronised in its own way (an event, another
+ * stream that waited for this one) sb_orb_status_decode(host_flags) gives SB_OK / SB_ERR_OVERFLOW / SB_ERR_CAPACITY. */
+int sb_orb_status_async(sb_orb_t *h, int32_t *host_flags);
+int sb_orb_status_decode(const int32_t *host_flags);
 /* Per-image keypoint capacity the caller must provide to the calls below
  * (sum over levels of max(quota + 3, 4 * nIni) for the pyramid calls). */
 int sb_orb_capacity(const sb_orb_t *h);
@@ -181,6 +186,12 @@ int sb_stereo_submit(sb_stereo_t *h, int pairs, const uint8_t *images, int64_t f
                      int hgt, int stride, sb_keypoint *kps, uint8_t *desc, int32_t *counts, int32_t *match_idx,
                      int32_t *match_dist);
 int sb_stereo_wait(sb_stereo_t *h);
+/* Several handles in flight, ONE kernel stream: after this call the handle's kernels run on `stream` (a cudaStream_t shared
+ * by all the handles of a pipeline, in submission order) while its host<->device copies stay on the handle's own stream,
+ * ordered against the kernels by events.  Batches then follow one another on the device like a single-stream loop — a
+ * concurrent fat-CTA kernel (local BA: one CTA = one whole SM) finds free SMs at every kernel boundary — and the copies of
+ * neighbouring batches still overlap the kernels.  stream = NULL restores the default (everything on the handle's stream). */
+int sb_stereo_set_compute_stream(sb_stereo_t *h, void *stream);
 int sb_stereo_extract_match(sb_stereo_t *h, int pairs, const uint8_t *images, int64_t frame_pitch, int64_t view_pitch,
                             int w, int hgt, int stride, sb_keypoint *kps, uint8_t *desc, int32_t *counts,
                             int32_t *match_idx, int32_t *match_dist);

@@ -31,8 +31,41 @@ def test_extract_match_batch_bit_exact(pkg, oracle, synth):
     fe2.wait()
     assert np.array_equal(o1["midx"], out["midx"]) and np.array_equal(o2["midx"][::-1], out["midx"])
     assert np.array_equal(o1["desc"], out["desc"])
+    # ... and so do three handles whose kernels share ONE stream while their copies stay on their own
+    # (sb_stereo_set_compute_stream), several batches each, results collected one round later
+    import torch
+    shared = torch.cuda.Stream()
+    fe3 = pkg.StereoFrontend(2000, 1.2, 8, 20, 7, max_pairs=4)
+    hs = [fe, fe2, fe3]
+    for h in hs:
+        h.set_compute_stream(shared.cuda_stream)
+    pinned = torch.from_numpy(np.stack([frames, frames[::-1].copy()])).pin_memory().numpy()
+    os_ = [h.alloc_outputs(3, pinned=True) for h in hs]
+    def same(got, flipped):                                  # rows past a frame's count are not defined
+        for p in range(3):
+            q = 2 - p if flipped else p
+            n0, n1 = out["counts"][q]
+            assert tuple(got["counts"][p]) == (n0, n1)
+            assert np.array_equal(got["midx"][p, :n0], out["midx"][q, :n0]) and np.array_equal(got["mdist"][p, :n0], out["mdist"][q, :n0])
+            assert np.array_equal(got["desc"][p, 0, :n0], out["desc"][q, 0, :n0]) and np.array_equal(got["desc"][p, 1, :n1], out["desc"][q, 1, :n1])
+            assert got["kps"][p, 1, :n1].tobytes() == out["kps"][q, 1, :n1].tobytes()
+
+    for rnd in range(3):
+        for k, h in enumerate(hs):
+            if rnd:
+                h.wait()
+                same(os_[k], (rnd - 1 + k) % 2 == 1)
+            h.submit(pinned[(rnd + k) % 2], os_[k])
+    for k, h in enumerate(hs):
+        h.wait()
+        same(os_[k], (2 + k) % 2 == 1)
+    fe.set_compute_stream(None)                              # back to the default mode
+    fe.submit(frames, o1)
+    fe.wait()
+    same(o1, False)
     fe.close()
     fe2.close()
+    fe3.close()
 
 
 def test_full_size_batch_properties(pkg, oracle, synth):
