@@ -751,11 +751,25 @@ struct DescArgs {
     int nlevels, selcap, cap;
 };
 
-#define DESC_KPB 64  // keypoints per CTA of k_describe
-__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ Geom g, DescArgs a) {
+// k_describe stages every keypoint's patch in shared memory with ONE TMA box per phase (no staging instructions): the
+// orientation disc (radius 15) from the pyramid, then the rBRIEF sampling window (the pattern reaches 18 px when rotated)
+// from the blurred pyramid into the same buffer.  The innermost TMA coordinate must be a multiple of 16 bytes, so a box
+// starts at the 16-byte boundary at or left of the wanted column.  With the patch at a compile-time pitch the row
+// offsets become LDS immediates (the global-memory version spent half its instructions on 64-bit addresses) and the
+// byte gathers hit shared-memory banks instead of 20+ L1 sectors per warp load.
+#define DESC_KPB 16      // keypoints per CTA: 2 per warp, both patches in flight
+#define DESC_AW 48       // orientation box: 48 x 31 bytes (x - 15 .. x + 15 after alignment)
+#define DESC_AH 31
+#define DESC_CW 64       // sampling box: 64 x 37 bytes (x - 18 .. x + 18 after alignment)
+#define DESC_CH 37
+#define DESC_PBYTES 2432  // 64 * 37 = 2368 rounded up to 128 (TMA destination alignment)
+__global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ TmaMaps pmaps,
+                                                             const __grid_constant__ TmaMaps bmaps,
+                                                             const __grid_constant__ Geom g, DescArgs a) {
+    extern __shared__ __align__(128) uint8_t patches[];  // [DESC_KPB][DESC_PBYTES]
     __shared__ float4 pat[256];
     __shared__ float s_ang[DESC_KPB], s_cos[DESC_KPB], s_sin[DESC_KPB];
-    load_pattern(pat);
+    __shared__ __align__(8) uint64_t bars[DESC_KPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int level = blockIdx.y, img = blockIdx.z;
     const int *cnt = a.sel_cnt + img * a.nlevels;
@@ -774,15 +788,36 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     if (nk <= 0) return;
     const LevelGeom &L = g.lv[level];
     const uint32_t *sel = a.sel + ((long long)img * a.nlevels + level) * a.selcap + k0;
-    const long long base = (long long)img * a.slab + L.off;
-    // phase A: orientation, one warp per keypoint (4 keypoints per warp)
-    // (measured: reading the patch as aligned words + DP4A against a weight table is slower — 367 vs 293 us per launch)
-    const int nv = ic_rows(g.umax, lane);
+    // every warp owns the barriers and buffers of its keypoints (i = warp, warp + 8, ...): no block-wide hand-over
+    if (lane == 0)
+        for (int i = warp; i < nk; i += DESC_WARPS) sb_mbar_init(&bars[i], 1);
+    __syncwarp();
     for (int i = warp; i < nk; i += DESC_WARPS) {
         const uint32_t w = sel[i];
         const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;  // :895-896
-        const float angle = warp_ic_angle(a.pyr + base + (long long)y * L.pitch + x, L.pitch, nv, lane);
+        if (lane == 0) {
+            sb_mbar_expect_tx(&bars[i], DESC_AW * DESC_AH);
+            sb_tma_load_3d(patches + i * DESC_PBYTES, &pmaps.m[level], (x - SB_HALF_PATCH) & ~15, y - SB_HALF_PATCH, img, &bars[i]);
+        }
+    }
+    load_pattern(pat);
+    // phase A: orientation, one warp per keypoint; the buffer is then refilled with the blurred sampling window
+    const int nv = ic_rows(g.umax, lane);
+    for (int i = warp; i < nk; i += DESC_WARPS) {
+        const uint32_t w = sel[i];
+        const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;
+        uint8_t *buf = patches + i * DESC_PBYTES;
+        sb_mbar_wait(&bars[i], 0);
+        const float angle = warp_ic_angle(buf + SB_HALF_PATCH * DESC_AW + SB_HALF_PATCH + ((x - SB_HALF_PATCH) & 15), DESC_AW, nv, lane);
         if (lane == 0) s_ang[i] = angle;
+        if (a.desc) {
+            __syncwarp();  // every lane has read the disc
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                sb_mbar_expect_tx(&bars[i], DESC_CW * DESC_CH);
+                sb_tma_load_3d(buf, &bmaps.m[level], (x - 18) & ~15, y - 18, img, &bars[i]);
+            }
+        }
     }
     __syncthreads();
     // phase B: cos / sin in double, ONE THREAD per keypoint (as a warp-wide computation it would cost 32x)
@@ -800,14 +835,15 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
         const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;
         const long long row = (long long)img * a.cap + offset + k0 + i;
         if (a.desc) {
-            const uint8_t *center = a.blur + base + (long long)y * L.pitch + x;
+            sb_mbar_wait(&bars[i], 1);
+            const uint8_t *center = patches + i * DESC_PBYTES + 18 * DESC_CW + 18 + ((x - 18) & 15);
             const float ca = s_cos[i], sb = s_sin[i];
             uint32_t val = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const float4 q = pat[j * 32 + lane];
-                const int t0 = sb_brief_sample(center, L.pitch, ca, sb, q.x, q.y);
-                const int t1 = sb_brief_sample(center, L.pitch, ca, sb, q.z, q.w);
+                const int t0 = sb_brief_sample(center, DESC_CW, ca, sb, q.x, q.y);
+                const int t1 = sb_brief_sample(center, DESC_CW, ca, sb, q.z, q.w);
                 val |= (uint32_t)(t0 < t1) << j;
             }
             a.desc[row * 32 + lane] = (uint8_t)val;
@@ -939,6 +975,7 @@ struct sb_orb {
     int cur_w, cur_h;
     Geom geom;
     TmaMaps fast_maps, blur_maps, blur_maps_mask_unused;
+    TmaMaps desc_pyr_maps, desc_blur_maps;  // k_describe's patch boxes over the pyramid / the blurred pyramid
     int n_cells, n_cells_l0, n_blur_tiles;  // n_cells: FAST cell groups (CTAs)
     int fast_tile_bytes, fast_list_cap, fast_seg;
     int selcap, ncap_pyr, ncap_detect;
@@ -1237,6 +1274,9 @@ static int configure(sb_orb *h, int w, int hgt) {
         const uint32_t bbox[3] = {BLUR_BW, BLUR_BH, 1};
         SB_TRY(sb_make_tensor_map_u8(&h->fast_maps.m[l], h->d_pyr + L.off, 3, dims, strides, fbox));
         SB_TRY(sb_make_tensor_map_u8(&h->blur_maps.m[l], h->d_pyr + L.off, 3, dims, strides, bbox));
+        const uint32_t dabox[3] = {DESC_AW, DESC_AH, 1}, dcbox[3] = {DESC_CW, DESC_CH, 1};
+        SB_TRY(sb_make_tensor_map_u8(&h->desc_pyr_maps.m[l], h->d_pyr + L.off, 3, dims, strides, dabox));
+        SB_TRY(sb_make_tensor_map_u8(&h->desc_blur_maps.m[l], h->d_blur + L.off, 3, dims, strides, dcbox));
     }
     h->cur_w = w;
     h->cur_h = hgt;
@@ -1560,7 +1600,8 @@ extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8
     da.selcap = h->selcap;
     da.cap = cap;
     prof_begin(h, SB_STAGE_DESCRIBE, 1, h->stream);
-    k_describe<<<dim3(sb_div_up(h->ncap_pyr, DESC_KPB), h->nlevels, batch), DESC_WARPS * 32, 0, h->stream>>>(h->geom, da);
+    k_describe<<<dim3(sb_div_up(h->ncap_pyr, DESC_KPB), h->nlevels, batch), DESC_WARPS * 32, DESC_KPB * DESC_PBYTES, h->stream>>>(
+        h->desc_pyr_maps, h->desc_blur_maps, h->geom, da);
     prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
