@@ -697,11 +697,19 @@ static __device__ __forceinline__ float warp_ic_angle(const uint8_t *center, int
 
 // The 256 test pairs as floats in shared memory, transposed so that lane i's j-th pair (pair 8i + j) sits
 // at [j * 32 + i]: conflict-free 16-byte loads, no int8 -> float conversions in the loop.
-static __device__ __forceinline__ void load_pattern(float4 *pat) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const int8_t *q = d_pattern + 4 * i;
-        pat[(i & 7) * 32 + (i >> 3)] = make_float4((float)q[0], (float)q[1], (float)q[2], (float)q[3]);
-    }
+struct PatternF4 { float v[1024]; };
+static constexpr PatternF4 make_pattern_f4() {  // the int8 table as floats, transposed: pair 8 i + j at [j * 32 + i]
+    constexpr int p[1024] = {
+#include "orb_pattern.inc"
+    };
+    PatternF4 t{};
+    for (int i = 0; i < 256; i++)
+        for (int k = 0; k < 4; k++) t.v[((i & 7) * 32 + (i >> 3)) * 4 + k] = (float)p[4 * i + k];
+    return t;
+}
+__device__ __align__(16) const PatternF4 d_pattern_f4 = make_pattern_f4();
+static __device__ __forceinline__ void load_pattern(float4 *pat) {  // one 16-byte load + store per thread
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) pat[i] = reinterpret_cast<const float4 *>(d_pattern_f4.v)[i];
 }
 
 // computeOrbDescriptor (:59-98): lane i produces byte i (pairs 8i .. 8i+7).
@@ -757,22 +765,33 @@ struct DescArgs {
 // starts at the 16-byte boundary at or left of the wanted column.  With the patch at a compile-time pitch the row
 // offsets become LDS immediates (the global-memory version spent half its instructions on 64-bit addresses) and the
 // byte gathers hit shared-memory banks instead of 20+ L1 sectors per warp load.
+#ifndef DESC_KPB
 #define DESC_KPB 16      // keypoints per CTA: 2 per warp, both patches in flight
+#endif
 #define DESC_AW 48       // orientation box: 48 x 31 bytes (x - 15 .. x + 15 after alignment)
 #define DESC_AH 31
 #define DESC_CW 64       // sampling box: 64 x 37 bytes (x - 18 .. x + 18 after alignment)
 #define DESC_CH 37
-#define DESC_PBYTES 2432  // 64 * 37 = 2368 rounded up to 128 (TMA destination alignment)
+#ifndef DESC_DUAL
+#define DESC_DUAL 0       // 1: separate buffers, both boxes requested up front (one memory round trip per CTA instead of two)
+#endif
+#define DESC_CBYTES 2432  // 64 * 37 = 2368 rounded up to 128 (TMA destination alignment)
+#define DESC_ABYTES 1536  // 48 * 31 = 1488 rounded up
+#define DESC_PBYTES (DESC_DUAL ? DESC_CBYTES + DESC_ABYTES : DESC_CBYTES)
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ TmaMaps pmaps,
                                                              const __grid_constant__ TmaMaps bmaps,
                                                              const __grid_constant__ Geom g, DescArgs a) {
     extern __shared__ __align__(128) uint8_t patches[];  // [DESC_KPB][DESC_PBYTES]
     __shared__ float4 pat[256];
     __shared__ float s_ang[DESC_KPB], s_cos[DESC_KPB], s_sin[DESC_KPB];
-    __shared__ __align__(8) uint64_t bars[DESC_KPB];
+    __shared__ __align__(8) uint64_t bars[DESC_KPB], bars2[DESC_KPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int level = blockIdx.y, img = blockIdx.z;
     const int *cnt = a.sel_cnt + img * a.nlevels;
+    const int k0 = blockIdx.x * DESC_KPB;
+    if (cnt[level] <= k0) {  // most CTAs of the sparse upper levels: nothing to do (the level-0 CTA 0 of an image never takes this exit)
+        if (!(level == 0 && blockIdx.x == 0)) return;
+    }
     int offset = 0, total = 0;
     for (int l = 0; l < a.nlevels; l++) {
         const int c = cnt[l];
@@ -783,21 +802,27 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
         a.counts[img] = min(total, a.cap);
         if (total > a.cap) a.flags[1] = 1;
     }
-    const int k0 = blockIdx.x * DESC_KPB;
     const int nk = min(min(cnt[level], a.cap - offset) - k0, DESC_KPB);  // keypoints of this CTA
     if (nk <= 0) return;
     const LevelGeom &L = g.lv[level];
     const uint32_t *sel = a.sel + ((long long)img * a.nlevels + level) * a.selcap + k0;
     // every warp owns the barriers and buffers of its keypoints (i = warp, warp + 8, ...): no block-wide hand-over
     if (lane == 0)
-        for (int i = warp; i < nk; i += DESC_WARPS) sb_mbar_init(&bars[i], 1);
+        for (int i = warp; i < nk; i += DESC_WARPS) {
+            sb_mbar_init(&bars[i], 1);
+            if (DESC_DUAL) sb_mbar_init(&bars2[i], 1);
+        }
     __syncwarp();
     for (int i = warp; i < nk; i += DESC_WARPS) {
         const uint32_t w = sel[i];
         const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;  // :895-896
         if (lane == 0) {
             sb_mbar_expect_tx(&bars[i], DESC_AW * DESC_AH);
-            sb_tma_load_3d(patches + i * DESC_PBYTES, &pmaps.m[level], (x - SB_HALF_PATCH) & ~15, y - SB_HALF_PATCH, img, &bars[i]);
+            sb_tma_load_3d(patches + i * DESC_PBYTES + (DESC_DUAL ? DESC_CBYTES : 0), &pmaps.m[level], (x - SB_HALF_PATCH) & ~15, y - SB_HALF_PATCH, img, &bars[i]);
+            if (DESC_DUAL && a.desc) {
+                sb_mbar_expect_tx(&bars2[i], DESC_CW * DESC_CH);
+                sb_tma_load_3d(patches + i * DESC_PBYTES, &bmaps.m[level], (x - 18) & ~15, y - 18, img, &bars2[i]);
+            }
         }
     }
     load_pattern(pat);
@@ -808,9 +833,9 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
         const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;
         uint8_t *buf = patches + i * DESC_PBYTES;
         sb_mbar_wait(&bars[i], 0);
-        const float angle = warp_ic_angle(buf + SB_HALF_PATCH * DESC_AW + SB_HALF_PATCH + ((x - SB_HALF_PATCH) & 15), DESC_AW, nv, lane);
+        const float angle = warp_ic_angle(buf + (DESC_DUAL ? DESC_CBYTES : 0) + SB_HALF_PATCH * DESC_AW + SB_HALF_PATCH + ((x - SB_HALF_PATCH) & 15), DESC_AW, nv, lane);
         if (lane == 0) s_ang[i] = angle;
-        if (a.desc) {
+        if (!DESC_DUAL && a.desc) {
             __syncwarp();  // every lane has read the disc
             if (lane == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -835,7 +860,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
         const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;
         const long long row = (long long)img * a.cap + offset + k0 + i;
         if (a.desc) {
-            sb_mbar_wait(&bars[i], 1);
+            if (DESC_DUAL) sb_mbar_wait(&bars2[i], 0); else sb_mbar_wait(&bars[i], 1);
             const uint8_t *center = patches + i * DESC_PBYTES + 18 * DESC_CW + 18 + ((x - 18) & 15);
             const float ca = s_cos[i], sb = s_sin[i];
             uint32_t val = 0;
@@ -1366,6 +1391,7 @@ extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float sc
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_KPB * DESC_PBYTES);
     if (e != cudaSuccess) {
         sb_set_error("sb_orb_create: %s", cudaGetErrorString(e));
         free_orb(h);
