@@ -669,20 +669,33 @@ static __device__ __forceinline__ int ic_rows(const int *umax, int lane) {
     for (int v = 1; v <= SB_HALF_PATCH; v++) nv += au <= umax[v];
     return nv;
 }
+// SMEM: the patch sits in shared memory at a compile-time pitch — fully unrolled, every row offset an LDS immediate.
+template <bool SMEM = false>
 static __device__ __forceinline__ float warp_ic_angle(const uint8_t *center, int pitch, int nv, int lane) {
     int m10 = 0, m01 = 0;
     if (nv >= 0) {
         const int u = lane - SB_HALF_PATCH;
         const uint8_t *pu = center + u, *pd = pu;
         int col = pu[0];
+        if (SMEM) {
+#pragma unroll
+            for (int v = 1; v <= SB_HALF_PATCH; v++) {
+                if (v <= nv) {
+                    const int vp = pu[v * pitch], vm = pu[-v * pitch];
+                    col += vp + vm;
+                    m01 += v * (vp - vm);
+                }
+            }
+        } else {
 #pragma unroll 5
-        for (int v = 1; v <= SB_HALF_PATCH; v++) {
-            pu += pitch;
-            pd -= pitch;
-            if (v <= nv) {
-                const int vp = *pu, vm = *pd;
-                col += vp + vm;
-                m01 += v * (vp - vm);
+            for (int v = 1; v <= SB_HALF_PATCH; v++) {
+                pu += pitch;
+                pd -= pitch;
+                if (v <= nv) {
+                    const int vp = *pu, vm = *pd;
+                    col += vp + vm;
+                    m01 += v * (vp - vm);
+                }
             }
         }
         m10 = u * col;
@@ -833,7 +846,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
         const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;
         uint8_t *buf = patches + i * DESC_PBYTES;
         sb_mbar_wait(&bars[i], 0);
-        const float angle = warp_ic_angle(buf + (DESC_DUAL ? DESC_CBYTES : 0) + SB_HALF_PATCH * DESC_AW + SB_HALF_PATCH + ((x - SB_HALF_PATCH) & 15), DESC_AW, nv, lane);
+        const float angle = warp_ic_angle<true>(buf + (DESC_DUAL ? DESC_CBYTES : 0) + SB_HALF_PATCH * DESC_AW + SB_HALF_PATCH + ((x - SB_HALF_PATCH) & 15), DESC_AW, nv, lane);
         if (lane == 0) s_ang[i] = angle;
         if (!DESC_DUAL && a.desc) {
             __syncwarp();  // every lane has read the disc
