@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -101,4 +103,12 @@ extern "C" int sb_host_free(void *ptr) {
     SB_NVTX_FN();
     if (ptr) cudaFreeHost(ptr);
     return SB_OK;
+}
+
+bool sb_pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("SLAMB200_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
 }

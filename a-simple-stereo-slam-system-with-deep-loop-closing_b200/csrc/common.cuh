@@ -65,7 +65,35 @@ int sb_make_tensor_map_u8(CUtensorMap *map, const void *base, int rank, const ui
 int sb_make_tensor_map_u8_sw128(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
                                 const uint64_t *strides_bytes, const uint32_t *box);
 
+// Programmatic dependent launch (SLAMB200_NO_PDL=1 turns it off for A/B runs)
+bool sb_pdl_enabled();
+
 #ifdef __CUDACC__
+// ---- programmatic dependent launch ---------------------------------------------------------------
+// The kernels of one extraction follow one another on a stream, each needing ALL of its predecessor's output.  Launched
+// with the programmatic-stream-serialisation attribute, a kernel's CTAs are scheduled while the predecessor's last wave
+// is still running and block in griddepcontrol.wait (first statement of the kernel) until that grid has completed and its
+// writes are visible: the launch latency and the ramp of the block scheduler disappear behind the predecessor's tail.
+// Every kernel lets ITS dependent start launching as soon as all of its own CTAs are resident.  Without the attribute
+// both instructions are no-ops.
+static __device__ __forceinline__ void sb_pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = sb_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 // ---- mbarrier + TMA (cp.async.bulk.tensor) -------------------------------------------------------
 static __device__ __forceinline__ uint32_t sb_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

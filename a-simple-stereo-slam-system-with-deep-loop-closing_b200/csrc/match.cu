@@ -40,22 +40,33 @@ struct sb_matcher {
 
 // Expanded operand rows: xq / xt [set][rows_pad][256] bytes (0/1), rows >= n are zero;
 // tkey[set][rows_pad] = (|t| + 512) << 22 | index  (0xffffffff for rows >= nt);  pq[set][rows_pad] = |q|.
-__global__ void __launch_bounds__(256) k_expand(const uint8_t *__restrict__ src, long long set_stride,
-                                               const int32_t *__restrict__ n_arr, int n_stride, int max_rows, int rows_pad,
-                                               uint8_t *__restrict__ dst, uint32_t *__restrict__ tkey, int32_t *__restrict__ pq,
-                                               uint32_t *__restrict__ init_key, long long init_stride) {
+struct ExpandSide {
+    const uint8_t *src;
+    long long set_stride;
+    const int32_t *n_arr;
+    int n_stride;
+    uint8_t *dst;
+    uint32_t *tkey;      // train side only
+    int32_t *pq;         // query side only
+    uint32_t *init_key;  // query side only: the atomicMin target of the query row
+    long long init_stride;
+};
+// blockIdx.z = 0: query sets, 1: train sets (one launch for both)
+__global__ void __launch_bounds__(256) k_expand(ExpandSide sq, ExpandSide st, int max_rows, int rows_pad) {
+    sb_pdl_enter();
+    const ExpandSide &S = blockIdx.z ? st : sq;
     const int set = blockIdx.y;
-    const int n = min(n_arr[(long long)set * n_stride], max_rows);
+    const int n = min(S.n_arr[(long long)set * S.n_stride], max_rows);
     const int row = blockIdx.x * 32 + (threadIdx.x >> 3), part = threadIdx.x & 7;  // 8 threads per row, one 32-bit word each
     if (row >= rows_pad) return;
     uint32_t w = 0;
-    if (row < n) w = reinterpret_cast<const uint32_t *>(src + (long long)set * set_stride + (long long)row * 32)[part];
+    if (row < n) w = reinterpret_cast<const uint32_t *>(S.src + (long long)set * S.set_stride + (long long)row * 32)[part];
     uint4 lo, hi;  // bits 0..15 and 16..31 of the word as 0/1 bytes
     lo.x = ((w >> 0) & 0xfu) * 0x00204081u & 0x01010101u;  lo.y = ((w >> 4) & 0xfu) * 0x00204081u & 0x01010101u;
     lo.z = ((w >> 8) & 0xfu) * 0x00204081u & 0x01010101u;  lo.w = ((w >> 12) & 0xfu) * 0x00204081u & 0x01010101u;
     hi.x = ((w >> 16) & 0xfu) * 0x00204081u & 0x01010101u; hi.y = ((w >> 20) & 0xfu) * 0x00204081u & 0x01010101u;
     hi.z = ((w >> 24) & 0xfu) * 0x00204081u & 0x01010101u; hi.w = ((w >> 28) & 0xfu) * 0x00204081u & 0x01010101u;
-    uint4 *d = reinterpret_cast<uint4 *>(dst + ((long long)set * rows_pad + row) * 256 + part * 32);
+    uint4 *d = reinterpret_cast<uint4 *>(S.dst + ((long long)set * rows_pad + row) * 256 + part * 32);
     d[0] = lo;
     d[1] = hi;
     int pc = __popc(w);
@@ -63,15 +74,16 @@ __global__ void __launch_bounds__(256) k_expand(const uint8_t *__restrict__ src,
     pc += __shfl_xor_sync(0xffffffffu, pc, 2);
     pc += __shfl_xor_sync(0xffffffffu, pc, 4);
     if (part == 0) {
-        if (tkey) tkey[(long long)set * rows_pad + row] = row < n ? (((uint32_t)pc + 512u) << MATCH_KEY_SHIFT) | (uint32_t)row : 0xffffffffu;
-        if (pq) pq[(long long)set * rows_pad + row] = pc;
-        if (init_key && row < n) init_key[(long long)set * init_stride + row] = 0xffffffffu;  // the atomicMin target of the query row
+        if (S.tkey) S.tkey[(long long)set * rows_pad + row] = row < n ? (((uint32_t)pc + 512u) << MATCH_KEY_SHIFT) | (uint32_t)row : 0xffffffffu;
+        if (S.pq) S.pq[(long long)set * rows_pad + row] = pc;
+        if (S.init_key && row < n) S.init_key[(long long)set * S.init_stride + row] = 0xffffffffu;
     }
 }
 
 // key -> (train index, distance = |q| + (key >> 22) - 512)
 __global__ void k_hamming_decode(const int32_t *__restrict__ nq_arr, int nq_stride, int max_rows, int rows_pad,
                                  const int32_t *__restrict__ pq, int32_t *idx_key, int32_t *out_dist, long long out_stride) {
+    sb_pdl_enter();
     const int set = blockIdx.y, qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= min(nq_arr[(long long)set * nq_stride], max_rows)) return;
     const uint32_t key = (uint32_t)idx_key[(long long)set * out_stride + qi];
@@ -122,6 +134,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) k_hamming_umma(const __grid_con
                                                                int nq_stride, const int32_t *__restrict__ nt_arr, int nt_stride,
                                                                int max_rows, int rows_pad, uint32_t *__restrict__ out_key,
                                                                long long out_stride, int nslices) {
+    sb_pdl_enter();
     extern __shared__ uint8_t um_raw[];
     __shared__ __align__(8) uint64_t a_full, b_full[UM_BST], b_empty[UM_BST], acc_full[UM_AST], acc_empty[UM_AST];
     __shared__ uint32_t tmem_slot;
@@ -321,19 +334,17 @@ extern "C" int sb_hamming_match_dev(sb_matcher_t *m, int batch, const uint8_t *d
     SB_TRY(sb_use_device(m->device));
     SB_REQUIRE(batch <= m->max_batch && max_rows <= m->max_rows, "batch / max_rows larger than given at create time");
     const int rp = m->rows_pad;
-    k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_q, q_set_stride, d_nq, nq_stride, max_rows, rp, m->d_xq, nullptr, m->d_pq,
-                                                                    reinterpret_cast<uint32_t *>(d_train_idx), out_stride);
-    k_expand<<<dim3(sb_div_up(rp, 32), batch), 256, 0, m->stream>>>(d_t, t_set_stride, d_nt, nt_stride, max_rows, rp, m->d_xt, m->d_tkey, nullptr,
-                                                                    nullptr, 0);
+    const ExpandSide sq = {d_q, q_set_stride, d_nq, nq_stride, m->d_xq, nullptr, m->d_pq, reinterpret_cast<uint32_t *>(d_train_idx), out_stride};
+    const ExpandSide st = {d_t, t_set_stride, d_nt, nt_stride, m->d_xt, m->d_tkey, nullptr, nullptr, 0};
+    SB_CUDA(sb_launch_pdl(k_expand, dim3(sb_div_up(rp, 32), batch, 2), dim3(256), 0, m->stream, sq, st, max_rows, rp));
     // enough CTAs to fill 148 SMs: slice the train set when the batch alone does not
     const int qblocks = sb_div_up(max_rows, UM_M);
     int nslices = 1;  // one CTA per SM (160 KB of shared memory, all of TMEM)
     while (nslices < 16 && (long long)qblocks * batch * nslices < 148 && max_rows / (nslices * 2) >= UM_N) nslices *= 2;
-    k_hamming_umma<<<dim3(qblocks, nslices, batch), UM_THREADS, UM_SMEM, m->stream>>>(
-        m->map_q, m->map_t, m->d_tkey, d_nq, nq_stride, d_nt, nt_stride, max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx),
-        out_stride, nslices);
-    k_hamming_decode<<<dim3(sb_div_up(max_rows, 256), batch), 256, 0, m->stream>>>(d_nq, nq_stride, max_rows, rp, m->d_pq, d_train_idx,
-                                                                                   d_dist, out_stride);
+    SB_CUDA(sb_launch_pdl(k_hamming_umma, dim3(qblocks, nslices, batch), dim3(UM_THREADS), UM_SMEM, m->stream, m->map_q, m->map_t, m->d_tkey, d_nq,
+                          nq_stride, d_nt, nt_stride, max_rows, rp, reinterpret_cast<uint32_t *>(d_train_idx), out_stride, nslices));
+    SB_CUDA(sb_launch_pdl(k_hamming_decode, dim3(sb_div_up(max_rows, 256), batch), dim3(256), 0, m->stream, d_nq, nq_stride, max_rows, rp, m->d_pq,
+                          d_train_idx, d_dist, out_stride));
     SB_CUDA(cudaGetLastError());
     return SB_OK;
 }

@@ -86,6 +86,7 @@ struct TmaMaps {
 // 16 bytes and funnel-shifts them into place; bytes past the row end are zeroed (they land in the pitch padding).
 __global__ void __launch_bounds__(256) k_copy_level0(const uint8_t *__restrict__ src, long long src_img_pitch, int stride, int w, int h,
                                                     uint8_t *__restrict__ dst, long long slab, int pitch, int batch) {
+    sb_pdl_enter();
     const int p16 = pitch >> 4;
     const long long total = (long long)batch * h * p16;
     const uint8_t *src_end = src + (long long)(batch - 1) * src_img_pitch + (long long)(h - 1) * stride + w;
@@ -151,6 +152,7 @@ __global__ void k_fill_level0(uint8_t *dst, long long slab, int pitch, int h, in
 // funnel shift brings (S[sx], S[sx+1]) into the low bytes and one DP2A forms S[sx] * c0 + S[sx+1] * c1.
 __global__ void __launch_bounds__(256) k_resize(uint8_t *__restrict__ pyr, long long slab, LevelGeom src, LevelGeom dst,
                                                const int2 *__restrict__ xtab, const int2 *__restrict__ ytab) {
+    sb_pdl_enter();
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     if (x0 >= dst.w) return;
@@ -202,6 +204,7 @@ struct __align__(16) ResizeQuad {
 #define RESIZE_ROWS 4
 __global__ void __launch_bounds__(256) k_resize_quads(uint8_t *__restrict__ pyr, long long slab, LevelGeom src, LevelGeom dst,
                                                      const ResizeQuad *__restrict__ qtab, const int2 *__restrict__ ytab, int nquads) {
+    sb_pdl_enter();
     const int q = blockIdx.x * 32 + threadIdx.x;
     if (q >= nquads) return;
     const int4 t0 = __ldg(reinterpret_cast<const int4 *>(qtab + q));
@@ -267,6 +270,7 @@ struct FastArgs {
 
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(const __grid_constant__ TmaMaps maps,
                                                             const __grid_constant__ Geom g, FastArgs a) {
+    sb_pdl_enter();
     // dynamic shared memory: [tile | response plane | maxima list | candidate-pixel list]; the array keeps its
     // shared address space through plain pointer arithmetic (an integer round trip would demote every
     // access to generic LD/ST with 64-bit address math)
@@ -509,6 +513,7 @@ static size_t qt_smem_bytes(int ncap) {
 }
 
 __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__ Geom g, QtArgs a) {
+    sb_pdl_enter();
     extern __shared__ __align__(16) uint8_t smem[];
     const int level = blockIdx.x, img = blockIdx.y;
     const LevelGeom &L = g.lv[level];
@@ -794,6 +799,7 @@ struct DescArgs {
 __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_constant__ TmaMaps pmaps,
                                                              const __grid_constant__ TmaMaps bmaps,
                                                              const __grid_constant__ Geom g, DescArgs a) {
+    sb_pdl_enter();
     extern __shared__ __align__(128) uint8_t patches[];  // [DESC_KPB][DESC_PBYTES]
     __shared__ float4 pat[256];
     __shared__ float s_ang[DESC_KPB], s_cos[DESC_KPB], s_sin[DESC_KPB];
@@ -1503,7 +1509,7 @@ static int launch_pyramid(sb_orb *h, uint8_t *pyr, const uint8_t *d_img, long lo
     const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
     prof_begin(h, SB_STAGE_COPY, 1, h->stream);
     if (d_img)
-        k_copy_level0<<<blocks, 256, 0, h->stream>>>(d_img, img_pitch, stride, L0.w, L0.h, pyr, g.slab, L0.pitch, batch);
+        SB_CUDA(sb_launch_pdl(k_copy_level0, dim3(blocks), dim3(256), 0, h->stream, d_img, img_pitch, stride, L0.w, L0.h, pyr, g.slab, L0.pitch, batch));
     else
         k_fill_level0<<<blocks, 256, 0, h->stream>>>(pyr, g.slab, L0.pitch, L0.h, batch);
     prof_end(h, h->stream);
@@ -1513,10 +1519,10 @@ static int launch_pyramid(sb_orb *h, uint8_t *pyr, const uint8_t *d_img, long lo
         if (D.qtab >= 0) {
             const int nq = sb_div_up(D.w, 4);
             dim3 grid(sb_div_up(nq, 32), sb_div_up(D.h, 8 * RESIZE_ROWS), batch);
-            k_resize_quads<<<grid, dim3(32, 8), 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_qtab + D.qtab, h->d_ytab, nq);
+            SB_CUDA(sb_launch_pdl(k_resize_quads, grid, dim3(32, 8), 0, h->stream, pyr, g.slab, g.lv[l - 1], D, h->d_qtab + D.qtab, h->d_ytab, nq));
         } else {
             dim3 grid(sb_div_up(sb_div_up(D.w, 4), 256), D.h, batch);
-            k_resize<<<grid, 256, 0, h->stream>>>(pyr, g.slab, g.lv[l - 1], D, h->d_xtab, h->d_ytab);
+            SB_CUDA(sb_launch_pdl(k_resize, grid, dim3(256), 0, h->stream, pyr, g.slab, g.lv[l - 1], D, h->d_xtab, h->d_ytab));
         }
     }
     if (nlevels_to_build > 1) prof_end(h, h->stream);
@@ -1539,7 +1545,6 @@ static int launch_blur(sb_orb *h, int batch, cudaStream_t s);
 // kernel, so that it fills the issue slots the latency-bound quadtree leaves idle (FAST itself is issue bound).
 static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool detect_only, bool blur_beside_quadtree = false) {
     const int nl = h->nlevels;
-    SB_CUDA(cudaMemsetAsync(h->d_cand_cnt, 0, (size_t)batch * nl * 4, h->stream));
     FastArgs fa;
     fa.groups = h->d_cells;
     fa.mask_pyr = use_mask ? h->d_mask : nullptr;
@@ -1558,7 +1563,7 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     const int ncells = detect_only ? h->n_cells_l0 : h->n_cells;
     const size_t fsmem = fast_smem_bytes(h);
     prof_begin(h, SB_STAGE_FAST, 1, h->stream);
-    k_fast_cells<<<dim3(ncells, batch), FAST_THREADS, fsmem, h->stream>>>(h->fast_maps, h->geom, fa);
+    SB_CUDA(sb_launch_pdl(k_fast_cells, dim3(ncells, batch), dim3(FAST_THREADS), fsmem, h->stream, h->fast_maps, h->geom, fa));
     prof_end(h, h->stream);
     if (blur_beside_quadtree) {
         SB_CUDA(cudaEventRecord(h->ev_fork, h->stream));
@@ -1577,7 +1582,7 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     qa.candcap_smem = SB_CAND_CAP;
     qa.N_override = detect_only ? h->nfeatures : 0;
     prof_begin(h, SB_STAGE_QUADTREE, 1, h->stream);
-    k_quadtree<<<dim3(detect_only ? 1 : nl, batch), QT_THREADS, qt_smem_bytes(qa.ncap), h->stream>>>(h->geom, qa);
+    SB_CUDA(sb_launch_pdl(k_quadtree, dim3(detect_only ? 1 : nl, batch), dim3(QT_THREADS), qt_smem_bytes(qa.ncap), h->stream, h->geom, qa));
     prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -1617,6 +1622,9 @@ extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8
     SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
     SB_REQUIRE(d_img && d_kps && d_counts, "null device pointer");
     SB_REQUIRE(!d_mask || mstride >= w, "bad mask stride");
+    // (the candidate counters are reset here, not between the pyramid and FAST: the kernels then follow one another without
+    //  a memset node in between, which programmatic dependent launch needs)
+    SB_CUDA(cudaMemsetAsync(h->d_cand_cnt, 0, (size_t)batch * h->nlevels * 4, h->stream));
     SB_TRY(launch_pyramid(h, h->d_pyr, d_img, img_pitch_bytes, stride, batch, h->nlevels));
     if (d_mask) {
         SB_TRY(ensure_mask_buffer(h));
@@ -1639,8 +1647,8 @@ extern "C" int sb_orb_detect_and_compute_dev(sb_orb_t *h, int batch, const uint8
     da.selcap = h->selcap;
     da.cap = cap;
     prof_begin(h, SB_STAGE_DESCRIBE, 1, h->stream);
-    k_describe<<<dim3(sb_div_up(h->ncap_pyr, DESC_KPB), h->nlevels, batch), DESC_WARPS * 32, DESC_KPB * DESC_PBYTES, h->stream>>>(
-        h->desc_pyr_maps, h->desc_blur_maps, h->geom, da);
+    SB_CUDA(sb_launch_pdl(k_describe, dim3(sb_div_up(h->ncap_pyr, DESC_KPB), h->nlevels, batch), dim3(DESC_WARPS * 32), DESC_KPB * DESC_PBYTES,
+                          h->stream, h->desc_pyr_maps, h->desc_blur_maps, h->geom, da));
     prof_end(h, h->stream);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
@@ -1654,6 +1662,7 @@ extern "C" int sb_orb_detect_dev(sb_orb_t *h, int batch, const uint8_t *d_img, i
     SB_TRY(check_shapes(h, batch, w, hgt, stride, cap));
     SB_REQUIRE(d_img && d_kps && d_counts, "null device pointer");
     SB_REQUIRE(!d_mask || mstride >= w, "bad mask stride");
+    SB_CUDA(cudaMemsetAsync(h->d_cand_cnt, 0, (size_t)batch * h->nlevels * 4, h->stream));
     SB_TRY(launch_pyramid(h, h->d_pyr, d_img, img_pitch_bytes, stride, batch, 1));
     if (d_mask) {
         SB_TRY(ensure_mask_buffer(h));

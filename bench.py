@@ -802,7 +802,7 @@ def main():
         stage_ms = {s: float(ms[i]) for i, s in enumerate(STAGES)}
         stage_ms["hamming_match"] = match_ms
         stage_launches = {s: int(launches[i]) for i, s in enumerate(STAGES)}
-        stage_launches["hamming_match"] = 4 * args.steps   # k_expand x 2, k_hamming_umma, k_hamming_decode
+        stage_launches["hamming_match"] = 3 * args.steps   # k_expand (both sides), k_hamming_umma, k_hamming_decode
         if with_ba:
             stage_ms["local_ba"] = ba_ms
             stage_launches["local_ba"] = args.steps

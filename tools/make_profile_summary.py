@@ -35,7 +35,7 @@ cols = [("gpu__time_duration.sum", "ms"), ("dram__bytes_read.sum", "MB rd"), ("d
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"), ("launch__registers_per_thread", "regs"),
         ("smsp__inst_executed.sum", "warp inst")]
-print(f"\nFull capture (`ncu --set full --clock-control none --import-source on -k regex:^k_(...) -s 51 -c 17`, one whole step; CSV of the raw page: "
+print(f"\nFull capture (`ncu --set full --clock-control none --import-source on -k regex:^k_(...) -s 48 -c 16`, one whole step; CSV of the raw page: "
       f"`{sys.argv[2].split('/')[-1]}`), per launch (128 images / 64 matching problems / 64 BA windows):\n")
 print("| kernel | " + " | ".join(c[1] for c in cols) + " |\n|" + "---|" * (len(cols) + 1))
 for row in r[2:]:

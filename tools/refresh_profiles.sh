@@ -13,7 +13,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/r2_bench_reference.js
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $O/r2_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/r2_launches_bench.log 2>&1
 K='^k_(ba_solve|copy_level0|resize_quads|fast_cells|blur|quadtree|describe|expand|hamming_umma|hamming_decode)$'
-ncu --set full --clock-control none --import-source on -k regex:"$K" -s 51 -c 17 -f -o $O/r2_full \
+ncu --set full --clock-control none --import-source on -k regex:"$K" -s 48 -c 16 -f -o $O/r2_full \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/r2_full.log 2>&1
 ncu -i $O/r2_full.ncu-rep --page raw --csv > $O/r2_ncu_full.csv 2> /dev/null
 python - <<'PY'
