@@ -520,16 +520,15 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    for e in exts:
-        lib.sb_orb_profile(e._h, 1)
+    # the timed region holds the kernels only: no per-stage events (an event record between two kernels also switches off
+    # their programmatic dependent launch); the stage times come from two short passes afterwards
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     main = torch.cuda.current_stream()
     e0.record(main)
     for st in sx + [b[2] for b in ba_set]:
         st.wait_stream(main)
     for i in range(args.steps):
-        step_dev(args.warmup + i, evs[i])
+        step_dev(args.warmup + i)
     for st in sx + [b[2] for b in ba_set]:
         main.wait_stream(st)
     e1.record(main)
@@ -538,6 +537,14 @@ def main():
     for e in exts:
         e.sync_status()
     dev_ms = e0.elapsed_time(e1)
+    # ---- concurrent stage pass: the same loop with the per-stage events on (both streams running, like the timed region)
+    CONC_STEPS = min(args.steps, 40)
+    for e in exts:
+        lib.sb_orb_profile(e._h, 1)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(CONC_STEPS)]
+    for i in range(CONC_STEPS):
+        step_dev(args.warmup + args.steps + i, evs[i])
+    barrier()
     ms = np.zeros(6, np.float32)
     launches = np.zeros(6, np.int32)
     for e in exts:
@@ -567,7 +574,7 @@ def main():
         lib.sb_orb_profile(e._h, 1)
     sev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(SER_STEPS)]
     for i in range(SER_STEPS):
-        step_dev(args.warmup + args.steps + i, sev[i])
+        step_dev(args.warmup + args.steps + CONC_STEPS + i, sev[i])
         torch.cuda.synchronize()
     ser_ms = {}
     ms_s = np.zeros(6, np.float32)
@@ -799,12 +806,12 @@ def main():
     e2e_value = frames / (e2e_ms_max * 1e-3)
 
     if rank == 0:
-        stage_ms = {s: float(ms[i]) for i, s in enumerate(STAGES)}
-        stage_ms["hamming_match"] = match_ms
-        stage_launches = {s: int(launches[i]) for i, s in enumerate(STAGES)}
+        stage_ms = {s: float(ms[i]) * args.steps / CONC_STEPS for i, s in enumerate(STAGES)}      # scaled to the timed region's steps
+        stage_ms["hamming_match"] = match_ms * args.steps / CONC_STEPS
+        stage_launches = {s: int(launches[i]) * args.steps // CONC_STEPS for i, s in enumerate(STAGES)}
         stage_launches["hamming_match"] = 3 * args.steps   # k_expand (both sides), k_hamming_umma, k_hamming_decode
         if with_ba:
-            stage_ms["local_ba"] = ba_ms
+            stage_ms["local_ba"] = ba_ms * args.steps / CONC_STEPS
             stage_launches["local_ba"] = args.steps
 
         def abytes(k):
@@ -847,7 +854,7 @@ def main():
         roofline["stage_ms_per_step_concurrent"] = {k: v / args.steps for k, v in stage_ms.items()}
         roofline["stage_gbs_serialised"] = {k: abytes(k) / (ser[k] * 1e-3) / 1e9 for k in ser if ser[k] > 0}
         roofline["note"] = ("serialised = each stream run alone after the timed region (CUDA events on the launching stream, "
-                            f"{SER_STEPS} steps); concurrent = inside the timed region, where the BA stream and the extract stream overlap")
+                            f"{SER_STEPS} steps); concurrent = a pass of {CONC_STEPS} steps right after the timed region with the BA stream and the extract stream overlapping as in it (the timed region itself carries no per-stage events)")
         roofline_extract = hbm_entry(top_extract)
         out = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
