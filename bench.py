@@ -459,7 +459,7 @@ def main():
     exts = [pkg.ORBextractor(*ORB_PARAMS, max_w=W, max_h=H, max_batch=2 * B, device=local_rank) for _ in range(NH)]
     mats = [pkg.HammingMatcher(max_batch=B, max_rows=exts[0].cap, device=local_rank) for _ in range(NH)]
     ba = pkg.LocalBA(max_windows=B, device=local_rank, **BA_CAPS)
-    NBA = int(os.environ.get("BENCH_BA_STREAMS", "1"))   # back-end batches in flight (each on its own stream and buffers)
+    NBA = int(os.environ.get("BENCH_BA_STREAMS", "2"))   # back-end batches in flight (each on its own stream and buffers)
     for k in range(NH):
         exts[k].set_stream(sx[k].cuda_stream)
         mats[k].set_stream(sx[k].cuda_stream)
