@@ -51,4 +51,4 @@ for row in r[2:]:
         vals.append(v)
     print("| " + row[h.index("Kernel Name")].split("(")[0] + " | " + " | ".join(vals) + " |")
 print("\nSASS evidence (cuobjdump -sass libslamb200.so): `UTCIMMA` (tcgen05.mma kind::i8), `UTMALDG.2D` (TMA), `LDTM.x32` (tcgen05.ld), "
-      "`UTCBAR` (tcgen05.commit) in `k_hamming_umma`; `UTMALDG.3D` in `k_fast_cells` and `k_blur`.")
+      "`UTCBAR` (tcgen05.commit) in `k_hamming_umma`; `UTMALDG.3D` in `k_fast_cells`, `k_blur` and `k_describe` (per-keypoint patch boxes); `ACQBULK` (griddepcontrol.wait) and `PREEXIT` (griddepcontrol.launch_dependents) at the top of every extract / match kernel (programmatic dependent launch).")
