@@ -32,15 +32,10 @@
 #define FAST_THREADS 256
 #define QT_THREADS 256
 #define BLUR_TW 128
-#ifndef BLUR_TH
-#define BLUR_TH 64  // 128 x 64 outputs per CTA (32 rows: 176 -> 183 us per 128 pyramids ... see DESIGN)
-#endif
+#define BLUR_TH 32
 #define BLUR_HX 16   // left halo: the innermost TMA coordinate must be a multiple of 16 bytes (measured: tools/tma_probe.cu)
 #define BLUR_BW 160  // BLUR_HX + BLUR_TW + 3, rounded up to the 16-byte TMA granule
-#define BLUR_BH (BLUR_TH + 6)
-#ifndef BLUR_MINB
-#define BLUR_MINB 6
-#endif
+#define BLUR_BH 38
 #define DESC_WARPS 8
 #define SB_PROF_MAX 8192
 
@@ -568,7 +563,7 @@ struct BlurArgs {
     long long slab;
 };
 
-__global__ void __launch_bounds__(256, BLUR_MINB) k_blur(const __grid_constant__ TmaMaps maps, const __grid_constant__ Geom g,
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ TmaMaps maps, const __grid_constant__ Geom g,
                                              BlurArgs a) {
     __shared__ __align__(128) uint8_t tile[BLUR_BH * BLUR_BW];
     __shared__ __align__(16) uint16_t hrow[BLUR_BH * BLUR_TW];
@@ -630,10 +625,9 @@ __global__ void __launch_bounds__(256, BLUR_MINB) k_blur(const __grid_constant__
     // vertical pass: a thread owns 4 columns x 4 output rows (10 input rows).  Vertically adjacent 16-bit row sums of one
     // column are paired in a word (PRMT) so that a 7-tap column is four DP2As against the byte pairs (18, 34), (48, 56),
     // (48, 34), (18, 0); output rows 0 / 2 use the pairs that start on even input rows, rows 1 / 3 those on odd rows.
-#pragma unroll 1
-    for (int half = 0; half < BLUR_TH / 32; half++) {
+    {
         const int gq = tid & 31, seg = tid >> 5;
-        const int ry0 = half * 32 + seg * 4;
+        const int ry0 = seg * 4;
         if (y0 + ry0 < L.h && x0 + 4 * gq < L.w) {
             uint2 u[10];
 #pragma unroll
