@@ -825,17 +825,14 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
     if (nk <= 0) return;
     const LevelGeom &L = g.lv[level];
     const uint32_t *sel = a.sel + ((long long)img * a.nlevels + level) * a.selcap + k0;
-    // every warp owns the barriers and buffers of its keypoints (i = warp, warp + 8, ...): no block-wide hand-over
-    if (lane == 0)
-        for (int i = warp; i < nk; i += DESC_WARPS) {
-            sb_mbar_init(&bars[i], 1);
-            if (DESC_DUAL) sb_mbar_init(&bars2[i], 1);
-        }
-    __syncwarp();
+    // every warp owns the barriers and buffers of its keypoints (i = warp, warp + 8, ...): no block-wide hand-over; lane 0
+    // initialises a barrier and requests the box in one go, the other lanes first touch it after the __syncwarp below
     for (int i = warp; i < nk; i += DESC_WARPS) {
         const uint32_t w = sel[i];
         const int x = (int)(w & 0xfff) + SB_EDGE - 3, y = (int)((w >> 12) & 0xfff) + SB_EDGE - 3;  // :895-896
         if (lane == 0) {
+            sb_mbar_init(&bars[i], 1);
+            if (DESC_DUAL) sb_mbar_init(&bars2[i], 1);
             sb_mbar_expect_tx(&bars[i], DESC_AW * DESC_AH);
             sb_tma_load_3d(patches + i * DESC_PBYTES + (DESC_DUAL ? DESC_CBYTES : 0), &pmaps.m[level], (x - SB_HALF_PATCH) & ~15, y - SB_HALF_PATCH, img, &bars[i]);
             if (DESC_DUAL && a.desc) {
@@ -844,6 +841,7 @@ __global__ void __launch_bounds__(DESC_WARPS * 32) k_describe(const __grid_const
             }
         }
     }
+    __syncwarp();
     load_pattern(pat);
     // phase A: orientation, one warp per keypoint; the buffer is then refilled with the blurred sampling window
     const int nv = ic_rows(g.umax, lane);

@@ -11,6 +11,20 @@ if which in ("all", "orb"):
     fe = pkg.StereoFrontend(2000, 1.2, 8, 20, 7, max_pairs=1)
     out = fe.extract_match(frames)
     print("stereo", out["counts"].tolist(), int((out["mdist"][0, :out["counts"][0, 0]] <= 30).sum()))
+    # low contrast: cells whose maxima stay below iniTh -> the second FAST tier (minTh) with its TMA re-fetch of the tile
+    flat = (frames // 6 + 100).astype(np.uint8)
+    out = fe.extract_match(flat)
+    print("stereo, low contrast", out["counts"].tolist())
+    # two handles with their kernels on one shared stream (sb_stereo_set_compute_stream), copies on their own
+    import torch
+    shared = torch.cuda.Stream()
+    fe2 = pkg.StereoFrontend(2000, 1.2, 8, 20, 7, max_pairs=1)
+    o1, o2 = fe.alloc_outputs(1, pinned=True), fe2.alloc_outputs(1, pinned=True)
+    pin = torch.from_numpy(np.stack([frames, flat])).pin_memory().numpy()
+    for h_ in (fe, fe2):
+        h_.set_compute_stream(shared.cuda_stream)
+    fe.submit(pin[0], o1); fe2.submit(pin[1], o2); fe.wait(); fe2.wait()
+    print("stereo, shared kernel stream", o1["counts"].tolist(), o2["counts"].tolist())
     ext = pkg.ORBextractor(300, 1.2, 8, 20, 7)
     mask = np.full(frames[0, 0].shape, 255, np.uint8); mask[100:200, 300:600] = 0
     k = ext.Detect(frames[0, 0], mask)
