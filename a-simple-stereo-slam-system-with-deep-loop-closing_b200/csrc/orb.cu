@@ -495,8 +495,16 @@ struct QtArgs {
     int *sel_cnt;    // [batch][nlevels]
     int nlevels, selcap, ncap, candcap_smem;
     int N_override;  // > 0: Detect() — level 0 with N = nfeatures
+    uint8_t *spill;  // [batch][nlevels][SB_CAND_CAP * 3]: candidate state of the slots with more than QT_CAND_SMEM candidates
 };
 
+// Candidates whose per-candidate state (node position, quadrant: 3 bytes) lives in shared memory.  A level of a KITTI-sized
+// frame has 1 000 - 4 000 candidates; sizing the arrays for the hard cap of 16 384 cost 48 KB per CTA — three quadtree CTAs
+// then fill an SM and starve the blur that runs beside them (blur + quadtree window 0.255 -> 0.235 ms).  A (image, level)
+// with more candidates keeps that state in a global scratch area instead (same code, generic pointers).
+#ifndef QT_CAND_SMEM
+#define QT_CAND_SMEM 6144
+#endif
 static size_t qt_smem_bytes(int ncap) {
     int P = 1;
     while (P < ncap) P <<= 1;
@@ -507,12 +515,12 @@ static size_t qt_smem_bytes(int ncap) {
     b += 5 * (size_t)ncap * 4;       // ord cpre spre cbase ubase
     b += 2 * (size_t)ncap * 8;       // boxes
     b += 2 * (size_t)ncap * 2;       // counts
-    b += (size_t)SB_CAND_CAP * 2;    // cnode
-    b += (size_t)SB_CAND_CAP;        // cq
+    b += (size_t)QT_CAND_SMEM * 2;    // cnode
+    b += (size_t)QT_CAND_SMEM;        // cq
     return b + 64;
 }
 
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__ Geom g, QtArgs a) {
+__global__ void __launch_bounds__(QT_THREADS, 5) k_quadtree(const __grid_constant__ Geom g, QtArgs a) {
     sb_pdl_enter();
     extern __shared__ __align__(16) uint8_t smem[];
     const int level = blockIdx.x, img = blockIdx.y;
@@ -536,7 +544,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
     c.box[1] = reinterpret_cast<int16_t *>(p); p += (size_t)ncap * 8;
     c.cnt[0] = reinterpret_cast<uint16_t *>(p); p += (size_t)ncap * 2;
     c.cnt[1] = reinterpret_cast<uint16_t *>(p); p += (size_t)ncap * 2;
-    c.cnode = reinterpret_cast<uint16_t *>(p); p += (size_t)SB_CAND_CAP * 2;
+    c.cnode = reinterpret_cast<uint16_t *>(p); p += (size_t)QT_CAND_SMEM * 2;
     c.cq = p;
     c.cand = a.cand + (long long)slot * SB_CAND_CAP;
     c.n = min(a.cand_cnt[slot], SB_CAND_CAP);
@@ -547,7 +555,17 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(const __grid_constant__
     c.nCols = L.nCols;
     c.wCell = L.wCell;
     c.hCell = L.hCell;
-    const int S = qt_distribute(c, a.sel + (long long)slot * a.selcap, a.selcap);
+    int S;
+    if (c.n > QT_CAND_SMEM) {  // rare: this CTA's candidate state goes to its slot of the global scratch area.  Two inlined copies
+                               // of the pass code, so that the common one keeps its shared-memory addressing (one copy on generic
+                               // pointers: 48 -> 60 registers and the blur + quadtree window back at 0.259 ms)
+        uint8_t *gs = a.spill + (size_t)slot * ((size_t)SB_CAND_CAP * 3);
+        c.cnode = reinterpret_cast<uint16_t *>(gs);
+        c.cq = gs + (size_t)SB_CAND_CAP * 2;
+        S = qt_distribute(c, a.sel + (long long)slot * a.selcap, a.selcap);
+    } else {
+        S = qt_distribute(c, a.sel + (long long)slot * a.selcap, a.selcap);
+    }
     if (threadIdx.x == 0) a.sel_cnt[slot] = min(S, a.selcap);
 }
 
@@ -1031,6 +1049,7 @@ struct sb_orb {
     ResizeQuad *d_qtab;
     uint32_t *d_cand, *d_sel;
     int *d_cand_cnt, *d_sel_cnt, *d_flags;
+    uint8_t *d_qt_spill;  // quadtree candidate state of crowded (image, level) slots
     int tab_cap, cell_cap, tile_cap;
     // staging for the host-pointer entry points
     uint8_t *d_in, *d_in_mask, *d_desc_out;
@@ -1074,7 +1093,7 @@ static void free_orb(sb_orb *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     void *ptrs[] = {h->d_pyr,  h->d_blur, h->d_mask,     h->d_cells,   h->d_tiles,   h->d_xtab,    h->d_ytab,    h->d_qtab,
-                    h->d_cand,     h->d_sel,     h->d_cand_cnt, h->d_sel_cnt, h->d_flags,
+                    h->d_cand,     h->d_sel,     h->d_cand_cnt, h->d_sel_cnt, h->d_flags, h->d_qt_spill,
                     h->d_in,   h->d_in_mask, h->d_desc_out, h->d_kps_out, h->d_counts_out, h->d_keep};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -1395,6 +1414,7 @@ extern "C" int sb_orb_create(sb_orb_t **out, int device, int nfeatures, float sc
     SB_ALLOC(h->d_ytab, (size_t)h->tab_cap * 8);
     SB_ALLOC(h->d_qtab, (size_t)h->tab_cap * sizeof(ResizeQuad));
     SB_ALLOC(h->d_cand, B * nlevels * SB_CAND_CAP * 4);
+    SB_ALLOC(h->d_qt_spill, B * nlevels * SB_CAND_CAP * 3);
     SB_ALLOC(h->d_sel, B * nlevels * h->selcap * 4);
     SB_ALLOC(h->d_cand_cnt, B * nlevels * 4);
     SB_ALLOC(h->d_sel_cnt, B * nlevels * 4);
@@ -1577,7 +1597,8 @@ static int launch_fast_and_quadtree(sb_orb *h, int batch, bool use_mask, bool de
     qa.nlevels = nl;
     qa.selcap = h->selcap;
     qa.ncap = detect_only ? h->ncap_detect : h->ncap_pyr;
-    qa.candcap_smem = SB_CAND_CAP;
+    qa.candcap_smem = QT_CAND_SMEM;
+    qa.spill = h->d_qt_spill;
     qa.N_override = detect_only ? h->nfeatures : 0;
     prof_begin(h, SB_STAGE_QUADTREE, 1, h->stream);
     SB_CUDA(sb_launch_pdl(k_quadtree, dim3(detect_only ? 1 : nl, batch), dim3(QT_THREADS), qt_smem_bytes(qa.ncap), h->stream, h->geom, qa));

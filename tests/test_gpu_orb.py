@@ -238,3 +238,23 @@ def test_low_texture_images_exercise_the_threshold_fallback(pkg, oracle):
     assert np.array_equal(gd, wd)
     assert 0 < len(gk) and (gk["response"] < 20).any() and (gk["response"] >= 20).any()
     g.close()
+
+
+def test_crowded_levels_keep_their_candidate_state_in_global_memory(pkg, oracle):
+    """A level with more candidates than the quadtree kernel keeps in shared memory (QT_CAND_SMEM = 6144, hard cap 16384):
+    levels 0 and 1 of a frame that is one third dense noise have about 12 000 and 7 000 — the spill path must give the
+    same keypoints as the oracle, next to ordinary levels in the same launch and next to an ordinary frame in the batch."""
+    rng = np.random.default_rng(5)
+    img = np.full((376, 1241), 120, np.uint8)
+    img[:, :434] = rng.integers(60, 200, (376, 434), dtype=np.uint8)
+    plain = np.ascontiguousarray(img[:, ::-1] // 2 + 60)
+    ext = pkg.ORBextractor(*PARAMS, max_w=1241, max_h=376, max_batch=2)
+    cpu = oracle.ORBextractor(*PARAMS)
+    got = ext.DetectAndComputeBatch([img, plain])
+    assert len(ext.debug_candidates(0, 0)) > 6144 and len(ext.debug_candidates(0, 1)) > 6144
+    assert len(ext.debug_candidates(0, 2)) < 6144
+    for (gk, gd), im in zip(got, (img, plain)):
+        wk, wd = cpu.DetectAndCompute(im)
+        assert_kps_equal(gk, wk)
+        assert np.array_equal(gd, wd)
+    ext.close()
