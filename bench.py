@@ -485,11 +485,20 @@ def main():
         ba_set.append((b_, {k: v.clone() for k, v in bd.items()}, s_))
     ba_bytes = int(bh["ne"].sum()) * (8 + 16 + 8 + 1) + int(bh["nl"].sum()) * (48 + 1) + int(bh["np"].sum()) * 112
 
+    # BA batch i starts with the extraction of step i: the BA stream waits for an event recorded on the extract stream at the start
+    # of the step.  Left alone, the BA stream runs steps ahead and overlaps with itself (128 SMs of BA, the extractor's latency-bound
+    # kernels squeezed onto 20); in lockstep its 64 whole-SM CTAs are placed while the short pyramid kernels run (40.7 k -> 43.0 k frames/s)
+    lockstep = os.environ.get("BENCH_BA_LOCKSTEP", "1") == "1"
+    ev_step = [torch.cuda.Event() for _ in range(4)]
+
     def step_dev(i, ev=None):
         off = (i * B) % P
         k = i % NH
         if with_ba:
             ba_, bd_, s_ = ba_set[i % len(ba_set)]
+            if lockstep:   # the BA batch of step i starts with the extraction of step i (not steps ahead of it)
+                ev_step[i % 4].record(sx[k])
+                s_.wait_event(ev_step[i % 4])
             with torch.cuda.stream(s_):
                 bd_["poses"].copy_(bd0["poses"], non_blocking=True)      # every step starts from the same windows
                 bd_["points"].copy_(bd0["points"], non_blocking=True)
@@ -661,8 +670,16 @@ def main():
             assert lib.sb_ba_wait(bas[k]._h) == 0, pkg.last_error()
             ba_pending[k] = False
 
+    # (the same lockstep between a BA batch and the front end's latest batch, through an event on the shared stream, was measured
+    #  here too: 41.7 k -> 39.0 k frames/s — the host already paces this loop; BENCH_E2E_LOCKSTEP=1 reproduces it)
+    e2e_lockstep = fe_shared and os.environ.get("BENCH_E2E_LOCKSTEP", "0") == "1"
+    ev_fe = [torch.cuda.Event() for _ in range(4)]
+    fe_marks = []                                   # events recorded on the shared front-end stream where a batch's kernels begin
+
     def ba_submit(k):
         ba_wait(k)                                  # this handle's previous batch (two steps ago): its results sit in the pinned buffers
+        if e2e_lockstep and fe_marks:               # start with the front end's latest batch, as in the device-resident loop
+            e2e_ba_streams[k].wait_event(fe_marks[-1])
         hbk, (c2, ol_, inf) = hbs[k], h_outs[k]
         hbk["poses"].copy_(hb0["poses"])
         hbk["points"].copy_(hb0["points"])
@@ -691,6 +708,10 @@ def main():
                 fes[k].wait()
             tc = time.perf_counter()
             off = (i * B) % hp
+            if e2e_lockstep:
+                ev_fe[i % 4].record(s_fe)           # fires when the previous batch's kernels are done = where this batch's begin
+                fe_marks.append(ev_fe[i % 4])
+                del fe_marks[:-1]
             fes[k].submit(host_np[off:off + B], outs[k])
             pending[k] = True
             td = time.perf_counter()
