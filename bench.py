@@ -449,9 +449,11 @@ def main():
     windows = [synth.ba_window(100 * rank + s) for s in range(n_uniq_w)]
     windows = [windows[i % n_uniq_w] for i in range(B)]
 
-    # Extractor + matcher on one stream, BA on a second one.  (NH = 2 alternates two handle pairs on two streams;
-    # measured gain 3 % — the kernels are issue-bound — at the price of smeared per-stage event times, so 1.)
-    NH = 1
+    # Extractor + matcher on one stream, BA on a second one.  Without BA (config 2) two handle pairs alternate on two streams: the
+    # latency-bound stretches of one batch (quadtree, the small pyramid levels, kernel tails) are filled by the other batch's
+    # kernels (57.6 k -> 60.9 k frames/s; the timed region carries no per-stage events, the serialised pass gives the stage times).
+    # Beside BA a second handle pair changes nothing (42.9 k either way): BA's CTAs already fill those stretches.
+    NH = int(os.environ.get("BENCH_EXT_HANDLES", "1" if with_ba else "2"))
     sx = [torch.cuda.Stream() for _ in range(NH)]
     # (BENCH_BA_PRIORITY=-1 gives the BA stream the higher priority: measured 39.0 k -> 36.0 k frames/s — a window's CTA needs a
     #  whole SM, and holding back the extractor's CTAs until 64 SMs have drained costs more SM-time than it saves)
@@ -886,7 +888,9 @@ def main():
                           "l2_policy": f"inputs larger than L2: {P * 2 * img_bytes / 1e6:.0f} MB pool of distinct frames cycled",
                           "keypoints_per_frame": n_kps / (2 * B), "matches_per_pair": n_matched / B,
                           "ba_obs_per_window": float(bh["ne"].mean()), "ba_lm_iterations_per_window": float(ba_info[:, 1].mean()),
-                          "sharding": "frames and windows round-robin by rank, no data-path collective"},
+                          "sharding": "frames and windows round-robin by rank, no data-path collective",
+                          "streams": (f"{NH} extract + match stream(s) (batches in flight), {len(ba_set) if with_ba else 0} BA stream(s)"
+                                      + (", BA batch i released at the start of extraction i" if with_ba and lockstep else ""))},
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": e2e_ms_max / args.steps,
