@@ -182,23 +182,31 @@ class ORBextractor:
         _check(lib().sb_orb_screen_params(self._h, _p(imgs[0]), w, h, w, _p(kin), len(kin), _p(out), C.byref(n_out)))
         return kin, out[:n_out.value].copy()
 
-    def ScreenAndDescribeBatch(self, images, kps_list):
+    def ScreenAndDescribeBatch(self, images, kps_list, n_in=None, copy=True):
         """sb_orb_screen_describe: ScreenAndComputeKPsParams + CalcDescriptors on the survivors for a batch of images.
-        -> list of (mutated input, surviving keypoints, descriptors) per image."""
+        -> list of (mutated input, surviving keypoints, descriptors) per image.  kps_list: a list of keypoint arrays, or — with
+        n_in — one packed [B, cap_in] array (no per-image packing); copy=False returns views into the batch arrays."""
         imgs, w, h = self._imgs(images)
         B = len(imgs)
-        cap_in = max(1, max(len(k) for k in kps_list))
-        kin = np.zeros((B, cap_in), KP_DTYPE)
-        n_in = np.zeros(B, np.int32)
-        for b, k in enumerate(kps_list):
-            kin[b, :len(k)] = k
-            n_in[b] = len(k)
-        out = np.zeros((B, cap_in), KP_DTYPE)
+        if n_in is None:
+            cap_in = max(1, max(len(k) for k in kps_list))
+            kin = np.zeros((B, cap_in), KP_DTYPE)
+            n_in = np.zeros(B, np.int32)
+            for b, k in enumerate(kps_list):
+                kin[b, :len(k)] = k
+                n_in[b] = len(k)
+        else:
+            kin = np.ascontiguousarray(kps_list, KP_DTYPE)
+            n_in = np.ascontiguousarray(n_in, np.int32)
+            cap_in = kin.shape[1]
+        out = np.empty((B, cap_in), KP_DTYPE)          # the library writes the first n_out[b] rows
         n_out = np.zeros(B, np.int32)
-        desc = np.zeros((B, cap_in, 32), np.uint8)
+        desc = np.empty((B, cap_in, 32), np.uint8)
         _check(lib().sb_orb_screen_describe(self._h, B, self._ptr_array(imgs), w, h, imgs[0].strides[0], _p(kin), _p(n_in), cap_in,
                                             _p(out), _p(n_out), _p(desc)))
-        return [(kin[b, :n_in[b]].copy(), out[b, :n_out[b]].copy(), desc[b, :n_out[b]].copy()) for b in range(B)]
+        if copy:
+            return [(kin[b, :n_in[b]].copy(), out[b, :n_out[b]].copy(), desc[b, :n_out[b]].copy()) for b in range(B)]
+        return [(kin[b, :n_in[b]], out[b, :n_out[b]], desc[b, :n_out[b]]) for b in range(B)]
 
     def CalcDescriptors(self, image, kps):
         imgs, w, h = self._imgs(image)

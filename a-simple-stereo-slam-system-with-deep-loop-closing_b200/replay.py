@@ -289,9 +289,11 @@ class GpuOps:
         """DeepLCD::calcDescrOriginalImg: returns descriptors; `lefts` come back blurred in place (quirk Q8)."""
         return self.net.calcDescrOriginalImgBatch(lefts, in_place=True)
 
-    def screen_and_describe(self, imgs, kins):
-        """ScreenAndComputeKPsParams + CalcDescriptors for a batch of keyframes (sb_orb_screen_describe) -> [(kps, desc)]."""
-        return [(kout, desc) for _, kout, desc in self.kf_ext.ScreenAndDescribeBatch(imgs, kins)]
+    def screen_and_describe(self, imgs, feats):
+        """src/loopclosing.cpp:94-113 for a batch of keyframes: every feature as a keypoint on each octave, then
+        ScreenAndComputeKPsParams + CalcDescriptors (sb_orb_screen_describe) -> [(kps, desc)]."""
+        kin, n_in = expand_octaves_batch(feats)
+        return [(kout, desc) for _, kout, desc in self.kf_ext.ScreenAndDescribeBatch(imgs, kin, n_in=n_in, copy=False)]
 
     # loop-closing stage ---------------------------------------------------------------------------------------------
     def lcd_add(self, kf_id, d):
@@ -344,6 +346,20 @@ def expand_octaves(feats, nlevels=8):
     kin["octave"] = np.tile(np.arange(nlevels), len(feats))
     kin["class_id"] = rep
     return kin
+
+
+def expand_octaves_batch(feats_list, nlevels=8):
+    """expand_octaves for a batch of keyframes, packed as the C ABI takes it: ([B, cap_in] keypoints, [B] counts)."""
+    n = np.array([len(f) for f in feats_list], np.int32) * nlevels
+    kin = np.zeros((len(feats_list), max(1, int(n.max()))), capi.KP_DTYPE)
+    for b, f in enumerate(feats_list):
+        row = kin[b, :n[b]].reshape(len(f), nlevels)
+        for name in ("x", "y", "size", "angle"):
+            row[name] = f[name][:, None]
+        row["response"] = -1
+        row["octave"] = np.arange(nlevels)[None, :]
+        row["class_id"] = np.arange(len(f))[:, None]
+    return kin, n
 
 
 def lap(t, key, t0):
@@ -440,7 +456,7 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
         tk = lap(t, "kf_lk_s", tk)
         descr = ops.cnn_descr(lefts)                    # blurs `lefts` in place: the ORB descriptors below see the blurred image
         tk = lap(t, "kf_cnn_s", tk)
-        described = ops.screen_and_describe(lefts, [expand_octaves(f) for f in feats])
+        described = ops.screen_and_describe(lefts, feats)
         tk = lap(t, "kf_screen_describe_s", tk)
         tri = ops.triangulate_batch(pts, [tr[0] for tr in tracked])
         tk = lap(t, "kf_triangulate_s", tk)

@@ -8,6 +8,18 @@ from oracle import pnp_oracle as PO
 from oracle import posegraph_oracle as PG
 
 
+def _expand_octaves(feats, kp_dtype, nlevels=8):
+    """Every feature as a keypoint on each octave, response -1, class_id = feature index (src/loopclosing.cpp:94-105)."""
+    kin = np.zeros(len(feats) * nlevels, kp_dtype)
+    rep = np.repeat(np.arange(len(feats)), nlevels)
+    for name in ("x", "y", "size", "angle"):
+        kin[name] = feats[name][rep]
+    kin["response"] = -1
+    kin["octave"] = np.tile(np.arange(nlevels), len(feats))
+    kin["class_id"] = rep
+    return kin
+
+
 class CpuOps:
     def __init__(self, synth, capi_kp_dtype, batch=8, kf_features=300, kf_batch=8):
         self.synth, self.batch, self.kf_batch = synth, batch, kf_batch
@@ -67,9 +79,10 @@ class CpuOps:
             out.append(np.asarray(d, np.float32).ravel())
         return np.stack(out)
 
-    def screen_and_describe(self, imgs, kins):
+    def screen_and_describe(self, imgs, feats):
         out = []
-        for img, kin in zip(imgs, kins):
+        for img, f in zip(imgs, feats):
+            kin = _expand_octaves(f, self.kp_dtype)      # src/loopclosing.cpp:94-105
             _, kout = self.kf_ext.ScreenAndComputeKPsParams(img, kin)
             out.append((kout, self.kf_ext.CalcDescriptors(img, kout) if len(kout) else np.zeros((0, 32), np.uint8)))
         return out

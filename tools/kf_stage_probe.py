@@ -21,11 +21,11 @@ tracked = timed("lk_right", lambda: ops.lk_right(lefts0, rights, pts))
 pinned = torch.from_numpy(np.stack(lefts0)).pin_memory().numpy()      # the replay keeps its keyframe images page-locked
 lefts = [pinned[i] for i in range(32)]
 timed("cnn_descr", lambda: ops.cnn_descr(lefts))
-kins = timed("expand_octaves (host)", lambda: [replay.expand_octaves(f) for f in feats])
-timed("screen_and_describe", lambda: ops.screen_and_describe(lefts, kins))
+timed("expand_octaves_batch (host)", lambda: replay.expand_octaves_batch(feats))
+timed("screen_and_describe", lambda: ops.screen_and_describe(lefts, feats))
 timed("triangulate_batch", lambda: ops.triangulate_batch(pts, [tr[0] for tr in tracked]))
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
 for _ in range(3):
-    ops.kf_detect(lefts0); ops.screen_and_describe(lefts, kins)
+    ops.kf_detect(lefts0); ops.screen_and_describe(lefts, feats)
 pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
