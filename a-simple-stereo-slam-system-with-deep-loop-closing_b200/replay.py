@@ -234,7 +234,8 @@ class KittiSequence(Sequence):
 class GpuOps:
     def __init__(self, device=0, batch=64, kf_features=300, kf_batch=32, n_kf=742, lcd_dtype=0, pin=True):
         self.device, self.batch, self.kf_batch, self._lcd_dtype = device, batch, kf_batch, lcd_dtype
-        self.fe = [capi.StereoFrontend(*ORB_PARAMS, max_pairs=batch, device=device) for _ in range(2)]
+        self.slots = 3                                    # front-end batches in flight (copy in, kernels, copy out overlap)
+        self.fe = [capi.StereoFrontend(*ORB_PARAMS, max_pairs=batch, device=device) for _ in range(self.slots)]
         self.fe_out = [f.alloc_outputs(batch, pinned=pin) for f in self.fe]
         self.ba = capi.LocalBA(max_windows=batch, max_poses=7, max_points=320, max_obs=2304, device=device)
         self.kf_ext = capi.ORBextractor(kf_features, 1.2, 8, 20, 7, max_batch=kf_batch, device=device)
@@ -398,6 +399,7 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
     frame_digest = {}
     n_kps = n_matches = 0
     nb = (len(my_frames) + B - 1) // B
+    NS = getattr(ops, "slots", 2)
     ba_results, wb = [], 0
 
     def collect(slot, b):
@@ -406,18 +408,19 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
         lo = b * B
         n = min(B, len(my_frames) - lo)
         n_kps += int(out["counts"][:n].sum())
-        for i in range(n):
-            cl, cr = int(out["counts"][i, 0]), int(out["counts"][i, 1])
-            n_matches += int((out["mdist"][i, :cl] >= 0).sum())
-            if with_digests:
+        live = np.arange(out["mdist"].shape[1])[None, :] < out["counts"][:n, 0, None]      # query rows of every frame
+        n_matches += int(((out["mdist"][:n] >= 0) & live).sum())
+        if with_digests:
+            for i in range(n):
+                cl, cr = int(out["counts"][i, 0]), int(out["counts"][i, 1])
                 frame_digest[int(my_frames[lo + i])] = digest(out["kps"][i, 0, :cl], out["kps"][i, 1, :cr], out["desc"][i, 0, :cl],
                                                               out["desc"][i, 1, :cr], out["midx"][i, :cl], out["mdist"][i, :cl])
 
     ba_pending = False
     for b in range(nb):
-        slot = b % 2
-        if b >= 2:
-            collect(slot, b - 2)
+        slot = b % NS
+        if b >= NS:
+            collect(slot, b - NS)
         if wb < len(windows):                           # the back end works beside the front end (src/backend.cpp:29-45)
             if ba_pending:
                 ba_results += ops.ba_wait()
@@ -427,8 +430,8 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
         lo = b * B
         batch = frames_np[lo:lo + B]
         ops.stereo_submit(slot, batch)
-    for b in range(max(0, nb - 2), nb):
-        collect(b % 2, b)
+    for b in range(max(0, nb - NS), nb):
+        collect(b % NS, b)
     while True:
         if ba_pending:
             ba_results += ops.ba_wait()
