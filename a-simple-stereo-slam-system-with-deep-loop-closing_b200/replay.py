@@ -454,6 +454,7 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
         tk = time.perf_counter()
         feats = ops.kf_detect(lefts)
         pts = [np.stack([f["x"], f["y"]], 1).astype(np.float32) for f in feats]
+        t.setdefault("kf_detect_batches_ms", []).append(round(1e3 * (time.perf_counter() - tk), 3))
         tk = lap(t, "kf_detect_s", tk)
         tracked = ops.lk_right(lefts, rights, pts)
         tk = lap(t, "kf_lk_s", tk)
@@ -481,16 +482,14 @@ def run(seq, ops, rank=0, world=1, db_min_size=50, min_gap=20, with_digests=Fals
         import torch.distributed as dist
         torch.cuda.set_device(ops.device)               # the C ABI selects its handle's device per call; make torch's explicit too
         poses_all = par.allgather_kf_poses(poses_ba, seq.n_kf, rank, world, device=torch.device("cuda", ops.device))
-        gathered = [None] * world
-        dist.all_gather_object(gathered, rec)
-        rec = {}
-        for g in gathered:
-            rec.update(g)
-        dd = [None] * world
-        dist.all_gather_object(dd, (frame_digest, n_kps, n_matches))
-        frame_digest = {}
+        import pickle
+        blobs = par.allgather_blobs(pickle.dumps((rec, frame_digest, n_kps, n_matches), protocol=pickle.HIGHEST_PROTOCOL),
+                                    device=torch.device("cuda", ops.device) if dist.get_backend() == "nccl" else None)
+        rec, frame_digest = {}, {}
         n_kps = n_matches = 0
-        for fd, a, b_ in dd:
+        for blob in blobs:
+            r_, fd, a, b_ = pickle.loads(blob)
+            rec.update(r_)
             frame_digest.update(fd)
             n_kps += a
             n_matches += b_

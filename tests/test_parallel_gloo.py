@@ -58,3 +58,24 @@ def test_single_process_path_needs_no_process_group():
     par = importlib.import_module(PKG + ".parallel")
     p = np.random.default_rng(0).normal(size=(9, 7))
     assert np.array_equal(par.allgather_kf_poses(p, 9, rank=0, world=1), p)
+
+
+def _blob_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    par = importlib.import_module(PKG + ".parallel")
+    mine = bytes([rank + 1]) * (0 if rank == 1 else 1000 * (rank + 1) + 7)       # ragged, one rank with nothing to send
+    got = par.allgather_blobs(mine)
+    ok = len(got) == world and all(got[r] == bytes([r + 1]) * (0 if r == 1 else 1000 * (r + 1) + 7) for r in range(world))
+    open(os.path.join(out_dir, f"blob_{rank}.txt"), "w").write("ok" if ok else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allgather_blobs_of_ragged_sizes(tmp_path):
+    """The replay's keyframe records travel as one byte string per rank (parallel.allgather_blobs)."""
+    port = _free_port()
+    mp.spawn(_blob_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    for r in range(3):
+        assert (tmp_path / f"blob_{r}.txt").read_text() == "ok", r
