@@ -20,6 +20,7 @@
 #ifndef SLAMB200_H
 #define SLAMB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -60,3 +60,13 @@ def test_nvtx_ranges_are_compiled_in(pkg):
     assert b"NVTX_INJECTION64_PATH" in blob
     for stage in (b"copy_level0", b"resize_pyramid", b"fast_cells", b"quadtree", b"gauss_blur", b"describe"):
         assert stage in blob
+
+
+def test_header_compiles_on_its_own_as_c_and_cxx(tmp_path):
+    """include/slamb200.h is the drop-in boundary: a C99 or C++11 translation unit that includes nothing else must compile."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "slamb200.h")
+    subprocess.check_call(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr])
+    subprocess.check_call(["g++", "-fsyntax-only", "-x", "c++", "-std=c++11", "-Wall", "-Werror", hdr])

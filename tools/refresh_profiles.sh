@@ -6,6 +6,7 @@ set -u
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -q > $O/r2_pytest_gpu.log 2>&1; tail -1 $O/r2_pytest_gpu.log
+python __graft_entry__.py smoke > $O/r2_smoke.log 2>&1; tail -1 $O/r2_smoke.log
 python bench.py > $O/r2_bench_default.json 2> $O/r2_bench_default.err
 python bench.py --config 2 --no-cpu-baseline > $O/r2_bench_c2.json 2> $O/r2_bench_c2.err
 python bench.py --config 4 > $O/r2_bench_c4.json 2> $O/r2_bench_c4.err
