@@ -335,9 +335,7 @@ def run_reference(args, rank, world):
            "config": {"workload": WORKLOAD if not args.no_ba else "config 2: ORB extract (both views) + L<->R Hamming match only",
                       "frames_per_step": per_step},
            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": ref.kind, "kind_detail": ref.kind_detail,
-                            "sample": f"{per_step} synthetic stereo frames per step through oracle/ (C restatement of "
-                                      "ORBextractor::DetectAndCompute + BFMatcher + the g2o-faithful LM/Schur BA; the reference "
-                                      "itself needs OpenCV/g2o and cannot be built here), one frame per thread"},
+                            "sample": f"{per_step} synthetic stereo frames per step, one frame per thread: " + ref.kind_detail},
            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
