@@ -907,7 +907,7 @@ def main():
                "loop_closing_extras": extras}
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n = max(2 * cores, 16)
+            n = max(8 * cores, 64)                         # about 10 s of CPU work (0.08 s per frame and core)
             sample = pool_np[:min(n, P)]
             fps, kind, kind_detail = cpu_reference_fps(sample, windows if with_ba else None, cores)
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "kind_detail": kind_detail,
