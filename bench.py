@@ -10,8 +10,16 @@ windows (7 keyframes x 300 landmarks, ~1400 observations) — one window per fra
 only optimises once per keyframe (~1 frame in 6).
   value : frames/s with the inputs already resident in HBM (device entry points, CUDA events)
   e2e   : frames/s through the host-pointer C ABI (pinned host buffers, H2D + D2H inside the timed region)
-  --impl reference : the CPU restatement of the reference (oracle/, all host cores) on the same workload
+  --impl reference : the reference's CPU path (its own ORBextractor.cpp from oracle/_ref + the C restatement of the OpenCV /
+                     g2o parts, all host cores) on the same workload
 Prints ONE JSON line on rank 0.
+
+Scheduling defaults (each env switch reproduces the A/B it was measured with; see the comment where it is read):
+  device-resident loop : 1 extract + match stream beside BA, 2 without BA (BENCH_EXT_HANDLES); 2 BA batches in flight
+                         (BENCH_BA_STREAMS), BA batch i released at the start of extraction i (BENCH_BA_LOCKSTEP),
+                         BA stream priority 0 (BENCH_BA_PRIORITY)
+  end-to-end loop      : 2 front-end handles beside BA, 3 without (BENCH_FE_HANDLES), their kernels on one shared stream beside BA
+                         (BENCH_FE_SHARED_STREAM), 2 prioritised BA streams (BENCH_BA_E2E_STREAMS, BENCH_BA_E2E_PRIORITY)
 """
 import argparse
 import ctypes as C
