@@ -56,3 +56,22 @@ def test_cuda_replay_equals_the_cpu_replay(cpu_result, pkg):
     assert got["posegraph_runs"] == want["posegraph_runs"]
     assert abs(got["mean_position_error_final_m"] - want["mean_position_error_final_m"]) < 0.05
     assert got["kf_pose_digest"] != "" and got["keypoints"] == want["keypoints"] and got["matches"] == want["matches"]
+
+
+def test_batched_octave_expansion_equals_the_per_keyframe_one(pkg):
+    """replay.expand_octaves_batch packs src/loopclosing.cpp:94-105 for a whole batch of keyframes (ragged, one empty)."""
+    import importlib
+    replay = importlib.import_module(pkg.__name__ + ".replay")
+    capi = importlib.import_module(pkg.__name__ + ".capi")
+    rng = np.random.default_rng(0)
+    feats = []
+    for n in (300, 17, 0, 123):
+        f = np.zeros(n, capi.KP_DTYPE)
+        f["x"], f["y"] = rng.uniform(0, 1241, n), rng.uniform(0, 376, n)
+        f["size"], f["angle"] = 7, -1
+        feats.append(f)
+    kin, n_in = replay.expand_octaves_batch(feats)
+    assert kin.shape == (4, 2400) and n_in.tolist() == [2400, 136, 0, 984]
+    for b, f in enumerate(feats):
+        assert kin[b, :n_in[b]].tobytes() == replay.expand_octaves(f).tobytes()
+        assert not kin[b, n_in[b]:].view(np.uint8).any()
